@@ -1,0 +1,168 @@
+/* libmidas_b200 -- C ABI of the B200-native particle-filter hot path for MidasTouch.
+ *
+ * Every entry point replaces one Python-level call of the reference (paths relative to
+ * the reference tree); the reference has no FFI of its own (it is pure Python over
+ * torch), so the binding a maintainer adds is the ctypes stub shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types cross this boundary.
+ *   - every pointer named d_* is a DEVICE pointer owned by the caller (tensor.data_ptr());
+ *     h_* is a host pointer.  The library owns only mt_ctx scratch.
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, no hidden
+ *     synchronisation unless stated.
+ *   - return value: 0 = ok, negative = error (mt_last_error() gives the text).  Nothing
+ *     throws or aborts.
+ *   - particle poses inside the engine are SoA "3 x float4": three arrays of `stride`
+ *     float4, array r holding row r of [R|t] = (R[r][0], R[r][1], R[r][2], t[r]);
+ *     the constant bottom row of the reference's (N,4,4) tensor is implicit.
+ *     d_soa points at 3*stride float4.  mt_aos_to_soa / mt_soa_to_aos convert from/to
+ *     the reference layout (N,4,4) float32 row-major (particle_filter.py:33-58).
+ */
+#ifndef MIDAS_B200_H
+#define MIDAS_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mt_ctx mt_ctx;
+
+#define MT_OK 0
+#define MT_ERR_ARG -1
+#define MT_ERR_CUDA -2
+#define MT_ERR_STATE -3
+#define MT_ERR_CAPACITY -4
+
+#define MT_DTYPE_F32 0
+#define MT_DTYPE_F64 1
+
+const char* mt_last_error(void);
+int mt_version(void);
+
+/* ---- context ------------------------------------------------------------------- */
+/* capacity = max particles resident on this GPU; M,D = codebook rows / embedding width. */
+int mt_ctx_create(int device, size_t capacity, int M, int D, mt_ctx** out);
+int mt_ctx_destroy(mt_ctx* ctx);
+
+/* ---- codebook: tactile_tree.__init__ / init_tree (tactile_tree.py:13-41) ---------- */
+/* h_keys: (M,6) float32 R3_SE3 keys on the HOST (a uniform grid over the translation
+ * part replaces the nanoflann tree); d_emb: (M,D) embeddings on the device in emb_dtype
+ * (the reference stores float64, build_codebook.py:72-74).  The library keeps the pointer,
+ * it does not copy the embeddings. */
+int mt_codebook_upload(mt_ctx* ctx, const float* h_keys, const void* d_emb, int emb_dtype);
+/* key grid introspection (tests): cell size, dims[3], number of occupied cells */
+int mt_codebook_grid_info(mt_ctx* ctx, float* h, int dims[3], int* occupied);
+
+/* cos(q, E_m) for all M rows -> ctx-resident float64 tables sim[M] and exp(sim)[M]
+ * (get_similarity(code, heatmap_embeddings, softmax=False), filter.py:213-215, and the
+ * per-particle weights of filter.py:170-173 by table lookup).  d_q: (D,) in q_dtype.
+ * d_sim_out (nullable): (M,) float64 copy of the table. */
+int mt_codebook_query(mt_ctx* ctx, const void* d_q, int q_dtype, double* d_sim_out, void* stream);
+/* general form: cos(q, T_n) for an explicit (rows, D) target matrix
+ * (get_similarity(queries, targets), particle_filter.py:449-457). */
+int mt_cosine_rows(mt_ctx* ctx, const void* d_q, int q_dtype, const void* d_targets, int t_dtype, long long rows,
+                   int D, double* d_out, void* stream);
+/* Q queries at once: out[q*rows + m] = cos(Q_q, T_m) in float32 (the M x M retrieval of
+ * eval/single_touch_test.py:35-73). */
+int mt_cosine_batched(mt_ctx* ctx, const float* d_Q, int nq, const float* d_T, long long rows, int D, float* d_out,
+                      void* stream);
+/* softmax over n float64 scores unless (max-min) is within 1e-8 of 0, then a copy
+ * (particle_filter.py:459-468).  d_out may alias d_in. */
+int mt_softmax_f64(mt_ctx* ctx, const double* d_in, long long n, double* d_out, void* stream);
+
+/* ---- layout converters --------------------------------------------------------- */
+int mt_aos_to_soa(const float* d_aos, long long n, float* d_soa, long long stride, void* stream);
+int mt_soa_to_aos(const float* d_soa, long long stride, long long n, float* d_aos, void* stream);
+
+/* ---- SE3_NN (tactile_tree.py:43-58) --------------------------------------------- */
+/* R3_SE3 keys of n poses -> d_keys (n,6) float32 */
+int mt_se3_keys(const float* d_soa, long long stride, long long n, float* d_keys, void* stream);
+/* exact L2 1-NN of n keys in the codebook; ties -> lowest index.  d_hint (nullable):
+ * a codebook index per query that seeds the search bound (any valid index is correct).
+ * mode 0 = grid search, 1 = exhaustive (tiled).  d_idx: (n,) int32. */
+int mt_nn_assign(mt_ctx* ctx, const float* d_keys, long long n, const int32_t* d_hint, int mode, int32_t* d_idx,
+                 void* stream);
+/* out[i] = table rows gathered by index: poses (M,4,4) f32 -> AoS (n,4,4) */
+int mt_gather_rows_f32(const float* d_table, const int32_t* d_idx, long long n, int row_floats, float* d_out,
+                       void* stream);
+
+/* ---- motionModel (particle_filter.py:319-377) ----------------------------------- */
+/* pose_n <- pose_n @ (odom @ [Rzyx(rot_n) | tn_n]).  h_odom: 16 floats (4,4) row-major on
+ * the host.  d_tn/d_rot: (n,3) float32 noise (translation m / rotation deg) drawn by the
+ * caller -- the reference's CPU RNG contract (326-335); if both are NULL the kernel draws
+ * Philox4x32-10 normals keyed by (seed, step, first_gid+n) scaled by sig_t/sig_r.
+ * d_invalid_count (nullable): incremented for poses check_quats would prune (347-357).
+ * euler_mode 0: Rn = Rz Ry Rx (euler_angles_to_matrix "ZYX", motionModel); 1: Rn = Rx Ry Rz
+ * (scipy from_euler("zyx"), init_filter at particle_filter.py:129-145). */
+int mt_motion(const float* d_soa_in, float* d_soa_out, long long stride, long long n, const float* h_odom,
+              const float* d_tn, const float* d_rot, float sig_t, float sig_r, uint64_t seed, uint64_t step,
+              uint64_t first_gid, int* d_invalid_count, int euler_mode, void* stream);
+
+/* ---- particle_rmse (particle_filter.py:472-496) --------------------------------- */
+/* d_out2: {rmse_t, rmse_r} float32 on the device */
+int mt_rmse(mt_ctx* ctx, const float* d_soa, long long stride, long long n, const float* h_gt, float* d_out2,
+            void* stream);
+
+/* ---- resampler("low_var") (particle_filter.py:230-261, 288-307) ------------------ */
+/* systematic resampling of n float64 weights: normalise by their sum, inclusive float64
+ * prefix, slot j <- first i with loc_j < C_i, loc_j = j/n + float32(u)/n.
+ * d_anc: (n,) int32 ancestor of every slot.  seq != 0 selects the strictly sequential
+ * float64 prefix (bit-identical to torch.cumsum on CPU; one thread, tests only).
+ * d_status (nullable): set to 1 when the reference would skip resampling (all-zero or
+ * NaN weights, 237-241); the ancestors are then the identity. */
+int mt_resample_systematic(mt_ctx* ctx, const double* d_w, long long n, float u, int seq, int32_t* d_anc,
+                           int* d_status, void* stream);
+int mt_gather_soa(const float* d_soa_in, long long stride_in, const int32_t* d_anc, long long n, float* d_soa_out,
+                  long long stride_out, void* stream);
+int mt_gather_f64(const double* d_in, const int32_t* d_anc, long long n, double* d_out, void* stream);
+
+/* ---- fused engine step (filter.py:152-190 without prune/cluster/anneal) ----------- */
+typedef struct mt_step_args {
+  /* particle state, SoA, ping-pong */
+  float* d_soa_cur;      /* in: poses at t-1 (moved in place) */
+  float* d_soa_next;     /* out: resampled poses */
+  long long stride;      /* float4 elements per row array, >= capacity */
+  int32_t* d_nn_cur;     /* in: NN hint per particle (-1 = none); out: NN of the moved pose */
+  int32_t* d_nn_next;    /* out: NN index inherited by every child (next step's hint) */
+  int32_t* d_anc;        /* out (nullable): ancestor (local index) of every child */
+  long long n;           /* particles on this GPU */
+  /* motion */
+  float odom[16];
+  const float* d_tn;     /* nullable -> Philox */
+  const float* d_rot;
+  float sig_t, sig_r;
+  uint64_t seed, step, first_gid;
+  /* measurement */
+  int softmax;           /* 1: w = exp(cos) (filter.py:171-173); 0: raw cosine (filter_real.py:208-210) */
+  /* resampling */
+  float u;               /* the single systematic offset torch.rand(1) (particle_filter.py:260) */
+  int resample;          /* 0: stop after weighting (kernel A only) */
+  /* metric (nullable gt): rmse of the moved poses vs gt (filter.py:164) */
+  const float* gt;       /* host, 16 floats, or NULL */
+  float* d_rmse2;        /* device, 2 floats */
+  /* sharding: this GPU holds ranks' slice `rank` of `world`; d_shard_sums (world doubles,
+   * device) holds every rank's weight sum, written by the caller's collective between
+   * mt_step_a and mt_step_b; NULL for a single GPU. */
+  int rank, world;
+  long long n_global;
+  double* d_shard_sums;
+  long long* d_n_out;    /* device (nullable): number of children written on this GPU */
+  const long long* d_n_in; /* device (nullable): particle count read by the kernels instead of n; n is then
+                            * only the upper bound that sizes the grid (no host sync between steps) */
+} mt_step_args;
+
+/* kernel A: motion + key + exact NN + weight lookup + deterministic weight sums */
+int mt_step_a(mt_ctx* ctx, const mt_step_args* a, void* stream);
+/* device pointer to this GPU's local weight sum (float64), valid after mt_step_a */
+int mt_step_local_sum_ptr(mt_ctx* ctx, double** d_sum);
+/* kernel B: normalise + prefix + systematic draw + scatter of children */
+int mt_step_b(mt_ctx* ctx, const mt_step_args* a, void* stream);
+/* normalised float64 weights of the current particles (after mt_step_a) */
+int mt_step_weights(mt_ctx* ctx, const mt_step_args* a, double* d_w, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

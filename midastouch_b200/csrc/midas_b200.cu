@@ -1,0 +1,1323 @@
+// libmidas_b200: hand-written sm_100a kernels + C ABI for the MidasTouch particle-filter
+// hot path (include/midas_b200.h).  No host compute path: every entry point launches
+// CUDA kernels on the caller's stream.
+//
+// Kernel inventory (DESIGN.md has the roofline for each):
+//   k_cosine_rows      1 x D against rows x D cosine (codebook query / get_similarity)
+//   k_cosine_batched   Q x D against rows x D, fp32 SIMT tiles
+//   k_step_a           motion + SE(3) key + exact grid 1-NN + weight lookup + chunk sums
+//   k_step_b           normalise + float64 prefix + systematic draw + child scatter
+//   k_nn_grid/brute    standalone SE3_NN index search
+//   k_resample_*       systematic resampling of explicit float64 weights
+//   small: converters, gathers, rmse, softmax
+#include <cuda_runtime.h>
+#include <float.h>
+#include <limits.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <numeric>
+#include <vector>
+
+#include "../../include/midas_b200.h"
+#include "mt_math.cuh"
+
+#define MT_MAX_D 6144  // query staged in 48 KB of shared memory as float64
+#define MT_CHUNK 256  // particles per chunk == threads per block of the sweep kernels
+
+// ------------------------------------------------------------------------- errors
+static thread_local char g_err[512] = "";
+static int set_err(int code, const char* fmt, const char* a = "", const char* b = "") {
+  snprintf(g_err, sizeof(g_err), fmt, a, b);
+  return code;
+}
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess) return set_err(MT_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e__)); \
+  } while (0)
+#define CK_LAUNCH() CK(cudaGetLastError())
+
+extern "C" const char* mt_last_error(void) { return g_err; }
+extern "C" int mt_version(void) { return 100; }
+
+// ------------------------------------------------------------------------- context
+struct GridParams {
+  float org[3];
+  float inv_h, h;
+  int dims[3];
+};
+
+struct mt_ctx {
+  int device;
+  size_t cap;
+  int M, D;
+  // codebook
+  float4* d_keys_orig;    // M x 2 float4 (k0..k3 | k4,k5,0,0), original order
+  float4* d_keys_sorted;  // same, sorted by grid cell
+  int* d_sorted_orig;     // sorted position -> original index
+  int* d_cell_start;      // ncells + 1
+  GridParams grid;
+  int occupied;
+  const void* d_emb;
+  int emb_dtype;
+  double* d_sim;   // cos(q, E_m)
+  double* d_esim;  // exp(cos)
+  bool cb_ready;
+  // scratch
+  int chunk_cap;
+  double* d_part;     // per-chunk weight sums
+  double* d_prefix;   // exclusive prefix of d_part, [nchunks] = total
+  double* d_rm_part;  // 2 x chunk_cap rmse partials
+  double* d_q64;      // staged query, float64, MT_MAX_D entries
+  double* d_scal;     // [0] local weight sum, [1] max, [2] min, [3] softmax denom, [4..7] spare
+  unsigned int* d_ticket;
+  int* d_flags;  // [0] overflow, [1] resample skipped
+};
+
+static size_t nchunks_of(long long n) { return (size_t)((n + MT_CHUNK - 1) / MT_CHUNK); }
+
+extern "C" int mt_ctx_create(int device, size_t capacity, int M, int D, mt_ctx** out) {
+  if (!out || capacity == 0 || M <= 0 || D <= 0) return set_err(MT_ERR_ARG, "mt_ctx_create: bad argument");
+  CK(cudaSetDevice(device));
+  mt_ctx* c = new mt_ctx();
+  memset(c, 0, sizeof(*c));
+  c->device = device;
+  c->cap = capacity;
+  c->M = M;
+  c->D = D;
+  c->chunk_cap = (int)nchunks_of((long long)capacity) + 2;
+  CK(cudaMalloc(&c->d_keys_orig, sizeof(float4) * 2 * M));
+  CK(cudaMalloc(&c->d_keys_sorted, sizeof(float4) * 2 * M));
+  CK(cudaMalloc(&c->d_sorted_orig, sizeof(int) * M));
+  CK(cudaMalloc(&c->d_sim, sizeof(double) * M));
+  CK(cudaMalloc(&c->d_esim, sizeof(double) * M));
+  CK(cudaMalloc(&c->d_part, sizeof(double) * c->chunk_cap));
+  CK(cudaMalloc(&c->d_prefix, sizeof(double) * (c->chunk_cap + 1)));
+  CK(cudaMalloc(&c->d_rm_part, sizeof(double) * 2 * c->chunk_cap));
+  CK(cudaMalloc(&c->d_scal, sizeof(double) * 8));
+  CK(cudaMalloc(&c->d_q64, sizeof(double) * MT_MAX_D));
+  CK(cudaMalloc(&c->d_ticket, sizeof(unsigned int) * 4));
+  CK(cudaMalloc(&c->d_flags, sizeof(int) * 4));
+  CK(cudaMemset(c->d_ticket, 0, sizeof(unsigned int) * 4));
+  CK(cudaMemset(c->d_flags, 0, sizeof(int) * 4));
+  CK(cudaMemset(c->d_scal, 0, sizeof(double) * 8));
+  *out = c;
+  return MT_OK;
+}
+
+extern "C" int mt_ctx_destroy(mt_ctx* c) {
+  if (!c) return MT_OK;
+  cudaSetDevice(c->device);
+  cudaFree(c->d_keys_orig);
+  cudaFree(c->d_keys_sorted);
+  cudaFree(c->d_sorted_orig);
+  cudaFree(c->d_cell_start);
+  cudaFree(c->d_sim);
+  cudaFree(c->d_esim);
+  cudaFree(c->d_part);
+  cudaFree(c->d_prefix);
+  cudaFree(c->d_rm_part);
+  cudaFree(c->d_scal);
+  cudaFree(c->d_q64);
+  cudaFree(c->d_ticket);
+  cudaFree(c->d_flags);
+  delete c;
+  return MT_OK;
+}
+
+// ------------------------------------------------------------------------- codebook grid
+// cell coordinate of a key component: identical float32 formula on host and device so that
+// monotonicity arguments about search boxes hold bit-for-bit.
+__host__ __device__ __forceinline__ int cell_coord(float x, float org, float inv_h, int dim) {
+#if defined(__CUDA_ARCH__)
+  float f = floorf(__fmul_rn(__fsub_rn(x, org), inv_h));
+#else
+  volatile float d = x - org;
+  volatile float m = d * inv_h;
+  float f = floorf(m);
+#endif
+  int c = (f < 0.f) ? 0 : (f >= (float)dim ? dim - 1 : (int)f);
+  return c;
+}
+
+extern "C" int mt_codebook_upload(mt_ctx* c, const float* h_keys, const void* d_emb, int emb_dtype) {
+  if (!c || !h_keys) return set_err(MT_ERR_ARG, "mt_codebook_upload: null argument");
+  if (emb_dtype != MT_DTYPE_F32 && emb_dtype != MT_DTYPE_F64) return set_err(MT_ERR_ARG, "mt_codebook_upload: dtype");
+  CK(cudaSetDevice(c->device));
+  const int M = c->M;
+  float lo[3], hi[3];
+  for (int k = 0; k < 3; ++k) lo[k] = FLT_MAX, hi[k] = -FLT_MAX;
+  for (int m = 0; m < M; ++m)
+    for (int k = 0; k < 3; ++k) {
+      float v = h_keys[6 * m + k];
+      if (!(v == v)) return set_err(MT_ERR_ARG, "mt_codebook_upload: NaN key");
+      lo[k] = std::min(lo[k], v);
+      hi[k] = std::max(hi[k], v);
+    }
+  float ext[3], maxext = 0.f;
+  for (int k = 0; k < 3; ++k) ext[k] = hi[k] - lo[k], maxext = std::max(maxext, ext[k]);
+  if (maxext <= 0.f) maxext = 1e-3f;
+  // cell size: shrink until <= 4 keys per occupied cell on average (keys lie on a surface),
+  // bounded by 4M cells in the box.
+  std::vector<long long> ids(M);
+  float best_h = maxext;
+  int best_dims[3] = {1, 1, 1};
+  int best_occ = 1;
+  for (float h = maxext / 2.f; h > maxext * 1e-4f; h /= 1.5f) {
+    int dims[3];
+    double total = 1;
+    for (int k = 0; k < 3; ++k) dims[k] = (int)floorf(ext[k] / h) + 1, total *= dims[k];
+    if (total > 4.0e6) break;
+    float inv_h = 1.0f / h;
+    for (int m = 0; m < M; ++m) {
+      int x = cell_coord(h_keys[6 * m], lo[0], inv_h, dims[0]);
+      int y = cell_coord(h_keys[6 * m + 1], lo[1], inv_h, dims[1]);
+      int z = cell_coord(h_keys[6 * m + 2], lo[2], inv_h, dims[2]);
+      ids[m] = ((long long)z * dims[1] + y) * dims[0] + x;
+    }
+    std::vector<long long> s(ids);
+    std::sort(s.begin(), s.end());
+    int occ = (int)(std::unique(s.begin(), s.end()) - s.begin());
+    best_h = h;
+    best_occ = occ;
+    for (int k = 0; k < 3; ++k) best_dims[k] = dims[k];
+    if ((double)M / occ <= 4.0) break;
+  }
+  GridParams g;
+  for (int k = 0; k < 3; ++k) g.org[k] = lo[k], g.dims[k] = best_dims[k];
+  g.h = best_h;
+  g.inv_h = 1.0f / best_h;
+  const long long ncell = (long long)g.dims[0] * g.dims[1] * g.dims[2];
+  std::vector<int> cell(M);
+  for (int m = 0; m < M; ++m) {
+    int x = cell_coord(h_keys[6 * m], g.org[0], g.inv_h, g.dims[0]);
+    int y = cell_coord(h_keys[6 * m + 1], g.org[1], g.inv_h, g.dims[1]);
+    int z = cell_coord(h_keys[6 * m + 2], g.org[2], g.inv_h, g.dims[2]);
+    cell[m] = (int)(((long long)z * g.dims[1] + y) * g.dims[0] + x);
+  }
+  std::vector<int> order(M);
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cell[a] < cell[b]; });
+  std::vector<int> start(ncell + 1, 0);
+  for (int m = 0; m < M; ++m) start[cell[m] + 1]++;
+  for (long long i = 0; i < ncell; ++i) start[i + 1] += start[i];
+  std::vector<float> ko(8 * (size_t)M, 0.f), ks(8 * (size_t)M, 0.f);
+  for (int m = 0; m < M; ++m)
+    for (int k = 0; k < 6; ++k) {
+      ko[8 * (size_t)m + k] = h_keys[6 * m + k];
+      ks[8 * (size_t)m + k] = h_keys[6 * order[m] + k];
+    }
+  if (c->d_cell_start) cudaFree(c->d_cell_start), c->d_cell_start = nullptr;
+  CK(cudaMalloc(&c->d_cell_start, sizeof(int) * (ncell + 1)));
+  CK(cudaMemcpy(c->d_cell_start, start.data(), sizeof(int) * (ncell + 1), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(c->d_keys_orig, ko.data(), sizeof(float) * 8 * M, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(c->d_keys_sorted, ks.data(), sizeof(float) * 8 * M, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(c->d_sorted_orig, order.data(), sizeof(int) * M, cudaMemcpyHostToDevice));
+  c->grid = g;
+  c->occupied = best_occ;
+  c->d_emb = d_emb;
+  c->emb_dtype = emb_dtype;
+  c->cb_ready = true;
+  return MT_OK;
+}
+
+extern "C" int mt_codebook_grid_info(mt_ctx* c, float* h, int dims[3], int* occupied) {
+  if (!c || !c->cb_ready) return set_err(MT_ERR_STATE, "mt_codebook_grid_info: no codebook");
+  if (h) *h = c->grid.h;
+  if (dims)
+    for (int k = 0; k < 3; ++k) dims[k] = c->grid.dims[k];
+  if (occupied) *occupied = c->occupied;
+  return MT_OK;
+}
+
+// ------------------------------------------------------------------------- block helpers
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// fixed-topology sum over a 256-thread block; result valid in thread 0
+__device__ __forceinline__ double block_sum_256(double v, double* s8) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) s8[w] = v;
+  __syncthreads();
+  double t = 0.0;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < MT_CHUNK / 32; ++k) t += s8[k];
+  }
+  return t;
+}
+
+// inclusive scan over a 256-thread block (Kogge-Stone per warp, sequential warp carry)
+__device__ __forceinline__ double block_incl_scan_256(double v, double* s8) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    double t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += t;
+  }
+  __syncthreads();
+  if (lane == 31) s8[w] = v;
+  __syncthreads();
+  double carry = 0.0;
+#pragma unroll
+  for (int k = 0; k < MT_CHUNK / 32; ++k)
+    if (k < w) carry += s8[k];
+  return carry + v;
+}
+
+// Last block standing: exclusive prefix over `n` chunk sums with one 256-thread block.
+// Each thread owns a contiguous run (sequential), thread totals are block-scanned; the
+// topology depends only on n, so results are reproducible run to run.
+__device__ void scan_chunk_sums(const double* part, int n, double* prefix, double* total_out, double* s8) {
+  __shared__ double s_incl[MT_CHUNK];
+  const int per = (n + MT_CHUNK - 1) / MT_CHUNK;
+  const int b = threadIdx.x * per;
+  double loc = 0.0;
+  for (int k = 0; k < per; ++k) {
+    int i = b + k;
+    if (i < n) loc += __ldcg(part + i);
+  }
+  const double incl = block_incl_scan_256(loc, s8);
+  s_incl[threadIdx.x] = incl;
+  __syncthreads();
+  double run = threadIdx.x ? s_incl[threadIdx.x - 1] : 0.0;  // exclusive base of this thread's run
+  for (int k = 0; k < per; ++k) {
+    int i = b + k;
+    if (i < n) {
+      prefix[i] = run;
+      run += __ldcg(part + i);
+    }
+  }
+  if (threadIdx.x == MT_CHUNK - 1) {
+    prefix[n] = incl;
+    *total_out = incl;
+  }
+}
+
+// ------------------------------------------------------------------------- cosine kernels
+template <typename T>
+struct VecLoad;
+template <>
+struct VecLoad<float> {
+  static constexpr int W = 4;
+  __device__ static void ld(const float* p, double* o) {
+    float4 v = __ldg(reinterpret_cast<const float4*>(p));
+    o[0] = v.x, o[1] = v.y, o[2] = v.z, o[3] = v.w;
+  }
+};
+template <>
+struct VecLoad<double> {
+  static constexpr int W = 2;
+  __device__ static void ld(const double* p, double* o) {
+    double2 v = __ldg(reinterpret_cast<const double2*>(p));
+    o[0] = v.x, o[1] = v.y;
+  }
+};
+
+// one warp per row.  q is staged in shared memory as float64.  Traffic: rows*D*sizeof(T).
+template <typename T, int UNROLL>
+__global__ void __launch_bounds__(256) k_cosine_rows(const double* __restrict__ qd, double qnorm_unused,
+                                                     const T* __restrict__ E, long long rows, int D,
+                                                     double* __restrict__ out, double* __restrict__ out_exp,
+                                                     double* __restrict__ out2) {
+  extern __shared__ double sq[];
+  for (int i = threadIdx.x; i < D; i += blockDim.x) sq[i] = qd[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  constexpr int W = VecLoad<T>::W;
+  const T* e = E + row * (long long)D;
+  double dot = 0.0, nn = 0.0, qq = 0.0;
+  const int nvec = D / W;
+  int v = lane;
+  for (; v + 32 * (UNROLL - 1) < nvec; v += 32 * UNROLL) {
+    double x[UNROLL][W];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) VecLoad<T>::ld(e + (size_t)(v + 32 * u) * W, x[u]);
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u)
+#pragma unroll
+      for (int k = 0; k < W; ++k) {
+        double qv = sq[(v + 32 * u) * W + k];
+        dot = fma(x[u][k], qv, dot);
+        nn = fma(x[u][k], x[u][k], nn);
+      }
+  }
+  for (; v < nvec; v += 32) {
+    double x[W];
+    VecLoad<T>::ld(e + (size_t)v * W, x);
+#pragma unroll
+    for (int k = 0; k < W; ++k) {
+      dot = fma(x[k], sq[v * W + k], dot);
+      nn = fma(x[k], x[k], nn);
+    }
+  }
+  for (int i = nvec * W + lane; i < D; i += 32) {  // ragged tail
+    double x = (double)e[i];
+    dot = fma(x, sq[i], dot);
+    nn = fma(x, x, nn);
+  }
+  for (int i = lane; i < D; i += 32) qq = fma(sq[i], sq[i], qq);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    nn += __shfl_xor_sync(0xffffffffu, nn, o);
+    qq += __shfl_xor_sync(0xffffffffu, qq, o);
+  }
+  if (lane == 0) {
+    // torch cosine_similarity: x/max(|x|,eps) . y/max(|y|,eps), eps = 1e-8
+    double c = dot / (fmax(sqrt(qq), 1e-8) * fmax(sqrt(nn), 1e-8));
+    out[row] = c;
+    if (out_exp) out_exp[row] = exp(c);
+    if (out2) out2[row] = c;
+  }
+}
+
+template <typename TQ>
+__global__ void k_to_f64(const TQ* in, int n, double* out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (double)in[i];
+}
+
+static int launch_cosine(const double* d_q64, const void* E, int dt, long long rows, int D, double* out,
+                         double* out_exp, double* out2, cudaStream_t st) {
+  const int warps = 8;
+  const unsigned grid = (unsigned)((rows + warps - 1) / warps);
+  const size_t sh = sizeof(double) * D;
+  if (rows == 0) return MT_OK;
+  if (dt == MT_DTYPE_F32) {
+    if (D % 4) return set_err(MT_ERR_ARG, "cosine: D must be a multiple of 4 for float32 rows");
+    k_cosine_rows<float, 4><<<grid, 256, sh, st>>>(d_q64, 0.0, (const float*)E, rows, D, out, out_exp, out2);
+  } else {
+    if (D % 2) return set_err(MT_ERR_ARG, "cosine: D must be a multiple of 2 for float64 rows");
+    k_cosine_rows<double, 4><<<grid, 256, sh, st>>>(d_q64, 0.0, (const double*)E, rows, D, out, out_exp, out2);
+  }
+  CK_LAUNCH();
+  return MT_OK;
+}
+
+static int stage_query(mt_ctx* c, const void* d_q, int q_dtype, int D, double** out, cudaStream_t st) {
+  if (D > MT_MAX_D) return set_err(MT_ERR_ARG, "cosine: D exceeds MT_MAX_D (6144)");
+  if (q_dtype == MT_DTYPE_F32)
+    k_to_f64<float><<<(D + 255) / 256, 256, 0, st>>>((const float*)d_q, D, c->d_q64);
+  else if (q_dtype == MT_DTYPE_F64)
+    k_to_f64<double><<<(D + 255) / 256, 256, 0, st>>>((const double*)d_q, D, c->d_q64);
+  else
+    return set_err(MT_ERR_ARG, "cosine: bad query dtype");
+  CK_LAUNCH();
+  *out = c->d_q64;
+  return MT_OK;
+}
+
+extern "C" int mt_codebook_query(mt_ctx* c, const void* d_q, int q_dtype, double* d_sim_out, void* stream) {
+  if (!c || !c->cb_ready || !c->d_emb) return set_err(MT_ERR_STATE, "mt_codebook_query: no codebook");
+  if (!d_q) return set_err(MT_ERR_ARG, "mt_codebook_query: null query");
+  cudaStream_t st = (cudaStream_t)stream;
+  double* q64;
+  int r = stage_query(c, d_q, q_dtype, c->D, &q64, st);
+  if (r) return r;
+  return launch_cosine(q64, c->d_emb, c->emb_dtype, c->M, c->D, c->d_sim, c->d_esim, d_sim_out, st);
+}
+
+extern "C" int mt_cosine_rows(mt_ctx* c, const void* d_q, int q_dtype, const void* d_t, int t_dtype, long long rows,
+                              int D, double* d_out, void* stream) {
+  if (!c || !d_q || (!d_t && rows) || !d_out || D <= 0 || rows < 0) return set_err(MT_ERR_ARG, "mt_cosine_rows: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  double* q64;
+  int r = stage_query(c, d_q, q_dtype, D, &q64, st);
+  if (r) return r;
+  return launch_cosine(q64, d_t, t_dtype, rows, D, d_out, nullptr, nullptr, st);
+}
+
+// Q x rows cosine in fp32: 64x64 output tile per block, K-step 16, register 4x4 micro-tile.
+// Norms are accumulated alongside.  (SIMT version; the tcgen05 path is in DESIGN.md "next".)
+__global__ void __launch_bounds__(256) k_cosine_batched(const float* __restrict__ Q, int nq,
+                                                        const float* __restrict__ T, long long rows, int D,
+                                                        float* __restrict__ out) {
+  __shared__ float sQ[16][64 + 1];
+  __shared__ float sT[16][64 + 1];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const long long m0 = (long long)blockIdx.x * 64;
+  const int q0 = blockIdx.y * 64;
+  float acc[4][4] = {};
+  float nq2[4] = {}, nt2[4] = {};
+  for (int k0 = 0; k0 < D; k0 += 16) {
+    for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+      int r = i >> 4, k = i & 15;
+      sQ[k][r] = (q0 + r < nq && k0 + k < D) ? Q[(size_t)(q0 + r) * D + k0 + k] : 0.f;
+      sT[k][r] = (m0 + r < rows && k0 + k < D) ? T[(size_t)(m0 + r) * D + k0 + k] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = sQ[k][ty * 4 + i], b[i] = sT[k][tx * 4 + i];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        nq2[i] = fmaf(a[i], a[i], nq2[i]);
+        nt2[i] = fmaf(b[i], b[i], nt2[i]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int q = q0 + ty * 4 + i;
+      long long m = m0 + tx * 4 + j;
+      if (q < nq && m < rows) out[(size_t)q * rows + m] = acc[i][j] / (fmaxf(sqrtf(nq2[i]), 1e-8f) * fmaxf(sqrtf(nt2[j]), 1e-8f));
+    }
+}
+
+extern "C" int mt_cosine_batched(mt_ctx* c, const float* d_Q, int nq, const float* d_T, long long rows, int D,
+                                 float* d_out, void* stream) {
+  if (!d_Q || !d_T || !d_out || nq <= 0 || rows <= 0 || D <= 0) return set_err(MT_ERR_ARG, "mt_cosine_batched: bad argument");
+  dim3 grid((unsigned)((rows + 63) / 64), (unsigned)((nq + 63) / 64));
+  k_cosine_batched<<<grid, 256, 0, (cudaStream_t)stream>>>(d_Q, nq, d_T, rows, D, d_out);
+  CK_LAUNCH();
+  return MT_OK;
+}
+
+// ------------------------------------------------------------------------- softmax (f64)
+__global__ void __launch_bounds__(256) k_minmax(const double* __restrict__ x, long long n, double* part,
+                                                unsigned int* ticket, double* scal) {
+  __shared__ double smx[8], smn[8];
+  const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+  double mx = -DBL_MAX, mn = DBL_MAX;
+  int nan = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    double v = x[i];
+    nan |= (v != v);
+    mx = fmax(mx, v);  // fmax/fmin ignore NaN; NaN is tracked separately
+    mn = fmin(mn, v);
+  }
+  nan = __syncthreads_or(nan);
+  for (int o = 16; o > 0; o >>= 1) {
+    mx = fmax(mx, __shfl_down_sync(0xffffffffu, mx, o));
+    mn = fmin(mn, __shfl_down_sync(0xffffffffu, mn, o));
+  }
+  if ((threadIdx.x & 31) == 0) smx[threadIdx.x >> 5] = mx, smn[threadIdx.x >> 5] = mn;
+  __syncthreads();
+  __shared__ bool last;
+  if (threadIdx.x == 0) {
+    for (int k = 1; k < 8; ++k) mx = fmax(mx, smx[k]), mn = fmin(mn, smn[k]);
+    part[2 * blockIdx.x] = nan ? qnan : mx;
+    part[2 * blockIdx.x + 1] = nan ? qnan : mn;
+    __threadfence();
+    last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence();
+    double a = -DBL_MAX, b = DBL_MAX;
+    bool any_nan = false;
+    for (unsigned k = 0; k < gridDim.x; ++k) {
+      double pa = __ldcg(part + 2 * k), pb = __ldcg(part + 2 * k + 1);
+      any_nan |= (pa != pa);
+      a = fmax(a, pa);
+      b = fmin(b, pb);
+    }
+    scal[1] = any_nan ? qnan : a;  // torch: max()/min() propagate NaN -> softmax of NaN
+    scal[2] = any_nan ? qnan : b;
+    *ticket = 0;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_expsum(const double* __restrict__ x, long long n, double* part,
+                                                unsigned int* ticket, double* scal) {
+  __shared__ double s8[8];
+  const double mx = scal[1];
+  double acc = 0.0;
+  // contiguous run per block so the summation tree is a function of (n, grid) only
+  const long long per = (n + gridDim.x - 1) / gridDim.x;
+  const long long b = (long long)blockIdx.x * per, e = (b + per < n) ? b + per : n;
+  for (long long i = b + threadIdx.x; i < e; i += blockDim.x) acc += exp(x[i] - mx);
+  double t = block_sum_256(acc, s8);
+  __shared__ bool last;
+  if (threadIdx.x == 0) {
+    part[blockIdx.x] = t;
+    __threadfence();
+    last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence();
+    double s = 0.0;
+    for (unsigned k = 0; k < gridDim.x; ++k) s += __ldcg(part + k);
+    scal[3] = s;
+    *ticket = 0;
+  }
+}
+
+__global__ void k_softmax_apply(const double* __restrict__ x, long long n, const double* __restrict__ scal,
+                                double* __restrict__ out) {
+  const double mx = scal[1], mn = scal[2], den = scal[3];
+  // torch.isclose(max-min, 0): |d| <= atol(1e-8) + rtol*|0|; NaN is never close -> softmax
+  const bool skip = fabs(mx - mn) <= 1e-8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    double v = x[i];
+    out[i] = skip ? v : exp(v - mx) / den;
+  }
+}
+
+extern "C" int mt_softmax_f64(mt_ctx* c, const double* d_in, long long n, double* d_out, void* stream) {
+  if (!c || !d_in || !d_out || n <= 0) return set_err(MT_ERR_ARG, "mt_softmax_f64: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  int grid = (int)std::min<long long>((n + 255) / 256, std::min<long long>(c->chunk_cap, 1184));
+  k_minmax<<<grid, 256, 0, st>>>(d_in, n, c->d_rm_part, c->d_ticket + 1, c->d_scal);
+  CK_LAUNCH();
+  k_expsum<<<grid, 256, 0, st>>>(d_in, n, c->d_part, c->d_ticket + 2, c->d_scal);
+  CK_LAUNCH();
+  k_softmax_apply<<<grid, 256, 0, st>>>(d_in, n, c->d_scal, d_out);
+  CK_LAUNCH();
+  return MT_OK;
+}
+
+// ------------------------------------------------------------------------- layout
+__device__ __forceinline__ void load_pose(const float4* __restrict__ soa, long long stride, long long i, float P[3][4]) {
+  float4 a = soa[i], b = soa[stride + i], c = soa[2 * stride + i];
+  P[0][0] = a.x, P[0][1] = a.y, P[0][2] = a.z, P[0][3] = a.w;
+  P[1][0] = b.x, P[1][1] = b.y, P[1][2] = b.z, P[1][3] = b.w;
+  P[2][0] = c.x, P[2][1] = c.y, P[2][2] = c.z, P[2][3] = c.w;
+}
+__device__ __forceinline__ void store_pose(float4* __restrict__ soa, long long stride, long long i, const float P[3][4]) {
+  soa[i] = make_float4(P[0][0], P[0][1], P[0][2], P[0][3]);
+  soa[stride + i] = make_float4(P[1][0], P[1][1], P[1][2], P[1][3]);
+  soa[2 * stride + i] = make_float4(P[2][0], P[2][1], P[2][2], P[2][3]);
+}
+
+__global__ void k_aos_to_soa(const float4* __restrict__ aos, long long n, float4* __restrict__ soa, long long stride) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  soa[i] = aos[4 * i];
+  soa[stride + i] = aos[4 * i + 1];
+  soa[2 * stride + i] = aos[4 * i + 2];
+}
+__global__ void k_soa_to_aos(const float4* __restrict__ soa, long long stride, long long n, float4* __restrict__ aos) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  aos[4 * i] = soa[i];
+  aos[4 * i + 1] = soa[stride + i];
+  aos[4 * i + 2] = soa[2 * stride + i];
+  aos[4 * i + 3] = make_float4(0.f, 0.f, 0.f, 1.f);
+}
+extern "C" int mt_aos_to_soa(const float* d_aos, long long n, float* d_soa, long long stride, void* stream) {
+  if (n < 0 || stride < n || (n && (!d_aos || !d_soa))) return set_err(MT_ERR_ARG, "mt_aos_to_soa: bad argument");
+  if (!n) return MT_OK;
+  k_aos_to_soa<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const float4*)d_aos, n, (float4*)d_soa, stride);
+  CK_LAUNCH();
+  return MT_OK;
+}
+extern "C" int mt_soa_to_aos(const float* d_soa, long long stride, long long n, float* d_aos, void* stream) {
+  if (n < 0 || stride < n || (n && (!d_aos || !d_soa))) return set_err(MT_ERR_ARG, "mt_soa_to_aos: bad argument");
+  if (!n) return MT_OK;
+  k_soa_to_aos<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const float4*)d_soa, stride, n, (float4*)d_aos);
+  CK_LAUNCH();
+  return MT_OK;
+}
+
+// ------------------------------------------------------------------------- exact 1-NN
+struct NNTables {
+  const float4* keys_orig;
+  const float4* keys_sorted;
+  const int* sorted_orig;
+  const int* cell_start;
+  GridParams g;
+  int M;
+};
+
+__device__ __forceinline__ void load_key(const float4* __restrict__ t, int i, float k[6]) {
+  float4 a = __ldg(t + 2 * i), b = __ldg(t + 2 * i + 1);
+  k[0] = a.x, k[1] = a.y, k[2] = a.z, k[3] = a.w, k[4] = b.x, k[5] = b.y;
+}
+
+__device__ __forceinline__ void nn_scan_range(const NNTables& T, const float q[6], int s, int e, float& best_d, int& best_i) {
+  for (int p = s; p < e; ++p) {
+    float k[6];
+    load_key(T.keys_sorted, p, k);
+    float d = mt_key_dist(q, k);
+    if (d <= best_d) {
+      int o = __ldg(T.sorted_orig + p);
+      if (d < best_d || o < best_i) best_d = d, best_i = o;
+    }
+  }
+}
+
+// exact nearest codebook key.  Correctness argument: after the seeding phase best_d is the
+// distance to a real key, so the true nearest key lies within r = sqrt(best_d) of q in
+// every coordinate; all cells overlapping the (slightly inflated) translation box are
+// scanned, rows whose translation lower bound already exceeds best_d are skipped.
+__device__ int nn_search(const NNTables& T, const float q[6], int hint) {
+  float best_d = FLT_MAX;
+  int best_i = INT_MAX;
+  const GridParams& g = T.g;
+  if (hint >= 0 && hint < T.M) {
+    float k[6];
+    load_key(T.keys_orig, hint, k);
+    best_d = mt_key_dist(q, k);
+    best_i = hint;
+  } else {
+    // seed: own cell and its 26 neighbours
+    int cx = cell_coord(q[0], g.org[0], g.inv_h, g.dims[0]);
+    int cy = cell_coord(q[1], g.org[1], g.inv_h, g.dims[1]);
+    int cz = cell_coord(q[2], g.org[2], g.inv_h, g.dims[2]);
+    int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.dims[0] - 1);
+    for (int z = max(cz - 1, 0); z <= min(cz + 1, g.dims[2] - 1); ++z)
+      for (int y = max(cy - 1, 0); y <= min(cy + 1, g.dims[1] - 1); ++y) {
+        int rb = (z * g.dims[1] + y) * g.dims[0];
+        nn_scan_range(T, q, __ldg(T.cell_start + rb + x0), __ldg(T.cell_start + rb + x1 + 1), best_d, best_i);
+      }
+    if (best_i == INT_MAX) {
+      float k[6];
+      load_key(T.keys_orig, 0, k);
+      best_d = mt_key_dist(q, k);
+      best_i = 0;
+    }
+  }
+  if (!(best_d == best_d)) return best_i;  // NaN query: keep the seed
+  const float r = sqrtf(best_d) * 1.0001f + 1e-12f;
+  const int xlo = cell_coord(q[0] - r, g.org[0], g.inv_h, g.dims[0]);
+  const int xhi = cell_coord(q[0] + r, g.org[0], g.inv_h, g.dims[0]);
+  const int ylo = cell_coord(q[1] - r, g.org[1], g.inv_h, g.dims[1]);
+  const int yhi = cell_coord(q[1] + r, g.org[1], g.inv_h, g.dims[1]);
+  const int zlo = cell_coord(q[2] - r, g.org[2], g.inv_h, g.dims[2]);
+  const int zhi = cell_coord(q[2] + r, g.org[2], g.inv_h, g.dims[2]);
+  for (int z = zlo; z <= zhi; ++z) {
+    // translation lower bound of slab z (0 when q is inside the slab)
+    float z0 = g.org[2] + z * g.h, z1 = z0 + g.h;
+    const float slack = 1e-3f * g.h;  // cell edges recomputed in float32 are off by ulps
+    float dz = fmaxf(fmaxf(z0 - q[2], q[2] - z1) - slack, 0.f);
+    for (int y = ylo; y <= yhi; ++y) {
+      float y0 = g.org[1] + y * g.h, y1 = y0 + g.h;
+      float dy = fmaxf(fmaxf(y0 - q[1], q[1] - y1) - slack, 0.f);
+      float lb = dz * dz + dy * dy;
+      if (lb * 0.998f > best_d && z > 0 && z < g.dims[2] - 1 && y > 0 && y < g.dims[1] - 1) continue;
+      int rb = (z * g.dims[1] + y) * g.dims[0];
+      nn_scan_range(T, q, __ldg(T.cell_start + rb + xlo), __ldg(T.cell_start + rb + xhi + 1), best_d, best_i);
+    }
+  }
+  return best_i;
+}
+
+__global__ void __launch_bounds__(256) k_nn_grid(NNTables T, const float* __restrict__ keys, long long n,
+                                                 const int* __restrict__ hint, int* __restrict__ idx) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float q[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) q[k] = keys[6 * i + k];
+  idx[i] = nn_search(T, q, hint ? hint[i] : -1);
+}
+
+// exhaustive search: codebook keys staged through shared memory in original order so that
+// a strict '<' keeps the lowest index on ties.
+__global__ void __launch_bounds__(256) k_nn_brute(const float4* __restrict__ keys_orig, int M,
+                                                  const float* __restrict__ keys, long long n, int* __restrict__ idx) {
+  __shared__ float4 sk[2 * 512];
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  float q[6] = {0, 0, 0, 0, 0, 0};
+  if (i < n) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) q[k] = keys[6 * i + k];
+  }
+  float best_d = FLT_MAX;
+  int best_i = 0;
+  for (int m0 = 0; m0 < M; m0 += 512) {
+    int cnt = min(512, M - m0);
+    __syncthreads();
+    for (int t = threadIdx.x; t < 2 * cnt; t += blockDim.x) sk[t] = keys_orig[2 * (size_t)m0 + t];
+    __syncthreads();
+    for (int p = 0; p < cnt; ++p) {
+      float4 a = sk[2 * p], b = sk[2 * p + 1];
+      float k[6] = {a.x, a.y, a.z, a.w, b.x, b.y};
+      float d = mt_key_dist(q, k);
+      if (d < best_d) best_d = d, best_i = m0 + p;
+    }
+  }
+  if (i < n) idx[i] = best_i;
+}
+
+static NNTables tables_of(mt_ctx* c) {
+  NNTables T;
+  T.keys_orig = c->d_keys_orig;
+  T.keys_sorted = c->d_keys_sorted;
+  T.sorted_orig = c->d_sorted_orig;
+  T.cell_start = c->d_cell_start;
+  T.g = c->grid;
+  T.M = c->M;
+  return T;
+}
+
+__global__ void k_se3_keys(const float4* __restrict__ soa, long long stride, long long n, float* __restrict__ keys) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float P[3][4], key[6];
+  load_pose(soa, stride, i, P);
+  mt_se3_key(P, key);
+#pragma unroll
+  for (int k = 0; k < 6; ++k) keys[6 * i + k] = key[k];
+}
+
+extern "C" int mt_se3_keys(const float* d_soa, long long stride, long long n, float* d_keys, void* stream) {
+  if (n < 0 || stride < n || (n && (!d_soa || !d_keys))) return set_err(MT_ERR_ARG, "mt_se3_keys: bad argument");
+  if (!n) return MT_OK;
+  k_se3_keys<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const float4*)d_soa, stride, n, d_keys);
+  CK_LAUNCH();
+  return MT_OK;
+}
+
+extern "C" int mt_nn_assign(mt_ctx* c, const float* d_keys, long long n, const int32_t* d_hint, int mode,
+                            int32_t* d_idx, void* stream) {
+  if (!c || !c->cb_ready) return set_err(MT_ERR_STATE, "mt_nn_assign: no codebook");
+  if (n < 0 || (n && (!d_keys || !d_idx))) return set_err(MT_ERR_ARG, "mt_nn_assign: bad argument");
+  if (!n) return MT_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (mode == 1)
+    k_nn_brute<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c->d_keys_orig, c->M, d_keys, n, d_idx);
+  else
+    k_nn_grid<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(tables_of(c), d_keys, n, d_hint, d_idx);
+  CK_LAUNCH();
+  return MT_OK;
+}
+
+__global__ void k_gather_rows_f32(const float* __restrict__ table, const int* __restrict__ idx, long long n,
+                                  int row_floats, float* __restrict__ out) {
+  // one thread per float4 of output
+  const int v = row_floats / 4;
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * v) return;
+  long long i = t / v;
+  int k = (int)(t - i * v);
+  reinterpret_cast<float4*>(out)[t] = __ldg(reinterpret_cast<const float4*>(table) + (size_t)idx[i] * v + k);
+}
+extern "C" int mt_gather_rows_f32(const float* d_table, const int32_t* d_idx, long long n, int row_floats,
+                                  float* d_out, void* stream) {
+  if (n < 0 || row_floats <= 0 || row_floats % 4 || (n && (!d_table || !d_idx || !d_out)))
+    return set_err(MT_ERR_ARG, "mt_gather_rows_f32: bad argument");
+  if (!n) return MT_OK;
+  long long tot = n * (row_floats / 4);
+  k_gather_rows_f32<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_table, d_idx, n, row_floats, d_out);
+  CK_LAUNCH();
+  return MT_OK;
+}
+
+// ------------------------------------------------------------------------- motion
+struct Affine {
+  float m[3][4];
+};
+static Affine affine_from_host16(const float* h) {
+  Affine a;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 4; ++j) a.m[i][j] = h[4 * i + j];
+  return a;
+}
+
+__device__ __forceinline__ void draw_or_load_noise(const float* __restrict__ tn, const float* __restrict__ rot,
+                                                   long long i, float sig_t, float sig_r, uint64_t seed,
+                                                   uint64_t step, uint64_t gid, float t[3], float r[3]) {
+  if (tn) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) t[k] = __ldg(tn + 3 * i + k), r[k] = __ldg(rot + 3 * i + k);
+  } else {
+    mt_motion_normals(seed, step, gid, t, r);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) t[k] *= sig_t, r[k] *= sig_r;
+  }
+}
+
+__device__ __forceinline__ void apply_motion(const float P[3][4], const Affine& odom, const float t[3], const float r[3], float out[3][4], int euler_mode = 0) {
+  float Tn[3][4], G[3][4];
+  if (euler_mode)
+    mt_noise_affine_extrinsic(t, r, Tn);
+  else
+    mt_noise_affine(t, r, Tn);
+  mt_compose(odom.m, Tn, G);  // noisyOdom = odom @ Tn   (particle_filter.py:345)
+  mt_compose(P, G, out);      // pose @ noisyOdom         (particle_filter.py:374)
+}
+
+__global__ void __launch_bounds__(256) k_motion(const float4* __restrict__ in, float4* __restrict__ out,
+                                                long long stride, long long n, Affine odom,
+                                                const float* __restrict__ tn, const float* __restrict__ rot,
+                                                float sig_t, float sig_r, uint64_t seed, uint64_t step,
+                                                uint64_t first_gid, int* invalid, int euler_mode) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float P[3][4], t[3], r[3], O[3][4];
+  load_pose(in, stride, i, P);
+  draw_or_load_noise(tn, rot, i, sig_t, sig_r, seed, step, first_gid + (uint64_t)i, t, r);
+  apply_motion(P, odom, t, r, O, euler_mode);
+  store_pose(out, stride, i, O);
+  if (invalid && mt_pose_invalid(O)) atomicAdd(invalid, 1);
+}
+
+extern "C" int mt_motion(const float* d_in, float* d_out, long long stride, long long n, const float* h_odom,
+                         const float* d_tn, const float* d_rot, float sig_t, float sig_r, uint64_t seed,
+                         uint64_t step, uint64_t first_gid, int* d_invalid, int euler_mode, void* stream) {
+  if (n < 0 || stride < n || !h_odom || (n && (!d_in || !d_out)) || ((d_tn == nullptr) != (d_rot == nullptr)))
+    return set_err(MT_ERR_ARG, "mt_motion: bad argument");
+  if (!n) return MT_OK;
+  k_motion<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      (const float4*)d_in, (float4*)d_out, stride, n, affine_from_host16(h_odom), d_tn, d_rot, sig_t, sig_r, seed, step,
+      first_gid, d_invalid, euler_mode);
+  CK_LAUNCH();
+  return MT_OK;
+}
+
+// ------------------------------------------------------------------------- rmse
+__device__ __forceinline__ void rmse_terms(const Affine& gt, const float P[3][4], double& et2, double& ang2) {
+  float dx = gt.m[0][3] - P[0][3], dy = gt.m[1][3] - P[1][3], dz = gt.m[2][3] - P[2][3];
+  float e = sqrtf(dx * dx + dy * dy + dz * dz);  // torch.norm then **2 (particle_filter.py:488-492)
+  et2 = (double)(e * e);
+  float a = mt_rot_err_deg(gt.m, P);
+  ang2 = (double)(a * a);
+}
+
+// finalise by one thread of the last block: fixed-order sum of the chunk partials
+__device__ void rmse_finalize(const double* part, int nch, long long n, float* out2) {
+  double a = 0.0, b = 0.0;
+  for (int k = 0; k < nch; ++k) a += __ldcg(part + 2 * k), b += __ldcg(part + 2 * k + 1);
+  out2[0] = (float)sqrt(a / (double)n);
+  out2[1] = (float)sqrt(b / (double)n);
+}
+
+__global__ void __launch_bounds__(256) k_rmse(const float4* __restrict__ soa, long long stride, long long n, Affine gt,
+                                              double* part, unsigned int* ticket, float* out2) {
+  __shared__ double s8[8];
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  double et2 = 0.0, ang2 = 0.0;
+  if (i < n) {
+    float P[3][4];
+    load_pose(soa, stride, i, P);
+    rmse_terms(gt, P, et2, ang2);
+  }
+  double a = block_sum_256(et2, s8);
+  double b = block_sum_256(ang2, s8);
+  __shared__ bool last;
+  if (threadIdx.x == 0) {
+    part[2 * blockIdx.x] = a;
+    part[2 * blockIdx.x + 1] = b;
+    __threadfence();
+    last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence();
+    rmse_finalize(part, gridDim.x, n, out2);
+    *ticket = 0;
+  }
+}
+
+extern "C" int mt_rmse(mt_ctx* c, const float* d_soa, long long stride, long long n, const float* h_gt, float* d_out2,
+                       void* stream) {
+  if (!c || !d_soa || !h_gt || !d_out2 || n <= 0 || stride < n) return set_err(MT_ERR_ARG, "mt_rmse: bad argument");
+  if ((long long)nchunks_of(n) > c->chunk_cap) return set_err(MT_ERR_CAPACITY, "mt_rmse: n exceeds context capacity");
+  k_rmse<<<(unsigned)nchunks_of(n), 256, 0, (cudaStream_t)stream>>>((const float4*)d_soa, stride, n, affine_from_host16(h_gt),
+                                                                    c->d_rm_part, c->d_ticket + 3, d_out2);
+  CK_LAUNCH();
+  return MT_OK;
+}
+
+// ------------------------------------------------------------------------- gathers
+__global__ void k_gather_soa(const float4* __restrict__ in, long long sin, const int* __restrict__ anc, long long n,
+                             float4* __restrict__ out, long long sout) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int a = anc[i];
+  float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  out[i] = a >= 0 ? in[a] : z;  // unfilled slots stay zero like the reference (particle_filter.py:290)
+  out[sout + i] = a >= 0 ? in[sin + a] : z;
+  out[2 * sout + i] = a >= 0 ? in[2 * sin + a] : z;
+}
+extern "C" int mt_gather_soa(const float* d_in, long long sin, const int32_t* d_anc, long long n, float* d_out,
+                             long long sout, void* stream) {
+  if (n < 0 || (n && (!d_in || !d_anc || !d_out)) || sout < n) return set_err(MT_ERR_ARG, "mt_gather_soa: bad argument");
+  if (!n) return MT_OK;
+  k_gather_soa<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const float4*)d_in, sin, d_anc, n, (float4*)d_out, sout);
+  CK_LAUNCH();
+  return MT_OK;
+}
+__global__ void k_gather_f64(const double* __restrict__ in, const int* __restrict__ anc, long long n, double* __restrict__ out) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = anc[i] >= 0 ? in[anc[i]] : 0.0;
+}
+extern "C" int mt_gather_f64(const double* d_in, const int32_t* d_anc, long long n, double* d_out, void* stream) {
+  if (n < 0 || (n && (!d_in || !d_anc || !d_out))) return set_err(MT_ERR_ARG, "mt_gather_f64: bad argument");
+  if (!n) return MT_OK;
+  k_gather_f64<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_in, d_anc, n, d_out);
+  CK_LAUNCH();
+  return MT_OK;
+}
+
+// ------------------------------------------------------------------------- fused step
+struct StepDev {
+  float4* soa_cur;
+  float4* soa_next;
+  long long stride;
+  int* nn_cur;
+  int* nn_next;
+  int* anc;
+  long long n;
+  Affine odom;
+  const float* tn;
+  const float* rot;
+  float sig_t, sig_r;
+  uint64_t seed, step, first_gid;
+  const double* wtab;  // exp(sim) or sim
+  const double* wsrc;  // explicit weights (resample-only path) or NULL
+  float u;
+  int has_gt;
+  Affine gt;
+  float* rmse2;
+  int rank, world;
+  long long n_global;
+  const double* shard_sums;
+  long long* n_out;
+  const long long* n_in;  // device-resident particle count (nullable): overrides n
+  // scratch
+  double* part;
+  double* prefix;
+  double* rm_part;
+  double* scal;
+  unsigned int* ticket;
+  int* flags;
+  int nchunks;
+};
+
+// Kernel A.  One particle per thread, one 256-particle chunk per block.
+//   HBM per particle: read 48 B pose + 4 B hint (+ 24 B noise when supplied), write 48 B + 4 B.
+//   Codebook keys / grid / weight table are L2-resident (M*64 B + cells*4 B + M*8 B).
+__global__ void __launch_bounds__(256) k_step_a(StepDev p, NNTables T) {
+  __shared__ double s8[8];
+  const long long i = (long long)blockIdx.x * MT_CHUNK + threadIdx.x;
+  const long long n = p.n_in ? *p.n_in : p.n;
+  double e = 0.0, et2 = 0.0, ang2 = 0.0;
+  if (i < n) {
+    float P[3][4], t[3], r[3], O[3][4], key[6];
+    load_pose(p.soa_cur, p.stride, i, P);
+    const int hint = p.nn_cur[i];
+    draw_or_load_noise(p.tn, p.rot, i, p.sig_t, p.sig_r, p.seed, p.step, p.first_gid + (uint64_t)i, t, r);
+    apply_motion(P, p.odom, t, r, O);
+    store_pose(p.soa_cur, p.stride, i, O);
+    mt_se3_key(O, key);
+    const int nn = nn_search(T, key, hint);
+    p.nn_cur[i] = nn;
+    e = __ldg(p.wtab + nn);
+    if (mt_pose_invalid(O)) {
+      e = 0.0;  // check_quats would delete the particle (particle_filter.py:347-357)
+      atomicAdd(p.flags + 2, 1);
+    }
+    if (p.has_gt) rmse_terms(p.gt, O, et2, ang2);
+  }
+  double se = block_sum_256(e, s8);
+  double sa = 0.0, sb = 0.0;
+  if (p.has_gt) {
+    sa = block_sum_256(et2, s8);
+    sb = block_sum_256(ang2, s8);
+  }
+  __shared__ bool last;
+  if (threadIdx.x == 0) {
+    p.part[blockIdx.x] = se;
+    if (p.has_gt) p.rm_part[2 * blockIdx.x] = sa, p.rm_part[2 * blockIdx.x + 1] = sb;
+    __threadfence();
+    last = (atomicAdd(p.ticket, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last) {
+    __threadfence();
+    scan_chunk_sums(p.part, (int)gridDim.x, p.prefix, p.scal, s8);
+    if (threadIdx.x == 0) {
+      if (p.has_gt) rmse_finalize(p.rm_part, (int)gridDim.x, n, p.rmse2);
+      *p.ticket = 0;
+    }
+  }
+}
+
+// chunk sums + prefix for explicit weights (resampler on caller-provided weights)
+__global__ void __launch_bounds__(256) k_weight_sums(StepDev p) {
+  __shared__ double s8[8];
+  const long long i = (long long)blockIdx.x * MT_CHUNK + threadIdx.x;
+  double e = (i < p.n) ? p.wsrc[i] : 0.0;
+  double se = block_sum_256(e, s8);
+  __shared__ bool last;
+  if (threadIdx.x == 0) {
+    p.part[blockIdx.x] = se;
+    __threadfence();
+    last = (atomicAdd(p.ticket, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last) {
+    __threadfence();
+    scan_chunk_sums(p.part, (int)gridDim.x, p.prefix, p.scal, s8);
+    if (threadIdx.x == 0) *p.ticket = 0;
+  }
+}
+
+// Kernel B.  One chunk per block.  CDF value of particle i:
+//     C_i = (A_rank + prefix[chunk] + incl_i) / S     (float64, fixed topology)
+// with chunk ends pinned to (A_rank + prefix[chunk+1]) / S so neighbouring blocks and
+// neighbouring GPUs agree bit-for-bit on the slot boundary.  Slots owned by particle i are
+// [cnt(C_{i-1}), cnt(C_i)), cnt(C) = #{j : loc_j < C}; each parent writes its own children
+// (reads and writes are both contiguous up to the child-count jitter).
+//   HBM per particle: read 4 B nn + 48 B pose, write 48 B pose + 4 B nn + 4 B ancestor.
+template <bool FROM_TABLE, bool SCATTER>
+__global__ void __launch_bounds__(256) k_step_b(StepDev p) {
+  __shared__ double s8[8];
+  __shared__ long long s_cnt[MT_CHUNK + 1];
+  const int c = blockIdx.x;
+  const long long i = (long long)c * MT_CHUNK + threadIdx.x;
+  const long long n = p.n_in ? *p.n_in : p.n;
+  const bool valid = i < n;
+  // issue the loads first
+  int nn = 0;
+  double e = 0.0;
+  float P[3][4];
+  if (valid) {
+    if (FROM_TABLE) {
+      nn = p.nn_cur[i];
+      e = __ldg(p.wtab + nn);
+    } else {
+      e = p.wsrc[i];
+    }
+    if (SCATTER) load_pose(p.soa_cur, p.stride, i, P);
+  }
+  // global normaliser and this shard's CDF offset (sequential, identical on every GPU)
+  double S = 0.0, A = 0.0;
+  if (p.world > 1) {
+    for (int r = 0; r < p.world; ++r) {
+      if (r == p.rank) A = S;
+      S += p.shard_sums[r];
+    }
+  } else {
+    S = p.prefix[p.nchunks];
+  }
+  const long long N = p.n_global;
+  const double dN = (double)N;
+  const double off = (double)(p.u / (float)N);  // float32 division, then promoted (particle_filter.py:260)
+  const bool bad = !(S > 0.0) || !(S <= DBL_MAX);  // all-zero / NaN / Inf weights: identity (237-241)
+  const double incl = block_incl_scan_256(e, s8);
+  const double base = A + p.prefix[c];
+  const double endv = (c + 1 == p.nchunks) ? (A + p.prefix[p.nchunks]) : (A + p.prefix[c + 1]);
+  long long cnt;
+  if (bad) {
+    cnt = valid ? i + 1 : n;
+    if (threadIdx.x == 0) s_cnt[0] = (long long)c * MT_CHUNK, p.flags[1] = 1;
+  } else {
+    const bool is_end = (threadIdx.x == MT_CHUNK - 1) || (i == n - 1);
+    double C = is_end ? endv / S : (base + incl) / S;
+    cnt = valid ? mt_count_below(C, N, dN, off) : 0;
+    if (threadIdx.x == 0) s_cnt[0] = mt_count_below(base / S, N, dN, off);
+  }
+  s_cnt[threadIdx.x + 1] = cnt;
+  __syncthreads();
+  const long long slot_base = (bad || p.world == 1) ? 0 : mt_count_below(A / S, N, dN, off);
+  if (valid && i == n - 1 && p.n_out) *p.n_out = cnt - slot_base;
+  long long prev = s_cnt[threadIdx.x];
+  long long kids = valid ? (cnt - prev) : 0;
+  if (kids < 0) kids = 0;
+  long long dst = prev - slot_base;
+  const long long cap = p.stride;
+  // light parents write their own children; heavy parents are spread over the warp
+  const int lane = threadIdx.x & 31;
+  const bool heavy = kids > 8;
+  if (!heavy) {
+    for (long long k = 0; k < kids; ++k) {
+      long long s = dst + k;
+      if (s >= cap) {
+        p.flags[0] = 1;
+        break;
+      }
+      if (SCATTER) {
+        store_pose(p.soa_next, p.stride, s, P);
+        if (FROM_TABLE) p.nn_next[s] = nn;
+      }
+      if (p.anc) p.anc[s] = (int)i;
+    }
+  }
+  unsigned hm = __ballot_sync(0xffffffffu, heavy);
+  while (hm) {
+    const int src = __ffs(hm) - 1;
+    hm &= hm - 1;
+    float Q[3][4];
+    if (SCATTER) {
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) Q[a][b] = __shfl_sync(0xffffffffu, P[a][b], src);
+    }
+    const long long d0 = __shfl_sync(0xffffffffu, dst, src);
+    const long long kn = __shfl_sync(0xffffffffu, kids, src);
+    const int pn = __shfl_sync(0xffffffffu, nn, src);
+    const long long pi = __shfl_sync(0xffffffffu, i, src);
+    for (long long k = lane; k < kn; k += 32) {
+      long long s = d0 + k;
+      if (s >= cap) {
+        p.flags[0] = 1;
+        break;
+      }
+      if (SCATTER) {
+        store_pose(p.soa_next, p.stride, s, Q);
+        if (FROM_TABLE) p.nn_next[s] = pn;
+      }
+      if (p.anc) p.anc[s] = (int)pi;
+    }
+  }
+}
+
+// strictly sequential float64 prefix (parity mode): one thread reproduces torch.cumsum on
+// CPU bit-for-bit, including slots the reference leaves unfilled (-1).
+__global__ void k_resample_seq(StepDev p) {
+  if (threadIdx.x || blockIdx.x) return;
+  const long long N = p.n;
+  const double dN = (double)N;
+  const double off = (double)(p.u / (float)N);
+  const double S = p.prefix[p.nchunks];
+  if (!(S > 0.0) || !(S <= DBL_MAX)) {
+    p.flags[1] = 1;
+    for (long long i = 0; i < N; ++i) p.anc[i] = (int)i;
+    return;
+  }
+  double run = 0.0;
+  long long prev = 0;
+  for (long long i = 0; i < N; ++i) {
+    run += p.wsrc[i] / S;
+    long long cnt = mt_count_below(run, N, dN, off);
+    for (long long s = prev; s < cnt; ++s) p.anc[s] = (int)i;
+    if (cnt > prev) prev = cnt;
+  }
+  for (long long s = prev; s < N; ++s) p.anc[s] = -1;
+}
+
+static int fill_step(mt_ctx* c, const mt_step_args* a, StepDev* d) {
+  if (!c || !a) return set_err(MT_ERR_ARG, "step: null argument");
+  if (a->n <= 0 || (size_t)a->n > c->cap || a->stride < a->n) return set_err(MT_ERR_CAPACITY, "step: n/stride out of range");
+  memset(d, 0, sizeof(*d));
+  d->soa_cur = (float4*)a->d_soa_cur;
+  d->soa_next = (float4*)a->d_soa_next;
+  d->stride = a->stride;
+  d->nn_cur = a->d_nn_cur;
+  d->nn_next = a->d_nn_next;
+  d->anc = a->d_anc;
+  d->n = a->n;
+  d->odom = affine_from_host16(a->odom);
+  d->tn = a->d_tn;
+  d->rot = a->d_rot;
+  d->sig_t = a->sig_t;
+  d->sig_r = a->sig_r;
+  d->seed = a->seed;
+  d->step = a->step;
+  d->first_gid = a->first_gid;
+  d->wtab = a->softmax ? c->d_esim : c->d_sim;
+  d->u = a->u;
+  d->has_gt = a->gt != nullptr;
+  if (a->gt) d->gt = affine_from_host16(a->gt);
+  d->rmse2 = a->d_rmse2;
+  d->rank = a->world > 1 ? a->rank : 0;
+  d->world = a->world > 1 ? a->world : 1;
+  d->n_global = a->world > 1 ? a->n_global : a->n;
+  d->shard_sums = a->d_shard_sums;
+  d->n_out = a->d_n_out;
+  d->n_in = a->d_n_in;
+  d->part = c->d_part;
+  d->prefix = c->d_prefix;
+  d->rm_part = c->d_rm_part;
+  d->scal = c->d_scal;
+  d->ticket = c->d_ticket;
+  d->flags = c->d_flags;
+  d->nchunks = (int)nchunks_of(a->n);
+  return MT_OK;
+}
+
+extern "C" int mt_step_a(mt_ctx* c, const mt_step_args* a, void* stream) {
+  StepDev d;
+  int r = fill_step(c, a, &d);
+  if (r) return r;
+  if (!c->cb_ready) return set_err(MT_ERR_STATE, "mt_step_a: no codebook");
+  if (!a->d_soa_cur || !a->d_nn_cur) return set_err(MT_ERR_ARG, "mt_step_a: null particle buffers");
+  if ((a->d_tn == nullptr) != (a->d_rot == nullptr)) return set_err(MT_ERR_ARG, "mt_step_a: tn/rot must both be given");
+  if (a->gt && !a->d_rmse2) return set_err(MT_ERR_ARG, "mt_step_a: gt without rmse output");
+  k_step_a<<<d.nchunks, MT_CHUNK, 0, (cudaStream_t)stream>>>(d, tables_of(c));
+  CK_LAUNCH();
+  return MT_OK;
+}
+
+extern "C" int mt_step_local_sum_ptr(mt_ctx* c, double** d_sum) {
+  if (!c || !d_sum) return set_err(MT_ERR_ARG, "mt_step_local_sum_ptr: null");
+  *d_sum = c->d_scal;
+  return MT_OK;
+}
+
+extern "C" int mt_step_b(mt_ctx* c, const mt_step_args* a, void* stream) {
+  StepDev d;
+  int r = fill_step(c, a, &d);
+  if (r) return r;
+  if (!a->d_soa_cur || !a->d_soa_next || !a->d_nn_cur || !a->d_nn_next) return set_err(MT_ERR_ARG, "mt_step_b: null particle buffers");
+  if (a->world > 1 && (!a->d_shard_sums || a->n_global <= 0)) return set_err(MT_ERR_ARG, "mt_step_b: sharded step needs shard sums");
+  k_step_b<true, true><<<d.nchunks, MT_CHUNK, 0, (cudaStream_t)stream>>>(d);
+  CK_LAUNCH();
+  return MT_OK;
+}
+
+__global__ void k_step_weights(StepDev p, double* __restrict__ w) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (p.n_in ? *p.n_in : p.n)) return;
+  double S = 0.0;
+  if (p.world > 1)
+    for (int r = 0; r < p.world; ++r) S += p.shard_sums[r];
+  else
+    S = p.prefix[p.nchunks];
+  w[i] = __ldg(p.wtab + p.nn_cur[i]) / S;
+}
+
+extern "C" int mt_step_weights(mt_ctx* c, const mt_step_args* a, double* d_w, void* stream) {
+  StepDev d;
+  int r = fill_step(c, a, &d);
+  if (r) return r;
+  if (!d_w || !a->d_nn_cur) return set_err(MT_ERR_ARG, "mt_step_weights: null");
+  k_step_weights<<<(unsigned)((a->n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d, d_w);
+  CK_LAUNCH();
+  return MT_OK;
+}
+
+extern "C" int mt_resample_systematic(mt_ctx* c, const double* d_w, long long n, float u, int seq, int32_t* d_anc,
+                                      int* d_status, void* stream) {
+  if (!c || !d_w || !d_anc || n <= 0) return set_err(MT_ERR_ARG, "mt_resample_systematic: bad argument");
+  if ((size_t)n > c->cap) return set_err(MT_ERR_CAPACITY, "mt_resample_systematic: n exceeds context capacity");
+  cudaStream_t st = (cudaStream_t)stream;
+  StepDev d;
+  memset(&d, 0, sizeof(d));
+  d.n = n;
+  d.n_global = n;
+  d.stride = n;
+  d.world = 1;
+  d.wsrc = d_w;
+  d.u = u;
+  d.anc = d_anc;
+  d.part = c->d_part;
+  d.prefix = c->d_prefix;
+  d.scal = c->d_scal + 4;
+  d.ticket = c->d_ticket;
+  d.flags = c->d_flags;
+  d.nchunks = (int)nchunks_of(n);
+  CK(cudaMemsetAsync(c->d_flags + 1, 0, sizeof(int), st));
+  k_weight_sums<<<d.nchunks, MT_CHUNK, 0, st>>>(d);
+  CK_LAUNCH();
+  if (seq)
+    k_resample_seq<<<1, 32, 0, st>>>(d);
+  else
+    k_step_b<false, false><<<d.nchunks, MT_CHUNK, 0, st>>>(d);
+  CK_LAUNCH();
+  if (d_status) CK(cudaMemcpyAsync(d_status, c->d_flags + 1, sizeof(int), cudaMemcpyDeviceToDevice, st));
+  return MT_OK;
+}

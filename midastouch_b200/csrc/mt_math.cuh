@@ -1,0 +1,255 @@
+// Per-particle arithmetic shared by every kernel of libmidas_b200 (sm_100a).
+//
+// All functions are MT_HD (host+device) so the same source is unit-tested on the build
+// box by compiling tests/host_math_harness.cpp with g++ -- the CUDA library itself has
+// no host compute path.  Citations are file:line under the reference tree.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define MT_HD __host__ __device__ __forceinline__
+#else
+#define MT_HD inline
+#endif
+
+// float ops that must not be contracted into FMAs (bit-stable distance ordering).
+#if defined(__CUDA_ARCH__)
+#define MT_FSUB(a, b) __fsub_rn((a), (b))
+#define MT_FMUL(a, b) __fmul_rn((a), (b))
+#define MT_FADD(a, b) __fadd_rn((a), (b))
+#else
+static inline float mt_nofma_sub(float a, float b) { volatile float r = a - b; return r; }
+static inline float mt_nofma_mul(float a, float b) { volatile float r = a * b; return r; }
+static inline float mt_nofma_add(float a, float b) { volatile float r = a + b; return r; }
+#define MT_FSUB(a, b) mt_nofma_sub((a), (b))
+#define MT_FMUL(a, b) mt_nofma_mul((a), (b))
+#define MT_FADD(a, b) mt_nofma_add((a), (b))
+#endif
+
+struct mt_pose {  // rows of the 3x4 [R|t]; the constant bottom row (0,0,0,1) is implicit
+  float r[3][4];
+};
+
+// odometry pre-multiplied form: G = odom (3x4 affine)
+struct mt_affine {
+  float m[3][4];
+};
+
+// ---------------------------------------------------------------- SE(3) helpers
+// C = A * B for 3x4 affines with implicit bottom row; same association as
+// torch.matmul on (4,4) operands (particle_filter.py:345,374): each entry is a 4-term
+// dot product whose products with the constant row are exact.
+MT_HD void mt_compose(const float A[3][4], const float B[3][4], float C[3][4]) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float s = A[i][0] * B[0][j];
+      s = fmaf(A[i][1], B[1][j], s);
+      s = fmaf(A[i][2], B[2][j], s);
+      if (j == 3) s += A[i][3];
+      C[i][j] = s;
+    }
+  }
+}
+
+// Rn = Rz(a0) Ry(a1) Rx(a2), angles = deg2rad(rot_deg) in float32
+// (euler_angles_to_matrix(.., "ZYX"), pose.py:215-269; deg2rad at particle_filter.py:336).
+MT_HD void mt_noise_affine(const float tn[3], const float rot_deg[3], float Tn[3][4]) {
+  const float d2r = 0.017453292519943295f;  // torch.deg2rad: x * (pi/180) in float32
+  float a0 = rot_deg[0] * d2r, a1 = rot_deg[1] * d2r, a2 = rot_deg[2] * d2r;
+  float cz, sz, cy, sy, cx, sx;
+#if defined(__CUDA_ARCH__)
+  sincosf(a0, &sz, &cz);
+  sincosf(a1, &sy, &cy);
+  sincosf(a2, &sx, &cx);
+#else
+  sz = sinf(a0); cz = cosf(a0); sy = sinf(a1); cy = cosf(a1); sx = sinf(a2); cx = cosf(a2);
+#endif
+  // (Rz Ry) first, then times Rx -- matrices[0] @ matrices[1] @ matrices[2]
+  float zy[3][3] = {{cz * cy, -sz, cz * sy}, {sz * cy, cz, sz * sy}, {-sy, 0.f, cy}};
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    Tn[i][0] = zy[i][0];
+    Tn[i][1] = zy[i][1] * cx + zy[i][2] * sx;
+    Tn[i][2] = zy[i][2] * cx - zy[i][1] * sx;
+    Tn[i][3] = tn[i];
+  }
+}
+
+// scipy Rotation.from_euler("zyx", rot, degrees=True) -- lowercase = extrinsic axes, i.e.
+// Rn = Rx(a2) Ry(a1) Rz(a0) -- as used by init_filter (particle_filter.py:139-141).
+MT_HD void mt_noise_affine_extrinsic(const float tn[3], const float rot_deg[3], float Tn[3][4]) {
+  const float d2r = 0.017453292519943295f;
+  float a0 = rot_deg[0] * d2r, a1 = rot_deg[1] * d2r, a2 = rot_deg[2] * d2r;
+  float sz = sinf(a0), cz = cosf(a0), sy = sinf(a1), cy = cosf(a1), sx = sinf(a2), cx = cosf(a2);
+  float xy[3][3] = {{cy, 0.f, sy}, {sx * sy, cx, -sx * cy}, {-cx * sy, sx, cx * cy}};
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    Tn[i][0] = xy[i][0] * cz + xy[i][1] * sz;
+    Tn[i][1] = xy[i][1] * cz - xy[i][0] * sz;
+    Tn[i][2] = xy[i][2];
+    Tn[i][3] = tn[i];
+  }
+}
+
+// theseus SO3.log_map restated in float32 (call site pose.py:19-23); thresholds are the
+// float32 entries of theseus/constants.py (near-zero 5e-3, near-pi 1e-2).
+MT_HD void mt_so3_log(const float R[3][4], float out[3]) {
+  float sa0 = 0.5f * (R[2][1] - R[1][2]);
+  float sa1 = 0.5f * (R[0][2] - R[2][0]);
+  float sa2 = 0.5f * (R[1][0] - R[0][1]);
+  float cosine = 0.5f * ((R[0][0] + R[1][1] + R[2][2]) - 1.f);
+  float sine = sqrtf(sa0 * sa0 + sa1 * sa1 + sa2 * sa2);
+  float theta = atan2f(sine, cosine);
+  bool near_zero = theta < 5e-3f;
+  bool near_pi = (1.f + cosine) <= 1e-2f;
+  if (!near_pi) {
+    float scale = near_zero ? (1.f + sine * sine / 6.f) : (theta / sine);
+    out[0] = sa0 * scale; out[1] = sa1 * scale; out[2] = sa2 * scale;
+    return;
+  }
+  float d0 = R[0][0], d1 = R[1][1], d2 = R[2][2];
+  int major = ((d1 > d0) && (d1 > d2) ? 1 : 0) + 2 * ((d2 > d0) && (d2 > d1) ? 1 : 0);
+  float sel[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    float a = (major == 0 ? R[0][k] : (major == 1 ? R[1][k] : R[2][k]));  // row `major`
+    float b = (major == 0 ? R[k][0] : (major == 1 ? R[k][1] : R[k][2]));  // column `major`
+    sel[k] = 0.5f * (a + b);
+  }
+  if (major == 0) sel[0] -= cosine; else if (major == 1) sel[1] -= cosine; else sel[2] -= cosine;
+  float nrm = sqrtf(sel[0] * sel[0] + sel[1] * sel[1] + sel[2] * sel[2]);
+  float sgn_src = (major == 0 ? sa0 : (major == 1 ? sa1 : sa2));
+  float sign = (sgn_src < 0.f) ? -1.f : 1.f;  // sign(0) -> +1
+  float k = theta * sign;
+  out[0] = sel[0] / nrm * k; out[1] = sel[1] / nrm * k; out[2] = sel[2] / nrm * k;
+}
+
+// R3_SE3 (tactile_tree.py:73-77): key = [(1-w) t, w Log(R)], w = 0.01
+MT_HD void mt_se3_key(const float P[3][4], float key[6]) {
+  const float w = 0.01f;
+  float lg[3];
+  mt_so3_log(P, lg);
+  key[0] = (1.0f - w) * P[0][3]; key[1] = (1.0f - w) * P[1][3]; key[2] = (1.0f - w) * P[2][3];
+  key[3] = w * lg[0]; key[4] = w * lg[1]; key[5] = w * lg[2];
+}
+
+// squared L2 over the 6-D key with a fixed, FMA-free evaluation order (matches
+// oracle.l2_sq_f32) so that argmin ties are decided identically everywhere.
+MT_HD float mt_key_dist(const float a[6], const float b[6]) {
+  float d = MT_FSUB(a[0], b[0]);
+  float acc = MT_FMUL(d, d);
+#pragma unroll
+  for (int k = 1; k < 6; ++k) {
+    d = MT_FSUB(a[k], b[k]);
+    acc = MT_FADD(acc, MT_FMUL(d, d));
+  }
+  return acc;
+}
+
+// check_quats (particle_filter.py:347-357): a pose is pruned when its quaternion norm is 0
+// or NaN.  For finite inputs theseus' to_quaternion never has zero norm (w = 0.5 sqrt(1+tr)
+// and the near-pi branch returns a unit axis), so the test reduces to non-finite entries.
+MT_HD bool mt_pose_invalid(const float P[3][4]) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) s += P[i][j] * 0.f;  // NaN/Inf -> NaN
+  return !(s == 0.f);
+}
+
+// rot2euler of R_gt R_n^T (particle_filter.py:484, pose.py:201-208) + nan_to_num + wrap
+MT_HD float mt_rot_err_deg(const float G[3][4], const float P[3][4]) {
+  float tr = 0.f;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) tr += G[i][0] * P[i][0] + G[i][1] * P[i][1] + G[i][2] * P[i][2];
+  float a = acosf((tr - 1.0f) * 0.5f) * 57.29577951308232f;
+  if (a != a) a = 0.f;
+  if (a > 180.f) a -= 360.f;
+  if (a < -180.f) a += 360.f;
+  return a;
+}
+
+// ---------------------------------------------------------------- systematic draw
+// sample location of slot k exactly as particle_filter.py:254-261: fl64(k/N) + off with
+// off = float32(u)/N promoted to float64, then remainder 1.
+MT_HD double mt_loc(long long k, double dN, double off) {
+  double l = (double)k / dN + off;
+  if (l >= 1.0) l -= 1.0;  // torch.remainder(x, 1) for x in [1, 2)
+  return l;
+}
+
+// loc with the two-pointer semantics of the reference loop (particle_filter.py:295-302):
+// if the last location wraps to ~0 it is assigned to whichever parent owns slot N-2, i.e.
+// it behaves like loc(N-2) for counting.
+MT_HD double mt_loc_mono(long long k, long long N, double dN, double off) {
+  double l = (double)k / dN + off;
+  if (l >= 1.0) l = (k > 0) ? ((double)(k - 1) / dN + off) : (l - 1.0);  // only k = N-1 can wrap
+  (void)N;
+  return l;
+}
+
+// cnt(C) = #{k in [0,N) : loc_k < C}; locs are non-decreasing so this is the first k
+// whose loc is >= C.  A closed-form guess is corrected with exact comparisons.
+MT_HD long long mt_count_below(double C, long long N, double dN, double off) {
+  if (!(C == C)) return 0;  // NaN CDF value owns nothing
+  double g = ceil((C - off) * dN);
+  long long k = (g <= 0.0) ? 0 : (g >= dN ? N : (long long)g);
+  while (k > 0 && !(mt_loc_mono(k - 1, N, dN, off) < C)) --k;
+  while (k < N && (mt_loc_mono(k, N, dN, off) < C)) ++k;
+  return k;
+}
+
+// ---------------------------------------------------------------- Philox4x32-10
+struct mt_u4 {
+  uint32_t x, y, z, w;
+};
+
+MT_HD void mt_mulhilo(uint32_t a, uint32_t b, uint32_t* hi, uint32_t* lo) {
+  uint64_t p = (uint64_t)a * (uint64_t)b;
+  *hi = (uint32_t)(p >> 32);
+  *lo = (uint32_t)p;
+}
+
+MT_HD mt_u4 mt_philox(mt_u4 c, uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t h0, l0, h1, l1;
+    mt_mulhilo(0xD2511F53u, c.x, &h0, &l0);
+    mt_mulhilo(0xCD9E8D57u, c.z, &h1, &l1);
+    mt_u4 n = {h1 ^ c.y ^ k0, l1, h0 ^ c.w ^ k1, l0};
+    c = n;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return c;
+}
+
+MT_HD float mt_u01(uint32_t x) { return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f); }
+
+MT_HD void mt_box_muller(uint32_t a, uint32_t b, float* n0, float* n1) {
+  float r = sqrtf(-2.0f * logf(mt_u01(a)));
+  float ang = 6.283185307179586f * mt_u01(b);
+#if defined(__CUDA_ARCH__)
+  float s, c;
+  sincosf(ang, &s, &c);
+#else
+  float s = sinf(ang), c = cosf(ang);
+#endif
+  *n0 = r * c;
+  *n1 = r * s;
+}
+
+// six N(0,1) draws for particle `gid` of filter step `step`: (tn[3], rot[3])
+MT_HD void mt_motion_normals(uint64_t seed, uint64_t step, uint64_t gid, float tn[3], float rot[3]) {
+  mt_u4 c0 = {(uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)step, 0u};
+  mt_u4 c1 = {(uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)step, 1u};
+  mt_u4 a = mt_philox(c0, (uint32_t)seed, (uint32_t)(seed >> 32));
+  mt_u4 b = mt_philox(c1, (uint32_t)seed, (uint32_t)(seed >> 32));
+  mt_box_muller(a.x, a.y, &tn[0], &tn[1]);
+  mt_box_muller(a.z, a.w, &tn[2], &rot[0]);
+  mt_box_muller(b.x, b.y, &rot[1], &rot[2]);
+}

@@ -1,0 +1,199 @@
+"""FilterEngine: the resident, fused form of the loop body ``filter.py:152-190``.
+
+Particles live on the GPU as SoA 3 x float4 rows (48 B / particle) in two ping-pong
+buffers; one ``step()`` is
+    codebook query   sim[M] = cos(q, E_m)                      (get_similarity, 449-469)
+    kernel A         motion + R3_SE3 key + exact 1-NN + weight lookup + chunk sums
+                                                            (motionModel, SE3_NN, 170-173)
+    [sharded only]   all-gather of the per-GPU weight sums     (one 8-byte value per GPU)
+    kernel B         normalise + float64 prefix + systematic draw + child scatter
+                                                            (resampler "low_var", 251-307)
+with no host synchronisation.  Sharding: each GPU owns a contiguous block of particles and
+the children of its own parents, so poses never cross NVLink; only the weight sums do.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from ._lib import MidasError, StepArgs, call, lib, ptr, stream_ptr
+from .context import aos_to_soa, dtype_code, require_cuda, soa_to_aos
+from .tactile_tree import tactile_tree
+
+
+Odom16 = C.c_float * 16
+
+
+def prepare_odom(odom) -> "Odom16":
+    """(4,4) tensor / 16 floats -> the by-value kernel argument (do this once per frame)."""
+    vals = odom.reshape(-1).tolist() if isinstance(odom, torch.Tensor) else list(odom)
+    return Odom16(*[float(x) for x in vals])
+
+
+class FilterEngine:
+    def __init__(self, codebook: tactile_tree, capacity: int, sig_t: float = 2e-4, sig_r: float = 0.5,
+                 seed: int = 0, rank: int = 0, world: int = 1, group=None, n_global: int | None = None):
+        if codebook.ctx is None:
+            raise MidasError("FilterEngine: codebook.to_device(cuda) first")
+        self.cb = codebook
+        self.dev = codebook.poses.device
+        self.capacity = int(capacity)
+        codebook.ctx.ensure_capacity(self.capacity)
+        self.ctx = codebook.ctx
+        self.sig_t, self.sig_r, self.seed = float(sig_t), float(sig_r), int(seed)
+        self.rank, self.world, self.group = int(rank), int(world), group
+        self.n_global = n_global
+        d = self.dev
+        self.soa = [torch.zeros((3, self.capacity, 4), dtype=torch.float32, device=d) for _ in range(2)]
+        self.nn = [torch.full((self.capacity,), -1, dtype=torch.int32, device=d) for _ in range(2)]
+        self.anc = torch.zeros(self.capacity, dtype=torch.int32, device=d)
+        self.rmse = torch.zeros(2, dtype=torch.float32, device=d)
+        self.n_dev = [torch.zeros(1, dtype=torch.int64, device=d) for _ in range(2)]
+        self.shard_sums = torch.zeros(max(self.world, 1), dtype=torch.float64, device=d)
+        self.q_dev = torch.zeros(codebook.embeddings.shape[1], dtype=torch.float64, device=d)
+        self.cur = 0
+        self.n = 0  # host-side upper bound of the local particle count
+        self.t = 0
+        self.use_n_dev = False
+        p = C.c_void_p()
+        call("mt_step_local_sum_ptr", self.ctx.h, C.byref(p))
+        self._local_sum_ptr = p.value
+        self._a = StepArgs()
+        self._rng = torch.Generator().manual_seed(self.seed)
+
+    # ------------------------------------------------------------------ state in / out
+    def load_particles(self, poses: torch.Tensor, nn_hint: torch.Tensor | None = None):
+        require_cuda(poses, "poses")
+        n = poses.shape[0]
+        if n > self.capacity:
+            raise MidasError("load_particles: more particles than capacity")
+        with torch.cuda.device(self.dev):
+            call("mt_aos_to_soa", ptr(poses.reshape(-1, 4, 4).float().contiguous()), n, ptr(self.soa[self.cur]), self.capacity, stream_ptr())
+        if nn_hint is None:
+            self.nn[self.cur][:n] = -1
+        else:
+            self.nn[self.cur][:n] = nn_hint.to(torch.int32)
+        self.n = n
+        self.n_dev[self.cur].fill_(n)
+        if self.n_global is None or self.world == 1:
+            self.n_global = n if self.world == 1 else self.n_global
+
+    def snap_to_codebook(self):
+        """filter.py:159-160: particles.poses = codebook.SE3_NN(particles.poses)[0] (exhaustive NN)."""
+        n = self.n
+        keys = torch.empty((n, 6), dtype=torch.float32, device=self.dev)
+        idx = self.nn[self.cur]
+        with torch.cuda.device(self.dev):
+            s = stream_ptr()
+            call("mt_se3_keys", ptr(self.soa[self.cur]), self.capacity, n, ptr(keys), s)
+            call("mt_nn_assign", self.ctx.h, ptr(keys), n, 0, 1, ptr(idx), s)
+            aos = torch.empty((n, 4, 4), dtype=torch.float32, device=self.dev)
+            call("mt_gather_rows_f32", ptr(self.cb.poses), ptr(idx), n, 16, ptr(aos), s)
+            call("mt_aos_to_soa", ptr(aos), n, ptr(self.soa[self.cur]), self.capacity, s)
+
+    def poses(self) -> torch.Tensor:
+        n = self.count()
+        return soa_to_aos(self.soa[self.cur], n)
+
+    def count(self) -> int:
+        if self.use_n_dev:
+            self.n = int(self.n_dev[self.cur].item())
+        return self.n
+
+    def nn_idx(self) -> torch.Tensor:
+        return self.nn[self.cur][: self.count()]
+
+    def ancestors(self) -> torch.Tensor:
+        return self.anc[: self.count()]
+
+    # ------------------------------------------------------------------ one filter step
+    def _fill(self, odom, u, tn, rot, gt, softmax):
+        a = self._a
+        a.d_soa_cur, a.d_soa_next = ptr(self.soa[self.cur]), ptr(self.soa[1 - self.cur])
+        a.stride = self.capacity
+        a.d_nn_cur, a.d_nn_next, a.d_anc = ptr(self.nn[self.cur]), ptr(self.nn[1 - self.cur]), ptr(self.anc)
+        a.n = self.n
+        a.odom = odom
+        a.d_tn, a.d_rot = ptr(tn), ptr(rot)
+        a.sig_t, a.sig_r = self.sig_t, self.sig_r
+        a.seed, a.step, a.first_gid = self.seed, self.t, self.rank * (1 << 40)
+        a.softmax, a.u, a.resample = int(bool(softmax)), float(u), 1
+        a.gt = ptr(gt) if gt is not None else None
+        a.d_rmse2 = ptr(self.rmse)
+        a.rank, a.world = self.rank, self.world
+        a.n_global = int(self.n_global if self.n_global is not None else self.n)
+        a.d_shard_sums = ptr(self.shard_sums) if self.world > 1 else None
+        a.d_n_out = ptr(self.n_dev[1 - self.cur])
+        a.d_n_in = ptr(self.n_dev[self.cur]) if self.use_n_dev else None
+        return a
+
+    def step(self, code: torch.Tensor, odom: torch.Tensor, u: float | None = None, tn: torch.Tensor | None = None,
+             rot: torch.Tensor | None = None, gt: torch.Tensor | None = None, softmax: bool = True,
+             resample: bool = True):
+        """code: (1,D)/(D,) tactile code, host or device, float32/float64.
+        odom: (4,4) host tensor / 16 floats.  u: systematic offset in [0,1) (drawn from the
+        engine's CPU generator when None).  tn/rot: optional (n,3) float32 CUDA noise
+        (parity mode); Philox in-kernel otherwise.  gt: optional (4,4) host pose -> self.rmse."""
+        if self.n == 0:
+            raise MidasError("step: no particles loaded")
+        if u is None:
+            u = float(torch.rand(1, generator=self._rng).item())
+        if code.is_cuda:
+            q = code.reshape(-1).contiguous()
+        else:  # H2D of the step's only per-frame input (D*8 bytes)
+            self.q_dev.copy_(code.reshape(-1).to(torch.float64), non_blocking=True)
+            q = self.q_dev
+        odom16 = odom if isinstance(odom, Odom16) else prepare_odom(odom)
+        gt_h = None
+        if gt is not None:
+            gt_h = gt if (gt.device.type == "cpu" and gt.dtype == torch.float32 and gt.is_contiguous()) else gt.detach().float().cpu().contiguous()
+        if tn is not None:
+            tn, rot = tn.contiguous(), rot.contiguous()
+        a = self._fill(odom16, u, tn, rot, gt_h, softmax)
+        with torch.cuda.device(self.dev):
+            s = stream_ptr()
+            call("mt_codebook_query", self.ctx.h, ptr(q), dtype_code(q), 0, s)
+            call("mt_step_a", self.ctx.h, C.byref(a), s)
+            if self.world > 1:
+                self._allgather_sums()
+            if resample:
+                call("mt_step_b", self.ctx.h, C.byref(a), s)
+        if resample:
+            self.cur = 1 - self.cur
+            if self.world > 1:
+                self.use_n_dev = True
+                # children per GPU drift by O(sqrt) per step; keep the host bound safe
+                self.n = min(self.capacity, self.n + max(64, self.n // 1024))
+        self.t += 1
+
+    def _allgather_sums(self):
+        import torch.distributed as dist
+
+        local = torch.empty(0)  # placeholder for type checkers
+        # view of the library's local weight sum (device double written by kernel A)
+        local = _device_double_view(self._local_sum_ptr, self.dev)
+        dist.all_gather_into_tensor(self.shard_sums, local, group=self.group)
+
+    def weights(self) -> torch.Tensor:
+        """normalised float64 weights of the current particles (valid after a step with
+        resample=False, i.e. before the children replace them)."""
+        n = self.count()
+        w = torch.empty(n, dtype=torch.float64, device=self.dev)
+        a = self._a
+        with torch.cuda.device(self.dev):
+            call("mt_step_weights", self.ctx.h, C.byref(a), ptr(w), stream_ptr())
+        return w
+
+
+def _device_double_view(address: int, device) -> torch.Tensor:
+    """zero-copy (1,) float64 CUDA tensor over a raw device address (library scratch)."""
+
+    class _Holder:
+        pass
+
+    h = _Holder()
+    h.__cuda_array_interface__ = {
+        "shape": (1,), "typestr": "<f8", "data": (address, False), "version": 3, "strides": None,
+    }
+    return torch.as_tensor(h, device=device)

@@ -1,0 +1,64 @@
+// TEST INFRASTRUCTURE ONLY: compiles midastouch_b200/csrc/mt_math.cuh (the per-particle
+// arithmetic shared by the CUDA kernels) for the host with g++ so the no-GPU test tier can
+// check it against the oracle.  Never loaded by the product.
+#include "../midastouch_b200/csrc/mt_math.cuh"
+
+extern "C" {
+void h_se3_keys(const float* aos, long long n, float* keys) {
+  for (long long i = 0; i < n; ++i) {
+    float P[3][4];
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 4; ++c) P[r][c] = aos[16 * i + 4 * r + c];
+    mt_se3_key(P, keys + 6 * i);
+  }
+}
+void h_motion(const float* aos, long long n, const float* odom16, const float* tn, const float* rot, float* out) {
+  float O[3][4];
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 4; ++c) O[r][c] = odom16[4 * r + c];
+  for (long long i = 0; i < n; ++i) {
+    float P[3][4], Tn[3][4], G[3][4], R[3][4];
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 4; ++c) P[r][c] = aos[16 * i + 4 * r + c];
+    mt_noise_affine(tn + 3 * i, rot + 3 * i, Tn);
+    mt_compose(O, Tn, G);
+    mt_compose(P, G, R);
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 4; ++c) out[16 * i + 4 * r + c] = R[r][c];
+    out[16 * i + 12] = out[16 * i + 13] = out[16 * i + 14] = 0.f;
+    out[16 * i + 15] = 1.f;
+  }
+}
+void h_key_dist(const float* keys, long long m, const float* q, float* out) {
+  for (long long i = 0; i < m; ++i) out[i] = mt_key_dist(q, keys + 6 * i);
+}
+// systematic ancestors from an explicit CDF (sequential reference of kernel B's slot logic)
+void h_ancestors_from_cdf(const double* C, long long n, float u, long long* anc) {
+  double dN = (double)n, off = (double)(u / (float)n);
+  long long prev = 0;
+  for (long long i = 0; i < n; ++i) {
+    long long cnt = mt_count_below(C[i], n, dN, off);
+    for (long long s = prev; s < cnt; ++s) anc[s] = i;
+    if (cnt > prev) prev = cnt;
+  }
+  for (long long s = prev; s < n; ++s) anc[s] = -1;
+}
+void h_locs(long long n, float u, double* out) {
+  double dN = (double)n, off = (double)(u / (float)n);
+  for (long long k = 0; k < n; ++k) out[k] = mt_loc(k, dN, off);
+}
+void h_normals(unsigned long long seed, unsigned long long step, long long n, float* out6) {
+  for (long long i = 0; i < n; ++i) mt_motion_normals(seed, step, (uint64_t)i, out6 + 6 * i, out6 + 6 * i + 3);
+}
+void h_rot_err(const float* gt16, const float* aos, long long n, float* out) {
+  float G[3][4];
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 4; ++c) G[r][c] = gt16[4 * r + c];
+  for (long long i = 0; i < n; ++i) {
+    float P[3][4];
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 4; ++c) P[r][c] = aos[16 * i + 4 * r + c];
+    out[i] = mt_rot_err_deg(G, P);
+  }
+}
+}

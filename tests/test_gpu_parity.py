@@ -1,0 +1,452 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI
+(midastouch_b200._lib -> libmidas_b200.so), against the oracle and the golden vectors of the
+unmodified reference.  Bars: ancestor / NN indices bit-exact; float32 poses rtol 1e-5
+(atol 1e-6 for entries near zero); float64 weights rtol 1e-5 (typically 1e-14)."""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as O
+from midastouch_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 1e-5, 1e-6
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def mt():
+    import midastouch_b200 as m
+    from midastouch_b200 import _lib, context, engine, particle_filter, tactile_tree
+
+    class NS:
+        pass
+
+    ns = NS()
+    ns.lib, ns.ctxm, ns.eng, ns.pf, ns.tt = _lib, context, engine, particle_filter, tactile_tree
+    return ns
+
+
+@pytest.fixture(scope="module")
+def box():
+    return synth.make_object("004_sugar_box")
+
+
+@pytest.fixture(scope="module")
+def cb_small(box, mt, dev):
+    cbs = synth.make_codebook(box, M=4096, D=256, seed=0)
+    cb = mt.tt.tactile_tree(cbs.poses, cbs.cam_poses, cbs.embeddings)
+    cb.to_device(dev)
+    return cbs, cb
+
+
+@pytest.fixture(scope="module")
+def cb_big(box, mt, dev):
+    cbs = synth.make_codebook(box, M=50000, D=256, seed=0)
+    cb = mt.tt.tactile_tree(cbs.poses, cbs.cam_poses, cbs.embeddings)
+    cb.to_device(dev)
+    return cbs, cb
+
+
+def T(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+# ----------------------------------------------------------------------------- layout
+def test_aos_soa_roundtrip(mt, dev):
+    p = torch.randn(1000, 4, 4, device=dev)
+    p[:, 3, :] = torch.tensor([0, 0, 0, 1.0], device=dev)
+    soa = mt.ctxm.aos_to_soa(p, stride=1024)
+    assert torch.equal(mt.ctxm.soa_to_aos(soa, 1000), p)
+
+
+# ----------------------------------------------------------------------------- keys + NN
+def test_keys_match_oracle(mt, dev, cb_big):
+    cbs, cb = cb_big
+    ref = O.r3_se3(cbs.poses)
+    assert torch.allclose(cb.logmap_pose.cpu(), ref, rtol=1e-5, atol=2e-7)
+
+
+@pytest.mark.parametrize("exhaustive", [False, True])
+def test_nn_bit_exact_on_given_keys(mt, dev, cb_big, exhaustive):
+    """given identical float32 keys the index search is bit-exact vs the oracle (ties -> lowest)."""
+    cbs, cb = cb_big
+    keys_cb = cb.logmap_pose.cpu().numpy()
+    rng = np.random.default_rng(3)
+    n = 4096 if exhaustive else 65536
+    base = keys_cb[rng.integers(0, 50000, n)]
+    q = (base + rng.normal(size=(n, 6)).astype(np.float32) * np.float32(6e-4)).astype(np.float32)
+    q[:64] = keys_cb[:64]  # exact hits
+    qd = torch.from_numpy(q).to(dev)
+    idx = torch.empty(n, dtype=torch.int32, device=dev)
+    mt.lib.call("mt_nn_assign", cb.ctx.h, qd.data_ptr(), n, 0, 1 if exhaustive else 0, idx.data_ptr(), mt.lib.stream_ptr())
+    ref = O.nn_exact(keys_cb, q)
+    assert np.array_equal(idx.cpu().numpy().astype(np.int64), ref)
+    if not exhaustive:  # any hint, good or bad, gives the same answer
+        for hint in (torch.from_numpy(ref.astype(np.int32)), torch.randint(0, 50000, (n,), dtype=torch.int32)):
+            hd = hint.to(dev)
+            idx2 = torch.empty_like(idx)
+            mt.lib.call("mt_nn_assign", cb.ctx.h, qd.data_ptr(), n, hd.data_ptr(), 0, idx2.data_ptr(), mt.lib.stream_ptr())
+            assert torch.equal(idx2, idx)
+
+
+def test_nn_far_queries_and_duplicates(mt, dev, box):
+    cbs = synth.make_codebook(box, M=3000, D=8, seed=5)
+    poses = torch.cat([cbs.poses, cbs.poses[:200]])  # duplicate keys -> ties
+    cb = mt.tt.tactile_tree(poses, poses, torch.cat([cbs.embeddings, cbs.embeddings[:200]]))
+    cb.to_device(dev)
+    keys_cb = cb.logmap_pose.cpu().numpy()
+    rng = np.random.default_rng(0)
+    q = np.concatenate([keys_cb[:200], (rng.normal(size=(500, 6)) * 0.2).astype(np.float32)]).astype(np.float32)
+    qd = torch.from_numpy(q).to(dev)
+    n = q.shape[0]
+    for mode in (0, 1):
+        idx = torch.empty(n, dtype=torch.int32, device=dev)
+        mt.lib.call("mt_nn_assign", cb.ctx.h, qd.data_ptr(), n, 0, mode, idx.data_ptr(), mt.lib.stream_ptr())
+        assert np.array_equal(idx.cpu().numpy().astype(np.int64), O.nn_brute(keys_cb, q)), mode
+
+
+def test_se3_nn_dropin(mt, dev, cb_big):
+    cbs, cb = cb_big
+    g = torch.Generator().manual_seed(0)
+    sel = torch.randint(0, 50000, (2048,), generator=g)
+    poses = cbs.poses[sel].clone()
+    poses[:, :3, 3] += 3e-4 * torch.randn(2048, 3, generator=g)
+    p, c, e = cb.SE3_NN(poses.to(dev))
+    ref = O.se3_nn(O.r3_se3(cbs.poses), poses)
+    # oracle keys and CUDA keys differ by float32 ulps: indices must agree unless the two
+    # candidates are equidistant to rounding
+    idx = cb.SE3_NN_idx(poses.to(dev)).cpu().long()
+    diff = (idx != ref).nonzero().flatten()
+    keys_cb = O.r3_se3(cbs.poses).numpy()
+    qk = O.r3_se3(poses).numpy()
+    for j in diff.tolist():
+        da, db = O.l2_sq_f32(keys_cb[idx[j]], qk[j]), O.l2_sq_f32(keys_cb[ref[j]], qk[j])
+        assert abs(float(da) - float(db)) <= 1e-5 * float(db) + 1e-12
+    assert len(diff) <= 2
+    assert torch.equal(p.cpu(), cbs.poses[idx]) and torch.equal(c.cpu(), cbs.cam_poses[idx]) and torch.equal(e.cpu(), cbs.embeddings[idx])
+
+
+# ----------------------------------------------------------------------------- motion
+def test_motion_vs_reference_golden(mt, dev, golden, box):
+    g = golden("motion")
+    cfg = synth_cfg()
+    pf = mt.pf.particle_filter(cfg, box.vertices)
+    torch.manual_seed(int(g["seed"]))
+    out = pf.motionModel(mt.pf.Particles(T(g["poses"]).to(dev)), T(g["odom"]))
+    assert len(out) == g["poses"].shape[0]
+    assert torch.allclose(out.poses.cpu(), T(g["moved"]), rtol=RTOL, atol=ATOL)
+    assert float((out.poses.cpu() - T(g["moved"])).abs().max()) < 1e-6
+
+
+def synth_cfg(n=1024):
+    from oracle.ref_shim import default_cfg
+
+    return default_cfg(num_particles=n)
+
+
+def test_motion_philox_statistics(mt, dev, cb_small):
+    cbs, cb = cb_small
+    n = 200000
+    poses = torch.eye(4)[None].repeat(n, 1, 1).to(dev)
+    soa = mt.ctxm.aos_to_soa(poses)
+    eye = torch.eye(4).contiguous()
+    for step in (0, 1):
+        out = torch.empty_like(soa)
+        mt.lib.call("mt_motion", soa.data_ptr(), out.data_ptr(), n, n, eye.data_ptr(), 0, 0, 2e-4, 0.5, 7, step, 0, 0, 0, mt.lib.stream_ptr())
+        p = mt.ctxm.soa_to_aos(out, n).cpu()
+        t = p[:, :3, 3].double()
+        assert abs(t.mean()) < 5e-6 and abs(t.std() / 2e-4 - 1) < 0.01
+        ang = torch.rad2deg(torch.acos(((p[:, 0, 0] + p[:, 1, 1] + p[:, 2, 2] - 1) / 2).clamp(-1, 1))).double()
+        # |rotation| of three independent 0.5 deg Euler angles ~ chi(3) * 0.5
+        assert abs(ang.pow(2).mean().sqrt() / (0.5 * math.sqrt(3)) - 1) < 0.02
+        if step == 0:
+            first = p
+    assert not torch.equal(first, p)
+    out2 = torch.empty_like(soa)
+    mt.lib.call("mt_motion", soa.data_ptr(), out2.data_ptr(), n, n, eye.data_ptr(), 0, 0, 2e-4, 0.5, 7, 1, 0, 0, 0, mt.lib.stream_ptr())
+    assert torch.equal(out2, out)  # deterministic in (seed, step, particle)
+
+
+def test_init_filter_vs_oracle(mt, dev, box):
+    pf = mt.pf.particle_filter(synth_cfg(), box.vertices)
+    gt, _ = synth.make_trajectory(box, T=2)
+    torch.manual_seed(3)
+    parts = pf.init_filter(gt[0].to(dev), 4096)
+    torch.manual_seed(3)
+    tn = torch.normal(mean=0.0, std=pf.init_noise[0], size=(4096, 3))
+    rot = torch.normal(mean=0.0, std=pf.init_noise[1], size=(4096, 3))
+    ref = O.init_filter(gt[0], tn, rot)
+    assert torch.allclose(parts.poses.cpu(), ref, rtol=RTOL, atol=2e-6)
+
+
+# ----------------------------------------------------------------------------- similarity
+def test_similarity_vs_reference_golden(mt, dev, golden, box, cb_small):
+    g = golden("similarity")
+    cbs, cb = cb_small
+    pf = mt.pf.particle_filter(synth_cfg(), box.vertices)
+    q, sel = T(g["q"]).to(dev), T(g["sel"])
+    targets = cbs.embeddings[sel].to(dev)
+    w = pf.get_similarity(q, targets, softmax=True).cpu()
+    assert torch.allclose(w, T(g["w_soft"]), rtol=1e-12, atol=0)
+    w = pf.get_similarity(q, targets, softmax=False).cpu()
+    assert torch.allclose(w, T(g["w_raw"]), rtol=1e-12, atol=0)
+    w = pf.get_similarity(q, targets[:1].repeat(16, 1), softmax=True).cpu()  # constant -> softmax skipped
+    assert torch.allclose(w, T(g["w_const"]), rtol=1e-12, atol=0)
+    heat = cb.query(q).cpu()
+    assert torch.allclose(heat, T(g["heat"]), rtol=1e-12, atol=0)
+    # float32 storage of the codebook: still inside the 1e-5 bar
+    cb32 = mt.tt.tactile_tree(cbs.poses, cbs.cam_poses, cbs.embeddings.float())
+    cb32.to_device(dev)
+    assert torch.allclose(cb32.query(q).cpu(), T(g["heat"]), rtol=RTOL, atol=0)
+
+
+def test_cosine_ragged_and_nan(mt, dev):
+    pf_ctx = mt.pf._ctx_for(dev, 10)
+    for D, dt in ((6, torch.float64), (12, torch.float32), (514, torch.float64)):
+        q = torch.rand(D, dtype=torch.float64)
+        t = torch.rand(37, D, dtype=dt)
+        t[5] = 0  # zero row: clamp at eps
+        out = torch.empty(37, dtype=torch.float64, device=dev)
+        mt.lib.call("mt_cosine_rows", pf_ctx.h, q.to(dev).data_ptr(), 1, t.to(dev).data_ptr(), 1 if dt == torch.float64 else 0, 37, D,
+                    out.data_ptr(), mt.lib.stream_ptr())
+        ref = torch.nn.functional.cosine_similarity(q[None], t.double())
+        assert torch.allclose(out.cpu(), ref, rtol=1e-6 if dt == torch.float32 else 1e-12, atol=1e-300)
+
+
+def test_cosine_batched(mt, dev):
+    Q = torch.rand(70, 256)
+    Tm = torch.rand(1000, 256)
+    out = torch.empty(70, 1000, device=dev)
+    ctx = mt.pf._ctx_for(dev, 10)
+    mt.lib.call("mt_cosine_batched", ctx.h, Q.to(dev).data_ptr(), 70, Tm.to(dev).data_ptr(), 1000, 256, out.data_ptr(), mt.lib.stream_ptr())
+    ref = torch.nn.functional.cosine_similarity(Q.double()[:, None, :], Tm.double()[None], dim=2)
+    assert torch.allclose(out.cpu().double(), ref, rtol=1e-5, atol=0)
+
+
+# ----------------------------------------------------------------------------- resampling
+@pytest.mark.parametrize("name", ["soft", "raw", "masked", "peaked"])
+@pytest.mark.parametrize("seq", [0, 1])
+def test_low_var_vs_reference_loop_golden(mt, dev, golden, name, seq):
+    g = golden("resample_low_var")
+    ctx = mt.pf._ctx_for(dev, 1024)
+    for seed in (3, 4):
+        w = T(g[f"{name}_{seed}_w"]).to(dev)
+        u = float(g[f"{name}_{seed}_u"][0])
+        n = w.shape[0]
+        anc = torch.empty(n, dtype=torch.int32, device=dev)
+        mt.lib.call("mt_resample_systematic", ctx.h, w.data_ptr(), n, C.c_float(u), seq, anc.data_ptr(), 0, mt.lib.stream_ptr())
+        filled = g[f"{name}_{seed}_filled"]
+        a = anc.cpu().numpy().astype(np.int64)
+        assert np.array_equal(a[filled], g[f"{name}_{seed}_anc"][filled])
+        if seq:
+            assert np.array_equal(a >= 0, filled)
+
+
+def test_low_var_dropin_vs_reference_golden(mt, dev, golden, box):
+    g = golden("resample_low_var")
+    pf = mt.pf.particle_filter(synth_cfg(), box.vertices)
+    poses = T(g["in_poses"]).to(dev)
+    w = T(g["soft_3_w"]).to(dev)
+    n = w.shape[0]
+    labels = torch.arange(n, dtype=torch.float32, device=dev)
+    torch.manual_seed(3)
+    out = pf.resampler(mt.pf.Particles(poses, w, labels), resample="low_var", u=float(g["soft_3_u"][0]))
+    assert np.array_equal(out.labels.cpu().numpy().astype(np.int64), g["soft_3_anc"])
+    assert torch.equal(out.poses[:8].cpu(), T(g["soft_3_poses0"]))
+    assert torch.equal(out.weights.cpu(), T(g["soft_3_w"])[T(g["soft_3_anc"])])
+    # guards (particle_filter.py:237-241): all-zero and NaN weights return the input
+    z = pf.resampler(mt.pf.Particles(poses, torch.zeros_like(w), labels), resample="low_var")
+    assert torch.equal(z.poses, poses)
+    wn = w.clone()
+    wn[5] = float("nan")
+    z = pf.resampler(mt.pf.Particles(poses, wn, labels), resample="low_var")
+    assert torch.equal(z.poses, poses)
+
+
+@pytest.mark.parametrize("n", [1, 2, 255, 256, 257, 65536, 1000003])
+def test_low_var_sizes_vs_oracle(mt, dev, n):
+    ctx = mt.pf._ctx_for(dev, n)
+    g = torch.Generator().manual_seed(n)
+    for kind in ("flat", "peaked", "sparse"):
+        w = torch.rand(n, dtype=torch.float64, generator=g) + 0.5
+        if kind == "peaked":
+            w = torch.softmax(20 * w, 0)
+        if kind == "sparse":
+            w = w * (torch.rand(n, generator=g) < 0.1)
+            if w.sum() == 0:
+                w[0] = 1.0
+        for u in (0.0, 0.73, float(np.nextafter(np.float32(1), np.float32(0)))):
+            anc = torch.empty(n, dtype=torch.int32, device=dev)
+            mt.lib.call("mt_resample_systematic", ctx.h, w.to(dev).data_ptr(), n, C.c_float(u), 0, anc.data_ptr(), 0, mt.lib.stream_ptr())
+            a = anc.cpu().long()
+            ref = O.low_var_indices(w, u)
+            ok = ref >= 0
+            nd = int((a[ok] != ref[ok]).sum())
+            if nd:
+                # perf mode uses a parallel float64 prefix: an ancestor may flip only where a
+                # sample location sits within rounding distance of a CDF boundary
+                _, Cd = O.systematic_cdf(w)
+                locs = O.systematic_locs(n, u)
+                bad = (a != ref).nonzero().flatten()
+                for j in bad.tolist():
+                    i0, i1 = sorted((int(a[j]), int(ref[j])))
+                    assert i1 - i0 == 1 or float(w[i0 + 1 : i1].sum()) == 0.0
+                    assert abs(float(Cd[i0]) - float(locs[j])) < 1e-13
+            assert nd <= 1, (n, kind, u, nd)
+            assert (a[1:] >= a[:-1]).all()
+            if kind == "sparse":
+                assert (w[a] > 0).all()  # zero-weight particles never get children
+
+
+def test_low_var_heavy_parent(mt, dev):
+    """one particle owning ~all slots exercises the warp-cooperative child writes."""
+    n = 50000
+    w = torch.full((n,), 1e-9, dtype=torch.float64)
+    w[12345] = 1.0
+    ctx = mt.pf._ctx_for(dev, n)
+    anc = torch.empty(n, dtype=torch.int32, device=dev)
+    mt.lib.call("mt_resample_systematic", ctx.h, w.to(dev).data_ptr(), n, C.c_float(0.5), 0, anc.data_ptr(), 0, mt.lib.stream_ptr())
+    assert torch.equal(anc.cpu().long(), O.low_var_indices(w, 0.5))
+
+
+# ----------------------------------------------------------------------------- rmse
+def test_rmse_vs_reference_golden(mt, dev, golden):
+    g = golden("rmse")
+    rt, rr = mt.pf.particle_rmse(T(g["poses"]).to(dev), T(g["gt"]))
+    assert abs(float(rt) - float(g["rmse_t"])) <= RTOL * float(g["rmse_t"])
+    assert abs(float(rr) - float(g["rmse_r"])) <= RTOL * float(g["rmse_r"])
+
+
+# ----------------------------------------------------------------------------- fused step
+def _engine_case(mt, dev, cbs, cb, N, seed, softmax=True):
+    g = torch.Generator().manual_seed(seed)
+    M = cbs.poses.shape[0]
+    sel = torch.randint(0, M, (N,), generator=g)
+    poses = cbs.poses[sel].clone()
+    obj = synth.make_object("004_sugar_box")
+    gt, meas = synth.make_trajectory(obj, T=4, seed=seed)
+    odom = torch.inverse(meas[0]) @ meas[1]
+    torch.manual_seed(seed)
+    tn, rot = O.draw_motion_noise(N, 2e-4, 0.5)
+    q = synth.make_query(cbs, int(sel[0]), seed=seed)
+    return poses, sel, odom, tn, rot, q, gt
+
+
+@pytest.mark.parametrize("N,big", [(1024, False), (4099, False), (65536, True)])
+def test_fused_step_vs_oracle(mt, dev, cb_small, cb_big, N, big):
+    cbs, cb = cb_big if big else cb_small
+    poses, sel, odom, tn, rot, q, gt = _engine_case(mt, dev, cbs, cb, N, seed=N)
+    u = 0.618
+    eng = mt.eng.FilterEngine(cb, capacity=N + 100)
+    eng.load_particles(poses.to(dev), nn_hint=sel.int().to(dev))
+    # stage 1: weighting only (kernel A)
+    eng.step(q, odom, u=u, tn=tn.to(dev), rot=rot.to(dev), gt=gt[1], resample=False)
+    keys_cb = cb.logmap_pose.cpu()
+    moved, keep = O.motion_model(poses, odom, tn, rot)
+    assert keep.all()
+    got_moved = eng.poses().cpu()
+    assert torch.allclose(got_moved, moved, rtol=RTOL, atol=ATOL)
+    # NN on the CUDA-moved poses must be exactly the oracle's NN of those same poses/keys
+    nn = eng.nn_idx().cpu().long()
+    gkeys = mt.tt.R3_SE3(got_moved.to(dev)).cpu().numpy()
+    assert np.array_equal(nn.numpy(), O.nn_exact(keys_cb.numpy(), gkeys))
+    sim = O.codebook_similarity(q, cbs.embeddings)
+    w_ref = torch.softmax(sim[nn], 0)
+    w = eng.weights().cpu()
+    assert torch.allclose(w, w_ref, rtol=1e-10, atol=0)
+    assert abs(float(w.sum()) - 1.0) < 1e-12
+    rt, rr = O.particle_rmse(moved, gt[1])
+    r2 = eng.rmse.cpu()
+    assert abs(float(r2[0]) - float(rt)) <= RTOL * float(rt) and abs(float(r2[1]) - float(rr)) <= RTOL * float(rr)
+    # stage 2: a full step from the same start; ancestors vs the oracle's low_var on the CUDA weights
+    eng2 = mt.eng.FilterEngine(cb, capacity=N + 100)
+    eng2.load_particles(poses.to(dev))  # no hint: exercises the seeded search
+    eng2.step(q, odom, u=u, tn=tn.to(dev), rot=rot.to(dev))
+    anc = eng2.ancestors().cpu().long()
+    ref_anc = O.low_var_indices(w, u)
+    assert torch.equal(anc, ref_anc)
+    assert torch.equal(eng2.poses().cpu(), got_moved[anc])
+    assert torch.equal(eng2.nn_idx().cpu().long(), nn[anc])
+    # and against the reference formulation end to end (gather N x D float64, then cosine)
+    if N <= 4099:
+        full = O.filter_step(poses, odom, tn, rot, keys_cb, cbs.embeddings, q, u)
+        assert torch.equal(full["nn_idx"], nn) and torch.equal(full["anc"], anc)
+        assert torch.allclose(w, full["weights"], rtol=1e-10)
+
+
+def test_fused_step_philox_teacher_forced(mt, dev, cb_small):
+    """perf mode (in-kernel Philox): recover the drawn noise from the standalone motion kernel
+    with the same (seed, step, gid) and teacher-force the oracle with it."""
+    cbs, cb = cb_small
+    N = 8192
+    poses, sel, odom, _, _, q, gt = _engine_case(mt, dev, cbs, cb, N, seed=5)
+    eng = mt.eng.FilterEngine(cb, capacity=N, seed=99)
+    eng.load_particles(poses.to(dev))
+    eng.t = 3
+    eng.step(q, odom, u=0.25)
+    soa = mt.ctxm.aos_to_soa(poses.to(dev))
+    out = torch.empty_like(soa)
+    od = odom.contiguous()
+    mt.lib.call("mt_motion", soa.data_ptr(), out.data_ptr(), N, N, od.data_ptr(), 0, 0, 2e-4, 0.5, 99, 3, 0, 0, 0, mt.lib.stream_ptr())
+    moved = mt.ctxm.soa_to_aos(out, N).cpu()
+    nn = torch.from_numpy(O.nn_exact(cb.logmap_pose.cpu().numpy(), mt.tt.R3_SE3(moved.to(dev)).cpu().numpy()))
+    w = torch.softmax(O.codebook_similarity(q, cbs.embeddings)[nn], 0)
+    anc = O.low_var_indices(w, 0.25)
+    assert torch.equal(eng.ancestors().cpu().long(), anc)
+    assert torch.equal(eng.poses().cpu(), moved[anc])
+
+
+def test_fused_multi_step_invariants(mt, dev, cb_big):
+    """N = 1e6 for 5 steps (BASELINE config 3 scale): size-independent properties."""
+    cbs, cb = cb_big
+    N = 1_000_000
+    g = torch.Generator().manual_seed(0)
+    sel = torch.randint(0, 50000, (N,), generator=g)
+    obj = synth.make_object("004_sugar_box")
+    gt, meas = synth.make_trajectory(obj, T=8)
+    eng = mt.eng.FilterEngine(cb, capacity=N, seed=1)
+    eng.load_particles(cbs.poses.to(dev)[sel.to(dev)], nn_hint=sel.int().to(dev))
+    for t in range(1, 6):
+        odom = torch.inverse(meas[t - 1]) @ meas[t]
+        q = synth.make_query(cbs, int(sel[t]))
+        eng.step(q, odom, gt=gt[t])
+        anc = eng.ancestors()
+        assert int(anc.min()) >= 0 and int(anc.max()) < N
+        assert bool((anc[1:] >= anc[:-1]).all())  # systematic draw is sorted
+        cnt = torch.bincount(anc.long(), minlength=N)
+        assert int(cnt.sum()) == N and int(cnt.max()) <= 3  # weights within a factor e -> <= ceil(e) children
+        nn = eng.nn_idx()
+        assert int(nn.min()) >= 0 and int(nn.max()) < 50000
+        p = eng.poses()
+        RtR = p[:, :3, :3].transpose(1, 2) @ p[:, :3, :3]
+        assert float((RtR - torch.eye(3, device=dev)).abs().max()) < 1e-4
+        assert torch.isfinite(eng.rmse).all()
+    # exactness spot check on a 20k subsample of the final NN assignment
+    sub = torch.randperm(N, generator=g)[:20000]
+    keys = mt.tt.R3_SE3(p[sub.to(dev)])
+    # nn_idx holds the NN of the parents' moved poses == children poses
+    ref = O.nn_exact(cb.logmap_pose.cpu().numpy(), keys.cpu().numpy())
+    assert np.array_equal(eng.nn_idx()[sub.to(dev)].cpu().numpy().astype(np.int64), ref)
+
+
+def test_missing_library_fails_loudly(mt, monkeypatch):
+    monkeypatch.setattr(mt.lib, "LIB_PATH", "/nonexistent/libmidas_b200.so")
+    monkeypatch.setattr(mt.lib, "_lib", None)
+    with pytest.raises(mt.lib.MidasError):
+        mt.lib.lib()
+
+
+def test_cpu_tensor_rejected(mt, box):
+    pf = mt.pf.particle_filter(synth_cfg(), box.vertices)
+    with pytest.raises(mt.lib.MidasError):
+        pf.get_similarity(torch.rand(1, 8, dtype=torch.float64), torch.rand(4, 8, dtype=torch.float64))

@@ -1,0 +1,129 @@
+"""CPU: the per-particle arithmetic header shared by every CUDA kernel
+(midastouch_b200/csrc/mt_math.cuh) compiled for the host and checked against the oracle
+and the golden vectors.  This is a test of the kernel source, not a CPU product path."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as O
+from midastouch_b200 import synth
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def H():
+    build = os.path.join(HERE, "_build")
+    os.makedirs(build, exist_ok=True)
+    so = os.path.join(build, "host_math.so")
+    src = os.path.join(HERE, "host_math_harness.cpp")
+    hdr = os.path.join(HERE, "..", "midastouch_b200", "csrc", "mt_math.cuh")
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-x", "c++", "-shared", "-fPIC", "-o", so, src])
+    return ctypes.CDLL(so)
+
+
+def P(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def test_keys_match_oracle(H):
+    obj = synth.make_object("004_sugar_box")
+    cb = synth.make_codebook(obj, M=5000, D=8)
+    poses = cb.poses.numpy().copy()
+    keys = np.zeros((5000, 6), np.float32)
+    H.h_se3_keys(P(poses), ctypes.c_longlong(5000), P(keys))
+    ref = O.r3_se3(cb.poses).numpy()
+    assert np.abs(keys - ref).max() < 2e-7
+    # rotations near identity / near pi exercise both branches
+    from scipy.spatial.transform import Rotation as R
+
+    rng = np.random.default_rng(0)
+    ax = rng.normal(size=(300, 3))
+    ax /= np.linalg.norm(ax, axis=1, keepdims=True)
+    ang = np.concatenate([np.full(100, 1e-3), np.full(100, np.pi - 1e-3), rng.uniform(0, np.pi, 100)])
+    T = np.zeros((300, 4, 4), np.float32)
+    T[:, :3, :3] = R.from_rotvec(ax * ang[:, None]).as_matrix()
+    T[:, 3, 3] = 1
+    keys = np.zeros((300, 6), np.float32)
+    H.h_se3_keys(P(T), ctypes.c_longlong(300), P(keys))
+    ref = O.r3_se3(torch.from_numpy(T)).numpy()
+    assert np.abs(keys - ref).max() < 1e-6
+
+
+def test_motion_matches_reference_golden(H, golden):
+    g = golden("motion")
+    poses = g["poses"].astype(np.float32).copy()
+    n = poses.shape[0]
+    out = np.zeros_like(poses)
+    H.h_motion(P(poses), ctypes.c_longlong(n), P(g["odom"].astype(np.float32).copy()), P(g["tn"].copy()), P(g["rot_deg"].copy()), P(out))
+    assert np.allclose(out, g["moved"], rtol=1e-5, atol=1e-6)
+    assert np.abs(out - g["moved"]).max() < 5e-7
+
+
+def test_key_dist_bit_exact(H):
+    rng = np.random.default_rng(1)
+    keys = (rng.normal(size=(4096, 6)) * 0.05).astype(np.float32)
+    q = (rng.normal(size=6) * 0.05).astype(np.float32)
+    out = np.zeros(4096, np.float32)
+    H.h_key_dist(P(keys), ctypes.c_longlong(4096), P(q), P(out))
+    assert np.array_equal(out, O.l2_sq_f32(keys, q))
+
+
+@pytest.mark.parametrize("name", ["soft", "raw", "masked", "peaked"])
+def test_slot_logic_matches_reference_loop(H, golden, name):
+    g = golden("resample_low_var")
+    for seed in (3, 4):
+        w = torch.from_numpy(g[f"{name}_{seed}_w"])
+        u = float(g[f"{name}_{seed}_u"][0])
+        _, C = O.systematic_cdf(w)
+        C = C.numpy().copy()
+        n = len(C)
+        anc = np.zeros(n, np.int64)
+        H.h_ancestors_from_cdf(P(C), ctypes.c_longlong(n), ctypes.c_float(u), P(anc))
+        filled = g[f"{name}_{seed}_filled"]
+        assert np.array_equal(anc >= 0, filled)
+        assert np.array_equal(anc[filled], g[f"{name}_{seed}_anc"][filled])
+
+
+@pytest.mark.parametrize("n", [1, 2, 7, 1024, 65536, 1000003])
+def test_locs_and_counts(H, n):
+    for u in (0.0, 0.37, float(np.nextafter(np.float32(1), np.float32(0)))):
+        locs = np.zeros(n)
+        H.h_locs(ctypes.c_longlong(n), ctypes.c_float(u), P(locs))
+        assert np.array_equal(locs, O.systematic_locs(n, u).numpy())
+        w = torch.rand(n, dtype=torch.float64, generator=torch.Generator().manual_seed(n)) + 1e-3
+        _, C = O.systematic_cdf(w)
+        anc = np.zeros(n, np.int64)
+        H.h_ancestors_from_cdf(P(C.numpy().copy()), ctypes.c_longlong(n), ctypes.c_float(u), P(anc))
+        assert np.array_equal(anc, O.low_var_indices(w, u).numpy())
+
+
+def test_philox_normals_statistics(H):
+    n = 200000
+    out = np.zeros((n, 6), np.float32)
+    H.h_normals(ctypes.c_ulonglong(123), ctypes.c_ulonglong(5), ctypes.c_longlong(n), P(out))
+    assert np.isfinite(out).all()
+    assert np.abs(out.mean(0)).max() < 0.01 and np.abs(out.std(0) - 1).max() < 0.01
+    c = np.corrcoef(out.T)
+    assert np.abs(c - np.eye(6)).max() < 0.01
+    out2 = np.zeros((n, 6), np.float32)
+    H.h_normals(ctypes.c_ulonglong(123), ctypes.c_ulonglong(6), ctypes.c_longlong(n), P(out2))
+    assert np.abs(np.corrcoef(out[:, 0], out2[:, 0])[0, 1]) < 0.01
+    from scipy import stats
+
+    assert stats.kstest(out[:, 3].astype(np.float64), "norm").pvalue > 1e-3
+
+
+def test_rot_err_matches_reference_golden(H, golden):
+    g = golden("rmse")
+    poses = g["poses"].astype(np.float32).copy()
+    n = poses.shape[0]
+    out = np.zeros(n, np.float32)
+    H.h_rot_err(P(g["gt"].astype(np.float32).copy()), P(poses), ctypes.c_longlong(n), P(out))
+    rr = np.sqrt(np.mean(out.astype(np.float64) ** 2))
+    assert abs(rr - float(g["rmse_r"])) <= 1e-5 * float(g["rmse_r"])
