@@ -4,7 +4,7 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
 One "step" = one pass of the hot path (codebook query + motion + exact SE3_NN + weighting +
-systematic resampling) over all particles.  Workload (BASELINE.json configs[2]):
+drift pruning + systematic resampling) over all particles.  Workload (BASELINE.json configs[2]):
 "035_power_drill log 3, N=1e6 particles, 1xB200", synthetic stand-in assets,
 codebook M=50 000, D=256 float64 (the reference's shipped width and dtype).
 N>1: weak scaling, 1e6 particles per GPU, one all-gather of 8-byte weight sums per step.
@@ -107,7 +107,8 @@ def run_ours(args):
     cb.to_device(dev)
     n = N_PER_GPU
     cap = n + (n // 8 if world > 1 else 0)
-    eng = FilterEngine(cb, capacity=cap, sig_t=2e-4, sig_r=0.5, seed=1234, rank=rank, world=world, n_global=n * world)
+    eng = FilterEngine(cb, capacity=cap, sig_t=2e-4, sig_r=0.5, seed=1234, rank=rank, world=world, n_global=n * world,
+                       mesh_vertices=obj.vertices[::10], pen_max=0.002)
     # particles start on codebook poses around the trajectory start (what init + snap produce)
     g = torch.Generator().manual_seed(100 + rank)
     sel = torch.randint(0, M, (n,), generator=g)
@@ -154,6 +155,7 @@ def run_ours(args):
     total_ms = float(total_ms.item())
     value = n * world * args.steps / (total_ms * 1e-3)
 
+    stats_loop = eng.ctx.stats(reset=True)
     # ---- kernel-level timing of the two sweep kernels (same stream, CUDA events)
     a_ms, b_ms, q_ms = kernel_times(eng, codes_d, odoms, us, l2flush, min(args.steps, 20))
 
@@ -191,6 +193,8 @@ def run_ours(args):
                          "codebook_query_gbs": (M * D * 8 + D * 8 + M * 16) / (q_ms * 1e-3) / 1e9},
             "e2e": {"value": e2e, "unit": "particle-updates/s", "h2d_bytes_per_step": D * 8 + 64 + 64 + 4, "d2h_bytes_per_step": 8},
             "gpu_launches": 4 * args.steps, "clocks": clk.summary(),
+            "engine_stats": {"nn_grid_fallbacks_per_step": stats_loop["nn_fallbacks"] / (args.steps + args.warmup),
+                             "on_surface_last_step": stats_loop["on_surface"], "overflow": stats_loop["overflow"]},
         }
         if world == 1 and not args.no_cpu:
             out["cpu_baseline"] = cpu_baseline(budget_s=15.0)
@@ -200,16 +204,16 @@ def run_ours(args):
 
 
 def kernel_times(eng, codes_d, odoms, us, l2flush, reps):
-    """average device time of k_cosine_rows, k_step_a, k_step_b, each bracketed by events on the
-    launching stream with the L2 flushed first."""
+    """average device time of k_cosine_rows, k_step_a, k_step_b inside a live step: L2 flushed once
+    before the step (as in the timed loop), CUDA events on the launching stream between the kernels."""
     import ctypes as C
 
     from midastouch_b200._lib import call, ptr, stream_ptr
     from midastouch_b200.context import dtype_code
 
     acc = [0.0, 0.0, 0.0]
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
     for r in range(reps):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
         k = r % len(odoms)
         a = eng._fill(odoms[k], us[r], None, None, None, True)
         q = codes_d[k].reshape(-1).contiguous()
@@ -218,25 +222,21 @@ def kernel_times(eng, codes_d, odoms, us, l2flush, reps):
         ev[0].record()
         call("mt_codebook_query", eng.ctx.h, ptr(q), dtype_code(q), 0, s)
         ev[1].record()
-        l2flush.zero_()
-        ev[2].record()
         call("mt_step_a", eng.ctx.h, C.byref(a), s)
-        ev[3].record()
+        ev[2].record()
         if eng.world > 1:
             eng._allgather_sums()
-        l2flush.zero_()
-        e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e4.record()
+        ev[3].record()
         call("mt_step_b", eng.ctx.h, C.byref(a), s)
-        e5.record()
+        ev[4].record()
         eng.cur = 1 - eng.cur
         if eng.world > 1:
             eng.use_n_dev = True
         eng.t += 1
         torch.cuda.synchronize()
         acc[0] += ev[0].elapsed_time(ev[1])
-        acc[1] += ev[2].elapsed_time(ev[3])
-        acc[2] += e4.elapsed_time(e5)
+        acc[1] += ev[1].elapsed_time(ev[2])
+        acc[2] += ev[3].elapsed_time(ev[4])
     return acc[1] / reps, acc[2] / reps, acc[0] / reps
 
 
@@ -251,6 +251,7 @@ def cpu_baseline(budget_s=15.0, n=65536, steps=None):
     from scipy.spatial import cKDTree
 
     tree = cKDTree(keys.numpy().astype("float64"))
+    vds = obj.vertices[::10]
     g = torch.Generator().manual_seed(100)
     sel = torch.randint(0, M, (n,), generator=g)
     poses = cbs.poses[sel].clone()
@@ -267,6 +268,7 @@ def cpu_baseline(budget_s=15.0, n=65536, steps=None):
         qk = O.r3_se3(moved).numpy().astype("float64")
         _, idx = tree.query(qk, k=1, workers=-1)                               # SE3_NN (16-thread k-d tree)
         w = O.get_similarity(q, cbs.embeddings[torch.from_numpy(idx)], True)  # gather N x D f64 + cosine + softmax
+        w, _ = O.remove_invalid(moved, w, vds, 0.002)                          # remove_invalid_particles (k-d tree)
         anc = O.low_var_indices(w, float(torch.rand(1)))                      # resampler("low_var") (vectorised form)
         poses = moved[anc.clamp(min=0)]
         t_total += time.perf_counter() - t0

@@ -55,6 +55,30 @@ int mt_codebook_upload(mt_ctx* ctx, const float* h_keys, const void* d_emb, int 
 /* key grid introspection (tests): cell size, dims[3], number of occupied cells */
 int mt_codebook_grid_info(mt_ctx* ctx, float* h, int dims[3], int* occupied);
 
+/* neighbour-graph introspection (tests): device pointer to the (M, k, 8) float32 table
+ * [key(6), delta, index bits] of every key's k nearest other keys, ascending. */
+int mt_codebook_nbr_info(mt_ctx* ctx, const float** d_nbr, int* k);
+/* status / statistics words of the context (synchronises).  h_out8[MT_STAT_*]; reset != 0
+ * clears the cumulative slots (0..3). */
+#define MT_STAT_OVERFLOW 0      /* children did not fit the destination buffer (sharded steps) */
+#define MT_STAT_RESAMPLE_SKIP 1 /* a resampling saw all-zero / NaN weights and kept the particles */
+#define MT_STAT_INVALID_POSES 2 /* poses check_quats would prune (cumulative) */
+#define MT_STAT_NN_FALLBACKS 3  /* queries that left the hint graph for the grid search (cumulative) */
+#define MT_STAT_DRIFTED 5       /* last mt_step_a: every particle failed the drift test */
+#define MT_STAT_ON_SURFACE 6    /* last mt_step_a: particles that passed the drift test */
+int mt_ctx_stats(mt_ctx* ctx, long long* h_out8, int reset);
+
+/* ---- mesh: particle_filter.__init__ (particle_filter.py:108-110) ------------------- */
+/* h_vertices: (V,3) float64 down-sampled mesh vertices (mesh.vertices[::10]) on the HOST; a
+ * uniform grid of edge `cell` (>= the default invalid_dist, tdn.render.pen.max) replaces the
+ * sklearn KDTree. */
+int mt_mesh_upload(mt_ctx* ctx, const double* h_vertices, long long V, double cell);
+/* remove_invalid_particles (particle_filter.py:379-403) on (n,4,4) float32 poses:
+ * d_weights[i] *= (distance to the nearest vertex <= invalid_dist), float64, in place
+ * (nullable); *d_num_valid = number of particles that passed (device int, nullable). */
+int mt_prune_aos(mt_ctx* ctx, const float* d_poses, long long n, double invalid_dist, double* d_weights,
+                 int* d_num_valid, void* stream);
+
 /* cos(q, E_m) for all M rows -> ctx-resident float64 tables sim[M] and exp(sim)[M]
  * (get_similarity(code, heatmap_embeddings, softmax=False), filter.py:213-215, and the
  * per-particle weights of filter.py:170-173 by table lookup).  d_q: (D,) in q_dtype.
@@ -81,7 +105,7 @@ int mt_soa_to_aos(const float* d_soa, long long stride, long long n, float* d_ao
 int mt_se3_keys(const float* d_soa, long long stride, long long n, float* d_keys, void* stream);
 /* exact L2 1-NN of n keys in the codebook; ties -> lowest index.  d_hint (nullable):
  * a codebook index per query that seeds the search bound (any valid index is correct).
- * mode 0 = grid search, 1 = exhaustive (tiled).  d_idx: (n,) int32. */
+ * mode 0 = hint graph + grid search (mt_nn.cuh), 1 = exhaustive (tiled).  d_idx: (n,) int32. */
 int mt_nn_assign(mt_ctx* ctx, const float* d_keys, long long n, const int32_t* d_hint, int mode, int32_t* d_idx,
                  void* stream);
 /* out[i] = table rows gathered by index: poses (M,4,4) f32 -> AoS (n,4,4) */
@@ -151,6 +175,11 @@ typedef struct mt_step_args {
   long long* d_n_out;    /* device (nullable): number of children written on this GPU */
   const long long* d_n_in; /* device (nullable): particle count read by the kernels instead of n; n is then
                             * only the upper bound that sizes the grid (no host sync between steps) */
+  /* drift pruning (remove_invalid_particles, filter.py:176-179): > 0 zeroes the weight of particles
+   * further than this from the uploaded mesh; if all drift, mt_step_b re-projects the particles onto
+   * d_cb_poses[(M,4,4) float32 codebook poses, nullable] instead of resampling. */
+  double prune_dist;
+  const float* d_cb_poses;
 } mt_step_args;
 
 /* kernel A: motion + key + exact NN + weight lookup + deterministic weight sums */

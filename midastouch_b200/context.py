@@ -36,6 +36,7 @@ class Context:
         self._h = C.c_void_p()
         call("mt_ctx_create", self.index, C.c_size_t(self.capacity), self.M, self.D, C.byref(self._h))
         self._codebook = None  # (keys_host, emb) kept alive / for re-upload on growth
+        self._mesh = None      # (vertices_host float64, cell)
 
     @property
     def h(self):
@@ -61,6 +62,24 @@ class Context:
         call("mt_ctx_create", self.index, C.c_size_t(self.capacity), self.M, self.D, C.byref(self._h))
         if cb is not None:
             self.upload_codebook(*cb)
+        if self._mesh is not None:
+            self.upload_mesh(*self._mesh)
+
+    def upload_mesh(self, vertices, cell: float):
+        """down-sampled mesh vertices (V,3) float64 host array for the drift test."""
+        import numpy as np
+
+        v = np.ascontiguousarray(np.asarray(vertices, dtype=np.float64).reshape(-1, 3))
+        with torch.cuda.device(self.index):
+            call("mt_mesh_upload", self._h, v.ctypes.data_as(C.c_void_p), v.shape[0], float(cell))
+        self._mesh = (v, float(cell))
+
+    def stats(self, reset: bool = False) -> dict:
+        out = (C.c_longlong * 8)()
+        with torch.cuda.device(self.index):
+            call("mt_ctx_stats", self._h, out, int(reset))
+        return {"overflow": out[0], "resample_skipped": out[1], "invalid_poses": out[2], "nn_fallbacks": out[3],
+                "drifted": out[5], "on_surface": out[6]}
 
     def grid_info(self):
         h = C.c_float()

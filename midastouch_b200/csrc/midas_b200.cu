@@ -22,6 +22,9 @@
 
 #include "../../include/midas_b200.h"
 #include "mt_math.cuh"
+#define MT_NN_BLOCK 256
+#include "mt_nn.cuh"
+#include "mt_mesh.cuh"
 
 #define MT_MAX_D 6144  // query staged in 48 KB of shared memory as float64
 #define MT_CHUNK 256  // particles per chunk == threads per block of the sweep kernels
@@ -43,12 +46,6 @@ extern "C" const char* mt_last_error(void) { return g_err; }
 extern "C" int mt_version(void) { return 100; }
 
 // ------------------------------------------------------------------------- context
-struct GridParams {
-  float org[3];
-  float inv_h, h;
-  int dims[3];
-};
-
 struct mt_ctx {
   int device;
   size_t cap;
@@ -56,8 +53,9 @@ struct mt_ctx {
   // codebook
   float4* d_keys_orig;    // M x 2 float4 (k0..k3 | k4,k5,0,0), original order
   float4* d_keys_sorted;  // same, sorted by grid cell
-  int* d_sorted_orig;     // sorted position -> original index
+  int* d_sorted_orig;     // scratch: partner index per key during upload
   int* d_cell_start;      // ncells + 1
+  float4* d_nbr;          // M x MT_NBR_K x 2 float4 neighbour lists (mt_nn.cuh)
   GridParams grid;
   int occupied;
   const void* d_emb;
@@ -65,6 +63,12 @@ struct mt_ctx {
   double* d_sim;   // cos(q, E_m)
   double* d_esim;  // exp(cos)
   bool cb_ready;
+  // down-sampled mesh vertices for the drift test (mt_mesh.cuh)
+  double* d_mesh_verts;
+  int* d_mesh_cells;
+  MeshGrid mesh;
+  int mesh_V;
+  bool mesh_ready;
   // scratch
   int chunk_cap;
   double* d_part;     // per-chunk weight sums
@@ -73,7 +77,7 @@ struct mt_ctx {
   double* d_q64;      // staged query, float64, MT_MAX_D entries
   double* d_scal;     // [0] local weight sum, [1] max, [2] min, [3] softmax denom, [4..7] spare
   unsigned int* d_ticket;
-  int* d_flags;  // [0] overflow, [1] resample skipped
+  int* d_flags;  // MT_STAT_* slots (include/midas_b200.h)
 };
 
 static size_t nchunks_of(long long n) { return (size_t)((n + MT_CHUNK - 1) / MT_CHUNK); }
@@ -91,6 +95,7 @@ extern "C" int mt_ctx_create(int device, size_t capacity, int M, int D, mt_ctx**
   CK(cudaMalloc(&c->d_keys_orig, sizeof(float4) * 2 * M));
   CK(cudaMalloc(&c->d_keys_sorted, sizeof(float4) * 2 * M));
   CK(cudaMalloc(&c->d_sorted_orig, sizeof(int) * M));
+  CK(cudaMalloc(&c->d_nbr, sizeof(float4) * 2 * MT_NBR_K * (size_t)M));
   CK(cudaMalloc(&c->d_sim, sizeof(double) * M));
   CK(cudaMalloc(&c->d_esim, sizeof(double) * M));
   CK(cudaMalloc(&c->d_part, sizeof(double) * c->chunk_cap));
@@ -99,9 +104,9 @@ extern "C" int mt_ctx_create(int device, size_t capacity, int M, int D, mt_ctx**
   CK(cudaMalloc(&c->d_scal, sizeof(double) * 8));
   CK(cudaMalloc(&c->d_q64, sizeof(double) * MT_MAX_D));
   CK(cudaMalloc(&c->d_ticket, sizeof(unsigned int) * 4));
-  CK(cudaMalloc(&c->d_flags, sizeof(int) * 4));
+  CK(cudaMalloc(&c->d_flags, sizeof(int) * 8));
   CK(cudaMemset(c->d_ticket, 0, sizeof(unsigned int) * 4));
-  CK(cudaMemset(c->d_flags, 0, sizeof(int) * 4));
+  CK(cudaMemset(c->d_flags, 0, sizeof(int) * 8));
   CK(cudaMemset(c->d_scal, 0, sizeof(double) * 8));
   *out = c;
   return MT_OK;
@@ -114,6 +119,9 @@ extern "C" int mt_ctx_destroy(mt_ctx* c) {
   cudaFree(c->d_keys_sorted);
   cudaFree(c->d_sorted_orig);
   cudaFree(c->d_cell_start);
+  cudaFree(c->d_nbr);
+  cudaFree(c->d_mesh_verts);
+  cudaFree(c->d_mesh_cells);
   cudaFree(c->d_sim);
   cudaFree(c->d_esim);
   cudaFree(c->d_part);
@@ -128,20 +136,6 @@ extern "C" int mt_ctx_destroy(mt_ctx* c) {
 }
 
 // ------------------------------------------------------------------------- codebook grid
-// cell coordinate of a key component: identical float32 formula on host and device so that
-// monotonicity arguments about search boxes hold bit-for-bit.
-__host__ __device__ __forceinline__ int cell_coord(float x, float org, float inv_h, int dim) {
-#if defined(__CUDA_ARCH__)
-  float f = floorf(__fmul_rn(__fsub_rn(x, org), inv_h));
-#else
-  volatile float d = x - org;
-  volatile float m = d * inv_h;
-  float f = floorf(m);
-#endif
-  int c = (f < 0.f) ? 0 : (f >= (float)dim ? dim - 1 : (int)f);
-  return c;
-}
-
 extern "C" int mt_codebook_upload(mt_ctx* c, const float* h_keys, const void* d_emb, int emb_dtype) {
   if (!c || !h_keys) return set_err(MT_ERR_ARG, "mt_codebook_upload: null argument");
   if (emb_dtype != MT_DTYPE_F32 && emb_dtype != MT_DTYPE_F64) return set_err(MT_ERR_ARG, "mt_codebook_upload: dtype");
@@ -172,9 +166,9 @@ extern "C" int mt_codebook_upload(mt_ctx* c, const float* h_keys, const void* d_
     if (total > 4.0e6) break;
     float inv_h = 1.0f / h;
     for (int m = 0; m < M; ++m) {
-      int x = cell_coord(h_keys[6 * m], lo[0], inv_h, dims[0]);
-      int y = cell_coord(h_keys[6 * m + 1], lo[1], inv_h, dims[1]);
-      int z = cell_coord(h_keys[6 * m + 2], lo[2], inv_h, dims[2]);
+      int x = mt_cell_coord(h_keys[6 * m], lo[0], inv_h, dims[0]);
+      int y = mt_cell_coord(h_keys[6 * m + 1], lo[1], inv_h, dims[1]);
+      int z = mt_cell_coord(h_keys[6 * m + 2], lo[2], inv_h, dims[2]);
       ids[m] = ((long long)z * dims[1] + y) * dims[0] + x;
     }
     std::vector<long long> s(ids);
@@ -192,9 +186,9 @@ extern "C" int mt_codebook_upload(mt_ctx* c, const float* h_keys, const void* d_
   const long long ncell = (long long)g.dims[0] * g.dims[1] * g.dims[2];
   std::vector<int> cell(M);
   for (int m = 0; m < M; ++m) {
-    int x = cell_coord(h_keys[6 * m], g.org[0], g.inv_h, g.dims[0]);
-    int y = cell_coord(h_keys[6 * m + 1], g.org[1], g.inv_h, g.dims[1]);
-    int z = cell_coord(h_keys[6 * m + 2], g.org[2], g.inv_h, g.dims[2]);
+    int x = mt_cell_coord(h_keys[6 * m], g.org[0], g.inv_h, g.dims[0]);
+    int y = mt_cell_coord(h_keys[6 * m + 1], g.org[1], g.inv_h, g.dims[1]);
+    int z = mt_cell_coord(h_keys[6 * m + 2], g.org[2], g.inv_h, g.dims[2]);
     cell[m] = (int)(((long long)z * g.dims[1] + y) * g.dims[0] + x);
   }
   std::vector<int> order(M);
@@ -209,12 +203,19 @@ extern "C" int mt_codebook_upload(mt_ctx* c, const float* h_keys, const void* d_
       ko[8 * (size_t)m + k] = h_keys[6 * m + k];
       ks[8 * (size_t)m + k] = h_keys[6 * order[m] + k];
     }
+  for (int m = 0; m < M; ++m) memcpy(&ks[8 * (size_t)m + 6], &order[m], sizeof(int));  // original index rides in the padding
   if (c->d_cell_start) cudaFree(c->d_cell_start), c->d_cell_start = nullptr;
   CK(cudaMalloc(&c->d_cell_start, sizeof(int) * (ncell + 1)));
   CK(cudaMemcpy(c->d_cell_start, start.data(), sizeof(int) * (ncell + 1), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(c->d_keys_orig, ko.data(), sizeof(float) * 8 * M, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(c->d_keys_sorted, ks.data(), sizeof(float) * 8 * M, cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(c->d_sorted_orig, order.data(), sizeof(int) * M, cudaMemcpyHostToDevice));
+  k_build_nbr<false><<<(M + 7) / 8, 256>>>(c->d_keys_orig, M, c->d_nbr, nullptr);
+  CK_LAUNCH();
+  k_build_nbr<true><<<(M + 7) / 8, 256>>>(c->d_keys_orig, M, nullptr, c->d_sorted_orig);
+  CK_LAUNCH();
+  k_set_partner<<<(M + 255) / 256, 256>>>(c->d_keys_orig, M, c->d_sorted_orig);
+  CK_LAUNCH();
+  CK(cudaDeviceSynchronize());
   c->grid = g;
   c->occupied = best_occ;
   c->d_emb = d_emb;
@@ -229,6 +230,111 @@ extern "C" int mt_codebook_grid_info(mt_ctx* c, float* h, int dims[3], int* occu
   if (dims)
     for (int k = 0; k < 3; ++k) dims[k] = c->grid.dims[k];
   if (occupied) *occupied = c->occupied;
+  return MT_OK;
+}
+
+extern "C" int mt_codebook_nbr_info(mt_ctx* c, const float** d_nbr, int* k) {
+  if (!c || !c->cb_ready) return set_err(MT_ERR_STATE, "mt_codebook_nbr_info: no codebook");
+  if (d_nbr) *d_nbr = (const float*)c->d_nbr;
+  if (k) *k = MT_NBR_K;
+  return MT_OK;
+}
+
+extern "C" int mt_ctx_stats(mt_ctx* c, long long* h_out8, int reset) {
+  if (!c) return set_err(MT_ERR_ARG, "mt_ctx_stats: null context");
+  CK(cudaSetDevice(c->device));
+  int f[8];
+  CK(cudaMemcpy(f, c->d_flags, sizeof(f), cudaMemcpyDeviceToHost));
+  if (h_out8)
+    for (int k = 0; k < 8; ++k) h_out8[k] = f[k];
+  if (reset) {
+    CK(cudaMemset(c->d_flags, 0, 4 * sizeof(int)));
+  }
+  return MT_OK;
+}
+
+// ------------------------------------------------------------------------- mesh (drift test)
+extern "C" int mt_mesh_upload(mt_ctx* c, const double* h_vertices, long long V, double cell) {
+  if (!c || !h_vertices || V <= 0 || !(cell > 0.0)) return set_err(MT_ERR_ARG, "mt_mesh_upload: bad argument");
+  CK(cudaSetDevice(c->device));
+  double lo[3], hi[3];
+  for (int k = 0; k < 3; ++k) lo[k] = DBL_MAX, hi[k] = -DBL_MAX;
+  for (long long v = 0; v < V; ++v)
+    for (int k = 0; k < 3; ++k) {
+      double x = h_vertices[3 * v + k];
+      if (!(x == x)) return set_err(MT_ERR_ARG, "mt_mesh_upload: NaN vertex");
+      lo[k] = std::min(lo[k], x);
+      hi[k] = std::max(hi[k], x);
+    }
+  MeshGrid g;
+  for (;;) {  // grow the cell until the grid fits in 8M cells
+    double total = 1;
+    for (int k = 0; k < 3; ++k) g.dims[k] = (int)floor((hi[k] - lo[k]) / cell) + 1, total *= g.dims[k];
+    if (total <= 8.0e6) break;
+    cell *= 1.5;
+  }
+  g.cell = cell;
+  g.inv_cell = 1.0 / cell;
+  for (int k = 0; k < 3; ++k) g.org[k] = lo[k];
+  const long long ncell = (long long)g.dims[0] * g.dims[1] * g.dims[2];
+  std::vector<int> cellv(V), order(V), start(ncell + 1, 0);
+  for (long long v = 0; v < V; ++v) {
+    int x = mt_mesh_cell(h_vertices[3 * v], g.org[0], g.inv_cell, g.dims[0]);
+    int y = mt_mesh_cell(h_vertices[3 * v + 1], g.org[1], g.inv_cell, g.dims[1]);
+    int z = mt_mesh_cell(h_vertices[3 * v + 2], g.org[2], g.inv_cell, g.dims[2]);
+    cellv[v] = (z * g.dims[1] + y) * g.dims[0] + x;
+    start[cellv[v] + 1]++;
+  }
+  for (long long i = 0; i < ncell; ++i) start[i + 1] += start[i];
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cellv[a] < cellv[b]; });
+  std::vector<double> sorted(3 * (size_t)V);
+  for (long long v = 0; v < V; ++v)
+    for (int k = 0; k < 3; ++k) sorted[3 * v + k] = h_vertices[3 * (size_t)order[v] + k];
+  cudaFree(c->d_mesh_verts);
+  cudaFree(c->d_mesh_cells);
+  c->d_mesh_verts = nullptr, c->d_mesh_cells = nullptr, c->mesh_ready = false;
+  CK(cudaMalloc(&c->d_mesh_verts, sizeof(double) * 3 * V));
+  CK(cudaMalloc(&c->d_mesh_cells, sizeof(int) * (ncell + 1)));
+  CK(cudaMemcpy(c->d_mesh_verts, sorted.data(), sizeof(double) * 3 * V, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(c->d_mesh_cells, start.data(), sizeof(int) * (ncell + 1), cudaMemcpyHostToDevice));
+  c->mesh = g;
+  c->mesh_V = (int)V;
+  c->mesh_ready = true;
+  return MT_OK;
+}
+
+static MeshTables mesh_of(mt_ctx* c) {
+  MeshTables T;
+  T.verts = c->d_mesh_verts;
+  T.cell_start = c->d_mesh_cells;
+  T.g = c->mesh;
+  T.V = c->mesh_V;
+  return T;
+}
+
+// weights *= (nearest-vertex distance <= invalid_dist); *num_valid += #valid
+__global__ void __launch_bounds__(256) k_prune_aos(MeshTables T, const float* __restrict__ aos, long long n, double dist,
+                                                  double* __restrict__ w, int* __restrict__ num_valid) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  bool ok = false;
+  if (i < n) {
+    ok = mesh_within(T, aos[16 * i + 3], aos[16 * i + 7], aos[16 * i + 11], dist);
+    if (w) w[i] = ok ? w[i] * 1.0 : w[i] * 0.0;  // NaN weights stay NaN like `weights *= m`
+  }
+  const int cnt = __syncthreads_count(ok);
+  if (threadIdx.x == 0 && cnt && num_valid) atomicAdd(num_valid, cnt);
+}
+
+extern "C" int mt_prune_aos(mt_ctx* c, const float* d_poses, long long n, double invalid_dist, double* d_weights,
+                            int* d_num_valid, void* stream) {
+  if (!c || !c->mesh_ready) return set_err(MT_ERR_STATE, "mt_prune_aos: no mesh uploaded");
+  if (n < 0 || (n && !d_poses) || !(invalid_dist >= 0.0)) return set_err(MT_ERR_ARG, "mt_prune_aos: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (d_num_valid) CK(cudaMemsetAsync(d_num_valid, 0, sizeof(int), st));
+  if (!n) return MT_OK;
+  k_prune_aos<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(mesh_of(c), d_poses, n, invalid_dist, d_weights, d_num_valid);
+  CK_LAUNCH();
   return MT_OK;
 }
 
@@ -629,96 +735,19 @@ extern "C" int mt_soa_to_aos(const float* d_soa, long long stride, long long n, 
 }
 
 // ------------------------------------------------------------------------- exact 1-NN
-struct NNTables {
-  const float4* keys_orig;
-  const float4* keys_sorted;
-  const int* sorted_orig;
-  const int* cell_start;
-  GridParams g;
-  int M;
-};
-
-__device__ __forceinline__ void load_key(const float4* __restrict__ t, int i, float k[6]) {
-  float4 a = __ldg(t + 2 * i), b = __ldg(t + 2 * i + 1);
-  k[0] = a.x, k[1] = a.y, k[2] = a.z, k[3] = a.w, k[4] = b.x, k[5] = b.y;
-}
-
-__device__ __forceinline__ void nn_scan_range(const NNTables& T, const float q[6], int s, int e, float& best_d, int& best_i) {
-  for (int p = s; p < e; ++p) {
-    float k[6];
-    load_key(T.keys_sorted, p, k);
-    float d = mt_key_dist(q, k);
-    if (d <= best_d) {
-      int o = __ldg(T.sorted_orig + p);
-      if (d < best_d || o < best_i) best_d = d, best_i = o;
-    }
-  }
-}
-
-// exact nearest codebook key.  Correctness argument: after the seeding phase best_d is the
-// distance to a real key, so the true nearest key lies within r = sqrt(best_d) of q in
-// every coordinate; all cells overlapping the (slightly inflated) translation box are
-// scanned, rows whose translation lower bound already exceeds best_d are skipped.
-__device__ int nn_search(const NNTables& T, const float q[6], int hint) {
-  float best_d = FLT_MAX;
-  int best_i = INT_MAX;
-  const GridParams& g = T.g;
-  if (hint >= 0 && hint < T.M) {
-    float k[6];
-    load_key(T.keys_orig, hint, k);
-    best_d = mt_key_dist(q, k);
-    best_i = hint;
-  } else {
-    // seed: own cell and its 26 neighbours
-    int cx = cell_coord(q[0], g.org[0], g.inv_h, g.dims[0]);
-    int cy = cell_coord(q[1], g.org[1], g.inv_h, g.dims[1]);
-    int cz = cell_coord(q[2], g.org[2], g.inv_h, g.dims[2]);
-    int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.dims[0] - 1);
-    for (int z = max(cz - 1, 0); z <= min(cz + 1, g.dims[2] - 1); ++z)
-      for (int y = max(cy - 1, 0); y <= min(cy + 1, g.dims[1] - 1); ++y) {
-        int rb = (z * g.dims[1] + y) * g.dims[0];
-        nn_scan_range(T, q, __ldg(T.cell_start + rb + x0), __ldg(T.cell_start + rb + x1 + 1), best_d, best_i);
-      }
-    if (best_i == INT_MAX) {
-      float k[6];
-      load_key(T.keys_orig, 0, k);
-      best_d = mt_key_dist(q, k);
-      best_i = 0;
-    }
-  }
-  if (!(best_d == best_d)) return best_i;  // NaN query: keep the seed
-  const float r = sqrtf(best_d) * 1.0001f + 1e-12f;
-  const int xlo = cell_coord(q[0] - r, g.org[0], g.inv_h, g.dims[0]);
-  const int xhi = cell_coord(q[0] + r, g.org[0], g.inv_h, g.dims[0]);
-  const int ylo = cell_coord(q[1] - r, g.org[1], g.inv_h, g.dims[1]);
-  const int yhi = cell_coord(q[1] + r, g.org[1], g.inv_h, g.dims[1]);
-  const int zlo = cell_coord(q[2] - r, g.org[2], g.inv_h, g.dims[2]);
-  const int zhi = cell_coord(q[2] + r, g.org[2], g.inv_h, g.dims[2]);
-  for (int z = zlo; z <= zhi; ++z) {
-    // translation lower bound of slab z (0 when q is inside the slab)
-    float z0 = g.org[2] + z * g.h, z1 = z0 + g.h;
-    const float slack = 1e-3f * g.h;  // cell edges recomputed in float32 are off by ulps
-    float dz = fmaxf(fmaxf(z0 - q[2], q[2] - z1) - slack, 0.f);
-    for (int y = ylo; y <= yhi; ++y) {
-      float y0 = g.org[1] + y * g.h, y1 = y0 + g.h;
-      float dy = fmaxf(fmaxf(y0 - q[1], q[1] - y1) - slack, 0.f);
-      float lb = dz * dz + dy * dy;
-      if (lb * 0.998f > best_d && z > 0 && z < g.dims[2] - 1 && y > 0 && y < g.dims[1] - 1) continue;
-      int rb = (z * g.dims[1] + y) * g.dims[0];
-      nn_scan_range(T, q, __ldg(T.cell_start + rb + xlo), __ldg(T.cell_start + rb + xhi + 1), best_d, best_i);
-    }
-  }
-  return best_i;
-}
-
-__global__ void __launch_bounds__(256) k_nn_grid(NNTables T, const float* __restrict__ keys, long long n,
-                                                 const int* __restrict__ hint, int* __restrict__ idx) {
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  float q[6];
+// search algorithms: mt_nn.cuh.  Standalone index search (SE3_NN on explicit keys).
+__global__ void __launch_bounds__(MT_NN_BLOCK) k_nn_grid(NNTables T, const float* __restrict__ keys, long long n,
+                                                         const int* __restrict__ hint, int* __restrict__ idx,
+                                                         int* fallbacks) {
+  __shared__ NNQueue Q;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  float q[6] = {0, 0, 0, 0, 0, 0};
+  if (i < n) {
 #pragma unroll
-  for (int k = 0; k < 6; ++k) q[k] = keys[6 * i + k];
-  idx[i] = nn_search(T, q, hint ? hint[i] : -1);
+    for (int k = 0; k < 6; ++k) q[k] = keys[6 * i + k];
+  }
+  const int r = nn_block_assign(T, Q, i < n, q, (hint && i < n) ? hint[i] : -1, fallbacks);
+  if (i < n) idx[i] = r;
 }
 
 // exhaustive search: codebook keys staged through shared memory in original order so that
@@ -753,8 +782,8 @@ static NNTables tables_of(mt_ctx* c) {
   NNTables T;
   T.keys_orig = c->d_keys_orig;
   T.keys_sorted = c->d_keys_sorted;
-  T.sorted_orig = c->d_sorted_orig;
   T.cell_start = c->d_cell_start;
+  T.nbr = c->d_nbr;
   T.g = c->grid;
   T.M = c->M;
   return T;
@@ -787,7 +816,7 @@ extern "C" int mt_nn_assign(mt_ctx* c, const float* d_keys, long long n, const i
   if (mode == 1)
     k_nn_brute<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c->d_keys_orig, c->M, d_keys, n, d_idx);
   else
-    k_nn_grid<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(tables_of(c), d_keys, n, d_hint, d_idx);
+    k_nn_grid<<<(unsigned)((n + MT_NN_BLOCK - 1) / MT_NN_BLOCK), MT_NN_BLOCK, 0, st>>>(tables_of(c), d_keys, n, d_hint, d_idx, c->d_flags + 3);
   CK_LAUNCH();
   return MT_OK;
 }
@@ -985,6 +1014,8 @@ struct StepDev {
   const double* shard_sums;
   long long* n_out;
   const long long* n_in;  // device-resident particle count (nullable): overrides n
+  double prune_dist;      // > 0: drift test against the mesh (remove_invalid_particles)
+  const float4* cb_poses; // (M,4,4) codebook poses for the all-drifted re-projection (nullable)
   // scratch
   double* part;
   double* prefix;
@@ -998,27 +1029,38 @@ struct StepDev {
 // Kernel A.  One particle per thread, one 256-particle chunk per block.
 //   HBM per particle: read 48 B pose + 4 B hint (+ 24 B noise when supplied), write 48 B + 4 B.
 //   Codebook keys / grid / weight table are L2-resident (M*64 B + cells*4 B + M*8 B).
-__global__ void __launch_bounds__(256) k_step_a(StepDev p, NNTables T) {
+__global__ void __launch_bounds__(256) k_step_a(StepDev p, NNTables T, MeshTables Mh) {
   __shared__ double s8[8];
+  __shared__ NNQueue Q;
   const long long i = (long long)blockIdx.x * MT_CHUNK + threadIdx.x;
   const long long n = p.n_in ? *p.n_in : p.n;
+  const bool valid = i < n;
   double e = 0.0, et2 = 0.0, ang2 = 0.0;
-  if (i < n) {
-    float P[3][4], t[3], r[3], O[3][4], key[6];
+  float key[6] = {0, 0, 0, 0, 0, 0};
+  int hint = -1;
+  bool invalid = false, on_surface = valid;
+  if (valid) {
+    float P[3][4], t[3], r[3], O[3][4];
     load_pose(p.soa_cur, p.stride, i, P);
-    const int hint = p.nn_cur[i];
+    hint = p.nn_cur[i];
     draw_or_load_noise(p.tn, p.rot, i, p.sig_t, p.sig_r, p.seed, p.step, p.first_gid + (uint64_t)i, t, r);
     apply_motion(P, p.odom, t, r, O);
     store_pose(p.soa_cur, p.stride, i, O);
     mt_se3_key(O, key);
-    const int nn = nn_search(T, key, hint);
+    invalid = mt_pose_invalid(O);
+    if (p.has_gt) rmse_terms(p.gt, O, et2, ang2);
+    if (p.prune_dist > 0.0) on_surface = mesh_within(Mh, O[0][3], O[1][3], O[2][3], p.prune_dist);
+  }
+  const int nn = nn_block_assign(T, Q, valid, key, hint, p.flags + 3);
+  const int n_on = __syncthreads_count(on_surface);
+  if (valid) {
     p.nn_cur[i] = nn;
     e = __ldg(p.wtab + nn);
-    if (mt_pose_invalid(O)) {
+    if (!on_surface) e = 0.0;  // weights *= m (particle_filter.py:398-401)
+    if (invalid) {
       e = 0.0;  // check_quats would delete the particle (particle_filter.py:347-357)
       atomicAdd(p.flags + 2, 1);
     }
-    if (p.has_gt) rmse_terms(p.gt, O, et2, ang2);
   }
   double se = block_sum_256(e, s8);
   double sa = 0.0, sb = 0.0;
@@ -1030,6 +1072,7 @@ __global__ void __launch_bounds__(256) k_step_a(StepDev p, NNTables T) {
   if (threadIdx.x == 0) {
     p.part[blockIdx.x] = se;
     if (p.has_gt) p.rm_part[2 * blockIdx.x] = sa, p.rm_part[2 * blockIdx.x + 1] = sb;
+    if (n_on) atomicAdd(p.flags + 4, n_on);
     __threadfence();
     last = (atomicAdd(p.ticket, 1u) == gridDim.x - 1);
   }
@@ -1039,6 +1082,9 @@ __global__ void __launch_bounds__(256) k_step_a(StepDev p, NNTables T) {
     scan_chunk_sums(p.part, (int)gridDim.x, p.prefix, p.scal, s8);
     if (threadIdx.x == 0) {
       if (p.has_gt) rmse_finalize(p.rm_part, (int)gridDim.x, n, p.rmse2);
+      const int on = atomicExch(p.flags + 4, 0);
+      p.flags[6] = on;                                // particles on the surface this step
+      p.flags[5] = (p.prune_dist > 0.0 && on == 0);   // drifted (particle_filter.py:402)
       *p.ticket = 0;
     }
   }
@@ -1111,6 +1157,15 @@ __global__ void __launch_bounds__(256) k_step_b(StepDev p) {
   const double endv = (c + 1 == p.nchunks) ? (A + p.prefix[p.nchunks]) : (A + p.prefix[c + 1]);
   long long cnt;
   if (bad) {
+    // the reference returns the particles unchanged (237-241); when every particle has drifted off
+    // the mesh it first re-projects them onto the codebook (filter.py:176-179)
+    if (SCATTER && FROM_TABLE && valid && S == 0.0 && p.prune_dist > 0.0 && p.cb_poses) {
+      const float4 a = __ldg(p.cb_poses + 4 * (size_t)nn), b = __ldg(p.cb_poses + 4 * (size_t)nn + 1),
+                   c2 = __ldg(p.cb_poses + 4 * (size_t)nn + 2);
+      P[0][0] = a.x, P[0][1] = a.y, P[0][2] = a.z, P[0][3] = a.w;
+      P[1][0] = b.x, P[1][1] = b.y, P[1][2] = b.z, P[1][3] = b.w;
+      P[2][0] = c2.x, P[2][1] = c2.y, P[2][2] = c2.z, P[2][3] = c2.w;
+    }
     cnt = valid ? i + 1 : n;
     if (threadIdx.x == 0) s_cnt[0] = (long long)c * MT_CHUNK, p.flags[1] = 1;
   } else {
@@ -1229,6 +1284,8 @@ static int fill_step(mt_ctx* c, const mt_step_args* a, StepDev* d) {
   d->shard_sums = a->d_shard_sums;
   d->n_out = a->d_n_out;
   d->n_in = a->d_n_in;
+  d->prune_dist = (c->mesh_ready && a->prune_dist > 0.0) ? a->prune_dist : 0.0;
+  d->cb_poses = (const float4*)a->d_cb_poses;
   d->part = c->d_part;
   d->prefix = c->d_prefix;
   d->rm_part = c->d_rm_part;
@@ -1247,7 +1304,8 @@ extern "C" int mt_step_a(mt_ctx* c, const mt_step_args* a, void* stream) {
   if (!a->d_soa_cur || !a->d_nn_cur) return set_err(MT_ERR_ARG, "mt_step_a: null particle buffers");
   if ((a->d_tn == nullptr) != (a->d_rot == nullptr)) return set_err(MT_ERR_ARG, "mt_step_a: tn/rot must both be given");
   if (a->gt && !a->d_rmse2) return set_err(MT_ERR_ARG, "mt_step_a: gt without rmse output");
-  k_step_a<<<d.nchunks, MT_CHUNK, 0, (cudaStream_t)stream>>>(d, tables_of(c));
+  if (a->prune_dist > 0.0 && !c->mesh_ready) return set_err(MT_ERR_STATE, "mt_step_a: prune_dist given but no mesh uploaded");
+  k_step_a<<<d.nchunks, MT_CHUNK, 0, (cudaStream_t)stream>>>(d, tables_of(c), mesh_of(c));
   CK_LAUNCH();
   return MT_OK;
 }

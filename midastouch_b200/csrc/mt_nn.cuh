@@ -1,0 +1,393 @@
+// Exact 6-D nearest-neighbour search over the codebook keys (SE3_NN, tactile_tree.py:43-58;
+// the reference uses a nanoflann k-d tree on the CPU, which is exact -- so is this).
+//
+// Two cooperating searches, both returning argmin_m mt_key_dist(q, key_m) with ties broken
+// towards the lowest codebook index (== np.argmin over the float32 distances):
+//
+//  1. hint-graph search (one thread per query).  Every codebook key h carries the list of
+//     its MT_NBR_K nearest other keys sorted by delta_j = |key_j - key_h|.  For a query q
+//     with a hint h (the particle's match one step ago) and d_h = |q - key_h|, the true
+//     nearest key lies inside ball(q, best) with best <= d_h, hence within d_h + best of
+//     key_h (triangle inequality): scanning the list until delta_j > d_h + best proves the
+//     answer.  ~8 candidates per query in steady state.  If the list is exhausted first
+//     the query is handed to (2) with the best candidate so far.
+//     Rotation vectors flip sign at angle pi, so a pose that was matched to key h can jump
+//     2*pi*w away from it in key space; keys within 0.35 rad of pi therefore carry a
+//     "partner" (the key nearest to their antipodal image) which is tried as the centre too.
+//  2. grid search (one warp per query): uniform grid over the translation part of the
+//     keys, keys sorted by cell; lanes evaluate candidates of all rows of the search box
+//     in parallel (flattened with a warp prefix sum), rows whose translation lower bound
+//     exceeds the best distance are skipped.
+//
+// Float32 rounding: computed distances carry a relative error < 1e-6; every pruning
+// test is inflated by 1e-5 (relative) so that no candidate that could win or tie under the
+// computed distances is ever skipped.
+#pragma once
+#include <float.h>
+#include <limits.h>
+#include <string.h>
+
+#include "mt_math.cuh"
+
+#ifndef MT_NN_BLOCK
+#define MT_NN_BLOCK 256
+#endif
+#define MT_NBR_K 32  // neighbours per key; == warp width (the build kernel keeps one per lane)
+
+struct GridParams {
+  float org[3];
+  float inv_h, h;
+  int dims[3];
+};
+
+#if defined(__CUDACC__)
+struct NNTables {
+  const float4* keys_orig;    // M x 2 float4 (k0..k3 | k4,k5,partner bits,0), original order
+  const float4* keys_sorted;  // M x 2 float4 (k0..k3 | k4,k5,original index bits,0), sorted by grid cell
+  const int* cell_start;      // ncells + 1
+  const float4* nbr;          // M x MT_NBR_K x 2 float4: (k0..k3 | k4,k5,delta,idx bits)
+  GridParams g;
+  int M;
+};
+#endif
+
+// cell coordinate of a key component: identical float32 formula on host and device so that
+// monotonicity arguments about search boxes hold bit-for-bit.
+MT_HD int mt_cell_coord(float x, float org, float inv_h, int dim) {
+  float f = floorf(MT_FMUL(MT_FSUB(x, org), inv_h));
+  int c = (f < 0.f) ? 0 : (f >= (float)dim ? dim - 1 : (int)f);
+  return c;
+}
+
+// image of a key under v -> v (|v| - 2 pi)/|v| (the same rotation, other sign of the axis);
+// false when the rotation angle is further than 0.35 rad from pi.
+MT_HD bool mt_key_antipode(const float k[6], float out[6]) {
+  const float w = 0.01f, two_pi_w = 6.283185307179586f * w;
+  const float n = sqrtf(k[3] * k[3] + k[4] * k[4] + k[5] * k[5]);
+  if (!(n > (3.14159265f - 0.35f) * w)) return false;
+  const float s = (n - two_pi_w) / n;
+  out[0] = k[0], out[1] = k[1], out[2] = k[2];
+  out[3] = k[3] * s, out[4] = k[4] * s, out[5] = k[5] * s;
+  return true;
+}
+
+MT_HD bool mt_better(float d, int i, float best_d, int best_i) { return d < best_d || (d == best_d && i < best_i); }
+
+// stop bound of the hint-graph scan: delta beyond this cannot beat or tie `best`
+MT_HD float mt_hint_limit(float dh, float best_d) { return (dh + sqrtf(best_d)) * 1.00001f + 1e-30f; }
+
+// Hint-graph scan over a neighbour list given as plain floats (8 per entry); shared by the
+// device kernels and the host harness.  Returns true when (best_d, best_i) is proven exact.
+MT_HD bool mt_hint_scan(const float q[6], const float kh[6], int hint, const float* list8, int K, float& best_d,
+                        int& best_i) {
+  best_d = mt_key_dist(q, kh);
+  best_i = hint;
+  if (!(best_d == best_d)) {  // NaN query: np.argmin semantics (first NaN) -> index 0
+    best_i = 0;
+    return true;
+  }
+  const float dh = sqrtf(best_d);
+  float lim = mt_hint_limit(dh, best_d);
+  for (int j = 0; j < K; ++j) {
+    const float* e = list8 + 8 * j;
+    if (e[6] > lim) return true;
+    float d = mt_key_dist(q, e);
+    int idx;
+#if defined(__CUDA_ARCH__)
+    idx = __float_as_int(e[7]);
+#else
+    memcpy(&idx, e + 7, 4);
+#endif
+    if (mt_better(d, idx, best_d, best_i)) {
+      best_d = d;
+      best_i = idx;
+      lim = mt_hint_limit(dh, best_d);
+    }
+  }
+  return false;
+}
+
+#if defined(__CUDACC__)
+// ------------------------------------------------------------------------- device side
+__device__ __forceinline__ int load_key(const float4* __restrict__ t, int i, float k[6]) {
+  float4 a = __ldg(t + 2 * (size_t)i), b = __ldg(t + 2 * (size_t)i + 1);
+  k[0] = a.x, k[1] = a.y, k[2] = a.z, k[3] = a.w, k[4] = b.x, k[5] = b.y;
+  return __float_as_int(b.z);  // partner (keys_orig) / original index (keys_sorted)
+}
+
+// (1) one thread per query.  false -> needs the grid search (best_* = best so far, or
+// FLT_MAX / INT_MAX when there was no usable hint).
+__device__ __forceinline__ bool nn_hint_search(const NNTables& T, const float q[6], int hint, float& best_d, int& best_i) {
+  if (hint < 0 || hint >= T.M) {
+    best_d = FLT_MAX;
+    best_i = INT_MAX;
+    return false;
+  }
+  float kh[6];
+  const int partner = load_key(T.keys_orig, hint, kh);
+  best_d = mt_key_dist(q, kh);
+  best_i = hint;
+  if (!(best_d == best_d)) {
+    best_i = 0;
+    return true;
+  }
+  if (partner >= 0) {  // near angle pi: the pose may have jumped to the other sign of the axis
+    float kp[6];
+    load_key(T.keys_orig, partner, kp);
+    const float dp = mt_key_dist(q, kp);
+    if (mt_better(dp, partner, best_d, best_i)) best_d = dp, best_i = partner, hint = partner;
+  }
+  const float dh = sqrtf(best_d);
+  float lim = mt_hint_limit(dh, best_d);
+  const float4* __restrict__ L = T.nbr + (size_t)hint * (2 * MT_NBR_K);
+#pragma unroll 1
+  for (int j = 0; j < MT_NBR_K; j += 2) {
+    // two entries (64 contiguous bytes) per trip: both in flight together
+    const float4 a0 = __ldg(L + 2 * j), b0 = __ldg(L + 2 * j + 1);
+    const float4 a1 = __ldg(L + 2 * j + 2), b1 = __ldg(L + 2 * j + 3);
+    if (b0.z > lim) return true;
+    {
+      const float k[6] = {a0.x, a0.y, a0.z, a0.w, b0.x, b0.y};
+      const float d = mt_key_dist(q, k);
+      const int idx = __float_as_int(b0.w);
+      if (mt_better(d, idx, best_d, best_i)) best_d = d, best_i = idx, lim = mt_hint_limit(dh, d);
+    }
+    if (b1.z > lim) return true;
+    {
+      const float k[6] = {a1.x, a1.y, a1.z, a1.w, b1.x, b1.y};
+      const float d = mt_key_dist(q, k);
+      const int idx = __float_as_int(b1.w);
+      if (mt_better(d, idx, best_d, best_i)) best_d = d, best_i = idx, lim = mt_hint_limit(dh, d);
+    }
+  }
+  return false;
+}
+
+// warp-wide (best_d, best_i) = lexicographic min over lanes
+__device__ __forceinline__ void warp_best(float& d, int& i) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float od = __shfl_xor_sync(0xffffffffu, d, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, i, o);
+    if (mt_better(od, oi, d, i)) d = od, i = oi;
+  }
+}
+
+// (2a) all 32 lanes: scan the cells [xlo..xhi] x [ylo..yhi] x [zlo..zhi].  q / best_* are
+// warp-uniform on entry and on exit.
+__device__ void nn_warp_scan_box(const NNTables& T, const float q[6], int xlo, int xhi, int ylo, int yhi, int zlo,
+                                 int zhi, bool prune, float& best_d, int& best_i) {
+  const int lane = threadIdx.x & 31;
+  const GridParams& g = T.g;
+  const int ny = yhi - ylo + 1;
+  const int nrows = ny * (zhi - zlo + 1);
+  const float slack = 1e-3f * g.h;  // cell edges recomputed in float32 are off by ulps
+  for (int r0 = 0; r0 < nrows; r0 += 32) {
+    const int r = r0 + lane;
+    int s = 0, cnt = 0;
+    if (r < nrows) {
+      const int z = zlo + r / ny, y = ylo + r % ny;
+      bool skip = false;
+      if (prune && z > 0 && z < g.dims[2] - 1 && y > 0 && y < g.dims[1] - 1) {
+        // translation lower bound of row (y,z); 0 when q is inside the slab
+        const float z0 = g.org[2] + z * g.h, y0 = g.org[1] + y * g.h;
+        const float dz = fmaxf(fmaxf(z0 - q[2], q[2] - (z0 + g.h)) - slack, 0.f);
+        const float dy = fmaxf(fmaxf(y0 - q[1], q[1] - (y0 + g.h)) - slack, 0.f);
+        skip = (dz * dz + dy * dy) * 0.998f > best_d;
+      }
+      if (!skip) {
+        const int rb = (z * g.dims[1] + y) * g.dims[0];
+        s = __ldg(T.cell_start + rb + xlo);
+        cnt = __ldg(T.cell_start + rb + xhi + 1) - s;
+      }
+    }
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    const int excl = incl - cnt;
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    float ld = FLT_MAX;
+    int li = INT_MAX;
+    for (int t0 = 0; t0 < total; t0 += 32) {
+      const int t = t0 + lane;
+      int lo = 0;  // smallest lane whose inclusive count exceeds t
+#pragma unroll
+      for (int step = 16; step > 0; step >>= 1) {
+        const int v = __shfl_sync(0xffffffffu, incl, lo + step - 1);
+        if (v <= t) lo += step;
+      }
+      lo &= 31;
+      const int e_lo = __shfl_sync(0xffffffffu, excl, lo);
+      const int s_lo = __shfl_sync(0xffffffffu, s, lo);
+      if (t < total) {
+        const int p = s_lo + (t - e_lo);
+        float k[6];
+        const int o = load_key(T.keys_sorted, p, k);
+        const float d = mt_key_dist(q, k);
+        if (mt_better(d, o, ld, li)) ld = d, li = o;
+      }
+    }
+    warp_best(ld, li);
+    if (mt_better(ld, li, best_d, best_i)) best_d = ld, best_i = li;
+  }
+}
+
+// (2) all 32 lanes, one query: exact nearest key given an optional candidate (best_i ==
+// INT_MAX: none).  Correctness: once best_d is the distance to a real key the true nearest
+// key lies within r = sqrt(best_d) of q in every coordinate, so all cells overlapping the
+// (slightly inflated) translation box are scanned.
+__device__ __noinline__ int nn_search_warp(const NNTables& T, const float q[6], float best_d, int best_i) {
+  const int lane = threadIdx.x & 31;
+  const GridParams& g = T.g;
+  if (!(q[0] == q[0]) || !(q[1] == q[1]) || !(q[2] == q[2]) || !(q[3] == q[3]) || !(q[4] == q[4]) || !(q[5] == q[5]))
+    return 0;  // NaN query: np.argmin semantics
+  const int cx = mt_cell_coord(q[0], g.org[0], g.inv_h, g.dims[0]);
+  const int cy = mt_cell_coord(q[1], g.org[1], g.inv_h, g.dims[1]);
+  const int cz = mt_cell_coord(q[2], g.org[2], g.inv_h, g.dims[2]);
+  if (best_i == INT_MAX || sqrtf(best_d) > 2.f * g.h) {
+    // tighten the bound first: own cell + 26 neighbours, then (queries far off the
+    // surface) a strided sample of the whole codebook
+    nn_warp_scan_box(T, q, max(cx - 1, 0), min(cx + 1, g.dims[0] - 1), max(cy - 1, 0), min(cy + 1, g.dims[1] - 1),
+                     max(cz - 1, 0), min(cz + 1, g.dims[2] - 1), false, best_d, best_i);
+    if (best_i == INT_MAX) {
+      const int stride = max(1, T.M / 256);
+      float ld = FLT_MAX;
+      int li = INT_MAX;
+      for (int p = lane * stride; p < T.M; p += 32 * stride) {
+        float k[6];
+        const int o = load_key(T.keys_sorted, p, k);
+        const float d = mt_key_dist(q, k);
+        if (mt_better(d, o, ld, li)) ld = d, li = o;
+      }
+      warp_best(ld, li);
+      best_d = ld, best_i = li;
+    }
+  }
+  if (best_i == INT_MAX) return 0;  // Inf query: every distance is Inf/NaN
+  const float r = sqrtf(best_d) * 1.0001f + 1e-12f;
+  nn_warp_scan_box(T, q, mt_cell_coord(q[0] - r, g.org[0], g.inv_h, g.dims[0]),
+                   mt_cell_coord(q[0] + r, g.org[0], g.inv_h, g.dims[0]),
+                   mt_cell_coord(q[1] - r, g.org[1], g.inv_h, g.dims[1]),
+                   mt_cell_coord(q[1] + r, g.org[1], g.inv_h, g.dims[1]),
+                   mt_cell_coord(q[2] - r, g.org[2], g.inv_h, g.dims[2]),
+                   mt_cell_coord(q[2] + r, g.org[2], g.inv_h, g.dims[2]), true, best_d, best_i);
+  return best_i;
+}
+
+// Block-level driver used by every kernel that assigns neighbours: each thread first tries
+// the hint graph; the leftovers are queued in shared memory and served one query per warp.
+// `active` threads pass their key; all threads of the block must call.  Returns the index.
+struct NNQueue {
+  float q[MT_NN_BLOCK][6];
+  float bd[MT_NN_BLOCK];
+  int bi[MT_NN_BLOCK];
+  int n;
+};
+
+__device__ __forceinline__ int nn_block_assign(const NNTables& T, NNQueue& Q, bool active, const float q[6], int hint,
+                                               int* fallback_counter) {
+  if (threadIdx.x == 0) Q.n = 0;
+  __syncthreads();
+  float bd = FLT_MAX;
+  int bi = INT_MAX, pos = -1;
+  if (active && !nn_hint_search(T, q, hint, bd, bi)) {
+    pos = atomicAdd(&Q.n, 1);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) Q.q[pos][k] = q[k];
+    Q.bd[pos] = bd;
+    Q.bi[pos] = bi;
+  }
+  __syncthreads();
+  const int nq = Q.n;
+  if (nq) {
+    const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (int e = warp; e < nq; e += nwarps) {
+      float qq[6];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) qq[k] = Q.q[e][k];
+      const int res = nn_search_warp(T, qq, Q.bd[e], Q.bi[e]);
+      __syncwarp();
+      if ((threadIdx.x & 31) == 0) Q.bi[e] = res;
+    }
+    __syncthreads();
+    if (pos >= 0) bi = Q.bi[pos];
+    if (fallback_counter && threadIdx.x == 0) atomicAdd(fallback_counter, nq);
+  }
+  return bi;
+}
+
+// Build kernel (codebook upload).  One warp per key, lanes hold the running sorted list, the
+// codebook streams through shared memory.
+//   PARTNER = false: the MT_NBR_K nearest other keys of every key, ascending (distance, index)
+//   PARTNER = true : the key nearest to the antipodal image of every near-pi key -> partner[h]
+template <bool PARTNER>
+__global__ void __launch_bounds__(256) k_build_nbr(const float4* __restrict__ keys, int M, float4* __restrict__ nbr,
+                                                   int* __restrict__ partner) {
+  __shared__ float4 sk[2 * 256];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int h = blockIdx.x * 8 + warp;
+  float kh[6] = {0, 0, 0, 0, 0, 0};
+  bool act = h < M;
+  if (act) {
+    load_key(keys, h, kh);
+    if (PARTNER) {
+      float ka[6];
+      act = mt_key_antipode(kh, ka);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) kh[k] = act ? ka[k] : kh[k];
+    }
+  }
+  float val = FLT_MAX;  // lane l: l-th smallest squared distance so far
+  int idx = -1;
+  for (int m0 = 0; m0 < M; m0 += 256) {
+    const int cnt = min(256, M - m0);
+    __syncthreads();
+    for (int t = threadIdx.x; t < 2 * cnt; t += 256) sk[t] = keys[2 * (size_t)m0 + t];
+    __syncthreads();
+    if (!act) continue;
+    for (int s0 = 0; s0 < cnt; s0 += 32) {
+      const int m = m0 + s0 + lane;
+      float d = FLT_MAX;
+      if (s0 + lane < cnt && (PARTNER || m != h)) {
+        const float4 a = sk[2 * (s0 + lane)], b = sk[2 * (s0 + lane) + 1];
+        const float k[6] = {a.x, a.y, a.z, a.w, b.x, b.y};
+        d = mt_key_dist(kh, k);
+        if (!(d == d)) d = FLT_MAX;
+      }
+      unsigned cand = __ballot_sync(0xffffffffu, d < __shfl_sync(0xffffffffu, val, 31));
+      while (cand) {
+        const int src = __ffs(cand) - 1;
+        cand &= cand - 1;
+        const float cd = __shfl_sync(0xffffffffu, d, src);
+        if (!(cd < __shfl_sync(0xffffffffu, val, 31))) continue;
+        const int pos = __popc(__ballot_sync(0xffffffffu, val <= cd));  // stable: equal distances keep index order
+        const float nv = __shfl_up_sync(0xffffffffu, val, 1);
+        const int ni = __shfl_up_sync(0xffffffffu, idx, 1);
+        if (lane > pos) val = nv, idx = ni;
+        if (lane == pos) val = cd, idx = m0 + s0 + src;
+      }
+    }
+  }
+  if (h >= M) return;
+  if (PARTNER) {
+    if (lane == 0) partner[h] = act ? idx : -1;
+    return;
+  }
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = make_float4(0.f, 0.f, __int_as_float(0x7f800000), __int_as_float(-1));
+  if (idx >= 0) {
+    a = keys[2 * (size_t)idx];
+    const float4 kb = keys[2 * (size_t)idx + 1];
+    b = make_float4(kb.x, kb.y, sqrtf(val), __int_as_float(idx));
+  }
+  nbr[((size_t)h * MT_NBR_K + lane) * 2] = a;
+  nbr[((size_t)h * MT_NBR_K + lane) * 2 + 1] = b;
+}
+
+__global__ void k_set_partner(float4* __restrict__ keys, int M, const int* __restrict__ partner) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m < M) keys[2 * (size_t)m + 1].z = __int_as_float(partner[m]);
+}
+#endif  // __CUDACC__

@@ -33,7 +33,8 @@ def prepare_odom(odom) -> "Odom16":
 
 class FilterEngine:
     def __init__(self, codebook: tactile_tree, capacity: int, sig_t: float = 2e-4, sig_r: float = 0.5,
-                 seed: int = 0, rank: int = 0, world: int = 1, group=None, n_global: int | None = None):
+                 seed: int = 0, rank: int = 0, world: int = 1, group=None, n_global: int | None = None,
+                 mesh_vertices=None, pen_max: float = 0.002):
         if codebook.ctx is None:
             raise MidasError("FilterEngine: codebook.to_device(cuda) first")
         self.cb = codebook
@@ -42,6 +43,11 @@ class FilterEngine:
         codebook.ctx.ensure_capacity(self.capacity)
         self.ctx = codebook.ctx
         self.sig_t, self.sig_r, self.seed = float(sig_t), float(sig_r), int(seed)
+        # drift pruning (remove_invalid_particles): needs the down-sampled mesh vertices
+        self.pen_max = float(pen_max)
+        self.prune = mesh_vertices is not None
+        if self.prune:
+            self.ctx.upload_mesh(mesh_vertices, self.pen_max)
         self.rank, self.world, self.group = int(rank), int(world), group
         self.n_global = n_global
         d = self.dev
@@ -108,7 +114,7 @@ class FilterEngine:
         return self.anc[: self.count()]
 
     # ------------------------------------------------------------------ one filter step
-    def _fill(self, odom, u, tn, rot, gt, softmax):
+    def _fill(self, odom, u, tn, rot, gt, softmax, prune=True):
         a = self._a
         a.d_soa_cur, a.d_soa_next = ptr(self.soa[self.cur]), ptr(self.soa[1 - self.cur])
         a.stride = self.capacity
@@ -126,15 +132,18 @@ class FilterEngine:
         a.d_shard_sums = ptr(self.shard_sums) if self.world > 1 else None
         a.d_n_out = ptr(self.n_dev[1 - self.cur])
         a.d_n_in = ptr(self.n_dev[self.cur]) if self.use_n_dev else None
+        a.prune_dist = self.pen_max if (self.prune and prune) else 0.0
+        a.d_cb_poses = ptr(self.cb.poses) if self.prune else None
         return a
 
     def step(self, code: torch.Tensor, odom: torch.Tensor, u: float | None = None, tn: torch.Tensor | None = None,
              rot: torch.Tensor | None = None, gt: torch.Tensor | None = None, softmax: bool = True,
-             resample: bool = True):
+             resample: bool = True, prune: bool = True):
         """code: (1,D)/(D,) tactile code, host or device, float32/float64.
         odom: (4,4) host tensor / 16 floats.  u: systematic offset in [0,1) (drawn from the
         engine's CPU generator when None).  tn/rot: optional (n,3) float32 CUDA noise
-        (parity mode); Philox in-kernel otherwise.  gt: optional (4,4) host pose -> self.rmse."""
+        (parity mode); Philox in-kernel otherwise.  gt: optional (4,4) host pose -> self.rmse.
+        prune: apply remove_invalid_particles (needs mesh_vertices at construction)."""
         if self.n == 0:
             raise MidasError("step: no particles loaded")
         if u is None:
@@ -150,7 +159,7 @@ class FilterEngine:
             gt_h = gt if (gt.device.type == "cpu" and gt.dtype == torch.float32 and gt.is_contiguous()) else gt.detach().float().cpu().contiguous()
         if tn is not None:
             tn, rot = tn.contiguous(), rot.contiguous()
-        a = self._fill(odom16, u, tn, rot, gt_h, softmax)
+        a = self._fill(odom16, u, tn, rot, gt_h, softmax, prune)
         with torch.cuda.device(self.dev):
             s = stream_ptr()
             call("mt_codebook_query", self.ctx.h, ptr(q), dtype_code(q), 0, s)

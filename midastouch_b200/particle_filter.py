@@ -96,6 +96,7 @@ class particle_filter:
         self.motion_noise = {"mu": 0, "sig_r": float(sig_r), "sig_t": float(sig_t)}
         self.particle_var = torch.tensor([float("inf")])
         self.init_noise = [self.mesh_diagonal() / 3.0 * noise, 180.0 / 3.0 * noise]
+        self._mesh_ctx = {}  # device index -> Context holding the vertex grid of THIS mesh
 
     def mesh_diagonal(self):
         return self._scale
@@ -192,8 +193,34 @@ class particle_filter:
         return Particles(soa_to_aos(soa_out, nSamples), w_in[idx], particles.labels[idx])
 
     # ------------------------------------------------------------------ prune / anneal / clusters ("next" rows)
+    def _mesh_context(self, device) -> Context:
+        device = torch.device(device)
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        c = self._mesh_ctx.get(idx)
+        if c is None:
+            c = self._mesh_ctx[idx] = Context(device, 1024)
+            c.upload_mesh(self.mesh_vertices_ds, self.pen_max)
+        return c
+
     def remove_invalid_particles(self, _particles: Particles, invalid_dist: float = None) -> Tuple[Particles, bool]:
-        raise MidasError("remove_invalid_particles: CUDA nearest-vertex kernel not built yet (SURVEY 8f rank 1)")
+        """particle_filter.py:379-403: weights *= (nearest down-sampled mesh vertex within
+        invalid_dist); returns (particles, drifted) with drifted a 0-dim bool CUDA tensor.
+        Like the reference the multiply is in place on the (shallow-copied) weights tensor."""
+        particles = copy.copy(_particles)
+        poses = particles.poses
+        require_cuda(poses, "particle poses")
+        poses = poses.reshape(-1, 4, 4).float().contiguous()
+        n = poses.shape[0]
+        dist = self.pen_max if invalid_dist is None else float(invalid_dist)
+        ctx = self._mesh_context(poses.device)
+        w = particles.weights
+        w64 = w if (w.dtype == torch.float64 and w.is_contiguous()) else w.to(torch.float64).contiguous()
+        nvalid = torch.zeros(1, dtype=torch.int32, device=poses.device)
+        with torch.cuda.device(poses.device):
+            call("mt_prune_aos", ctx.h, ptr(poses), n, C.c_double(dist), ptr(w64), ptr(nvalid), stream_ptr())
+        if w64 is not w:  # float32 default weights (Particles.__init__): keep the caller's dtype
+            w.copy_(w64.to(w.dtype))
+        return particles, (nvalid == 0).reshape(())
 
     def annealing(self, _particles: Particles, var: float, floor: int = 1000) -> Particles:
         raise MidasError("annealing: CUDA compaction kernel not built yet (SURVEY 8f rank 2)")

@@ -2,6 +2,7 @@
 // arithmetic shared by the CUDA kernels) for the host with g++ so the no-GPU test tier can
 // check it against the oracle.  Never loaded by the product.
 #include "../midastouch_b200/csrc/mt_math.cuh"
+#include "../midastouch_b200/csrc/mt_nn.cuh"
 
 extern "C" {
 void h_se3_keys(const float* aos, long long n, float* keys) {
@@ -61,4 +62,18 @@ void h_rot_err(const float* gt16, const float* aos, long long n, float* out) {
     out[i] = mt_rot_err_deg(G, P);
   }
 }
+// hint-graph search (mt_nn.cuh) on the host: keys (M,6), nbr (M,K,8), queries (n,6), hints (n,)
+// -> idx (n,), ok (n,) [1 = proven exact by the list, 0 = would go to the grid search]
+void h_hint_scan(const float* keys, long long M, const float* nbr, int K, const float* q, long long n, const int* hint,
+                 int* idx, int* ok, float* dist) {
+  for (long long i = 0; i < n; ++i) {
+    float bd;
+    int bi;
+    bool r = mt_hint_scan(q + 6 * i, keys + 6 * hint[i], hint[i], nbr + (size_t)hint[i] * K * 8, K, bd, bi);
+    idx[i] = bi;
+    ok[i] = r ? 1 : 0;
+    dist[i] = bd;
+  }
+}
+int h_cell_coord(float x, float org, float inv_h, int dim) { return mt_cell_coord(x, org, inv_h, dim); }
 }

@@ -115,6 +115,67 @@ def test_nn_far_queries_and_duplicates(mt, dev, box):
         assert np.array_equal(idx.cpu().numpy().astype(np.int64), O.nn_brute(keys_cb, q)), mode
 
 
+def _nbr_view(mt, cb, dev):
+    p, k = C.c_void_p(), C.c_int()
+    mt.lib.call("mt_codebook_nbr_info", cb.ctx.h, C.byref(p), C.byref(k))
+    M = len(cb)
+    holder = type("H", (), {})()
+    holder.__cuda_array_interface__ = {"shape": (M, k.value, 8), "typestr": "<f4", "data": (p.value, False), "version": 3, "strides": None}
+    return torch.as_tensor(holder, device=dev).clone().cpu().numpy()
+
+
+def test_neighbour_graph_matches_host_model(mt, dev, box):
+    """k_build_nbr: every key's 32 nearest other keys, ascending (distance, index), duplicates included."""
+    cbs = synth.make_codebook(box, M=3000, D=8, seed=5)
+    poses = torch.cat([cbs.poses, cbs.poses[:50]])
+    cb = mt.tt.tactile_tree(poses, poses, torch.cat([cbs.embeddings, cbs.embeddings[:50]]))
+    cb.to_device(dev)
+    keys = cb.logmap_pose.cpu().numpy()
+    nbr = _nbr_view(mt, cb, dev)
+    M, K = keys.shape[0], nbr.shape[1]
+    assert K == 32
+    for h in list(range(0, M, 97)) + [0, 10, 3049, M - 1]:
+        d = O.l2_sq_f32(keys, keys[h])
+        d[h] = np.inf
+        order = np.lexsort((np.arange(M), d))[:K]
+        assert np.array_equal(nbr[h, :, 7].view(np.int32), order.astype(np.int32)), h
+        assert np.array_equal(nbr[h, :, :6], keys[order])
+        assert np.allclose(nbr[h, :, 6], np.sqrt(d[order]), rtol=1e-6, atol=0)
+    # tiny codebook: lists are padded with (inf, -1)
+    cb2 = mt.tt.tactile_tree(cbs.poses[:5], cbs.poses[:5], cbs.embeddings[:5])
+    cb2.to_device(dev)
+    nb2 = _nbr_view(mt, cb2, dev)
+    assert (nb2[:, 4:, 7].view(np.int32) == -1).all() and np.isinf(nb2[:, 4:, 6]).all()
+    assert (nb2[:, :4, 7].view(np.int32) >= 0).all()
+    q = torch.from_numpy(cb2.logmap_pose.cpu().numpy()[[3, 1, 4]] + np.float32(1e-5)).to(dev)
+    idx = torch.empty(3, dtype=torch.int32, device=dev)
+    hint = torch.tensor([0, 0, 0], dtype=torch.int32, device=dev)
+    mt.lib.call("mt_nn_assign", cb2.ctx.h, q.data_ptr(), 3, hint.data_ptr(), 0, idx.data_ptr(), mt.lib.stream_ptr())
+    assert idx.cpu().tolist() == [3, 1, 4]
+
+
+def test_nn_stale_hints_near_pi(mt, dev, cb_big):
+    """keys whose rotation vector flips sign near angle pi make the previous match a useless
+    hint (distance ~ 2*pi*w in key space): the search must stay exact and bounded."""
+    cbs, cb = cb_big
+    keys_cb = cb.logmap_pose.cpu().numpy()
+    rng = np.random.default_rng(11)
+    n = 20000
+    base = rng.integers(0, 50000, n)
+    q = keys_cb[base].copy()
+    q[:, 3:] *= -1.0  # antipodal rotation vector, same translation
+    q += rng.normal(size=(n, 6)).astype(np.float32) * np.float32(2e-4)
+    qd = torch.from_numpy(q.astype(np.float32)).to(dev)
+    hd = torch.from_numpy(base.astype(np.int32)).to(dev)
+    idx = torch.empty(n, dtype=torch.int32, device=dev)
+    cb.ctx.stats(reset=True)
+    mt.lib.call("mt_nn_assign", cb.ctx.h, qd.data_ptr(), n, hd.data_ptr(), 0, idx.data_ptr(), mt.lib.stream_ptr())
+    assert np.array_equal(idx.cpu().numpy().astype(np.int64), O.nn_exact(keys_cb, q.astype(np.float32), k=16))
+    fb = cb.ctx.stats(reset=True)["nn_fallbacks"]
+    assert 0 <= fb <= n
+    print("near-pi stale hints: grid fallbacks", fb, "of", n)
+
+
 def test_se3_nn_dropin(mt, dev, cb_big):
     cbs, cb = cb_big
     g = torch.Generator().manual_seed(0)
@@ -217,7 +278,8 @@ def test_cosine_ragged_and_nan(mt, dev):
         t = torch.rand(37, D, dtype=dt)
         t[5] = 0  # zero row: clamp at eps
         out = torch.empty(37, dtype=torch.float64, device=dev)
-        mt.lib.call("mt_cosine_rows", pf_ctx.h, q.to(dev).data_ptr(), 1, t.to(dev).data_ptr(), 1 if dt == torch.float64 else 0, 37, D,
+        qd, td = q.to(dev), t.to(dev)
+        mt.lib.call("mt_cosine_rows", pf_ctx.h, qd.data_ptr(), 1, td.data_ptr(), 1 if dt == torch.float64 else 0, 37, D,
                     out.data_ptr(), mt.lib.stream_ptr())
         ref = torch.nn.functional.cosine_similarity(q[None], t.double())
         assert torch.allclose(out.cpu(), ref, rtol=1e-6 if dt == torch.float32 else 1e-12, atol=1e-300)
@@ -228,7 +290,8 @@ def test_cosine_batched(mt, dev):
     Tm = torch.rand(1000, 256)
     out = torch.empty(70, 1000, device=dev)
     ctx = mt.pf._ctx_for(dev, 10)
-    mt.lib.call("mt_cosine_batched", ctx.h, Q.to(dev).data_ptr(), 70, Tm.to(dev).data_ptr(), 1000, 256, out.data_ptr(), mt.lib.stream_ptr())
+    Qd, Td = Q.to(dev), Tm.to(dev)
+    mt.lib.call("mt_cosine_batched", ctx.h, Qd.data_ptr(), 70, Td.data_ptr(), 1000, 256, out.data_ptr(), mt.lib.stream_ptr())
     ref = torch.nn.functional.cosine_similarity(Q.double()[:, None, :], Tm.double()[None], dim=2)
     assert torch.allclose(out.cpu().double(), ref, rtol=1e-5, atol=0)
 
@@ -287,7 +350,8 @@ def test_low_var_sizes_vs_oracle(mt, dev, n):
                 w[0] = 1.0
         for u in (0.0, 0.73, float(np.nextafter(np.float32(1), np.float32(0)))):
             anc = torch.empty(n, dtype=torch.int32, device=dev)
-            mt.lib.call("mt_resample_systematic", ctx.h, w.to(dev).data_ptr(), n, C.c_float(u), 0, anc.data_ptr(), 0, mt.lib.stream_ptr())
+            wd = w.to(dev)
+            mt.lib.call("mt_resample_systematic", ctx.h, wd.data_ptr(), n, C.c_float(u), 0, anc.data_ptr(), 0, mt.lib.stream_ptr())
             a = anc.cpu().long()
             ref = O.low_var_indices(w, u)
             ok = ref >= 0
@@ -315,7 +379,8 @@ def test_low_var_heavy_parent(mt, dev):
     w[12345] = 1.0
     ctx = mt.pf._ctx_for(dev, n)
     anc = torch.empty(n, dtype=torch.int32, device=dev)
-    mt.lib.call("mt_resample_systematic", ctx.h, w.to(dev).data_ptr(), n, C.c_float(0.5), 0, anc.data_ptr(), 0, mt.lib.stream_ptr())
+    wd = w.to(dev)
+    mt.lib.call("mt_resample_systematic", ctx.h, wd.data_ptr(), n, C.c_float(0.5), 0, anc.data_ptr(), 0, mt.lib.stream_ptr())
     assert torch.equal(anc.cpu().long(), O.low_var_indices(w, 0.5))
 
 
@@ -325,6 +390,46 @@ def test_rmse_vs_reference_golden(mt, dev, golden):
     rt, rr = mt.pf.particle_rmse(T(g["poses"]).to(dev), T(g["gt"]))
     assert abs(float(rt) - float(g["rmse_t"])) <= RTOL * float(g["rmse_t"])
     assert abs(float(rr) - float(g["rmse_r"])) <= RTOL * float(g["rmse_r"])
+
+
+# ----------------------------------------------------------------------------- drift pruning
+def test_prune_vs_reference_golden(mt, dev, golden, box):
+    g = golden("prune")
+    pf = mt.pf.particle_filter(synth_cfg(), box.vertices)
+    assert np.array_equal(pf.mesh_vertices_ds, g["vertices_ds"]) and pf.pen_max == float(g["pen_max"])
+    parts = mt.pf.Particles(T(g["poses"]).to(dev), T(g["w_in"]).to(dev))
+    out, drifted = pf.remove_invalid_particles(parts)
+    assert torch.equal(out.weights.cpu(), T(g["w_out"]))
+    assert bool(drifted) == bool(g["drifted"])
+    assert out.weights.data_ptr() == parts.weights.data_ptr()  # in-place like the reference (401)
+    # everything far away -> drifted
+    far = T(g["poses"]).clone()
+    far[:, :3, 3] += 1.0
+    out, drifted = pf.remove_invalid_particles(mt.pf.Particles(far.to(dev), T(g["w_in"]).to(dev)))
+    assert bool(drifted) and float(out.weights.abs().sum()) == 0.0
+    # explicit invalid_dist and float32 default weights
+    out, drifted = pf.remove_invalid_particles(mt.pf.Particles(T(g["poses"]).to(dev)), invalid_dist=10.0)
+    assert not bool(drifted) and out.weights.dtype == torch.float32 and bool((out.weights == 1).all())
+
+
+def test_prune_boundary_vs_oracle(mt, dev, box):
+    """points at ~pen_max from the nearest vertex: the float64 distance test must agree with the
+    k-d tree oracle point by point (n = 200k, incl. points outside the bounding box)."""
+    pf = mt.pf.particle_filter(synth_cfg(), box.vertices)
+    rng = np.random.default_rng(5)
+    n = 200000
+    v = pf.mesh_vertices_ds[rng.integers(0, pf.mesh_vertices_ds.shape[0], n)]
+    d = rng.normal(size=(n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    pts = (v + d * rng.uniform(0.0, 2.0 * pf.pen_max, (n, 1))).astype(np.float32)
+    pts[:1000] += 0.3
+    poses = torch.eye(4)[None].repeat(n, 1, 1)
+    poses[:, :3, 3] = torch.from_numpy(pts)
+    w = torch.rand(n, dtype=torch.float64)
+    out, drifted = pf.remove_invalid_particles(mt.pf.Particles(poses.to(dev), w.clone().to(dev)))
+    w_ref, dr = O.remove_invalid(poses, w.clone(), pf.mesh_vertices_ds, pf.pen_max)
+    assert torch.equal(out.weights.cpu(), w_ref) and bool(drifted) == dr
+    assert 0.2 < float((w_ref == 0).double().mean()) < 0.8
 
 
 # ----------------------------------------------------------------------------- fused step
@@ -382,6 +487,58 @@ def test_fused_step_vs_oracle(mt, dev, cb_small, cb_big, N, big):
         full = O.filter_step(poses, odom, tn, rot, keys_cb, cbs.embeddings, q, u)
         assert torch.equal(full["nn_idx"], nn) and torch.equal(full["anc"], anc)
         assert torch.allclose(w, full["weights"], rtol=1e-10)
+
+
+def test_fused_step_with_prune_vs_oracle(mt, dev, cb_small, box):
+    """loop order of filter.py:170-190 with remove_invalid_particles between weighting and
+    resampling: drifted particles get weight 0 and never become ancestors."""
+    cbs, cb = cb_small
+    N = 6000
+    poses, sel, odom, tn, rot, q, gt = _engine_case(mt, dev, cbs, cb, N, seed=21)
+    poses[::4, :3, 3] += 0.005 * poses[::4, :3, 2]  # a quarter of the cloud floats 5 mm off the surface
+    vds = box.vertices[::10]
+    eng = mt.eng.FilterEngine(cb, capacity=N, mesh_vertices=vds, pen_max=0.002)
+    eng.load_particles(poses.to(dev))
+    eng.step(q, odom, u=0.37, tn=tn.to(dev), rot=rot.to(dev), resample=False)
+    moved = eng.poses().cpu()
+    nn = eng.nn_idx().cpu().long()
+    w = eng.weights().cpu()
+    w_soft = torch.softmax(O.codebook_similarity(q, cbs.embeddings)[nn], 0)
+    w_ref, drifted = O.remove_invalid(moved, w_soft, vds, 0.002)
+    assert not drifted and 0.15 < float((w_ref == 0).double().mean()) < 0.5
+    assert torch.equal(w == 0, w_ref == 0)
+    assert torch.allclose(w, w_ref / w_ref.sum(), rtol=1e-10, atol=0)
+    st = cb.ctx.stats()
+    assert st["drifted"] == 0 and st["on_surface"] == int((w_ref != 0).sum())
+    eng2 = mt.eng.FilterEngine(cb, capacity=N, mesh_vertices=vds, pen_max=0.002)
+    eng2.load_particles(poses.to(dev))
+    eng2.step(q, odom, u=0.37, tn=tn.to(dev), rot=rot.to(dev))
+    anc = eng2.ancestors().cpu().long()
+    assert torch.equal(anc, O.low_var_indices(w_ref, 0.37))
+    assert bool((w_ref[anc] > 0).all())
+    assert torch.equal(eng2.poses().cpu(), moved[anc])
+
+
+def test_fused_step_all_drifted_reprojects(mt, dev, cb_small, box):
+    """filter.py:176-179: when every particle has drifted the poses are re-projected onto the
+    codebook (SE3_NN) and the resampler keeps them (all-zero weights, particle_filter.py:240)."""
+    cbs, cb = cb_small
+    N = 3000
+    poses, sel, odom, tn, rot, q, gt = _engine_case(mt, dev, cbs, cb, N, seed=22)
+    poses[:, :3, 3] += 0.02 * poses[:, :3, 2]
+    eng = mt.eng.FilterEngine(cb, capacity=N, mesh_vertices=box.vertices[::10], pen_max=0.002)
+    eng.load_particles(poses.to(dev))
+    eng.step(q, odom, u=0.5, tn=tn.to(dev), rot=rot.to(dev))
+    moved, _ = O.motion_model(poses, odom, tn, rot)
+    st = cb.ctx.stats()
+    assert st["drifted"] == 1 and st["on_surface"] == 0 and st["resample_skipped"] == 1
+    nn = eng.nn_idx().cpu().long()
+    got_keys = mt.tt.R3_SE3(eng.poses()).cpu()
+    assert torch.equal(eng.poses().cpu(), cbs.poses[nn])
+    assert torch.equal(eng.ancestors().cpu().long(), torch.arange(N))
+    ref_nn = O.se3_nn(O.r3_se3(cbs.poses), moved)
+    assert float((nn != ref_nn).double().mean()) < 2e-3  # float32 key ulps only
+    cb.ctx.stats(reset=True)
 
 
 def test_fused_step_philox_teacher_forced(mt, dev, cb_small):

@@ -21,8 +21,8 @@ def H():
     os.makedirs(build, exist_ok=True)
     so = os.path.join(build, "host_math.so")
     src = os.path.join(HERE, "host_math_harness.cpp")
-    hdr = os.path.join(HERE, "..", "midastouch_b200", "csrc", "mt_math.cuh")
-    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+    hdrs = [os.path.join(HERE, "..", "midastouch_b200", "csrc", h) for h in ("mt_math.cuh", "mt_nn.cuh")]
+    if not os.path.exists(so) or os.path.getmtime(so) < max([os.path.getmtime(src)] + [os.path.getmtime(h) for h in hdrs]):
         subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-x", "c++", "-shared", "-fPIC", "-o", so, src])
     return ctypes.CDLL(so)
 
@@ -127,3 +127,52 @@ def test_rot_err_matches_reference_golden(H, golden):
     H.h_rot_err(P(g["gt"].astype(np.float32).copy()), P(poses), ctypes.c_longlong(n), P(out))
     rr = np.sqrt(np.mean(out.astype(np.float64) ** 2))
     assert abs(rr - float(g["rmse_r"])) <= 1e-5 * float(g["rmse_r"])
+
+
+def _nbr_table(keys, K):
+    """host model of k_build_nbr: the K nearest other keys of every key, ascending (distance, index)."""
+    M = keys.shape[0]
+    out = np.zeros((M, K, 8), np.float32)
+    out[:, :, 6] = np.inf
+    out[:, :, 7] = np.int32(-1).view(np.float32)
+    for h in range(M):
+        d = O.l2_sq_f32(keys, keys[h])
+        d[h] = np.inf
+        order = np.lexsort((np.arange(M), d))[: min(K, M - 1)]
+        out[h, : len(order), :6] = keys[order]
+        out[h, : len(order), 6] = np.sqrt(d[order].astype(np.float32))
+        out[h, : len(order), 7] = order.astype(np.int32).view(np.float32)
+    return out
+
+
+@pytest.mark.parametrize("M,K", [(3000, 32), (20, 32), (2, 32)])
+def test_hint_graph_search_is_exact(H, M, K):
+    """whenever the neighbour-list scan claims a proven answer it equals the exhaustive argmin
+    (ties -> lowest index), for good, stale and random hints; duplicates included."""
+    obj = synth.make_object("004_sugar_box")
+    cb = synth.make_codebook(obj, M=max(M, 8), D=8, seed=2)
+    keys = O.r3_se3(cb.poses).numpy()[:M].copy()
+    if M >= 100:
+        keys[50:60] = keys[40:50]  # duplicate keys -> ties
+    nbr = _nbr_table(keys, K)
+    rng = np.random.default_rng(1)
+    n = 4000
+    base = rng.integers(0, M, n)
+    q = (keys[base] + rng.normal(size=(n, 6)).astype(np.float32) * np.float32(8e-4)).astype(np.float32)
+    q[:100] = keys[base[:100]]  # exact hits
+    ref = O.nn_brute(keys, q)
+    for kind in ("true", "base", "random"):
+        hint = {"true": ref, "base": base, "random": rng.integers(0, M, n)}[kind].astype(np.int32)
+        idx = np.zeros(n, np.int32)
+        ok = np.zeros(n, np.int32)
+        dist = np.zeros(n, np.float32)
+        H.h_hint_scan(P(keys), ctypes.c_longlong(M), P(nbr), K, P(q), ctypes.c_longlong(n), P(hint), P(idx), P(ok), P(dist))
+        proven = ok.astype(bool)
+        assert np.array_equal(idx[proven].astype(np.int64), ref[proven]), kind
+        if M - 1 <= K:
+            assert proven.all()  # the list holds every other key
+        elif kind != "random":
+            assert proven.mean() > 0.9, (kind, proven.mean())
+        # unproven queries still carry a real candidate for the grid search
+        d_ref = O.l2_sq_f32(keys[idx], q)
+        assert np.array_equal(d_ref, dist)
