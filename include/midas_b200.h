@@ -58,12 +58,17 @@ int mt_codebook_grid_info(mt_ctx* ctx, float* h, int dims[3], int* occupied);
 /* neighbour-graph introspection (tests): device pointer to the (M, k, 8) float32 table
  * [key(6), delta, index bits] of every key's k nearest other keys, ascending. */
 int mt_codebook_nbr_info(mt_ctx* ctx, const float** d_nbr, int* k);
+/* d_rank[m] = position of codebook row m in the library's spatial (grid-cell) order; sorting
+ * particles by the rank of their match keeps neighbouring threads on neighbouring keys. */
+int mt_codebook_rank(mt_ctx* ctx, int32_t* d_rank, void* stream);
 /* status / statistics words of the context (synchronises).  h_out8[MT_STAT_*]; reset != 0
- * clears the cumulative slots (0..3). */
+ * clears the cumulative slots (0..4, 7). */
 #define MT_STAT_OVERFLOW 0      /* children did not fit the destination buffer (sharded steps) */
 #define MT_STAT_RESAMPLE_SKIP 1 /* a resampling saw all-zero / NaN weights and kept the particles */
 #define MT_STAT_INVALID_POSES 2 /* poses check_quats would prune (cumulative) */
 #define MT_STAT_NN_FALLBACKS 3  /* queries that left the hint graph for the grid search (cumulative) */
+#define MT_STAT_GRID_ROWS 4     /* grid rows visited by those searches (cumulative) */
+#define MT_STAT_GRID_ROWS_MAX 7 /* most rows visited by a single search */
 #define MT_STAT_DRIFTED 5       /* last mt_step_a: every particle failed the drift test */
 #define MT_STAT_ON_SURFACE 6    /* last mt_step_a: particles that passed the drift test */
 int mt_ctx_stats(mt_ctx* ctx, long long* h_out8, int reset);
@@ -180,6 +185,10 @@ typedef struct mt_step_args {
    * d_cb_poses[(M,4,4) float32 codebook poses, nullable] instead of resampling. */
   double prune_dist;
   const float* d_cb_poses;
+  /* optional cudaEvent_t: mt_step_a makes `stream` wait for it before the weight lookup (its third
+   * kernel), so that mt_codebook_query may run concurrently on another stream with the motion /
+   * SE3_NN kernels.  NULL: the query was enqueued on `stream` before mt_step_a. */
+  void* table_ready_event;
 } mt_step_args;
 
 /* kernel A: motion + key + exact NN + weight lookup + deterministic weight sums */

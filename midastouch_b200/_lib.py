@@ -9,7 +9,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmidas_b200.so")
+LIB_PATH = os.environ.get("MIDAS_B200_LIB") or os.path.join(_HERE, "libmidas_b200.so")  # override: A/B builds only
 SOURCES = [os.path.join(_HERE, "csrc", "midas_b200.cu")]
 HEADERS = [os.path.join(_HERE, "csrc", "mt_math.cuh"), os.path.join(_HERE, "csrc", "mt_nn.cuh"), os.path.join(_HERE, "csrc", "mt_mesh.cuh"), os.path.join(_HERE, "..", "include", "midas_b200.h")]
 
@@ -45,7 +45,7 @@ class StepArgs(C.Structure):
         ("gt", C.c_void_p), ("d_rmse2", C.c_void_p),
         ("rank", C.c_int), ("world", C.c_int), ("n_global", C.c_longlong),
         ("d_shard_sums", C.c_void_p), ("d_n_out", C.c_void_p), ("d_n_in", C.c_void_p),
-        ("prune_dist", C.c_double), ("d_cb_poses", C.c_void_p),
+        ("prune_dist", C.c_double), ("d_cb_poses", C.c_void_p), ("table_ready_event", C.c_void_p),
     ]
 
 
@@ -57,6 +57,7 @@ _SIGS = {
     "mt_codebook_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "mt_codebook_grid_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "mt_codebook_nbr_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int)]),
+    "mt_codebook_rank": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "mt_ctx_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_longlong), C.c_int]),
     "mt_mesh_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_double]),
     "mt_prune_aos": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),

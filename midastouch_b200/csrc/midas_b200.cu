@@ -29,6 +29,12 @@
 #define MT_MAX_D 6144  // query staged in 48 KB of shared memory as float64
 #define MT_CHUNK 256  // particles per chunk == threads per block of the sweep kernels
 
+// nn_cur / nn_next hold the codebook match of every particle; a particle whose weight was
+// zeroed by the drift test or check_quats stores -(idx + 2) (so -1 stays "no match yet").
+__host__ __device__ __forceinline__ int nn_masked(int idx) { return -(idx + 2); }
+__host__ __device__ __forceinline__ int nn_index(int stored) { return stored < -1 ? -(stored + 2) : stored; }
+__host__ __device__ __forceinline__ bool nn_is_masked(int stored) { return stored < -1; }
+
 // ------------------------------------------------------------------------- errors
 static thread_local char g_err[512] = "";
 static int set_err(int code, const char* fmt, const char* a = "", const char* b = "") {
@@ -48,6 +54,7 @@ extern "C" int mt_version(void) { return 100; }
 // ------------------------------------------------------------------------- context
 struct mt_ctx {
   int device;
+  int sm_count;
   size_t cap;
   int M, D;
   // codebook
@@ -65,6 +72,7 @@ struct mt_ctx {
   bool cb_ready;
   // down-sampled mesh vertices for the drift test (mt_mesh.cuh)
   double* d_mesh_verts;
+  float4* d_mesh_verts32;
   int* d_mesh_cells;
   MeshGrid mesh;
   int mesh_V;
@@ -74,6 +82,12 @@ struct mt_ctx {
   double* d_part;     // per-chunk weight sums
   double* d_prefix;   // exclusive prefix of d_part, [nchunks] = total
   double* d_rm_part;  // 2 x chunk_cap rmse partials
+  int warp_cap;
+  double* d_wpart;    // per-warp weight sums of kernel A (32 particles each)
+  double* d_wrm;      // 2 x warp_cap rmse partials of kernel A
+  int* d_wcnt;        // per-warp count of particles that passed the drift test
+  int* d_queue;       // particles whose hint-graph search was not conclusive (kernel A -> A2)
+  unsigned int* d_qctl;  // [0] queue length, [1] queue head
   double* d_q64;      // staged query, float64, MT_MAX_D entries
   double* d_scal;     // [0] local weight sum, [1] max, [2] min, [3] softmax denom, [4..7] spare
   unsigned int* d_ticket;
@@ -88,6 +102,7 @@ extern "C" int mt_ctx_create(int device, size_t capacity, int M, int D, mt_ctx**
   mt_ctx* c = new mt_ctx();
   memset(c, 0, sizeof(*c));
   c->device = device;
+  CK(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
   c->cap = capacity;
   c->M = M;
   c->D = D;
@@ -99,6 +114,13 @@ extern "C" int mt_ctx_create(int device, size_t capacity, int M, int D, mt_ctx**
   CK(cudaMalloc(&c->d_sim, sizeof(double) * M));
   CK(cudaMalloc(&c->d_esim, sizeof(double) * M));
   CK(cudaMalloc(&c->d_part, sizeof(double) * c->chunk_cap));
+  c->warp_cap = (int)((capacity + 31) / 32) + 8;
+  CK(cudaMalloc(&c->d_wpart, sizeof(double) * c->warp_cap));
+  CK(cudaMalloc(&c->d_wrm, sizeof(double) * 2 * c->warp_cap));
+  CK(cudaMalloc(&c->d_wcnt, sizeof(int) * c->warp_cap));
+  CK(cudaMalloc(&c->d_queue, sizeof(int) * (capacity + 32)));
+  CK(cudaMalloc(&c->d_qctl, sizeof(unsigned int) * 4));
+  CK(cudaMemset(c->d_qctl, 0, sizeof(unsigned int) * 4));
   CK(cudaMalloc(&c->d_prefix, sizeof(double) * (c->chunk_cap + 1)));
   CK(cudaMalloc(&c->d_rm_part, sizeof(double) * 2 * c->chunk_cap));
   CK(cudaMalloc(&c->d_scal, sizeof(double) * 8));
@@ -121,12 +143,18 @@ extern "C" int mt_ctx_destroy(mt_ctx* c) {
   cudaFree(c->d_cell_start);
   cudaFree(c->d_nbr);
   cudaFree(c->d_mesh_verts);
+  cudaFree(c->d_mesh_verts32);
   cudaFree(c->d_mesh_cells);
   cudaFree(c->d_sim);
   cudaFree(c->d_esim);
   cudaFree(c->d_part);
   cudaFree(c->d_prefix);
   cudaFree(c->d_rm_part);
+  cudaFree(c->d_wpart);
+  cudaFree(c->d_wrm);
+  cudaFree(c->d_wcnt);
+  cudaFree(c->d_queue);
+  cudaFree(c->d_qctl);
   cudaFree(c->d_scal);
   cudaFree(c->d_q64);
   cudaFree(c->d_ticket);
@@ -213,7 +241,7 @@ extern "C" int mt_codebook_upload(mt_ctx* c, const float* h_keys, const void* d_
   CK_LAUNCH();
   k_build_nbr<true><<<(M + 7) / 8, 256>>>(c->d_keys_orig, M, nullptr, c->d_sorted_orig);
   CK_LAUNCH();
-  k_set_partner<<<(M + 255) / 256, 256>>>(c->d_keys_orig, M, c->d_sorted_orig);
+  k_set_partner<<<(M + 255) / 256, 256>>>(c->d_keys_orig, M, c->d_sorted_orig, c->d_nbr);
   CK_LAUNCH();
   CK(cudaDeviceSynchronize());
   c->grid = g;
@@ -240,6 +268,14 @@ extern "C" int mt_codebook_nbr_info(mt_ctx* c, const float** d_nbr, int* k) {
   return MT_OK;
 }
 
+extern "C" int mt_codebook_rank(mt_ctx* c, int32_t* d_rank, void* stream) {
+  if (!c || !c->cb_ready) return set_err(MT_ERR_STATE, "mt_codebook_rank: no codebook");
+  if (!d_rank) return set_err(MT_ERR_ARG, "mt_codebook_rank: null output");
+  k_key_rank<<<(c->M + 255) / 256, 256, 0, (cudaStream_t)stream>>>(c->d_keys_sorted, c->M, d_rank);
+  CK_LAUNCH();
+  return MT_OK;
+}
+
 extern "C" int mt_ctx_stats(mt_ctx* c, long long* h_out8, int reset) {
   if (!c) return set_err(MT_ERR_ARG, "mt_ctx_stats: null context");
   CK(cudaSetDevice(c->device));
@@ -248,7 +284,8 @@ extern "C" int mt_ctx_stats(mt_ctx* c, long long* h_out8, int reset) {
   if (h_out8)
     for (int k = 0; k < 8; ++k) h_out8[k] = f[k];
   if (reset) {
-    CK(cudaMemset(c->d_flags, 0, 4 * sizeof(int)));
+    CK(cudaMemset(c->d_flags, 0, 5 * sizeof(int)));
+    CK(cudaMemset(c->d_flags + 7, 0, sizeof(int)));
   }
   return MT_OK;
 }
@@ -275,7 +312,8 @@ extern "C" int mt_mesh_upload(mt_ctx* c, const double* h_vertices, long long V, 
   }
   g.cell = cell;
   g.inv_cell = 1.0 / cell;
-  for (int k = 0; k < 3; ++k) g.org[k] = lo[k];
+  for (int k = 0; k < 3; ++k) g.org[k] = lo[k], g.orgf[k] = (float)lo[k];
+  g.inv_cellf = (float)g.inv_cell;
   const long long ncell = (long long)g.dims[0] * g.dims[1] * g.dims[2];
   std::vector<int> cellv(V), order(V), start(ncell + 1, 0);
   for (long long v = 0; v < V; ++v) {
@@ -289,12 +327,22 @@ extern "C" int mt_mesh_upload(mt_ctx* c, const double* h_vertices, long long V, 
   std::iota(order.begin(), order.end(), 0);
   std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cellv[a] < cellv[b]; });
   std::vector<double> sorted(3 * (size_t)V);
+  std::vector<float> sorted32(4 * (size_t)V, 0.f);
+  g.coord_max = 0.0;
   for (long long v = 0; v < V; ++v)
-    for (int k = 0; k < 3; ++k) sorted[3 * v + k] = h_vertices[3 * (size_t)order[v] + k];
+    for (int k = 0; k < 3; ++k) {
+      const double x = h_vertices[3 * (size_t)order[v] + k];
+      sorted[3 * v + k] = x;
+      sorted32[4 * v + k] = (float)x;
+      g.coord_max = std::max(g.coord_max, fabs(x));
+    }
   cudaFree(c->d_mesh_verts);
+  cudaFree(c->d_mesh_verts32);
   cudaFree(c->d_mesh_cells);
-  c->d_mesh_verts = nullptr, c->d_mesh_cells = nullptr, c->mesh_ready = false;
+  c->d_mesh_verts = nullptr, c->d_mesh_verts32 = nullptr, c->d_mesh_cells = nullptr, c->mesh_ready = false;
   CK(cudaMalloc(&c->d_mesh_verts, sizeof(double) * 3 * V));
+  CK(cudaMalloc(&c->d_mesh_verts32, sizeof(float4) * V));
+  CK(cudaMemcpy(c->d_mesh_verts32, sorted32.data(), sizeof(float4) * V, cudaMemcpyHostToDevice));
   CK(cudaMalloc(&c->d_mesh_cells, sizeof(int) * (ncell + 1)));
   CK(cudaMemcpy(c->d_mesh_verts, sorted.data(), sizeof(double) * 3 * V, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(c->d_mesh_cells, start.data(), sizeof(int) * (ncell + 1), cudaMemcpyHostToDevice));
@@ -307,6 +355,7 @@ extern "C" int mt_mesh_upload(mt_ctx* c, const double* h_vertices, long long V, 
 static MeshTables mesh_of(mt_ctx* c) {
   MeshTables T;
   T.verts = c->d_mesh_verts;
+  T.verts32 = c->d_mesh_verts32;
   T.cell_start = c->d_mesh_cells;
   T.g = c->mesh;
   T.V = c->mesh_V;
@@ -381,30 +430,67 @@ __device__ __forceinline__ double block_incl_scan_256(double v, double* s8) {
 // Last block standing: exclusive prefix over `n` chunk sums with one 256-thread block.
 // Each thread owns a contiguous run (sequential), thread totals are block-scanned; the
 // topology depends only on n, so results are reproducible run to run.
+#define MT_SCAN_TILE 4096  // chunk sums staged per pass of the last block (32 KB of shared memory)
 __device__ void scan_chunk_sums(const double* part, int n, double* prefix, double* total_out, double* s8) {
+  __shared__ double s_tile[MT_SCAN_TILE];
   __shared__ double s_incl[MT_CHUNK];
-  const int per = (n + MT_CHUNK - 1) / MT_CHUNK;
-  const int b = threadIdx.x * per;
-  double loc = 0.0;
-  for (int k = 0; k < per; ++k) {
-    int i = b + k;
-    if (i < n) loc += __ldcg(part + i);
-  }
-  const double incl = block_incl_scan_256(loc, s8);
-  s_incl[threadIdx.x] = incl;
-  __syncthreads();
-  double run = threadIdx.x ? s_incl[threadIdx.x - 1] : 0.0;  // exclusive base of this thread's run
-  for (int k = 0; k < per; ++k) {
-    int i = b + k;
-    if (i < n) {
-      prefix[i] = run;
-      run += __ldcg(part + i);
+  constexpr int PER = MT_SCAN_TILE / MT_CHUNK;  // 16 contiguous chunk sums per thread
+  double carry = 0.0;
+  for (int t0 = 0; t0 < n; t0 += MT_SCAN_TILE) {
+    const int cnt = min(MT_SCAN_TILE, n - t0);
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {  // coalesced, 16 independent loads in flight per thread
+      const int j = threadIdx.x + k * MT_CHUNK;
+      s_tile[j] = (j < cnt) ? __ldcg(part + t0 + j) : 0.0;
     }
+    __syncthreads();
+    const int b = threadIdx.x * PER;
+    double loc = 0.0;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) loc += s_tile[b + k];
+    const double incl = block_incl_scan_256(loc, s8);
+    s_incl[threadIdx.x] = incl;
+    __syncthreads();
+    // exclusive base of this thread's run == the previous thread's inclusive value, so clamping
+    // the running sums to the own inclusive value keeps the whole prefix array monotone
+    double run = carry + (threadIdx.x ? s_incl[threadIdx.x - 1] : 0.0);
+    const double top = carry + incl;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+      const double v = s_tile[b + k];
+      s_tile[b + k] = fmin(run, top);
+      run += v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+      const int j = threadIdx.x + k * MT_CHUNK;
+      if (j < cnt) prefix[t0 + j] = s_tile[j];
+    }
+    carry += s_incl[MT_CHUNK - 1];
   }
-  if (threadIdx.x == MT_CHUNK - 1) {
-    prefix[n] = incl;
-    *total_out = incl;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    prefix[n] = carry;
+    *total_out = carry;
   }
+}
+
+// fixed-order sum of arr[0..n) with stride `stride` by one 256-thread block (valid in thread 0)
+__device__ double block_sum_array_256(const double* arr, int n, int stride, double* s8) {
+  double acc = 0.0;
+  for (int g0 = 0; g0 < n; g0 += 8 * MT_CHUNK) {
+    double v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int g = g0 + threadIdx.x + k * MT_CHUNK;
+      v[k] = (g < n) ? __ldcg(arr + (size_t)g * stride) : 0.0;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc += v[k];
+  }
+  return block_sum_256(acc, s8);
 }
 
 // ------------------------------------------------------------------------- cosine kernels
@@ -739,14 +825,13 @@ extern "C" int mt_soa_to_aos(const float* d_soa, long long stride, long long n, 
 __global__ void __launch_bounds__(MT_NN_BLOCK) k_nn_grid(NNTables T, const float* __restrict__ keys, long long n,
                                                          const int* __restrict__ hint, int* __restrict__ idx,
                                                          int* fallbacks) {
-  __shared__ NNQueue Q;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   float q[6] = {0, 0, 0, 0, 0, 0};
   if (i < n) {
 #pragma unroll
     for (int k = 0; k < 6; ++k) q[k] = keys[6 * i + k];
   }
-  const int r = nn_block_assign(T, Q, i < n, q, (hint && i < n) ? hint[i] : -1, fallbacks);
+  const int r = nn_assign(T, i < n, q, (hint && i < n) ? hint[i] : -1, fallbacks);
   if (i < n) idx[i] = r;
 }
 
@@ -1020,73 +1105,168 @@ struct StepDev {
   double* part;
   double* prefix;
   double* rm_part;
+  double* wpart;
+  double* wrm;
+  int* wcnt;
+  int* queue;
+  unsigned int* qctl;
   double* scal;
   unsigned int* ticket;
   int* flags;
   int nchunks;
 };
 
-// Kernel A.  One particle per thread, one 256-particle chunk per block.
-//   HBM per particle: read 48 B pose + 4 B hint (+ 24 B noise when supplied), write 48 B + 4 B.
-//   Codebook keys / grid / weight table are L2-resident (M*64 B + cells*4 B + M*8 B).
-__global__ void __launch_bounds__(256) k_step_a(StepDev p, NNTables T, MeshTables Mh) {
-  __shared__ double s8[8];
-  __shared__ NNQueue Q;
-  const long long i = (long long)blockIdx.x * MT_CHUNK + threadIdx.x;
+// The measurement half of a step is three kernels (mt_step_a launches them back to back):
+//
+//  k_step_a     one particle per thread, 64-thread blocks, no block-level synchronisation:
+//               motion, SE(3) key, drift test, hint-graph search.  Conclusive searches (~99 %)
+//               store the match; the others store their best candidate and append the
+//               particle to a queue.  Per-warp RMSE / on-surface partials.
+//               HBM per particle: read 48 B pose + 4 B hint (+ 24 B noise when supplied),
+//               write 48 B + 4 B.  Keys / neighbour lists / mesh grid are L2-resident.
+//  k_step_nnq   the queue, one warp per entry (grid search, mt_nn.cuh): the long-tailed work is
+//               spread over the whole GPU instead of stalling the warp that found it.
+//  k_step_sums  weight lookup w = table[match] (4 B / particle), deterministic float64 chunk
+//               sums, and in the last block the chunk prefix for kernel B, the RMSE and the
+//               drift flag.
+#define MT_A_BLOCK 64
+#ifndef MT_A_MINBLOCKS
+#define MT_A_MINBLOCKS 16
+#endif
+__global__ void __launch_bounds__(MT_A_BLOCK, MT_A_MINBLOCKS) k_step_a(StepDev p, NNTables T, MeshTables Mh) {
+  const long long i = (long long)blockIdx.x * MT_A_BLOCK + threadIdx.x;
   const long long n = p.n_in ? *p.n_in : p.n;
   const bool valid = i < n;
-  double e = 0.0, et2 = 0.0, ang2 = 0.0;
-  float key[6] = {0, 0, 0, 0, 0, 0};
-  int hint = -1;
-  bool invalid = false, on_surface = valid;
+  const int lane = threadIdx.x & 31;
+  double et2 = 0.0, ang2 = 0.0;
+  bool on_surface = valid, todo = false;
   if (valid) {
-    float P[3][4], t[3], r[3], O[3][4];
+    float P[3][4], t[3], r[3], O[3][4], key[6];
     load_pose(p.soa_cur, p.stride, i, P);
-    hint = p.nn_cur[i];
+    const int hint = nn_index(p.nn_cur[i]);
     draw_or_load_noise(p.tn, p.rot, i, p.sig_t, p.sig_r, p.seed, p.step, p.first_gid + (uint64_t)i, t, r);
     apply_motion(P, p.odom, t, r, O);
     store_pose(p.soa_cur, p.stride, i, O);
     mt_se3_key(O, key);
-    invalid = mt_pose_invalid(O);
+    const bool invalid = mt_pose_invalid(O);
+    if (invalid) atomicAdd(p.flags + 2, 1);  // check_quats would delete the particle (particle_filter.py:347-357)
     if (p.has_gt) rmse_terms(p.gt, O, et2, ang2);
     if (p.prune_dist > 0.0) on_surface = mesh_within(Mh, O[0][3], O[1][3], O[2][3], p.prune_dist);
+    float bd;
+    int bi;
+    todo = !nn_hint_search(T, key, hint, bd, bi);
+    if (bi == INT_MAX) bi = -1;  // no usable hint
+    // masked: weights *= m (particle_filter.py:398-401); a particle without any candidate yet
+    // (-1) has its mask re-derived by k_step_nnq
+    p.nn_cur[i] = (bi >= 0 && (!on_surface || invalid)) ? nn_masked(bi) : bi;
   }
-  const int nn = nn_block_assign(T, Q, valid, key, hint, p.flags + 3);
-  const int n_on = __syncthreads_count(on_surface);
-  if (valid) {
-    p.nn_cur[i] = nn;
-    e = __ldg(p.wtab + nn);
-    if (!on_surface) e = 0.0;  // weights *= m (particle_filter.py:398-401)
-    if (invalid) {
-      e = 0.0;  // check_quats would delete the particle (particle_filter.py:347-357)
-      atomicAdd(p.flags + 2, 1);
+  // queue the inconclusive searches (one atomic per warp)
+  const unsigned qm = __ballot_sync(0xffffffffu, todo);
+  if (qm) {
+    unsigned base = 0;
+    if (lane == 0) base = atomicAdd(p.qctl, (unsigned)__popc(qm));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (todo) p.queue[base + __popc(qm & ((1u << lane) - 1))] = (int)i;
+  }
+  const long long gw = i >> 5;  // global warp = 32 consecutive particles
+  const unsigned on = __ballot_sync(0xffffffffu, on_surface);
+  if (p.has_gt) et2 = warp_sum(et2), ang2 = warp_sum(ang2);
+  if (lane == 0) {
+    p.wcnt[gw] = __popc(on);
+    if (p.has_gt) p.wrm[2 * gw] = et2, p.wrm[2 * gw + 1] = ang2;
+  }
+}
+
+// queue consumer: blocks of 8 warps pull entries until the queue is empty
+__global__ void __launch_bounds__(256) k_step_nnq(StepDev p, NNTables T, MeshTables Mh) {
+  __shared__ unsigned s_e;
+  __shared__ float s_bd[8];
+  __shared__ int s_bi[8];
+  const unsigned qn = *p.qctl;
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_e = atomicAdd(p.qctl + 1, 1u);
+    __syncthreads();
+    const unsigned e = s_e;
+    if (e >= qn) break;
+    const long long i = p.queue[e];
+    float P[3][4], key[6];
+    load_pose(p.soa_cur, p.stride, i, P);
+    mt_se3_key(P, key);
+    const int stored = p.nn_cur[i];
+    int bi = nn_index(stored);
+    float bd = FLT_MAX;
+    bool masked = nn_is_masked(stored);
+    if (bi >= 0) {
+      float kh[6];
+      load_key(T.keys_orig, bi, kh);
+      bd = mt_key_dist(key, kh);
+    } else {  // no candidate yet: the mask was not recorded, derive it again
+      bi = INT_MAX;
+      masked = mt_pose_invalid(P) || (p.prune_dist > 0.0 && !mesh_within(Mh, P[0][3], P[1][3], P[2][3], p.prune_dist));
     }
+    const int res = nn_search_coop<8>(T, key, bd, bi, p.flags + 4, s_bd, s_bi);
+    __syncthreads();  // every thread has read nn_cur[i] before it is overwritten
+    if (threadIdx.x == 0) p.nn_cur[i] = masked ? nn_masked(res) : res;
   }
-  double se = block_sum_256(e, s8);
-  double sa = 0.0, sb = 0.0;
-  if (p.has_gt) {
-    sa = block_sum_256(et2, s8);
-    sb = block_sum_256(ang2, s8);
+}
+
+// chunk sums of the weights + (last block) prefix for kernel B, RMSE, drift flag
+__global__ void __launch_bounds__(256) k_step_sums(StepDev p) {
+  __shared__ double s8[8];
+  __shared__ int s_cnt;
+  const long long i = (long long)blockIdx.x * MT_CHUNK + threadIdx.x;
+  const long long n = p.n_in ? *p.n_in : p.n;
+  const int nwarps = (int)((n + 31) >> 5);
+  double e = 0.0;
+  if (i < n) {
+    const int stored = p.nn_cur[i];
+    e = nn_is_masked(stored) ? 0.0 : __ldg(p.wtab + nn_index(stored));
   }
+  const double se = block_sum_256(e, s8);
   __shared__ bool last;
   if (threadIdx.x == 0) {
     p.part[blockIdx.x] = se;
-    if (p.has_gt) p.rm_part[2 * blockIdx.x] = sa, p.rm_part[2 * blockIdx.x + 1] = sb;
-    if (n_on) atomicAdd(p.flags + 4, n_on);
+    // fold kernel A's 8 per-warp partials of this chunk (fixed order)
+    double ra = 0.0, rb = 0.0;
+    int cnt = 0;
+    for (int j = 0; j < 8; ++j) {
+      const int gw = 8 * blockIdx.x + j;
+      if (gw < nwarps) {
+        cnt += p.wcnt[gw];
+        if (p.has_gt) ra += p.wrm[2 * gw], rb += p.wrm[2 * gw + 1];
+      }
+    }
+    p.rm_part[2 * blockIdx.x] = ra, p.rm_part[2 * blockIdx.x + 1] = rb;
+    p.wcnt[8 * blockIdx.x] = cnt;  // slot 8c now holds the chunk count
     __threadfence();
     last = (atomicAdd(p.ticket, 1u) == gridDim.x - 1);
   }
   __syncthreads();
-  if (last) {
-    __threadfence();
-    scan_chunk_sums(p.part, (int)gridDim.x, p.prefix, p.scal, s8);
-    if (threadIdx.x == 0) {
-      if (p.has_gt) rmse_finalize(p.rm_part, (int)gridDim.x, n, p.rmse2);
-      const int on = atomicExch(p.flags + 4, 0);
-      p.flags[6] = on;                                // particles on the surface this step
-      p.flags[5] = (p.prune_dist > 0.0 && on == 0);   // drifted (particle_filter.py:402)
-      *p.ticket = 0;
+  if (!last) return;
+  __threadfence();
+  scan_chunk_sums(p.part, (int)gridDim.x, p.prefix, p.scal, s8);
+  double sa = 0.0, sb = 0.0;
+  if (p.has_gt) {
+    sa = block_sum_array_256(p.rm_part, (int)gridDim.x, 2, s8);
+    sb = block_sum_array_256(p.rm_part + 1, (int)gridDim.x, 2, s8);
+  }
+  if (threadIdx.x == 0) s_cnt = 0;
+  __syncthreads();
+  int cnt = 0;
+  for (int c = threadIdx.x; c < (int)gridDim.x; c += MT_CHUNK) cnt += __ldcg(p.wcnt + 8 * (size_t)c);
+  if (cnt) atomicAdd(&s_cnt, cnt);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (p.has_gt) {
+      p.rmse2[0] = (float)sqrt(sa / (double)n);
+      p.rmse2[1] = (float)sqrt(sb / (double)n);
     }
+    p.flags[6] = s_cnt;                               // particles on the surface this step
+    p.flags[5] = (p.prune_dist > 0.0 && s_cnt == 0);  // drifted (particle_filter.py:402)
+    p.flags[3] += (int)p.qctl[0];                     // searches that needed the grid (cumulative)
+    p.qctl[0] = 0, p.qctl[1] = 0;
+    *p.ticket = 0;
   }
 }
 
@@ -1131,8 +1311,9 @@ __global__ void __launch_bounds__(256) k_step_b(StepDev p) {
   float P[3][4];
   if (valid) {
     if (FROM_TABLE) {
-      nn = p.nn_cur[i];
-      e = __ldg(p.wtab + nn);
+      const int stored = p.nn_cur[i];
+      nn = nn_index(stored);
+      e = nn_is_masked(stored) ? 0.0 : __ldg(p.wtab + nn);
     } else {
       e = p.wsrc[i];
     }
@@ -1289,6 +1470,11 @@ static int fill_step(mt_ctx* c, const mt_step_args* a, StepDev* d) {
   d->part = c->d_part;
   d->prefix = c->d_prefix;
   d->rm_part = c->d_rm_part;
+  d->wpart = c->d_wpart;
+  d->wrm = c->d_wrm;
+  d->wcnt = c->d_wcnt;
+  d->queue = c->d_queue;
+  d->qctl = c->d_qctl;
   d->scal = c->d_scal;
   d->ticket = c->d_ticket;
   d->flags = c->d_flags;
@@ -1305,7 +1491,13 @@ extern "C" int mt_step_a(mt_ctx* c, const mt_step_args* a, void* stream) {
   if ((a->d_tn == nullptr) != (a->d_rot == nullptr)) return set_err(MT_ERR_ARG, "mt_step_a: tn/rot must both be given");
   if (a->gt && !a->d_rmse2) return set_err(MT_ERR_ARG, "mt_step_a: gt without rmse output");
   if (a->prune_dist > 0.0 && !c->mesh_ready) return set_err(MT_ERR_STATE, "mt_step_a: prune_dist given but no mesh uploaded");
-  k_step_a<<<d.nchunks, MT_CHUNK, 0, (cudaStream_t)stream>>>(d, tables_of(c), mesh_of(c));
+  cudaStream_t st = (cudaStream_t)stream;
+  k_step_a<<<(unsigned)((a->n + MT_A_BLOCK - 1) / MT_A_BLOCK), MT_A_BLOCK, 0, st>>>(d, tables_of(c), mesh_of(c));
+  CK_LAUNCH();
+  k_step_nnq<<<c->sm_count * 4, 256, 0, st>>>(d, tables_of(c), mesh_of(c));
+  CK_LAUNCH();
+  if (a->table_ready_event) CK(cudaStreamWaitEvent(st, (cudaEvent_t)a->table_ready_event, 0));
+  k_step_sums<<<d.nchunks, MT_CHUNK, 0, st>>>(d);
   CK_LAUNCH();
   return MT_OK;
 }
@@ -1335,7 +1527,8 @@ __global__ void k_step_weights(StepDev p, double* __restrict__ w) {
     for (int r = 0; r < p.world; ++r) S += p.shard_sums[r];
   else
     S = p.prefix[p.nchunks];
-  w[i] = __ldg(p.wtab + p.nn_cur[i]) / S;
+  const int stored = p.nn_cur[i];
+  w[i] = nn_is_masked(stored) ? 0.0 / S : __ldg(p.wtab + nn_index(stored)) / S;
 }
 
 extern "C" int mt_step_weights(mt_ctx* c, const mt_step_args* a, double* d_w, void* stream) {

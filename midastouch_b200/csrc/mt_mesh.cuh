@@ -11,8 +11,15 @@
 struct MeshGrid {
   double org[3];
   double cell, inv_cell;
+  double coord_max;  // max |coordinate| (sizes the float32 filter band)
+  float orgf[3], inv_cellf;  // float32 copies for the (conservatively inflated) search box
   int dims[3];
 };
+
+MT_HD int mt_mesh_cellf(float x, float org, float inv_cell, int dim) {
+  float f = floorf((x - org) * inv_cell);
+  return (f < 0.f) ? 0 : (f >= (float)dim ? dim - 1 : (int)f);
+}
 
 MT_HD int mt_mesh_cell(double x, double org, double inv_cell, int dim) {
   double f = floor((x - org) * inv_cell);
@@ -21,38 +28,62 @@ MT_HD int mt_mesh_cell(double x, double org, double inv_cell, int dim) {
 
 #if defined(__CUDACC__)
 struct MeshTables {
-  const double* verts;    // V x 3, sorted by cell
+  const double* verts;    // V x 3 float64, sorted by cell (exact test)
+  const float4* verts32;  // V x (x,y,z,0) float32 copies (filter)
   const int* cell_start;  // ncells + 1
   MeshGrid g;
   int V;
 };
 
-// true when some vertex lies within `dist` of (x,y,z) (i.e. the particle is NOT drifted).
-// NaN coordinates -> false (the reference's `dist > invalid_dist` is False for NaN distances
-// only if sklearn returned NaN; sklearn raises on NaN input, the engine treats such poses as
-// invalid already through check_quats).
+// exact float64 test of one vertex, sklearn's arithmetic
+__device__ __forceinline__ bool mesh_vertex_within(const MeshTables& T, int p, double x, double y, double z, double dist) {
+  const double dx = __dsub_rn(x, __ldg(T.verts + 3 * (size_t)p));
+  const double dy = __dsub_rn(y, __ldg(T.verts + 3 * (size_t)p + 1));
+  const double dz = __dsub_rn(z, __ldg(T.verts + 3 * (size_t)p + 2));
+  double d2 = __dmul_rn(dx, dx);
+  d2 = __dadd_rn(d2, __dmul_rn(dy, dy));
+  d2 = __dadd_rn(d2, __dmul_rn(dz, dz));
+  return !(sqrt(d2) > dist);
+}
+
+// true when some vertex lies within `dist` of (x,y,z) (i.e. the particle has NOT drifted).
+// Vertices are filtered in float32 (squared distance against dist^2 with a relative band
+// that covers the rounding of the float32 copies); only vertices inside the band take the
+// exact float64 test, so the answer is the float64 one.  NaN coordinates -> false.
 __device__ __forceinline__ bool mesh_within(const MeshTables& T, float xf, float yf, float zf, double dist) {
+  if (!(xf == xf) || !(yf == yf) || !(zf == zf)) return false;
   const double x = (double)xf, y = (double)yf, z = (double)zf;
-  if (!(x == x) || !(y == y) || !(z == z)) return false;
   const MeshGrid& g = T.g;
-  const double r = dist * (1.0 + 1e-9) + 1e-300;
-  const int xlo = mt_mesh_cell(x - r, g.org[0], g.inv_cell, g.dims[0]), xhi = mt_mesh_cell(x + r, g.org[0], g.inv_cell, g.dims[0]);
-  const int ylo = mt_mesh_cell(y - r, g.org[1], g.inv_cell, g.dims[1]), yhi = mt_mesh_cell(y + r, g.org[1], g.inv_cell, g.dims[1]);
-  const int zlo = mt_mesh_cell(z - r, g.org[2], g.inv_cell, g.dims[2]), zhi = mt_mesh_cell(z + r, g.org[2], g.inv_cell, g.dims[2]);
-  for (int cz = zlo; cz <= zhi; ++cz)
-    for (int cy = ylo; cy <= yhi; ++cy) {
+  // search box in float32, radius inflated by 1 % (>> the 1e-4-cell rounding of the float32 cell
+  // coordinates) so that it covers every cell holding a vertex within `dist`
+  const float r = (float)dist * 1.01f + 1e-30f;
+  const int xlo = mt_mesh_cellf(xf - r, g.orgf[0], g.inv_cellf, g.dims[0]), xhi = mt_mesh_cellf(xf + r, g.orgf[0], g.inv_cellf, g.dims[0]);
+  const int ylo = mt_mesh_cellf(yf - r, g.orgf[1], g.inv_cellf, g.dims[1]), yhi = mt_mesh_cellf(yf + r, g.orgf[1], g.inv_cellf, g.dims[1]);
+  const int zlo = mt_mesh_cellf(zf - r, g.orgf[2], g.inv_cellf, g.dims[2]), zhi = mt_mesh_cellf(zf + r, g.orgf[2], g.inv_cellf, g.dims[2]);
+  const float d2 = (float)(dist * dist);
+  const float band = 1e-3f + (float)(1e-6 * g.coord_max / dist);  // float32 copies are off by <= 6e-8 |coordinate|
+  const float lo2 = d2 * (1.f - band), hi2 = d2 * (1.f + band) + 1e-30f;
+  // rows nearest to the particle first: the common answer (on the surface) is found early
+  const int cy0 = min(max(mt_mesh_cellf(yf, g.orgf[1], g.inv_cellf, g.dims[1]), ylo), yhi);
+  const int cz0 = min(max(mt_mesh_cellf(zf, g.orgf[2], g.inv_cellf, g.dims[2]), zlo), zhi);
+  const int kzn = 2 * max(cz0 - zlo, zhi - cz0), kyn = 2 * max(cy0 - ylo, yhi - cy0);
+  for (int kz = 0; kz <= kzn; ++kz) {
+    const int cz = cz0 + ((kz & 1) ? -((kz + 1) >> 1) : (kz >> 1));  // cz0, cz0-1, cz0+1, ...
+    if (cz < zlo || cz > zhi) continue;
+    for (int ky = 0; ky <= kyn; ++ky) {
+      const int cy = cy0 + ((ky & 1) ? -((ky + 1) >> 1) : (ky >> 1));
+      if (cy < ylo || cy > yhi) continue;
       const int rb = (cz * g.dims[1] + cy) * g.dims[0];
       const int s = __ldg(T.cell_start + rb + xlo), e = __ldg(T.cell_start + rb + xhi + 1);
       for (int p = s; p < e; ++p) {
-        const double dx = __dsub_rn(x, __ldg(T.verts + 3 * (size_t)p));
-        const double dy = __dsub_rn(y, __ldg(T.verts + 3 * (size_t)p + 1));
-        const double dz = __dsub_rn(z, __ldg(T.verts + 3 * (size_t)p + 2));
-        double d2 = __dmul_rn(dx, dx);
-        d2 = __dadd_rn(d2, __dmul_rn(dy, dy));
-        d2 = __dadd_rn(d2, __dmul_rn(dz, dz));
-        if (!(sqrt(d2) > dist)) return true;
+        const float4 v = __ldg(T.verts32 + p);
+        const float dx = xf - v.x, dy = yf - v.y, dz = zf - v.z;
+        const float q2 = dx * dx + dy * dy + dz * dz;
+        if (q2 < lo2) return true;
+        if (q2 <= hi2 && mesh_vertex_within(T, p, x, y, z, dist)) return true;
       }
     }
+  }
   return false;
 }
 #endif

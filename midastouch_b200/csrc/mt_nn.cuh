@@ -32,7 +32,7 @@
 #ifndef MT_NN_BLOCK
 #define MT_NN_BLOCK 256
 #endif
-#define MT_NBR_K 32  // neighbours per key; == warp width (the build kernel keeps one per lane)
+#define MT_NBR_K 64  // neighbours per key (the build kernel keeps two per lane)
 
 struct GridParams {
   float org[3];
@@ -42,7 +42,7 @@ struct GridParams {
 
 #if defined(__CUDACC__)
 struct NNTables {
-  const float4* keys_orig;    // M x 2 float4 (k0..k3 | k4,k5,partner bits,0), original order
+  const float4* keys_orig;    // M x 2 float4 (k0..k3 | k4,k5,partner bits,delta_0), original order
   const float4* keys_sorted;  // M x 2 float4 (k0..k3 | k4,k5,original index bits,0), sorted by grid cell
   const int* cell_start;      // ncells + 1
   const float4* nbr;          // M x MT_NBR_K x 2 float4: (k0..k3 | k4,k5,delta,idx bits)
@@ -109,9 +109,10 @@ MT_HD bool mt_hint_scan(const float q[6], const float kh[6], int hint, const flo
 
 #if defined(__CUDACC__)
 // ------------------------------------------------------------------------- device side
-__device__ __forceinline__ int load_key(const float4* __restrict__ t, int i, float k[6]) {
+__device__ __forceinline__ int load_key(const float4* __restrict__ t, int i, float k[6], float* extra = nullptr) {
   float4 a = __ldg(t + 2 * (size_t)i), b = __ldg(t + 2 * (size_t)i + 1);
   k[0] = a.x, k[1] = a.y, k[2] = a.z, k[3] = a.w, k[4] = b.x, k[5] = b.y;
+  if (extra) *extra = b.w;     // keys_orig: delta_0 = distance to the nearest other key
   return __float_as_int(b.z);  // partner (keys_orig) / original index (keys_sorted)
 }
 
@@ -123,8 +124,8 @@ __device__ __forceinline__ bool nn_hint_search(const NNTables& T, const float q[
     best_i = INT_MAX;
     return false;
   }
-  float kh[6];
-  const int partner = load_key(T.keys_orig, hint, kh);
+  float kh[6], delta0;
+  const int partner = load_key(T.keys_orig, hint, kh, &delta0);
   best_d = mt_key_dist(q, kh);
   best_i = hint;
   if (!(best_d == best_d)) {
@@ -132,13 +133,14 @@ __device__ __forceinline__ bool nn_hint_search(const NNTables& T, const float q[
     return true;
   }
   if (partner >= 0) {  // near angle pi: the pose may have jumped to the other sign of the axis
-    float kp[6];
-    load_key(T.keys_orig, partner, kp);
+    float kp[6], dp0;
+    load_key(T.keys_orig, partner, kp, &dp0);
     const float dp = mt_key_dist(q, kp);
-    if (mt_better(dp, partner, best_d, best_i)) best_d = dp, best_i = partner, hint = partner;
+    if (mt_better(dp, partner, best_d, best_i)) best_d = dp, best_i = partner, hint = partner, delta0 = dp0;
   }
   const float dh = sqrtf(best_d);
   float lim = mt_hint_limit(dh, best_d);
+  if (delta0 > lim) return true;  // nearest other key of the centre is already out of reach
   const float4* __restrict__ L = T.nbr + (size_t)hint * (2 * MT_NBR_K);
 #pragma unroll 1
   for (int j = 0; j < MT_NBR_K; j += 2) {
@@ -176,13 +178,13 @@ __device__ __forceinline__ void warp_best(float& d, int& i) {
 // (2a) all 32 lanes: scan the cells [xlo..xhi] x [ylo..yhi] x [zlo..zhi].  q / best_* are
 // warp-uniform on entry and on exit.
 __device__ void nn_warp_scan_box(const NNTables& T, const float q[6], int xlo, int xhi, int ylo, int yhi, int zlo,
-                                 int zhi, bool prune, float& best_d, int& best_i) {
+                                 int zhi, bool prune, float& best_d, int& best_i, int wid = 0, int nw = 1) {
   const int lane = threadIdx.x & 31;
   const GridParams& g = T.g;
   const int ny = yhi - ylo + 1;
   const int nrows = ny * (zhi - zlo + 1);
   const float slack = 1e-3f * g.h;  // cell edges recomputed in float32 are off by ulps
-  for (int r0 = 0; r0 < nrows; r0 += 32) {
+  for (int r0 = 32 * wid; r0 < nrows; r0 += 32 * nw) {  // row batches are dealt round-robin to the nw warps
     const int r = r0 + lane;
     int s = 0, cnt = 0;
     if (r < nrows) {
@@ -235,97 +237,107 @@ __device__ void nn_warp_scan_box(const NNTables& T, const float q[6], int xlo, i
   }
 }
 
-// (2) all 32 lanes, one query: exact nearest key given an optional candidate (best_i ==
-// INT_MAX: none).  Correctness: once best_d is the distance to a real key the true nearest
-// key lies within r = sqrt(best_d) of q in every coordinate, so all cells overlapping the
-// (slightly inflated) translation box are scanned.
-__device__ __noinline__ int nn_search_warp(const NNTables& T, const float q[6], float best_d, int best_i) {
-  const int lane = threadIdx.x & 31;
+// (2) NW warps, one query: exact nearest key given an optional candidate (best_i == INT_MAX:
+// none).  NW == 1: the 32 lanes of a warp (no block synchronisation); NW > 1: a whole block of
+// NW warps, row batches dealt round-robin, results combined through shared memory (s_bd/s_bi:
+// NW entries each; every thread of the block must call with the same arguments).
+// A box of +-k cells around the query's cell contains every key within k*h of the query in each
+// coordinate, so once sqrt(best_d) <= k*h the candidate is proven.  With a reasonably close
+// candidate the box follows from it directly; otherwise (stale hint after a rotation-vector
+// sign flip, no hint at all) boxes of growing k are scanned until the bound closes -- the work
+// then depends on the true nearest distance, not on the quality of the hint.
+// stats (nullable): [0] += rows visited, [3] = max rows visited by one query.
+template <int NW>
+__device__ __forceinline__ void nn_combine(float& bd, int& bi, float* s_bd, int* s_bi) {
+  if (NW == 1) return;
+  const int w = threadIdx.x >> 5;
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) s_bd[w] = bd, s_bi[w] = bi;
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < NW; ++k)
+    if (mt_better(s_bd[k], s_bi[k], bd, bi)) bd = s_bd[k], bi = s_bi[k];
+}
+
+template <int NW>
+__device__ __noinline__ int nn_search_coop(const NNTables& T, const float q[6], float best_d, int best_i, int* stats,
+                                           float* s_bd, int* s_bi) {
   const GridParams& g = T.g;
   if (!(q[0] == q[0]) || !(q[1] == q[1]) || !(q[2] == q[2]) || !(q[3] == q[3]) || !(q[4] == q[4]) || !(q[5] == q[5]))
     return 0;  // NaN query: np.argmin semantics
+  const int wid = (NW == 1) ? 0 : (threadIdx.x >> 5);
   const int cx = mt_cell_coord(q[0], g.org[0], g.inv_h, g.dims[0]);
   const int cy = mt_cell_coord(q[1], g.org[1], g.inv_h, g.dims[1]);
   const int cz = mt_cell_coord(q[2], g.org[2], g.inv_h, g.dims[2]);
-  if (best_i == INT_MAX || sqrtf(best_d) > 2.f * g.h) {
-    // tighten the bound first: own cell + 26 neighbours, then (queries far off the
-    // surface) a strided sample of the whole codebook
-    nn_warp_scan_box(T, q, max(cx - 1, 0), min(cx + 1, g.dims[0] - 1), max(cy - 1, 0), min(cy + 1, g.dims[1] - 1),
-                     max(cz - 1, 0), min(cz + 1, g.dims[2] - 1), false, best_d, best_i);
-    if (best_i == INT_MAX) {
-      const int stride = max(1, T.M / 256);
-      float ld = FLT_MAX;
-      int li = INT_MAX;
-      for (int p = lane * stride; p < T.M; p += 32 * stride) {
-        float k[6];
-        const int o = load_key(T.keys_sorted, p, k);
-        const float d = mt_key_dist(q, k);
-        if (mt_better(d, o, ld, li)) ld = d, li = o;
-      }
-      warp_best(ld, li);
-      best_d = ld, best_i = li;
+  int rows = 0;
+  if (best_i != INT_MAX && sqrtf(best_d) <= 12.f * g.h) {
+    const float r = sqrtf(best_d) * 1.0001f + 1e-12f;
+    const int ylo = mt_cell_coord(q[1] - r, g.org[1], g.inv_h, g.dims[1]), yhi = mt_cell_coord(q[1] + r, g.org[1], g.inv_h, g.dims[1]);
+    const int zlo = mt_cell_coord(q[2] - r, g.org[2], g.inv_h, g.dims[2]), zhi = mt_cell_coord(q[2] + r, g.org[2], g.inv_h, g.dims[2]);
+    nn_warp_scan_box(T, q, mt_cell_coord(q[0] - r, g.org[0], g.inv_h, g.dims[0]),
+                     mt_cell_coord(q[0] + r, g.org[0], g.inv_h, g.dims[0]), ylo, yhi, zlo, zhi, true, best_d, best_i, wid, NW);
+    nn_combine<NW>(best_d, best_i, s_bd, s_bi);
+    rows = (yhi - ylo + 1) * (zhi - zlo + 1);
+  } else {
+    // a query outside the grid is `gap` away from the clamped cell it is assigned to: keys within
+    // D of it lie within (D - gap)/h cells of that cell in this coordinate
+    const float gx = fmaxf(fmaxf(g.org[0] - q[0], q[0] - (g.org[0] + g.dims[0] * g.h)), 0.f);
+    const float gy = fmaxf(fmaxf(g.org[1] - q[1], q[1] - (g.org[1] + g.dims[1] * g.h)), 0.f);
+    const float gz = fmaxf(fmaxf(g.org[2] - q[2], q[2] - (g.org[2] + g.dims[2] * g.h)), 0.f);
+    const int kmax = max(g.dims[0], max(g.dims[1], g.dims[2]));
+    for (int k = 2;; k += max(1, k >> 1)) {
+      const int ylo = max(cy - k, 0), yhi = min(cy + k, g.dims[1] - 1), zlo = max(cz - k, 0), zhi = min(cz + k, g.dims[2] - 1);
+      nn_warp_scan_box(T, q, max(cx - k, 0), min(cx + k, g.dims[0] - 1), ylo, yhi, zlo, zhi, true, best_d, best_i, wid, NW);
+      nn_combine<NW>(best_d, best_i, s_bd, s_bi);
+      rows += (yhi - ylo + 1) * (zhi - zlo + 1);
+      if (k >= kmax) break;  // whole grid scanned
+      const float need = sqrtf(best_d) * 1.001f, kh = k * g.h;
+      if (best_i != INT_MAX && need <= kh + gx && need <= kh + gy && need <= kh + gz) break;  // bound closed
     }
   }
-  if (best_i == INT_MAX) return 0;  // Inf query: every distance is Inf/NaN
-  const float r = sqrtf(best_d) * 1.0001f + 1e-12f;
-  nn_warp_scan_box(T, q, mt_cell_coord(q[0] - r, g.org[0], g.inv_h, g.dims[0]),
-                   mt_cell_coord(q[0] + r, g.org[0], g.inv_h, g.dims[0]),
-                   mt_cell_coord(q[1] - r, g.org[1], g.inv_h, g.dims[1]),
-                   mt_cell_coord(q[1] + r, g.org[1], g.inv_h, g.dims[1]),
-                   mt_cell_coord(q[2] - r, g.org[2], g.inv_h, g.dims[2]),
-                   mt_cell_coord(q[2] + r, g.org[2], g.inv_h, g.dims[2]), true, best_d, best_i);
-  return best_i;
+  if (stats && threadIdx.x == 0) {
+    atomicAdd(stats, rows);
+    atomicMax(stats + 3, rows);
+  }
+  return best_i == INT_MAX ? 0 : best_i;  // Inf query: every distance is Inf/NaN
 }
 
-// Block-level driver used by every kernel that assigns neighbours: each thread first tries
-// the hint graph; the leftovers are queued in shared memory and served one query per warp.
-// `active` threads pass their key; all threads of the block must call.  Returns the index.
-struct NNQueue {
-  float q[MT_NN_BLOCK][6];
-  float bd[MT_NN_BLOCK];
-  int bi[MT_NN_BLOCK];
-  int n;
-};
+__device__ __forceinline__ int nn_search_warp(const NNTables& T, const float q[6], float best_d, int best_i) {
+  return nn_search_coop<1>(T, q, best_d, best_i, nullptr, nullptr, nullptr);
+}
 
-__device__ __forceinline__ int nn_block_assign(const NNTables& T, NNQueue& Q, bool active, const float q[6], int hint,
-                                               int* fallback_counter) {
-  if (threadIdx.x == 0) Q.n = 0;
-  __syncthreads();
+// Driver used by every kernel that assigns neighbours: each thread first tries the hint
+// graph; the leftovers of a warp are then served one at a time by the whole warp (no block
+// barrier: warps that had no leftovers carry on).  All 32 lanes must call.
+__device__ __forceinline__ int nn_assign(const NNTables& T, bool active, const float q[6], int hint, int* fallback_counter) {
   float bd = FLT_MAX;
-  int bi = INT_MAX, pos = -1;
-  if (active && !nn_hint_search(T, q, hint, bd, bi)) {
-    pos = atomicAdd(&Q.n, 1);
+  int bi = INT_MAX;
+  const bool todo = active && !nn_hint_search(T, q, hint, bd, bi);
+  unsigned m = __ballot_sync(0xffffffffu, todo);
+  if (m && fallback_counter && (threadIdx.x & 31) == 0) atomicAdd(fallback_counter, __popc(m));
+  while (m) {
+    const int src = __ffs(m) - 1;
+    m &= m - 1;
+    float qq[6];
 #pragma unroll
-    for (int k = 0; k < 6; ++k) Q.q[pos][k] = q[k];
-    Q.bd[pos] = bd;
-    Q.bi[pos] = bi;
-  }
-  __syncthreads();
-  const int nq = Q.n;
-  if (nq) {
-    const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    for (int e = warp; e < nq; e += nwarps) {
-      float qq[6];
-#pragma unroll
-      for (int k = 0; k < 6; ++k) qq[k] = Q.q[e][k];
-      const int res = nn_search_warp(T, qq, Q.bd[e], Q.bi[e]);
-      __syncwarp();
-      if ((threadIdx.x & 31) == 0) Q.bi[e] = res;
-    }
-    __syncthreads();
-    if (pos >= 0) bi = Q.bi[pos];
-    if (fallback_counter && threadIdx.x == 0) atomicAdd(fallback_counter, nq);
+    for (int k = 0; k < 6; ++k) qq[k] = __shfl_sync(0xffffffffu, q[k], src);
+    const float sd = __shfl_sync(0xffffffffu, bd, src);
+    const int si = __shfl_sync(0xffffffffu, bi, src);
+    const int res = nn_search_warp(T, qq, sd, si);
+    if ((threadIdx.x & 31) == src) bi = res;
   }
   return bi;
 }
 
-// Build kernel (codebook upload).  One warp per key, lanes hold the running sorted list, the
-// codebook streams through shared memory.
+// Build kernel (codebook upload).  One warp per key; the running sorted list of 64 entries lives
+// in registers, two per lane (slot l in `lo`, slot 32 + l in `hi`); the codebook streams
+// through shared memory.
 //   PARTNER = false: the MT_NBR_K nearest other keys of every key, ascending (distance, index)
 //   PARTNER = true : the key nearest to the antipodal image of every near-pi key -> partner[h]
 template <bool PARTNER>
 __global__ void __launch_bounds__(256) k_build_nbr(const float4* __restrict__ keys, int M, float4* __restrict__ nbr,
                                                    int* __restrict__ partner) {
+  static_assert(MT_NBR_K == 64, "two list slots per lane");
   __shared__ float4 sk[2 * 256];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int h = blockIdx.x * 8 + warp;
@@ -340,8 +352,8 @@ __global__ void __launch_bounds__(256) k_build_nbr(const float4* __restrict__ ke
       for (int k = 0; k < 6; ++k) kh[k] = act ? ka[k] : kh[k];
     }
   }
-  float val = FLT_MAX;  // lane l: l-th smallest squared distance so far
-  int idx = -1;
+  float lo_v = FLT_MAX, hi_v = FLT_MAX;  // squared distances, ascending over (lo[0..31], hi[0..31])
+  int lo_i = -1, hi_i = -1;
   for (int m0 = 0; m0 < M; m0 += 256) {
     const int cnt = min(256, M - m0);
     __syncthreads();
@@ -357,37 +369,62 @@ __global__ void __launch_bounds__(256) k_build_nbr(const float4* __restrict__ ke
         d = mt_key_dist(kh, k);
         if (!(d == d)) d = FLT_MAX;
       }
-      unsigned cand = __ballot_sync(0xffffffffu, d < __shfl_sync(0xffffffffu, val, 31));
+      unsigned cand = __ballot_sync(0xffffffffu, d < __shfl_sync(0xffffffffu, hi_v, 31));
       while (cand) {
         const int src = __ffs(cand) - 1;
         cand &= cand - 1;
         const float cd = __shfl_sync(0xffffffffu, d, src);
-        if (!(cd < __shfl_sync(0xffffffffu, val, 31))) continue;
-        const int pos = __popc(__ballot_sync(0xffffffffu, val <= cd));  // stable: equal distances keep index order
-        const float nv = __shfl_up_sync(0xffffffffu, val, 1);
-        const int ni = __shfl_up_sync(0xffffffffu, idx, 1);
-        if (lane > pos) val = nv, idx = ni;
-        if (lane == pos) val = cd, idx = m0 + s0 + src;
+        if (!(cd < __shfl_sync(0xffffffffu, hi_v, 31))) continue;
+        // stable position: equal distances keep index order
+        const int pos = __popc(__ballot_sync(0xffffffffu, lo_v <= cd)) + __popc(__ballot_sync(0xffffffffu, hi_v <= cd));
+        const float lo31v = __shfl_sync(0xffffffffu, lo_v, 31);
+        const int lo31i = __shfl_sync(0xffffffffu, lo_i, 31);
+        const float lv = __shfl_up_sync(0xffffffffu, lo_v, 1), hv = __shfl_up_sync(0xffffffffu, hi_v, 1);
+        const int li = __shfl_up_sync(0xffffffffu, lo_i, 1), hi2 = __shfl_up_sync(0xffffffffu, hi_i, 1);
+        if (pos < 32) {
+          hi_v = lane ? hv : lo31v, hi_i = lane ? hi2 : lo31i;
+          if (lane > pos) lo_v = lv, lo_i = li;
+          if (lane == pos) lo_v = cd, lo_i = m0 + s0 + src;
+        } else {
+          if (lane > pos - 32) hi_v = hv, hi_i = hi2;
+          if (lane == pos - 32) hi_v = cd, hi_i = m0 + s0 + src;
+        }
       }
     }
   }
   if (h >= M) return;
-  if (PARTNER) {
-    if (lane == 0) partner[h] = act ? idx : -1;
-    return;
+  if constexpr (PARTNER) {
+    if (lane == 0) partner[h] = act ? lo_i : -1;
+  } else {
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int idx = half ? hi_i : lo_i;
+    const float val = half ? hi_v : lo_v;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = make_float4(0.f, 0.f, __int_as_float(0x7f800000), __int_as_float(-1));
+    if (idx >= 0) {
+      a = keys[2 * (size_t)idx];
+      const float4 kb = keys[2 * (size_t)idx + 1];
+      b = make_float4(kb.x, kb.y, sqrtf(val), __int_as_float(idx));
+    }
+    const size_t slot = (size_t)h * MT_NBR_K + 32 * half + lane;
+    nbr[slot * 2] = a;
+    nbr[slot * 2 + 1] = b;
   }
-  float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = make_float4(0.f, 0.f, __int_as_float(0x7f800000), __int_as_float(-1));
-  if (idx >= 0) {
-    a = keys[2 * (size_t)idx];
-    const float4 kb = keys[2 * (size_t)idx + 1];
-    b = make_float4(kb.x, kb.y, sqrtf(val), __int_as_float(idx));
   }
-  nbr[((size_t)h * MT_NBR_K + lane) * 2] = a;
-  nbr[((size_t)h * MT_NBR_K + lane) * 2 + 1] = b;
 }
 
-__global__ void k_set_partner(float4* __restrict__ keys, int M, const int* __restrict__ partner) {
+// keys_orig padding: (partner index bits, delta_0 = distance to the nearest other key)
+__global__ void k_set_partner(float4* __restrict__ keys, int M, const int* __restrict__ partner,
+                              const float4* __restrict__ nbr) {
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
-  if (m < M) keys[2 * (size_t)m + 1].z = __int_as_float(partner[m]);
+  if (m >= M) return;
+  keys[2 * (size_t)m + 1].z = __int_as_float(partner[m]);
+  keys[2 * (size_t)m + 1].w = nbr[(size_t)m * MT_NBR_K * 2 + 1].z;
+}
+
+// rank[m] = position of key m in the cell-sorted order (engine: spatial sort of particles)
+__global__ void k_key_rank(const float4* __restrict__ keys_sorted, int M, int* __restrict__ rank) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < M) rank[__float_as_int(keys_sorted[2 * (size_t)p + 1].z)] = p;
 }
 #endif  // __CUDACC__

@@ -66,14 +66,33 @@ class FilterEngine:
         call("mt_step_local_sum_ptr", self.ctx.h, C.byref(p))
         self._local_sum_ptr = p.value
         self._a = StepArgs()
+        # the codebook query runs on a side stream, concurrently with motion + SE3_NN
+        self.overlap_query = True
+        self._side = torch.cuda.Stream(device=self.dev)
+        self._ev_table = torch.cuda.Event()
+        self._ev_free = torch.cuda.Event()
         self._rng = torch.Generator().manual_seed(self.seed)
 
     # ------------------------------------------------------------------ state in / out
-    def load_particles(self, poses: torch.Tensor, nn_hint: torch.Tensor | None = None):
+    def load_particles(self, poses: torch.Tensor, nn_hint: torch.Tensor | None = None, spatial_sort: bool = False):
+        """poses: (n,4,4) CUDA.  nn_hint: optional codebook index per particle (any valid index is
+        correct; a good one makes the first search cheap).  spatial_sort=True reorders the
+        particles by the grid-cell rank of their codebook match so that neighbouring threads walk
+        neighbouring keys (systematic resampling preserves the order afterwards); the applied
+        permutation is returned (poses[perm] is what the engine holds), else None."""
         require_cuda(poses, "poses")
         n = poses.shape[0]
         if n > self.capacity:
             raise MidasError("load_particles: more particles than capacity")
+        perm = None
+        if spatial_sort:
+            poses = poses.reshape(-1, 4, 4).float().contiguous()
+            idx = self.cb.SE3_NN_idx(poses, hint=None if nn_hint is None else nn_hint.to(torch.int32).contiguous())
+            rank = torch.empty(len(self.cb), dtype=torch.int32, device=self.dev)
+            with torch.cuda.device(self.dev):
+                call("mt_codebook_rank", self.ctx.h, ptr(rank), stream_ptr())
+            perm = torch.sort(rank[idx.long()], stable=True).indices  # one-off, at load time only
+            poses, nn_hint = poses[perm], idx[perm]
         with torch.cuda.device(self.dev):
             call("mt_aos_to_soa", ptr(poses.reshape(-1, 4, 4).float().contiguous()), n, ptr(self.soa[self.cur]), self.capacity, stream_ptr())
         if nn_hint is None:
@@ -84,6 +103,7 @@ class FilterEngine:
         self.n_dev[self.cur].fill_(n)
         if self.n_global is None or self.world == 1:
             self.n_global = n if self.world == 1 else self.n_global
+        return perm
 
     def snap_to_codebook(self):
         """filter.py:159-160: particles.poses = codebook.SE3_NN(particles.poses)[0] (exhaustive NN)."""
@@ -108,7 +128,13 @@ class FilterEngine:
         return self.n
 
     def nn_idx(self) -> torch.Tensor:
-        return self.nn[self.cur][: self.count()]
+        """codebook match of every particle (particles zeroed by the drift test are stored as
+        -(idx+2) inside the engine; decoded here)."""
+        s = self.nn[self.cur][: self.count()]
+        return torch.where(s < -1, -(s + 2), s)
+
+    def pruned_mask(self) -> torch.Tensor:
+        return self.nn[self.cur][: self.count()] < -1
 
     def ancestors(self) -> torch.Tensor:
         return self.anc[: self.count()]
@@ -134,6 +160,7 @@ class FilterEngine:
         a.d_n_in = ptr(self.n_dev[self.cur]) if self.use_n_dev else None
         a.prune_dist = self.pen_max if (self.prune and prune) else 0.0
         a.d_cb_poses = ptr(self.cb.poses) if self.prune else None
+        a.table_ready_event = None
         return a
 
     def step(self, code: torch.Tensor, odom: torch.Tensor, u: float | None = None, tn: torch.Tensor | None = None,
@@ -162,7 +189,17 @@ class FilterEngine:
         a = self._fill(odom16, u, tn, rot, gt_h, softmax, prune)
         with torch.cuda.device(self.dev):
             s = stream_ptr()
-            call("mt_codebook_query", self.ctx.h, ptr(q), dtype_code(q), 0, s)
+            if self.overlap_query:
+                main = torch.cuda.current_stream()
+                self._ev_free.record(main)       # the previous step's readers of the weight table are done
+                self._side.wait_event(self._ev_free)
+                q.record_stream(self._side)
+                call("mt_codebook_query", self.ctx.h, ptr(q), dtype_code(q), 0, self._side.cuda_stream)
+                self._ev_table.record(self._side)
+                a.table_ready_event = self._ev_table.cuda_event
+            else:
+                a.table_ready_event = None
+                call("mt_codebook_query", self.ctx.h, ptr(q), dtype_code(q), 0, s)
             call("mt_step_a", self.ctx.h, C.byref(a), s)
             if self.world > 1:
                 self._allgather_sums()

@@ -9,7 +9,9 @@ tail -40 gpurun_out/pytest_gpu.log
 timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/smoke.log
 tail -3 gpurun_out/smoke.log
 timeout 600 python bench.py --steps 30 --warmup 5 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"
-tail -c 3000 gpurun_out/bench.json; tail -5 gpurun_out/bench.err
+tail -c 3500 gpurun_out/bench.json; tail -5 gpurun_out/bench.err
+timeout 600 python bench.py --steps 30 --warmup 5 --no-sort --no-cpu > gpurun_out/bench_nosort.json 2>> gpurun_out/bench.err; echo "bench nosort rc=$?"
+tail -c 3500 gpurun_out/bench_nosort.json
 if [ "${NCU:-1}" = "1" ]; then
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 3 --warmup 3 --no-cpu > gpurun_out/bench_ncu.log 2>&1

@@ -125,7 +125,7 @@ def _nbr_view(mt, cb, dev):
 
 
 def test_neighbour_graph_matches_host_model(mt, dev, box):
-    """k_build_nbr: every key's 32 nearest other keys, ascending (distance, index), duplicates included."""
+    """k_build_nbr: every key's 64 nearest other keys, ascending (distance, index), duplicates included."""
     cbs = synth.make_codebook(box, M=3000, D=8, seed=5)
     poses = torch.cat([cbs.poses, cbs.poses[:50]])
     cb = mt.tt.tactile_tree(poses, poses, torch.cat([cbs.embeddings, cbs.embeddings[:50]]))
@@ -133,7 +133,7 @@ def test_neighbour_graph_matches_host_model(mt, dev, box):
     keys = cb.logmap_pose.cpu().numpy()
     nbr = _nbr_view(mt, cb, dev)
     M, K = keys.shape[0], nbr.shape[1]
-    assert K == 32
+    assert K == 64
     for h in list(range(0, M, 97)) + [0, 10, 3049, M - 1]:
         d = O.l2_sq_f32(keys, keys[h])
         d[h] = np.inf
@@ -539,6 +539,30 @@ def test_fused_step_all_drifted_reprojects(mt, dev, cb_small, box):
     ref_nn = O.se3_nn(O.r3_se3(cbs.poses), moved)
     assert float((nn != ref_nn).double().mean()) < 2e-3  # float32 key ulps only
     cb.ctx.stats(reset=True)
+
+
+def test_engine_spatial_sort_is_a_permutation(mt, dev, cb_big):
+    """load_particles(spatial_sort=True) only reorders: every per-particle result equals the
+    unsorted engine's result at perm[i]."""
+    cbs, cb = cb_big
+    N = 20000
+    poses, sel, odom, tn, rot, q, gt = _engine_case(mt, dev, cbs, cb, N, seed=31)
+    e0 = mt.eng.FilterEngine(cb, capacity=N)
+    e0.load_particles(poses.to(dev))
+    e0.step(q, odom, u=0.1, tn=tn.to(dev), rot=rot.to(dev), resample=False)
+    e1 = mt.eng.FilterEngine(cb, capacity=N)
+    perm = e1.load_particles(poses.to(dev), spatial_sort=True)
+    assert torch.equal(torch.sort(perm).values.cpu(), torch.arange(N))
+    pc = perm.cpu()
+    e1.step(q, odom, u=0.1, tn=tn[pc].to(dev), rot=rot[pc].to(dev), resample=False)
+    assert torch.equal(e1.poses().cpu(), e0.poses().cpu()[pc])
+    assert torch.equal(e1.nn_idx().cpu(), e0.nn_idx().cpu()[pc])
+    assert torch.allclose(e1.weights().cpu(), e0.weights().cpu()[pc], rtol=1e-12, atol=0)
+    rank = torch.empty(50000, dtype=torch.int32, device=dev)
+    mt.lib.call("mt_codebook_rank", cb.ctx.h, rank.data_ptr(), mt.lib.stream_ptr())
+    assert torch.equal(torch.sort(rank).values.cpu(), torch.arange(50000, dtype=torch.int32))
+    r = rank[e1.nn_idx().long()].cpu()
+    assert float((r[1:] >= r[:-1]).double().mean()) > 0.8  # still (nearly) in rank order after one step
 
 
 def test_fused_step_philox_teacher_forced(mt, dev, cb_small):

@@ -145,7 +145,7 @@ def _nbr_table(keys, K):
     return out
 
 
-@pytest.mark.parametrize("M,K", [(3000, 32), (20, 32), (2, 32)])
+@pytest.mark.parametrize("M,K", [(3000, 64), (3000, 8), (20, 64), (2, 64)])
 def test_hint_graph_search_is_exact(H, M, K):
     """whenever the neighbour-list scan claims a proven answer it equals the exhaustive argmin
     (ties -> lowest index), for good, stale and random hints; duplicates included."""
@@ -171,7 +171,7 @@ def test_hint_graph_search_is_exact(H, M, K):
         assert np.array_equal(idx[proven].astype(np.int64), ref[proven]), kind
         if M - 1 <= K:
             assert proven.all()  # the list holds every other key
-        elif kind != "random":
+        elif kind != "random" and K >= 32:
             assert proven.mean() > 0.9, (kind, proven.mean())
         # unproven queries still carry a real candidate for the grid search
         d_ref = O.l2_sq_f32(keys[idx], q)
