@@ -27,7 +27,8 @@ sys.path.insert(0, ROOT)
 N_PER_GPU = 1_000_000
 M, D = 50_000, 256
 OBJ = "035_power_drill"
-ALGO_BYTES_PER_UPDATE = 208  # SURVEY 8d / DESIGN.md
+ALGO_BYTES_PER_UPDATE = 208  # whole sweep, SURVEY 8d / DESIGN.md
+A_BYTES_PER_UPDATE = 104     # k_step_a: pose 48 R + 48 W, match index 4 R + 4 W
 T_TRAJ = 64
 
 
@@ -89,10 +90,13 @@ def make_assets(seed=3):
 
 
 def run_ours(args):
+    import ctypes as C
+
     import torch.distributed as dist
 
     from midastouch_b200 import synth
-    from midastouch_b200.engine import FilterEngine
+    from midastouch_b200._lib import call
+    from midastouch_b200.engine import FilterEngine, prepare_odom
     from midastouch_b200.tactile_tree import tactile_tree
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -109,15 +113,14 @@ def run_ours(args):
     cap = n + (n // 8 if world > 1 else 0)
     eng = FilterEngine(cb, capacity=cap, sig_t=2e-4, sig_r=0.5, seed=1234, rank=rank, world=world, n_global=n * world,
                        mesh_vertices=obj.vertices, pen_max=0.002)
-    # particles start on codebook poses around the trajectory start (what init + snap produce)
+    # particles start on codebook poses (what init_filter + the SE3_NN snap of filter.py:159-160 produce)
     g = torch.Generator().manual_seed(100 + rank)
     sel = torch.randint(0, M, (n,), generator=g)
     eng.load_particles(cbs.poses.to(dev)[sel.to(dev)], nn_hint=sel.int().to(dev), spatial_sort=not args.no_sort)
-    from midastouch_b200.engine import prepare_odom
 
     odoms = [prepare_odom(torch.inverse(meas[t - 1]) @ meas[t]) for t in range(1, T_TRAJ)]
     gts = [gt[t].float().contiguous() for t in range(T_TRAJ)]
-    # tactile codes: pinned host buffers, one per frame (the step's only per-frame input)
+    # tactile codes: pinned host buffers, one per frame (the step's only per-frame tensor input)
     codes_h = [synth.make_query(cbs, int(sel[t]) if rank == 0 else 0, seed=t).pin_memory() for t in range(T_TRAJ - 1)]
     codes_d = [c.to(dev) for c in codes_h]
     us = torch.rand(4096, generator=torch.Generator().manual_seed(7)).tolist()
@@ -135,29 +138,44 @@ def run_ours(args):
         if host_inputs:
             return eng.rmse.cpu()  # D2H of the step's result (8 bytes)
 
+    def new_events(k):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(k)]
+        for e in ev:
+            e.record()  # materialises the cudaEvent_t handle
+        return ev
+
     for t in range(args.warmup):
         one(t, False)
     sync()
-    # ---- device-resident timing: per-step events, L2 flushed between steps (untimed)
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    # ---- device-resident timing: per-step events, L2 flushed between steps (untimed); the library
+    # records events between the kernels of mt_step_a on the same stream (mt_ctx_set_timing_events)
+    evs = [new_events(6) for _ in range(args.steps)]
+    sync()
     with ClockSampler(local) as clk:
         sync()
         for t in range(args.steps):
             l2flush.zero_()
-            evs[t][0].record()
+            e = evs[t]
+            call("mt_ctx_set_timing_events", eng.ctx.h, (C.c_void_p * 4)(*[x.cuda_event for x in e[1:5]]))
+            e[0].record()
             one(args.warmup + t, False)
-            evs[t][1].record()
+            e[5].record()
         sync()
-    ms = [a.elapsed_time(b) for a, b in evs]
+    call("mt_ctx_set_timing_events", eng.ctx.h, None)
+    ms = [e[0].elapsed_time(e[5]) for e in evs]
+    k_a = sum(e[1].elapsed_time(e[2]) for e in evs) / args.steps
+    k_q = sum(e[2].elapsed_time(e[3]) for e in evs) / args.steps
+    k_w = sum(e[3].elapsed_time(e[4]) for e in evs) / args.steps   # includes any wait for the side-stream query
+    k_b = sum(e[4].elapsed_time(e[5]) for e in evs) / args.steps
     total_ms = torch.tensor([sum(ms)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
     total_ms = float(total_ms.item())
     value = n * world * args.steps / (total_ms * 1e-3)
-
     stats_loop = eng.ctx.stats(reset=True)
-    # ---- kernel-level timing of the two sweep kernels (same stream, CUDA events)
-    a_ms, b_ms, q_ms = kernel_times(eng, codes_d, odoms, us, l2flush, min(args.steps, 20))
+
+    # ---- codebook query kernel alone (it overlaps the motion/NN kernel inside a step)
+    q_ms = query_time(eng, codes_d, l2flush, min(args.steps, 20))
 
     # ---- end to end through the public API: host code + odom in, rmse out, every step
     sync()
@@ -175,26 +193,35 @@ def run_ours(args):
 
     if rank == 0:
         peak, how = peaks()
-        sweep_ms = a_ms + b_ms
-        achieved = ALGO_BYTES_PER_UPDATE * n / (sweep_ms * 1e-3) / 1e9
+        sweep_ms = k_a + k_q + k_w + k_b
+        a_gbs = A_BYTES_PER_UPDATE * n / (k_a * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get("k_step_a", {}).get("dram_bytes_per_launch")
         out = {
             "metric": "particle-updates/sec", "value": value, "unit": "particle-updates/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 poses / f64 weights+prefix",
             "data": "synthetic (seeded stand-ins for YCB-Slide assets; no datasets offline)",
-            "config": {"workload": f"{OBJ} log 3, N=1e6 particles per GPU, fused motion+SE3_NN+weight+systematic-resample step",
+            "config": {"workload": f"{OBJ} log 3, N=1e6 particles per GPU, fused motion+SE3_NN+weight+prune+systematic-resample step",
                        "particles_per_gpu": n, "codebook_M": M, "embedding_D": D, "embedding_dtype": "f64",
                        "noise": "in-kernel Philox4x32-10", "particle_order": "random" if args.no_sort else "sorted by codebook cell at load",
-                       "drift_pruning": "pen_max 2 mm against the 1 mm surface vertex set (density of nontextured.stl[::10])", "l2": "flushed (256 MiB write) before every timed step",
-                       "parallelism": f"particles sharded x{world}"},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": how, "kernel": "k_step_a + k_step_b (particle sweep)",
-                         "algorithmic_bytes_per_launch_pair": ALGO_BYTES_PER_UPDATE * n,
-                         "k_step_a_ms": a_ms, "k_step_b_ms": b_ms, "k_cosine_rows_ms": q_ms,
-                         "codebook_query_gbs": (M * D * 8 + D * 8 + M * 16) / (q_ms * 1e-3) / 1e9},
+                       "drift_pruning": "pen_max 2 mm against the 1 mm surface vertex set (density of nontextured.stl[::10])",
+                       "l2": "flushed (256 MiB write) before every timed step", "parallelism": f"particles sharded x{world}"},
+            "roofline": {"bound": "hbm", "achieved": a_gbs, "peak": peak, "unit": "GB/s", "frac": a_gbs / peak,
+                         "traffic": traffic, "peak_source": how, "kernel": "k_step_a (motion + drift test + hint-graph SE3_NN)",
+                         "algorithmic_bytes_per_launch": A_BYTES_PER_UPDATE * n, "avg_launch_ms": k_a,
+                         "sweep": {"kernels_ms": {"k_step_a": k_a, "k_step_nnq": k_q, "k_step_sums(+query wait)": k_w, "k_step_b": k_b},
+                                   "algorithmic_bytes_per_step": ALGO_BYTES_PER_UPDATE * n,
+                                   "achieved": ALGO_BYTES_PER_UPDATE * n / (sweep_ms * 1e-3) / 1e9,
+                                   "frac": ALGO_BYTES_PER_UPDATE * n / (sweep_ms * 1e-3) / 1e9 / peak},
+                         "codebook_query": {"kernel": "k_cosine_rows<double>", "ms": q_ms, "algorithmic_bytes": M * D * 8 + D * 8 + M * 16,
+                                            "achieved": (M * D * 8 + D * 8 + M * 16) / (q_ms * 1e-3) / 1e9,
+                                            "frac": (M * D * 8 + D * 8 + M * 16) / (q_ms * 1e-3) / 1e9 / peak}},
             "e2e": {"value": e2e, "unit": "particle-updates/s", "h2d_bytes_per_step": D * 8 + 64 + 64 + 4, "d2h_bytes_per_step": 8},
             "gpu_launches": 6 * args.steps, "clocks": clk.summary(),
-            "engine_stats": {"nn_grid_fallbacks_per_step": stats_loop["nn_fallbacks"] / (args.steps + args.warmup),
+            "engine_stats": {"nn_grid_searches_per_step": stats_loop["nn_fallbacks"] / args.steps,
                              "on_surface_last_step": stats_loop["on_surface"], "overflow": stats_loop["overflow"]},
         }
         if world == 1 and not args.no_cpu:
@@ -204,41 +231,22 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def kernel_times(eng, codes_d, odoms, us, l2flush, reps):
-    """average device time of k_cosine_rows, k_step_a, k_step_b inside a live step: L2 flushed once
-    before the step (as in the timed loop), CUDA events on the launching stream between the kernels."""
-    import ctypes as C
-
+def query_time(eng, codes_d, l2flush, reps):
+    """average device time of the codebook query (k_to_f64 + k_cosine_rows) with the L2 flushed first."""
     from midastouch_b200._lib import call, ptr, stream_ptr
     from midastouch_b200.context import dtype_code
 
-    acc = [0.0, 0.0, 0.0]
+    acc = 0.0
     for r in range(reps):
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
-        k = r % len(odoms)
-        a = eng._fill(odoms[k], us[r], None, None, None, True)
-        q = codes_d[k].reshape(-1).contiguous()
-        s = stream_ptr()
+        q = codes_d[r % len(codes_d)].reshape(-1).contiguous()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l2flush.zero_()
-        ev[0].record()
-        call("mt_codebook_query", eng.ctx.h, ptr(q), dtype_code(q), 0, s)
-        ev[1].record()
-        call("mt_step_a", eng.ctx.h, C.byref(a), s)
-        ev[2].record()
-        if eng.world > 1:
-            eng._allgather_sums()
-        ev[3].record()
-        call("mt_step_b", eng.ctx.h, C.byref(a), s)
-        ev[4].record()
-        eng.cur = 1 - eng.cur
-        if eng.world > 1:
-            eng.use_n_dev = True
-        eng.t += 1
+        e0.record()
+        call("mt_codebook_query", eng.ctx.h, ptr(q), dtype_code(q), 0, stream_ptr())
+        e1.record()
         torch.cuda.synchronize()
-        acc[0] += ev[0].elapsed_time(ev[1])
-        acc[1] += ev[1].elapsed_time(ev[2])
-        acc[2] += ev[3].elapsed_time(ev[4])
-    return acc[1] / reps, acc[2] / reps, acc[0] / reps
+        acc += e0.elapsed_time(e1)
+    return acc / reps
 
 
 def cpu_baseline(budget_s=15.0, n=65536, steps=None):

@@ -61,6 +61,9 @@ int mt_codebook_nbr_info(mt_ctx* ctx, const float** d_nbr, int* k);
 /* d_rank[m] = position of codebook row m in the library's spatial (grid-cell) order; sorting
  * particles by the rank of their match keeps neighbouring threads on neighbouring keys. */
 int mt_codebook_rank(mt_ctx* ctx, int32_t* d_rank, void* stream);
+/* instrumentation: four cudaEvent_t (before k_step_a, after it, after k_step_nnq, after
+ * k_step_sums) recorded on the step's stream by every following mt_step_a; NULL switches it off. */
+int mt_ctx_set_timing_events(mt_ctx* ctx, void* const* events4);
 /* status / statistics words of the context (synchronises).  h_out8[MT_STAT_*]; reset != 0
  * clears the cumulative slots (0..4, 7). */
 #define MT_STAT_OVERFLOW 0      /* children did not fit the destination buffer (sharded steps) */

@@ -70,6 +70,7 @@ struct mt_ctx {
   double* d_sim;   // cos(q, E_m)
   double* d_esim;  // exp(cos)
   bool cb_ready;
+  cudaEvent_t timing[4];  // optional: recorded around the kernels of mt_step_a (bench instrumentation)
   // down-sampled mesh vertices for the drift test (mt_mesh.cuh)
   double* d_mesh_verts;
   float4* d_mesh_verts32;
@@ -273,6 +274,12 @@ extern "C" int mt_codebook_rank(mt_ctx* c, int32_t* d_rank, void* stream) {
   if (!d_rank) return set_err(MT_ERR_ARG, "mt_codebook_rank: null output");
   k_key_rank<<<(c->M + 255) / 256, 256, 0, (cudaStream_t)stream>>>(c->d_keys_sorted, c->M, d_rank);
   CK_LAUNCH();
+  return MT_OK;
+}
+
+extern "C" int mt_ctx_set_timing_events(mt_ctx* c, void* const* events4) {
+  if (!c) return set_err(MT_ERR_ARG, "mt_ctx_set_timing_events: null context");
+  for (int k = 0; k < 4; ++k) c->timing[k] = events4 ? (cudaEvent_t)events4[k] : nullptr;
   return MT_OK;
 }
 
@@ -1144,6 +1151,7 @@ __global__ void __launch_bounds__(MT_A_BLOCK, MT_A_MINBLOCKS) k_step_a(StepDev p
     float P[3][4], t[3], r[3], O[3][4], key[6];
     load_pose(p.soa_cur, p.stride, i, P);
     const int hint = nn_index(p.nn_cur[i]);
+    nn_prefetch(T, hint);
     draw_or_load_noise(p.tn, p.rot, i, p.sig_t, p.sig_r, p.seed, p.step, p.first_gid + (uint64_t)i, t, r);
     apply_motion(P, p.odom, t, r, O);
     store_pose(p.soa_cur, p.stride, i, O);
@@ -1492,13 +1500,17 @@ extern "C" int mt_step_a(mt_ctx* c, const mt_step_args* a, void* stream) {
   if (a->gt && !a->d_rmse2) return set_err(MT_ERR_ARG, "mt_step_a: gt without rmse output");
   if (a->prune_dist > 0.0 && !c->mesh_ready) return set_err(MT_ERR_STATE, "mt_step_a: prune_dist given but no mesh uploaded");
   cudaStream_t st = (cudaStream_t)stream;
+  if (c->timing[0]) CK(cudaEventRecord(c->timing[0], st));
   k_step_a<<<(unsigned)((a->n + MT_A_BLOCK - 1) / MT_A_BLOCK), MT_A_BLOCK, 0, st>>>(d, tables_of(c), mesh_of(c));
   CK_LAUNCH();
+  if (c->timing[1]) CK(cudaEventRecord(c->timing[1], st));
   k_step_nnq<<<c->sm_count * 4, 256, 0, st>>>(d, tables_of(c), mesh_of(c));
   CK_LAUNCH();
+  if (c->timing[2]) CK(cudaEventRecord(c->timing[2], st));
   if (a->table_ready_event) CK(cudaStreamWaitEvent(st, (cudaEvent_t)a->table_ready_event, 0));
   k_step_sums<<<d.nchunks, MT_CHUNK, 0, st>>>(d);
   CK_LAUNCH();
+  if (c->timing[3]) CK(cudaEventRecord(c->timing[3], st));
   return MT_OK;
 }
 

@@ -116,6 +116,18 @@ __device__ __forceinline__ int load_key(const float4* __restrict__ t, int i, flo
   return __float_as_int(b.z);  // partner (keys_orig) / original index (keys_sorted)
 }
 
+// Issue as soon as the hint is known (kernel A does it before the motion arithmetic): the
+// search below is a chain of dependent reads -- key of the hint, then its neighbour list -- and
+// these prefetches turn it into cache hits.
+__device__ __forceinline__ void nn_prefetch(const NNTables& T, int hint) {
+  if (hint < 0 || hint >= T.M) return;
+  const float4* L = T.nbr + (size_t)hint * (2 * MT_NBR_K);
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(T.keys_orig + 2 * (size_t)hint));
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(L));
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(L + 8));
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(L + 16));
+}
+
 // (1) one thread per query.  false -> needs the grid search (best_* = best so far, or
 // FLT_MAX / INT_MAX when there was no usable hint).
 __device__ __forceinline__ bool nn_hint_search(const NNTables& T, const float q[6], int hint, float& best_d, int& best_i) {

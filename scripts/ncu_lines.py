@@ -13,10 +13,12 @@ subprocess.check_call(["cuobjdump", "-xelf", "all", so], cwd=tmp, stdout=subproc
 cubin = [os.path.join(tmp, f) for f in os.listdir(tmp) if f.endswith(".cubin")][0]
 dis = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout.splitlines()
 # collect (line info) per instruction of the kernel, in order
-lines, cur, on = [], None, False
+sections, cur, on = {}, None, None
 for l in dis:
     if l.startswith("//--------------------- .text."):
-        on = ksub in l
+        on = l if ksub in l else None
+        if on:
+            sections[on] = []
         continue
     if not on:
         continue
@@ -25,7 +27,7 @@ for l in dis:
         cur = (os.path.basename(m.group(1)), int(m.group(2)), "inlined" in m.group(3))
         continue
     if re.match(r"\s+/\*[0-9a-f]{4,}\*/", l):
-        lines.append(cur)
+        sections[on].append(cur)
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 # first kernel instance only
@@ -35,7 +37,9 @@ end = hdr_i[1] - 1 if len(hdr_i) > 1 else len(rows)
 hdr = rows[start]
 body = [r for r in rows[start + 1:end] if r and r[0].startswith("0x")]
 ci = {h: i for i, h in enumerate(hdr)}
-assert len(body) == len(lines), (len(body), len(lines))
+cands = [v for v in sections.values() if len(v) == len(body)]
+assert cands, (len(body), {k[:60]: len(v) for k, v in sections.items()})
+lines = cands[0]
 agg = collections.defaultdict(lambda: [0, 0, 0])
 tot = [0, 0]
 for r, li in zip(body, lines):

@@ -76,4 +76,23 @@ void h_hint_scan(const float* keys, long long M, const float* nbr, int K, const 
   }
 }
 int h_cell_coord(float x, float org, float inv_h, int dim) { return mt_cell_coord(x, org, inv_h, dim); }
+// slot ownership of one shard (the arithmetic of k_step_b for rank r of a sharded step): this
+// shard holds weights w[0..n) whose CDF interval is [A, A + sum(w)) of the global total S over N
+// slots.  anc_local[k] = local parent of the shard's k-th child; returns the number of children
+// and *slot_base = global index of its first slot.
+long long h_shard_children(const double* w, long long n, double A, double S, long long N, float u, long long* anc_local,
+                           long long* slot_base) {
+  const double dN = (double)N, off = (double)(u / (float)N);
+  const long long base = mt_count_below(A / S, N, dN, off);
+  long long prev = base;
+  double run = 0.0;
+  for (long long i = 0; i < n; ++i) {
+    run += w[i];
+    long long cnt = mt_count_below((A + run) / S, N, dN, off);
+    for (long long s = prev; s < cnt; ++s) anc_local[s - base] = i;
+    if (cnt > prev) prev = cnt;
+  }
+  *slot_base = base;
+  return prev - base;
+}
 }
