@@ -104,6 +104,9 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # NCCL prints its version banner on stdout: keep fd 1 clean for the one JSON line
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     obj, cbs, gt, meas = make_assets()
@@ -226,6 +229,8 @@ def run_ours(args):
         }
         if world == 1 and not args.no_cpu:
             out["cpu_baseline"] = cpu_baseline(budget_s=15.0)
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -203,6 +203,28 @@ int mt_step_b(mt_ctx* ctx, const mt_step_args* a, void* stream);
 /* normalised float64 weights of the current particles (after mt_step_a) */
 int mt_step_weights(mt_ctx* ctx, const mt_step_args* a, double* d_w, void* stream);
 
+/* ---- TCN: tactile code network forward (contrib/tcn_minkloc/{tcn,minkloc,minkfpn}.py) ------- */
+/* MinkLoc3D (sparse 3-D FPN + GeM) for the shipped topology (config/tcn/default.yaml): conv0 k5,
+ * three stride-2 stages with one BasicBlock each, one top-down block, GeM, L2 normalisation.
+ * Parameters are passed in MinkowskiEngine's layout: kernels (kvol, cin, cout) float32 with
+ * offset index x-fastest; BatchNorm as (weight, bias, running_mean, running_var).
+ * conv ids: 0 conv0 | 1+s convs[s] | 4+2s, 5+2s blocks[s].conv1/conv2 | 10+s blocks[s].downsample
+ *           | 13 conv1x1[0] | 14 tconvs[0] | 15 conv1x1[1]
+ * bn ids:   0 bn0 | 1+s bn[s] | 4+2s, 5+2s blocks[s].norm1/norm2 | 10+s blocks[s].downsample.1 */
+typedef struct mt_tcn mt_tcn;
+int mt_tcn_create(int device, int max_points, int max_batch, mt_tcn** out);
+int mt_tcn_destroy(mt_tcn* t);
+int mt_tcn_set_conv(mt_tcn* t, int conv_id, const float* h_kernel, int kvol, int cin, int cout);
+int mt_tcn_set_bn(mt_tcn* t, int bn_id, const float* h_weight, const float* h_bias, const float* h_mean, const float* h_var,
+                  int c, float eps);
+int mt_tcn_set_gem(mt_tcn* t, float p, float eps);
+/* d_keys: n sorted unique 64-bit coordinates of the quantised clouds of `batch` frames
+ * (batch << 54 | (x + 2^17) << 36 | (y + 2^17) << 18 | (z + 2^17); ME.utils.sparse_quantize +
+ * batched_coordinates, tcn.py:124-131).  d_out: (batch, feature) float64 descriptors, L2-normalised
+ * when normalize != 0 (tcn.py:138-148).  d_counts (nullable): active points per level (4 ints). */
+int mt_tcn_forward(mt_tcn* t, const unsigned long long* d_keys, int n, int batch, int normalize, double* d_out,
+                   int* d_counts, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

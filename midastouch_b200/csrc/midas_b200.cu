@@ -1584,3 +1584,6 @@ extern "C" int mt_resample_systematic(mt_ctx* c, const double* d_w, long long n,
   if (d_status) CK(cudaMemcpyAsync(d_status, c->d_flags + 1, sizeof(int), cudaMemcpyDeviceToDevice, st));
   return MT_OK;
 }
+
+// ------------------------------------------------------------------------- tactile code network
+#include "mt_tcn.cuh"
