@@ -203,6 +203,18 @@ int mt_step_b(mt_ctx* ctx, const mt_step_args* a, void* stream);
 /* normalised float64 weights of the current particles (after mt_step_a) */
 int mt_step_weights(mt_ctx* ctx, const mt_step_args* a, double* d_w, void* stream);
 
+/* ---- get_cluster_centers(method="quat_avg") (particle_filter.py:153-206, pose.py:112-147) ---- */
+/* d_poses (n,4,4) float32, d_weights (n,) float64 (cast to float32 like the reference), d_labels (n,)
+ * int32 cluster ids 0..K-1 (negative = ignored).  d_centers (K,4,4), d_stds (K,3) float32. */
+int mt_cluster_centers(mt_ctx* ctx, const float* d_poses, const double* d_weights, const int32_t* d_labels, long long n, int K,
+                       float* d_centers, float* d_stds, void* stream);
+/* ---- annealing (particle_filter.py:405-447): order statistics of the weights ---------------- */
+/* the k smallest (largest != 0: largest) of n float64 weights: d_sel (k,) their indices in ascending
+ * index order, d_keep (n-k,) the remaining indices in ascending order (either may be NULL).  Ties at
+ * the threshold are resolved towards the lowest index. */
+int mt_select_k(mt_ctx* ctx, const double* d_w, long long n, long long k, int largest, int32_t* d_sel, int32_t* d_keep,
+                void* stream);
+
 /* ---- TCN: tactile code network forward (contrib/tcn_minkloc/{tcn,minkloc,minkfpn}.py) ------- */
 /* MinkLoc3D (sparse 3-D FPN + GeM) for the shipped topology (config/tcn/default.yaml): conv0 k5,
  * three stride-2 stages with one BasicBlock each, one top-down block, GeM, L2 normalisation.

@@ -11,7 +11,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MIDAS_B200_LIB") or os.path.join(_HERE, "libmidas_b200.so")  # override: A/B builds only
 SOURCES = [os.path.join(_HERE, "csrc", "midas_b200.cu")]
-HEADERS = [os.path.join(_HERE, "csrc", "mt_math.cuh"), os.path.join(_HERE, "csrc", "mt_nn.cuh"), os.path.join(_HERE, "csrc", "mt_mesh.cuh"), os.path.join(_HERE, "csrc", "mt_tcn.cuh"), os.path.join(_HERE, "..", "include", "midas_b200.h")]
+HEADERS = [os.path.join(_HERE, "csrc", "mt_math.cuh"), os.path.join(_HERE, "csrc", "mt_nn.cuh"), os.path.join(_HERE, "csrc", "mt_mesh.cuh"), os.path.join(_HERE, "csrc", "mt_tcn.cuh"), os.path.join(_HERE, "csrc", "mt_cluster.cuh"), os.path.join(_HERE, "..", "include", "midas_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -77,6 +77,8 @@ _SIGS = {
     "mt_resample_systematic": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mt_gather_soa": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_void_p]),
     "mt_gather_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]),
+    "mt_cluster_centers": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mt_select_k": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mt_tcn_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "mt_tcn_destroy": (C.c_int, [C.c_void_p]),
     "mt_tcn_set_conv": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int]),

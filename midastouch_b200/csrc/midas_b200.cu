@@ -70,6 +70,8 @@ struct mt_ctx {
   double* d_sim;   // cos(q, E_m)
   double* d_esim;  // exp(cos)
   bool cb_ready;
+  void* d_scratch;       // grow-on-demand scratch of the cluster / selection entry points
+  size_t scratch_bytes;
   cudaEvent_t timing[4];  // optional: recorded around the kernels of mt_step_a (bench instrumentation)
   // down-sampled mesh vertices for the drift test (mt_mesh.cuh)
   double* d_mesh_verts;
@@ -155,6 +157,7 @@ extern "C" int mt_ctx_destroy(mt_ctx* c) {
   cudaFree(c->d_wrm);
   cudaFree(c->d_wcnt);
   cudaFree(c->d_queue);
+  cudaFree(c->d_scratch);
   cudaFree(c->d_qctl);
   cudaFree(c->d_scal);
   cudaFree(c->d_q64);
@@ -1582,6 +1585,72 @@ extern "C" int mt_resample_systematic(mt_ctx* c, const double* d_w, long long n,
     k_step_b<false, false><<<d.nchunks, MT_CHUNK, 0, st>>>(d);
   CK_LAUNCH();
   if (d_status) CK(cudaMemcpyAsync(d_status, c->d_flags + 1, sizeof(int), cudaMemcpyDeviceToDevice, st));
+  return MT_OK;
+}
+
+// ------------------------------------------------------------------------- cluster centres / annealing
+#include "mt_cluster.cuh"
+
+static int ensure_scratch(mt_ctx* c, size_t bytes) {
+  if (bytes <= c->scratch_bytes) return MT_OK;
+  cudaFree(c->d_scratch);
+  c->d_scratch = nullptr, c->scratch_bytes = 0;
+  CK(cudaMalloc(&c->d_scratch, bytes));
+  c->scratch_bytes = bytes;
+  return MT_OK;
+}
+
+extern "C" int mt_cluster_centers(mt_ctx* c, const float* d_poses, const double* d_weights, const int32_t* d_labels, long long n,
+                                  int K, float* d_centers, float* d_stds, void* stream) {
+  if (!c || !d_poses || !d_weights || !d_labels || !d_centers || !d_stds || n <= 0 || K <= 0 || K > MT_MAX_CLUSTERS)
+    return set_err(MT_ERR_ARG, "mt_cluster_centers: bad argument (1 <= K <= 16)");
+  CK(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nb = (int)((n + 255) / 256);
+  const size_t mom = sizeof(double) * (size_t)nb * K * MT_CL_VALS, mm = sizeof(float) * (size_t)nb * K * 2;
+  int r = ensure_scratch(c, mom + mm + sizeof(int) * MT_MAX_CLUSTERS + 64);
+  if (r) return r;
+  double* part = (double*)c->d_scratch;
+  float* mpart = (float*)((char*)c->d_scratch + mom);
+  int* uniform = (int*)((char*)c->d_scratch + mom + mm);
+  k_cluster_minmax<<<nb, 256, 0, st>>>(d_weights, d_labels, n, K, mpart);
+  CK_LAUNCH();
+  k_cluster_minmax_final<<<K, 256, 0, st>>>(mpart, nb, K, uniform);
+  CK_LAUNCH();
+  k_cluster_moments<<<nb, 256, 0, st>>>((const float4*)d_poses, d_weights, d_labels, n, K, uniform, part);
+  CK_LAUNCH();
+  k_cluster_final<<<K, 256, 0, st>>>(part, nb, K, d_centers, d_stds);
+  CK_LAUNCH();
+  return MT_OK;
+}
+
+extern "C" int mt_select_k(mt_ctx* c, const double* d_w, long long n, long long k, int largest, int32_t* d_sel, int32_t* d_keep,
+                           void* stream) {
+  if (!c || !d_w || n <= 0 || k <= 0 || k > n) return set_err(MT_ERR_ARG, "mt_select_k: bad argument (1 <= k <= n)");
+  CK(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nb = (int)((n + 255) / 256);
+  int r = ensure_scratch(c, sizeof(int) * 2 * (size_t)nb + 256 * sizeof(unsigned int) + 64);
+  if (r) return r;
+  unsigned long long* state = (unsigned long long*)c->d_scratch;
+  unsigned int* hist = (unsigned int*)((char*)c->d_scratch + 32);
+  int* blk = (int*)((char*)c->d_scratch + 32 + 256 * sizeof(unsigned int));
+  const unsigned long long init[2] = {0ull, (unsigned long long)(k - 1)};
+  CK(cudaMemcpyAsync(state, init, sizeof(init), cudaMemcpyHostToDevice, st));
+  CK(cudaMemsetAsync(hist, 0, 256 * sizeof(unsigned int), st));
+  const int hgrid = std::min(nb, c->sm_count * 8);
+  for (int pass = 0; pass < 8; ++pass) {
+    k_select_hist<<<hgrid, 256, 0, st>>>(d_w, n, largest, pass, state, hist);
+    CK_LAUNCH();
+    k_select_pick<<<1, 32, 0, st>>>(hist, pass, state);
+    CK_LAUNCH();
+  }
+  k_select_count<<<nb, 256, 0, st>>>(d_w, n, largest, state, blk);
+  CK_LAUNCH();
+  k_select_scan<<<1, 1024, 0, st>>>(blk, nb);
+  CK_LAUNCH();
+  k_select_scatter<<<nb, 256, 0, st>>>(d_w, n, largest, state, blk, d_sel, d_keep);
+  CK_LAUNCH();
   return MT_OK;
 }
 

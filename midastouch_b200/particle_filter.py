@@ -223,10 +223,69 @@ class particle_filter:
         return particles, (nvalid == 0).reshape(())
 
     def annealing(self, _particles: Particles, var: float, floor: int = 1000) -> Particles:
-        raise MidasError("annealing: CUDA compaction kernel not built yet (SURVEY 8f rank 2)")
+        """particle_filter.py:405-447: shrink / grow the particle set with the cluster variance.  The
+        k lowest (highest) weights are found by the CUDA radix select (``mt_select_k``) instead of
+        ``torch.topk``; survivors keep their order, duplicates are appended (in index order)."""
+        particles = copy.copy(_particles)
+        var = var if torch.is_tensor(var) else torch.tensor(float(var))
+        if torch.isinf(self.particle_var).any():
+            self.particle_var = var
+            self.init_particles = len(particles.weights)
+            return particles
+        if float(var) == 0.0:
+            return particles
+        ratio = float(var) / float(self.particle_var)
+        self.particle_var = var
+        n_particles = len(particles.weights)
+        N = particles.poses.shape[0]
+        if ratio < 1:
+            num = min(int((1.0 - ratio) * N), abs(n_particles - floor), n_particles // 3)
+            if not num:
+                return particles
+            keep = self._select(particles.weights, num, largest=False)[1]
+            particles.poses, particles.weights, particles.labels = particles.poses[keep], particles.weights[keep], particles.labels[keep]
+        elif ratio > 1:
+            num = min(int((ratio - 1.0) * N), n_particles // 3)
+            if num + n_particles > self.init_particles or not num:
+                return particles
+            add = self._select(particles.weights, num, largest=True)[0]
+            particles.add(particles.poses[add, :], particles.weights[add], particles.labels[add])
+        return particles
+
+    def _select(self, weights: torch.Tensor, k: int, largest: bool):
+        require_cuda(weights, "particle weights")
+        w = weights.to(torch.float64).contiguous()
+        n = w.shape[0]
+        ctx = _ctx_for(w.device, n)
+        sel = torch.empty(k, dtype=torch.int32, device=w.device)
+        keep = torch.empty(n - k, dtype=torch.int32, device=w.device)
+        with torch.cuda.device(w.device):
+            call("mt_select_k", ctx.h, ptr(w), n, k, int(largest), ptr(sel), ptr(keep), stream_ptr())
+        return sel.long(), keep.long()
 
     def get_cluster_centers(self, _particles: Particles, method: str = "logmap"):
-        raise MidasError("get_cluster_centers: not built yet (SURVEY 8f rank 2)")
+        """particle_filter.py:153-206 -> (cluster_poses (K,4,4), cluster_stds (K,3)) float32.  The loop
+        calls it with method="quat_avg" (filter.py:184-186); the theseus Lie-algebra average
+        ("logmap") is not implemented."""
+        if method != "quat_avg":
+            raise MidasError("get_cluster_centers: only method='quat_avg' (what filter.py uses) is implemented")
+        particles = copy.copy(_particles)
+        poses = particles.poses.reshape(-1, 4, 4)
+        require_cuda(poses, "particle poses")
+        poses = poses.float().contiguous()
+        n = poses.shape[0]
+        uniq, inv = torch.unique(particles.labels, return_inverse=True)  # the reference's torch.unique (164)
+        K = int(uniq.shape[0])
+        if K > 16:
+            raise MidasError("get_cluster_centers: more than 16 clusters")
+        ctx = _ctx_for(poses.device, n)
+        w = particles.weights.to(torch.float64).contiguous()
+        lab = inv.to(torch.int32).contiguous()
+        centers = torch.empty((K, 4, 4), dtype=torch.float32, device=poses.device)
+        stds = torch.empty((K, 3), dtype=torch.float32, device=poses.device)
+        with torch.cuda.device(poses.device):
+            call("mt_cluster_centers", ctx.h, ptr(poses), ptr(w), ptr(lab), n, K, ptr(centers), ptr(stds), stream_ptr())
+        return centers, stds
 
     def cluster_particles(self, _particles: Particles, method: str = "euclidean", eps: float = 1e-2) -> Particles:
         raise MidasError("cluster_particles: DBSCAN is out of scope (SURVEY 8f rank 4)")

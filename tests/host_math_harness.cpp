@@ -3,6 +3,7 @@
 // check it against the oracle.  Never loaded by the product.
 #include "../midastouch_b200/csrc/mt_math.cuh"
 #include "../midastouch_b200/csrc/mt_nn.cuh"
+#include "../midastouch_b200/csrc/mt_cluster.cuh"
 
 extern "C" {
 void h_se3_keys(const float* aos, long long n, float* keys) {
@@ -94,5 +95,13 @@ long long h_shard_children(const double* w, long long n, double A, double S, lon
   }
   *slot_base = base;
   return prev - base;
+}
+void h_so3_to_quat(const float* aos, long long n, float* out4) {
+  for (long long i = 0; i < n; ++i) {
+    float P[3][4];
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 4; ++c) P[r][c] = aos[16 * i + 4 * r + c];
+    mt_so3_to_quat(P, out4 + 4 * i);
+  }
 }
 }

@@ -432,6 +432,88 @@ def test_prune_boundary_vs_oracle(mt, dev, box):
     assert 0.2 < float((w_ref == 0).double().mean()) < 0.8
 
 
+# ----------------------------------------------------------------------------- annealing / cluster centres
+def test_annealing_vs_reference_golden(mt, dev, golden, box):
+    g = golden("annealing")
+    gm = golden("motion")
+    pf = mt.pf.particle_filter(synth_cfg(), box.vertices)
+    N = g["w_in"].shape[0]
+    poses = T(gm["moved"])[:N].to(dev)
+    w = T(g["w_in"]).to(dev)
+    labels = torch.arange(N, dtype=torch.float32, device=dev)
+    p0 = pf.annealing(mt.pf.Particles(poses, w.clone(), labels), torch.tensor(1e-3), floor=100)  # first call: records var
+    assert len(p0) == N and pf.init_particles == N
+    p1 = pf.annealing(p0, torch.tensor(0.8e-3), floor=100)  # ratio 0.8 -> remove the lowest 20 %
+    assert len(p1) == int(g["remove_n"])
+    assert torch.equal(p1.weights.cpu(), T(g["remove_w"]))  # survivors keep their order (torch_delete)
+    assert torch.equal(p1.poses, poses[p1.labels.long()])
+    pf.particle_var = torch.tensor(1e-3)
+    pf.init_particles = 2 * N
+    p2 = pf.annealing(mt.pf.Particles(poses, w.clone(), labels), torch.tensor(1.2e-3), floor=100)  # add the top 20 %
+    assert len(p2) == int(g["add_n"])
+    assert torch.equal(p2.weights[:N].cpu(), T(g["w_in"]))
+    assert torch.equal(torch.sort(p2.weights[N:].cpu()).values, torch.sort(T(g["add_w"])[N:]).values)
+    assert torch.equal(p2.poses[N:], poses[p2.labels[N:].long()])
+    # var == 0 and growth beyond init_particles are no-ops (particle_filter.py:417-419, 438-439)
+    assert len(pf.annealing(p2, torch.tensor(0.0))) == len(p2)
+    pf.init_particles = N
+    pf.particle_var = torch.tensor(1e-3)
+    assert len(pf.annealing(mt.pf.Particles(poses, w.clone(), labels), torch.tensor(2e-3))) == N
+
+
+@pytest.mark.parametrize("n,k", [(1, 1), (1000, 1), (1000, 999), (65536, 20000), (1000003, 333334)])
+def test_select_k_vs_sort(mt, dev, n, k):
+    g = torch.Generator().manual_seed(n + k)
+    w = torch.rand(n, dtype=torch.float64, generator=g)
+    w[::5] = w[0]          # heavy ties
+    w[1::97] = 0.0
+    if n > 10:
+        w[7] = -1.5        # negative and special values order correctly
+        w[9] = float("inf")
+    ctx = mt.pf._ctx_for(dev, n)
+    wd = w.to(dev)
+    for largest in (0, 1):
+        sel = torch.empty(k, dtype=torch.int32, device=dev)
+        keep = torch.empty(n - k, dtype=torch.int32, device=dev)
+        mt.lib.call("mt_select_k", ctx.h, wd.data_ptr(), n, k, largest, sel.data_ptr(), keep.data_ptr(), mt.lib.stream_ptr())
+        s, kp = sel.cpu().long(), keep.cpu().long()
+        assert bool((s[1:] > s[:-1]).all()) and bool((kp[1:] > kp[:-1]).all())
+        assert torch.equal(torch.sort(torch.cat([s, kp])).values, torch.arange(n))
+        ref = torch.sort(w, descending=bool(largest)).values[:k]
+        assert torch.equal(torch.sort(w[s], descending=bool(largest)).values, ref)
+        # ties at the threshold go to the lowest indices
+        thr = ref[-1]
+        eq_sel = s[w[s] == thr]
+        eq_all = (w == thr).nonzero().flatten()
+        assert torch.equal(eq_sel, eq_all[: len(eq_sel)])
+
+
+def test_cluster_centers_vs_oracle(mt, dev, box):
+    pf = mt.pf.particle_filter(synth_cfg(), box.vertices)
+    cbs = synth.make_codebook(box, M=3000, D=8, seed=9)
+    g = torch.Generator().manual_seed(2)
+    # three tight clusters around codebook poses + noise, labels -1/0/1 like DBSCAN output
+    centres = cbs.poses[[10, 500, 2000]]
+    n = 6000
+    lab = torch.randint(0, 3, (n,), generator=g)
+    tn = 1e-3 * torch.randn(n, 3, generator=g)
+    rot = 3.0 * torch.randn(n, 3, generator=g)
+    poses = centres[lab] @ O.noisy_odom(torch.eye(4), tn, rot)
+    w = torch.rand(n, dtype=torch.float64, generator=g) + 0.1
+    labels = (lab - 1).float()
+    cp, cs = pf.get_cluster_centers(mt.pf.Particles(poses.to(dev), w.to(dev), labels.to(dev)), method="quat_avg")
+    rp, rs = O.cluster_centers(poses, w, labels)
+    assert cp.shape == (3, 4, 4) and cs.shape == (3, 3)
+    assert torch.allclose(cp.cpu(), rp, rtol=1e-4, atol=2e-6), (cp.cpu() - rp).abs().max()
+    assert torch.allclose(cs.cpu(), rs, rtol=1e-3, atol=1e-7), (cs.cpu() - rs).abs().max()
+    # constant weights -> uniform (particle_filter.py:178-184); single default label (zeros)
+    cp1, cs1 = pf.get_cluster_centers(mt.pf.Particles(poses[lab == 0].to(dev)), method="quat_avg")
+    rp1, rs1 = O.cluster_centers(poses[lab == 0], torch.ones(int((lab == 0).sum())), torch.zeros(int((lab == 0).sum())))
+    assert torch.allclose(cp1.cpu(), rp1, rtol=1e-4, atol=2e-6) and torch.allclose(cs1.cpu(), rs1, rtol=1e-3, atol=1e-7)
+    RtR = cp[:, :3, :3].transpose(1, 2) @ cp[:, :3, :3]
+    assert float((RtR.cpu() - torch.eye(3)).abs().max()) < 1e-5
+
+
 # ----------------------------------------------------------------------------- fused step
 def _engine_case(mt, dev, cbs, cb, N, seed, softmax=True):
     g = torch.Generator().manual_seed(seed)

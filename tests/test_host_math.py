@@ -21,7 +21,7 @@ def H():
     os.makedirs(build, exist_ok=True)
     so = os.path.join(build, "host_math.so")
     src = os.path.join(HERE, "host_math_harness.cpp")
-    hdrs = [os.path.join(HERE, "..", "midastouch_b200", "csrc", h) for h in ("mt_math.cuh", "mt_nn.cuh")]
+    hdrs = [os.path.join(HERE, "..", "midastouch_b200", "csrc", h) for h in ("mt_math.cuh", "mt_nn.cuh", "mt_cluster.cuh")]
     if not os.path.exists(so) or os.path.getmtime(so) < max([os.path.getmtime(src)] + [os.path.getmtime(h) for h in hdrs]):
         subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-x", "c++", "-shared", "-fPIC", "-o", so, src])
     return ctypes.CDLL(so)
@@ -176,3 +176,19 @@ def test_hint_graph_search_is_exact(H, M, K):
         # unproven queries still carry a real candidate for the grid search
         d_ref = O.l2_sq_f32(keys[idx], q)
         assert np.array_equal(d_ref, dist)
+
+
+def test_so3_to_quaternion_matches_oracle(H):
+    from scipy.spatial.transform import Rotation as R
+
+    rng = np.random.default_rng(4)
+    ax = rng.normal(size=(600, 3))
+    ax /= np.linalg.norm(ax, axis=1, keepdims=True)
+    ang = np.concatenate([rng.uniform(0, np.pi, 400), np.full(100, np.pi - 1e-4), np.full(100, 1e-4)])
+    T = np.zeros((600, 4, 4), np.float32)
+    T[:, :3, :3] = R.from_rotvec(ax * ang[:, None]).as_matrix()
+    T[:, 3, 3] = 1
+    q = np.zeros((600, 4), np.float32)
+    H.h_so3_to_quat(P(T), ctypes.c_longlong(600), P(q))
+    ref = O.so3_to_quaternion(torch.from_numpy(T[:, :3, :3].copy())).numpy()
+    assert np.abs(q - ref).max() < 2e-6
