@@ -50,7 +50,8 @@ int mt_ctx_destroy(mt_ctx* ctx);
 /* h_keys: (M,6) float32 R3_SE3 keys on the HOST (a uniform grid over the translation
  * part replaces the nanoflann tree); d_emb: (M,D) embeddings on the device in emb_dtype
  * (the reference stores float64, build_codebook.py:72-74).  The library keeps the pointer,
- * it does not copy the embeddings. */
+ * it does not copy the embeddings; their row norms are cached by the first query, so call
+ * mt_codebook_upload again if the embeddings change. */
 int mt_codebook_upload(mt_ctx* ctx, const float* h_keys, const void* d_emb, int emb_dtype);
 /* key grid introspection (tests): cell size, dims[3], number of occupied cells */
 int mt_codebook_grid_info(mt_ctx* ctx, float* h, int dims[3], int* occupied);
@@ -192,6 +193,10 @@ typedef struct mt_step_args {
    * kernel), so that mt_codebook_query may run concurrently on another stream with the motion /
    * SE3_NN kernels.  NULL: the query was enqueued on `stream` before mt_step_a. */
   void* table_ready_event;
+  /* != 0 (single GPU, resample != 0): mt_step_a leaves the weight sums to mt_step_b, which then runs
+   * sums + resampling as one persistent cooperative kernel; mt_step_weights / the local sum are only
+   * valid after mt_step_b in that mode. */
+  int fuse_sums;
 } mt_step_args;
 
 /* kernel A: motion + key + exact NN + weight lookup + deterministic weight sums */

@@ -45,7 +45,7 @@ class StepArgs(C.Structure):
         ("gt", C.c_void_p), ("d_rmse2", C.c_void_p),
         ("rank", C.c_int), ("world", C.c_int), ("n_global", C.c_longlong),
         ("d_shard_sums", C.c_void_p), ("d_n_out", C.c_void_p), ("d_n_in", C.c_void_p),
-        ("prune_dist", C.c_double), ("d_cb_poses", C.c_void_p), ("table_ready_event", C.c_void_p),
+        ("prune_dist", C.c_double), ("d_cb_poses", C.c_void_p), ("table_ready_event", C.c_void_p), ("fuse_sums", C.c_int),
     ]
 
 

@@ -69,6 +69,8 @@ struct mt_ctx {
   int emb_dtype;
   double* d_sim;   // cos(q, E_m)
   double* d_esim;  // exp(cos)
+  double* d_rnorm; // max(|E_m|, 1e-8), computed by the first query after an upload
+  bool rnorm_ready;
   bool cb_ready;
   void* d_scratch;       // grow-on-demand scratch of the cluster / selection entry points
   size_t scratch_bytes;
@@ -76,6 +78,8 @@ struct mt_ctx {
   // down-sampled mesh vertices for the drift test (mt_mesh.cuh)
   double* d_mesh_verts;
   float4* d_mesh_verts32;
+  unsigned char* d_mesh_vox;
+  MeshVoxels vox;
   int* d_mesh_cells;
   MeshGrid mesh;
   int mesh_V;
@@ -91,6 +95,11 @@ struct mt_ctx {
   int* d_wcnt;        // per-warp count of particles that passed the drift test
   int* d_queue;       // particles whose hint-graph search was not conclusive (kernel A -> A2)
   unsigned int* d_qctl;  // [0] queue length, [1] queue head
+  unsigned long long* d_bar;  // grid barrier of k_step_bw (monotone counter)
+  unsigned long long bar_target;
+  double* d_bw;       // 3 x MT_BW_MAX_GRID block totals (weights, rmse_t, rmse_r)
+  int* d_bwcnt;       // MT_BW_MAX_GRID on-surface counts
+  int bw_blocks_per_sm;
   double* d_q64;      // staged query, float64, MT_MAX_D entries
   double* d_scal;     // [0] local weight sum, [1] max, [2] min, [3] softmax denom, [4..7] spare
   unsigned int* d_ticket;
@@ -116,6 +125,7 @@ extern "C" int mt_ctx_create(int device, size_t capacity, int M, int D, mt_ctx**
   CK(cudaMalloc(&c->d_nbr, sizeof(float4) * 2 * MT_NBR_K * (size_t)M));
   CK(cudaMalloc(&c->d_sim, sizeof(double) * M));
   CK(cudaMalloc(&c->d_esim, sizeof(double) * M));
+  CK(cudaMalloc(&c->d_rnorm, sizeof(double) * M));
   CK(cudaMalloc(&c->d_part, sizeof(double) * c->chunk_cap));
   c->warp_cap = (int)((capacity + 31) / 32) + 8;
   CK(cudaMalloc(&c->d_wpart, sizeof(double) * c->warp_cap));
@@ -124,6 +134,10 @@ extern "C" int mt_ctx_create(int device, size_t capacity, int M, int D, mt_ctx**
   CK(cudaMalloc(&c->d_queue, sizeof(int) * (capacity + 32)));
   CK(cudaMalloc(&c->d_qctl, sizeof(unsigned int) * 4));
   CK(cudaMemset(c->d_qctl, 0, sizeof(unsigned int) * 4));
+  CK(cudaMalloc(&c->d_bar, sizeof(unsigned long long)));
+  CK(cudaMemset(c->d_bar, 0, sizeof(unsigned long long)));
+  CK(cudaMalloc(&c->d_bw, sizeof(double) * 3 * 1184));
+  CK(cudaMalloc(&c->d_bwcnt, sizeof(int) * 1184));
   CK(cudaMalloc(&c->d_prefix, sizeof(double) * (c->chunk_cap + 1)));
   CK(cudaMalloc(&c->d_rm_part, sizeof(double) * 2 * c->chunk_cap));
   CK(cudaMalloc(&c->d_scal, sizeof(double) * 8));
@@ -147,9 +161,11 @@ extern "C" int mt_ctx_destroy(mt_ctx* c) {
   cudaFree(c->d_nbr);
   cudaFree(c->d_mesh_verts);
   cudaFree(c->d_mesh_verts32);
+  cudaFree(c->d_mesh_vox);
   cudaFree(c->d_mesh_cells);
   cudaFree(c->d_sim);
   cudaFree(c->d_esim);
+  cudaFree(c->d_rnorm);
   cudaFree(c->d_part);
   cudaFree(c->d_prefix);
   cudaFree(c->d_rm_part);
@@ -159,6 +175,9 @@ extern "C" int mt_ctx_destroy(mt_ctx* c) {
   cudaFree(c->d_queue);
   cudaFree(c->d_scratch);
   cudaFree(c->d_qctl);
+  cudaFree(c->d_bar);
+  cudaFree(c->d_bw);
+  cudaFree(c->d_bwcnt);
   cudaFree(c->d_scal);
   cudaFree(c->d_q64);
   cudaFree(c->d_ticket);
@@ -252,6 +271,7 @@ extern "C" int mt_codebook_upload(mt_ctx* c, const float* h_keys, const void* d_
   c->occupied = best_occ;
   c->d_emb = d_emb;
   c->emb_dtype = emb_dtype;
+  c->rnorm_ready = false;
   c->cb_ready = true;
   return MT_OK;
 }
@@ -301,9 +321,11 @@ extern "C" int mt_ctx_stats(mt_ctx* c, long long* h_out8, int reset) {
 }
 
 // ------------------------------------------------------------------------- mesh (drift test)
+static MeshTables mesh_of(mt_ctx* c);
 extern "C" int mt_mesh_upload(mt_ctx* c, const double* h_vertices, long long V, double cell) {
   if (!c || !h_vertices || V <= 0 || !(cell > 0.0)) return set_err(MT_ERR_ARG, "mt_mesh_upload: bad argument");
   CK(cudaSetDevice(c->device));
+  const double cell0 = cell;
   double lo[3], hi[3];
   for (int k = 0; k < 3; ++k) lo[k] = DBL_MAX, hi[k] = -DBL_MAX;
   for (long long v = 0; v < V; ++v)
@@ -349,7 +371,9 @@ extern "C" int mt_mesh_upload(mt_ctx* c, const double* h_vertices, long long V, 
   cudaFree(c->d_mesh_verts);
   cudaFree(c->d_mesh_verts32);
   cudaFree(c->d_mesh_cells);
-  c->d_mesh_verts = nullptr, c->d_mesh_verts32 = nullptr, c->d_mesh_cells = nullptr, c->mesh_ready = false;
+  cudaFree(c->d_mesh_vox);
+  c->d_mesh_verts = nullptr, c->d_mesh_verts32 = nullptr, c->d_mesh_cells = nullptr, c->d_mesh_vox = nullptr, c->mesh_ready = false;
+  memset(&c->vox, 0, sizeof(c->vox));
   CK(cudaMalloc(&c->d_mesh_verts, sizeof(double) * 3 * V));
   CK(cudaMalloc(&c->d_mesh_verts32, sizeof(float4) * V));
   CK(cudaMemcpy(c->d_mesh_verts32, sorted32.data(), sizeof(float4) * V, cudaMemcpyHostToDevice));
@@ -359,6 +383,35 @@ extern "C" int mt_mesh_upload(mt_ctx* c, const double* h_vertices, long long V, 
   c->mesh = g;
   c->mesh_V = (int)V;
   c->mesh_ready = true;
+  // voxel classes for invalid_dist == cell0 (the default, tdn.render.pen.max): voxel edge dist/4,
+  // at most 64 M voxels
+  {
+    const double dist = cell0;
+    double v = dist / 4.0;
+    MeshVoxels vx;
+    memset(&vx, 0, sizeof(vx));
+    for (;;) {
+      double total = 1;
+      for (int k = 0; k < 3; ++k) vx.dims[k] = (int)ceil((hi[k] - lo[k] + 2.0 * (dist + 2.0 * v)) / v) + 1, total *= vx.dims[k];
+      if (total <= 64.0e6) break;
+      v *= 1.26;
+    }
+    for (int k = 0; k < 3; ++k) vx.org[k] = (float)(lo[k] - (dist + 2.0 * v));
+    vx.inv_v = (float)(1.0 / v);
+    vx.dist = dist;
+    const float vf = 1.0f / vx.inv_v;  // the edge the float32 index arithmetic effectively uses
+    const size_t total = (size_t)vx.dims[0] * vx.dims[1] * vx.dims[2];
+    CK(cudaMalloc(&c->d_mesh_vox, total));
+    MeshTables T = mesh_of(c);
+    T.vox.cls = nullptr;
+    // slack: float32 rounding of (x - org) * inv_v, in metres
+    const float slack = (float)(4e-7 * (g.coord_max + fabs((double)vx.org[0]) + fabs((double)vx.org[1]) + fabs((double)vx.org[2])) + 1e-9);
+    k_mesh_classify<<<(unsigned)((total + 255) / 256), 256>>>(T, vx, vf, slack, c->d_mesh_vox);
+    CK_LAUNCH();
+    CK(cudaDeviceSynchronize());
+    vx.cls = c->d_mesh_vox;
+    c->vox = vx;
+  }
   return MT_OK;
 }
 
@@ -366,6 +419,7 @@ static MeshTables mesh_of(mt_ctx* c) {
   MeshTables T;
   T.verts = c->d_mesh_verts;
   T.verts32 = c->d_mesh_verts32;
+  T.vox = c->vox;
   T.cell_start = c->d_mesh_cells;
   T.g = c->mesh;
   T.V = c->mesh_V;
@@ -606,6 +660,117 @@ static int launch_cosine(const double* d_q64, const void* E, int dt, long long r
   return MT_OK;
 }
 
+
+// ---- codebook query (static codebook: row norms are precomputed at upload) ----------------------
+// row norms max(|E_m|, 1e-8) (the clamp of torch.cosine_similarity), one warp per row
+template <typename T>
+__global__ void __launch_bounds__(256) k_row_norms(const T* __restrict__ E, int M, int D, double* __restrict__ rnorm) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const T* e = E + (size_t)row * D;
+  double nn = 0.0;
+  for (int i = lane; i < D; i += 32) {
+    const double x = (double)e[i];
+    nn = fma(x, x, nn);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) nn += __shfl_xor_sync(0xffffffffu, nn, o);
+  if (lane == 0) rnorm[row] = fmax(sqrt(nn), 1e-8);
+}
+
+// query -> float64 + its clamped norm (one block)
+template <typename TQ>
+__global__ void __launch_bounds__(256) k_stage_query(const TQ* __restrict__ in, int D, double* __restrict__ out, double* __restrict__ qnorm) {
+  __shared__ double s8[8];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < D; i += 256) {
+    const double x = (double)in[i];
+    out[i] = x;
+    acc = fma(x, x, acc);
+  }
+  const double t = block_sum_256(acc, s8);
+  if (threadIdx.x == 0) *qnorm = fmax(sqrt(t), 1e-8);
+}
+
+// sim[m] = <q, E_m> / (|q| |E_m|), exp(sim[m]).  Persistent warps, four rows per trip: the query
+// vector is read from shared memory once per four rows, sixteen 16-byte loads are in flight per
+// lane, and the four dot products are reduced with a transposing butterfly (12 shuffles instead
+// of 40).  Traffic: M*D*sizeof(T) + 24*M bytes.
+template <typename T>
+__global__ void __launch_bounds__(256) k_codebook_query(const double* __restrict__ qd, const double* __restrict__ qnorm,
+                                                        const T* __restrict__ E, const double* __restrict__ rnorm, int M, int D,
+                                                        double* __restrict__ sim, double* __restrict__ esim,
+                                                        double* __restrict__ sim2) {
+  extern __shared__ double sq[];
+  for (int i = threadIdx.x; i < D; i += blockDim.x) sq[i] = qd[i];
+  __syncthreads();
+  constexpr int W = VecLoad<T>::W;
+  const int lane = threadIdx.x & 31;
+  const int nvec = D / W;
+  const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nw = gridDim.x * (blockDim.x >> 5);
+  const double qn = *qnorm;
+  for (int r0 = 4 * gw; r0 < M; r0 += 4 * nw) {
+    const T* e[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) e[j] = E + (size_t)min(r0 + j, M - 1) * D;
+    double dot[4] = {0.0, 0.0, 0.0, 0.0};
+    int v = lane;
+    for (; v + 96 < nvec; v += 128) {  // 4 vectors x 4 rows in flight
+      double x[4][4][W];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) VecLoad<T>::ld(e[j] + (size_t)(v + 32 * u) * W, x[u][j]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int k = 0; k < W; ++k) {
+          const double qv = sq[(v + 32 * u) * W + k];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dot[j] = fma(x[u][j][k], qv, dot[j]);
+        }
+    }
+    for (; v < nvec; v += 32) {
+      double x[4][W];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) VecLoad<T>::ld(e[j] + (size_t)v * W, x[j]);
+#pragma unroll
+      for (int k = 0; k < W; ++k) {
+        const double qv = sq[v * W + k];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dot[j] = fma(x[j][k], qv, dot[j]);
+      }
+    }
+    for (int i = nvec * W + lane; i < D; i += 32)  // ragged tail
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dot[j] = fma((double)e[j][i], sq[i], dot[j]);
+    // transposing butterfly: 4 values -> 2 -> 1 per lane, then a plain reduction over 8 lanes
+    {
+      const bool hi = lane & 16;
+      const double s0 = hi ? dot[0] : dot[2], s1 = hi ? dot[1] : dot[3];
+      const double r0v = __shfl_xor_sync(0xffffffffu, s0, 16), r1v = __shfl_xor_sync(0xffffffffu, s1, 16);
+      double a = (hi ? dot[2] : dot[0]) + r0v, b = (hi ? dot[3] : dot[1]) + r1v;  // lanes<16: rows 0,1; lanes>=16: rows 2,3
+      const bool h8 = lane & 8;
+      const double snd = h8 ? a : b;
+      const double rcv = __shfl_xor_sync(0xffffffffu, snd, 8);
+      double c = (h8 ? b : a) + rcv;  // row = 2*(lane>=16) + (lane&8 ? 1 : 0)
+      c += __shfl_xor_sync(0xffffffffu, c, 4);
+      c += __shfl_xor_sync(0xffffffffu, c, 2);
+      c += __shfl_xor_sync(0xffffffffu, c, 1);
+      if ((lane & 7) == 0) {
+        const int row = r0 + 2 * (lane >> 4) + ((lane >> 3) & 1);
+        if (row < M) {
+          const double cs = c / (qn * __ldg(rnorm + row));
+          sim[row] = cs;
+          esim[row] = exp(cs);
+          if (sim2) sim2[row] = cs;
+        }
+      }
+    }
+  }
+}
+
 static int stage_query(mt_ctx* c, const void* d_q, int q_dtype, int D, double** out, cudaStream_t st) {
   if (D > MT_MAX_D) return set_err(MT_ERR_ARG, "cosine: D exceeds MT_MAX_D (6144)");
   if (q_dtype == MT_DTYPE_F32)
@@ -623,10 +788,34 @@ extern "C" int mt_codebook_query(mt_ctx* c, const void* d_q, int q_dtype, double
   if (!c || !c->cb_ready || !c->d_emb) return set_err(MT_ERR_STATE, "mt_codebook_query: no codebook");
   if (!d_q) return set_err(MT_ERR_ARG, "mt_codebook_query: null query");
   cudaStream_t st = (cudaStream_t)stream;
-  double* q64;
-  int r = stage_query(c, d_q, q_dtype, c->D, &q64, st);
-  if (r) return r;
-  return launch_cosine(q64, c->d_emb, c->emb_dtype, c->M, c->D, c->d_sim, c->d_esim, d_sim_out, st);
+  const int D = c->D, M = c->M;
+  if (D > MT_MAX_D) return set_err(MT_ERR_ARG, "cosine: D exceeds MT_MAX_D (6144)");
+  if (q_dtype == MT_DTYPE_F32)
+    k_stage_query<float><<<1, 256, 0, st>>>((const float*)d_q, D, c->d_q64, c->d_scal + 7);
+  else if (q_dtype == MT_DTYPE_F64)
+    k_stage_query<double><<<1, 256, 0, st>>>((const double*)d_q, D, c->d_q64, c->d_scal + 7);
+  else
+    return set_err(MT_ERR_ARG, "cosine: bad query dtype");
+  CK_LAUNCH();
+  if (!c->rnorm_ready) {  // the embeddings are static between uploads: their norms are computed once
+    if (c->emb_dtype == MT_DTYPE_F32)
+      k_row_norms<float><<<(M + 7) / 8, 256, 0, st>>>((const float*)c->d_emb, M, D, c->d_rnorm);
+    else
+      k_row_norms<double><<<(M + 7) / 8, 256, 0, st>>>((const double*)c->d_emb, M, D, c->d_rnorm);
+    CK_LAUNCH();
+    c->rnorm_ready = true;
+  }
+  const int grid = std::min((M + 31) / 32, c->sm_count * 8);
+  const size_t sh = sizeof(double) * D;
+  if (c->emb_dtype == MT_DTYPE_F32) {
+    if (D % 4) return set_err(MT_ERR_ARG, "cosine: D must be a multiple of 4 for float32 rows");
+    k_codebook_query<float><<<grid, 256, sh, st>>>(c->d_q64, c->d_scal + 7, (const float*)c->d_emb, c->d_rnorm, M, D, c->d_sim, c->d_esim, d_sim_out);
+  } else {
+    if (D % 2) return set_err(MT_ERR_ARG, "cosine: D must be a multiple of 2 for float64 rows");
+    k_codebook_query<double><<<grid, 256, sh, st>>>(c->d_q64, c->d_scal + 7, (const double*)c->d_emb, c->d_rnorm, M, D, c->d_sim, c->d_esim, d_sim_out);
+  }
+  CK_LAUNCH();
+  return MT_OK;
 }
 
 extern "C" int mt_cosine_rows(mt_ctx* c, const void* d_q, int q_dtype, const void* d_t, int t_dtype, long long rows,
@@ -1308,45 +1497,45 @@ __global__ void __launch_bounds__(256) k_weight_sums(StepDev p) {
 // [cnt(C_{i-1}), cnt(C_i)), cnt(C) = #{j : loc_j < C}; each parent writes its own children
 // (reads and writes are both contiguous up to the child-count jitter).
 //   HBM per particle: read 4 B nn + 48 B pose, write 48 B pose + 4 B nn + 4 B ancestor.
-template <bool FROM_TABLE, bool SCATTER>
-__global__ void __launch_bounds__(256) k_step_b(StepDev p) {
-  __shared__ double s8[8];
-  __shared__ long long s_cnt[MT_CHUNK + 1];
-  const int c = blockIdx.x;
-  const long long i = (long long)c * MT_CHUNK + threadIdx.x;
-  const long long n = p.n_in ? *p.n_in : p.n;
-  const bool valid = i < n;
-  // issue the loads first
-  int nn = 0;
-  double e = 0.0;
+// One 256-particle chunk of kernel B: CDF values from (base, inclusive scan, endv), slot ownership,
+// scatter of the children.  base / endv are the chunk's CDF interval in un-normalised units
+// (A + prefix[c], A + prefix[c+1]); S the global normaliser; A this shard's offset.
+// the per-particle inputs of one chunk of kernel B (loaded ahead of their use)
+struct ChunkIn {
+  int nn;
+  double e;
   float P[3][4];
-  if (valid) {
+};
+template <bool FROM_TABLE, bool SCATTER>
+__device__ __forceinline__ void step_b_load(const StepDev& p, const int c, const long long n, ChunkIn& in) {
+  const long long i = (long long)c * MT_CHUNK + threadIdx.x;
+  in.nn = 0;
+  in.e = 0.0;
+  if (i < n) {
     if (FROM_TABLE) {
       const int stored = p.nn_cur[i];
-      nn = nn_index(stored);
-      e = nn_is_masked(stored) ? 0.0 : __ldg(p.wtab + nn);
+      in.nn = nn_index(stored);
+      in.e = nn_is_masked(stored) ? 0.0 : __ldg(p.wtab + in.nn);
     } else {
-      e = p.wsrc[i];
+      in.e = p.wsrc[i];
     }
-    if (SCATTER) load_pose(p.soa_cur, p.stride, i, P);
+    if (SCATTER) load_pose(p.soa_cur, p.stride, i, in.P);
   }
-  // global normaliser and this shard's CDF offset (sequential, identical on every GPU)
-  double S = 0.0, A = 0.0;
-  if (p.world > 1) {
-    for (int r = 0; r < p.world; ++r) {
-      if (r == p.rank) A = S;
-      S += p.shard_sums[r];
-    }
-  } else {
-    S = p.prefix[p.nchunks];
-  }
+}
+
+template <bool FROM_TABLE, bool SCATTER>
+__device__ __forceinline__ void step_b_chunk(const StepDev& p, const int c, const long long n, const double S, const double A,
+                                             const double base, const double endv, double* s8, long long* s_cnt, ChunkIn& in) {
+  const long long i = (long long)c * MT_CHUNK + threadIdx.x;
+  const bool valid = i < n;
+  const int nn = in.nn;
+  const double e = in.e;
+  float (&P)[3][4] = in.P;
   const long long N = p.n_global;
   const double dN = (double)N;
   const double off = (double)(p.u / (float)N);  // float32 division, then promoted (particle_filter.py:260)
   const bool bad = !(S > 0.0) || !(S <= DBL_MAX);  // all-zero / NaN / Inf weights: identity (237-241)
   const double incl = block_incl_scan_256(e, s8);
-  const double base = A + p.prefix[c];
-  const double endv = (c + 1 == p.nchunks) ? (A + p.prefix[p.nchunks]) : (A + p.prefix[c + 1]);
   long long cnt;
   if (bad) {
     // the reference returns the particles unchanged (237-241); when every particle has drifted off
@@ -1422,6 +1611,135 @@ __global__ void __launch_bounds__(256) k_step_b(StepDev p) {
   }
 }
 
+template <bool FROM_TABLE, bool SCATTER>
+__global__ void __launch_bounds__(256) k_step_b(StepDev p) {
+  __shared__ double s8[8];
+  __shared__ long long s_cnt[MT_CHUNK + 1];
+  const int c = blockIdx.x;
+  const long long n = p.n_in ? *p.n_in : p.n;
+  // global normaliser and this shard's CDF offset (sequential, identical on every GPU)
+  double S = 0.0, A = 0.0;
+  if (p.world > 1) {
+    for (int r = 0; r < p.world; ++r) {
+      if (r == p.rank) A = S;
+      S += p.shard_sums[r];
+    }
+  } else {
+    S = p.prefix[p.nchunks];
+  }
+  const double base = A + p.prefix[c];
+  const double endv = (c + 1 == p.nchunks) ? (A + p.prefix[p.nchunks]) : (A + p.prefix[c + 1]);
+  ChunkIn in;
+  step_b_load<FROM_TABLE, SCATTER>(p, c, n, in);
+  step_b_chunk<FROM_TABLE, SCATTER>(p, c, n, S, A, base, endv, s8, s_cnt, in);
+}
+
+// Single-GPU fused form of k_step_sums + k_step_b: a persistent cooperative grid.  Phase 1: every
+// block sums the weights of its contiguous run of chunks; grid barrier; phase 2: every block adds
+// the block totals before it in the same sequential order (so neighbouring blocks agree bit for bit
+// on their common boundary), then resamples its chunks.  Saves a launch, the 4 B/particle re-read
+// and the serial last-block scan.
+#define MT_BW_MAX_PER 32
+#define MT_BW_MAX_GRID 1184
+__global__ void __launch_bounds__(256) k_step_bw(StepDev p, unsigned long long* bar, unsigned long long bar_target,
+                                                 double* __restrict__ blocktot /* 3 x grid */, int* __restrict__ blockcnt) {
+  __shared__ double s8[8];
+  __shared__ long long s_cnt[MT_CHUNK + 1];
+  __shared__ double s_part[MT_BW_MAX_PER];
+  __shared__ double s_tot[MT_BW_MAX_GRID];
+  __shared__ double s_bc[3];
+  const int G = gridDim.x, g = blockIdx.x;
+  const long long n = p.n_in ? *p.n_in : p.n;
+  const int nwarps = (int)((n + 31) >> 5);
+  const int per = (p.nchunks + G - 1) / G;
+  const int c_lo = g * per, c_hi = min(c_lo + per, p.nchunks);
+  // ---- phase 1
+  double tot = 0.0, ra = 0.0, rb = 0.0;
+  int cnt = 0;
+  for (int c = c_lo; c < c_hi; ++c) {
+    const long long i = (long long)c * MT_CHUNK + threadIdx.x;
+    double e = 0.0;
+    if (i < n) {
+      const int stored = p.nn_cur[i];
+      e = nn_is_masked(stored) ? 0.0 : __ldg(p.wtab + nn_index(stored));
+    }
+    const double se = block_sum_256(e, s8);
+    if (threadIdx.x == 0) {
+      s_part[c - c_lo] = se;
+      tot += se;
+      for (int j = 0; j < 8; ++j) {  // kernel A's per-warp partials of this chunk (fixed order)
+        const int gw = 8 * c + j;
+        if (gw < nwarps) {
+          cnt += p.wcnt[gw];
+          if (p.has_gt) ra += p.wrm[2 * gw], rb += p.wrm[2 * gw + 1];
+        }
+      }
+    }
+  }
+  if (threadIdx.x == 0) {
+    blocktot[g] = tot, blocktot[G + g] = ra, blocktot[2 * G + g] = rb;
+    blockcnt[g] = cnt;
+    __threadfence();
+    atomicAdd(bar, 1ull);
+    while (*(volatile unsigned long long*)bar < bar_target) {
+    }
+    __threadfence();
+  }
+  __syncthreads();
+  // ---- phase 2
+  for (int j = threadIdx.x; j < G; j += blockDim.x) s_tot[j] = __ldcg(blocktot + j);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double acc = 0.0, base = 0.0;
+    for (int j = 0; j < G; ++j) {
+      if (j == g) base = acc;
+      acc += s_tot[j];
+    }
+    s_bc[0] = base, s_bc[1] = base + s_tot[g], s_bc[2] = acc;
+  }
+  __syncthreads();
+  const double base_g = s_bc[0], next_g = s_bc[1], S = s_bc[2];
+  double run = base_g;
+  ChunkIn cur, nxt;
+  if (c_lo < c_hi) step_b_load<true, true>(p, c_lo, n, cur);
+  for (int c = c_lo; c < c_hi; ++c) {
+    const double base = fmin(run, next_g);
+    run += s_part[c - c_lo];
+    const double endv = (c + 1 == c_hi) ? next_g : fmin(run, next_g);
+    if (c + 1 < c_hi) step_b_load<true, true>(p, c + 1, n, nxt);  // in flight while this chunk is resampled
+    __syncthreads();  // s8 / s_cnt of the previous chunk are free
+    step_b_chunk<true, true>(p, c, n, S, 0.0, base, endv, s8, s_cnt, cur);
+    cur = nxt;
+  }
+  if (g == 0) {  // RMSE, drift flag, bookkeeping (what the last block of k_step_sums does)
+    __syncthreads();
+    double sa = 0.0, sb = 0.0;
+    if (p.has_gt) {
+      sa = block_sum_array_256(blocktot + G, G, 1, s8);
+      sb = block_sum_array_256(blocktot + 2 * G, G, 1, s8);
+    }
+    int ctot = 0;
+    for (int j = threadIdx.x; j < G; j += blockDim.x) ctot += __ldcg(blockcnt + j);
+    __shared__ int s_on;
+    if (threadIdx.x == 0) s_on = 0;
+    __syncthreads();
+    if (ctot) atomicAdd(&s_on, ctot);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      if (p.has_gt) {
+        p.rmse2[0] = (float)sqrt(sa / (double)n);
+        p.rmse2[1] = (float)sqrt(sb / (double)n);
+      }
+      p.prefix[p.nchunks] = S;
+      p.scal[0] = S;
+      p.flags[6] = s_on;
+      p.flags[5] = (p.prune_dist > 0.0 && s_on == 0);
+      p.flags[3] += (int)p.qctl[0];
+      p.qctl[0] = 0, p.qctl[1] = 0;
+    }
+  }
+}
+
 // strictly sequential float64 prefix (parity mode): one thread reproduces torch.cumsum on
 // CPU bit-for-bit, including slots the reference leaves unfilled (-1).
 __global__ void k_resample_seq(StepDev p) {
@@ -1493,6 +1811,21 @@ static int fill_step(mt_ctx* c, const mt_step_args* a, StepDev* d) {
   return MT_OK;
 }
 
+// single GPU, resampling requested, few enough chunks per block: k_step_sums + k_step_b run as one
+// persistent cooperative kernel (k_step_bw)
+static bool step_fused(mt_ctx* c, const mt_step_args* a) {
+  if (!a->fuse_sums || a->world > 1 || !a->resample) return false;
+  if (c->bw_blocks_per_sm == 0) {
+    int coop = 0, occ = 0;
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->device);
+    if (coop) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_step_bw, 256, 0);
+    c->bw_blocks_per_sm = (coop && occ > 0) ? std::min(occ, 4) : -1;
+  }
+  if (c->bw_blocks_per_sm < 0) return false;
+  const int grid = std::min(std::min((int)nchunks_of(a->n), c->sm_count * c->bw_blocks_per_sm), MT_BW_MAX_GRID);
+  return (nchunks_of(a->n) + grid - 1) / grid <= MT_BW_MAX_PER;
+}
+
 extern "C" int mt_step_a(mt_ctx* c, const mt_step_args* a, void* stream) {
   StepDev d;
   int r = fill_step(c, a, &d);
@@ -1510,9 +1843,11 @@ extern "C" int mt_step_a(mt_ctx* c, const mt_step_args* a, void* stream) {
   k_step_nnq<<<c->sm_count * 4, 256, 0, st>>>(d, tables_of(c), mesh_of(c));
   CK_LAUNCH();
   if (c->timing[2]) CK(cudaEventRecord(c->timing[2], st));
-  if (a->table_ready_event) CK(cudaStreamWaitEvent(st, (cudaEvent_t)a->table_ready_event, 0));
-  k_step_sums<<<d.nchunks, MT_CHUNK, 0, st>>>(d);
-  CK_LAUNCH();
+  if (!step_fused(c, a)) {  // otherwise the sums are folded into mt_step_b's kernel
+    if (a->table_ready_event) CK(cudaStreamWaitEvent(st, (cudaEvent_t)a->table_ready_event, 0));
+    k_step_sums<<<d.nchunks, MT_CHUNK, 0, st>>>(d);
+    CK_LAUNCH();
+  }
   if (c->timing[3]) CK(cudaEventRecord(c->timing[3], st));
   return MT_OK;
 }
@@ -1529,7 +1864,20 @@ extern "C" int mt_step_b(mt_ctx* c, const mt_step_args* a, void* stream) {
   if (r) return r;
   if (!a->d_soa_cur || !a->d_soa_next || !a->d_nn_cur || !a->d_nn_next) return set_err(MT_ERR_ARG, "mt_step_b: null particle buffers");
   if (a->world > 1 && (!a->d_shard_sums || a->n_global <= 0)) return set_err(MT_ERR_ARG, "mt_step_b: sharded step needs shard sums");
-  k_step_b<true, true><<<d.nchunks, MT_CHUNK, 0, (cudaStream_t)stream>>>(d);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (step_fused(c, a)) {
+    if (a->table_ready_event) CK(cudaStreamWaitEvent(st, (cudaEvent_t)a->table_ready_event, 0));
+    const int grid = std::min(std::min(d.nchunks, c->sm_count * c->bw_blocks_per_sm), MT_BW_MAX_GRID);
+    c->bar_target += (unsigned long long)grid;
+    unsigned long long* bar = c->d_bar;
+    unsigned long long target = c->bar_target;
+    double* bw = c->d_bw;
+    int* bwc = c->d_bwcnt;
+    void* args[] = {&d, &bar, &target, &bw, &bwc};
+    CK(cudaLaunchCooperativeKernel((const void*)k_step_bw, dim3(grid), dim3(256), args, 0, st));
+    return MT_OK;
+  }
+  k_step_b<true, true><<<d.nchunks, MT_CHUNK, 0, st>>>(d);
   CK_LAUNCH();
   return MT_OK;
 }

@@ -27,11 +27,22 @@ MT_HD int mt_mesh_cell(double x, double org, double inv_cell, int dim) {
 }
 
 #if defined(__CUDACC__)
+// Voxel classification for the default invalid_dist (built at upload): 0 = every point of the
+// voxel is within the distance of some vertex, 1 = no point of the voxel is, 2 = undecided (run the
+// search).  Particles on the surface are answered by one byte.
+struct MeshVoxels {
+  const unsigned char* cls;  // nullptr: not built
+  float org[3], inv_v;
+  int dims[3];
+  double dist;               // the distance the classes were computed for
+};
+
 struct MeshTables {
   const double* verts;    // V x 3 float64, sorted by cell (exact test)
   const float4* verts32;  // V x (x,y,z,0) float32 copies (filter)
   const int* cell_start;  // ncells + 1
   MeshGrid g;
+  MeshVoxels vox;
   int V;
 };
 
@@ -52,6 +63,13 @@ __device__ __forceinline__ bool mesh_vertex_within(const MeshTables& T, int p, d
 // exact float64 test, so the answer is the float64 one.  NaN coordinates -> false.
 __device__ __forceinline__ bool mesh_within(const MeshTables& T, float xf, float yf, float zf, double dist) {
   if (!(xf == xf) || !(yf == yf) || !(zf == zf)) return false;
+  if (T.vox.cls && dist == T.vox.dist) {
+    const float fx = (xf - T.vox.org[0]) * T.vox.inv_v, fy = (yf - T.vox.org[1]) * T.vox.inv_v, fz = (zf - T.vox.org[2]) * T.vox.inv_v;
+    if (!(fx >= 0.f && fy >= 0.f && fz >= 0.f && fx < (float)T.vox.dims[0] && fy < (float)T.vox.dims[1] && fz < (float)T.vox.dims[2]))
+      return false;  // the voxel grid covers the vertices' bounding box inflated by more than dist
+    const unsigned char k = __ldg(T.vox.cls + ((size_t)(int)fz * T.vox.dims[1] + (int)fy) * T.vox.dims[0] + (int)fx);
+    if (k != 2) return k == 0;
+  }
   const double x = (double)xf, y = (double)yf, z = (double)zf;
   const MeshGrid& g = T.g;
   // search box in float32, radius inflated by 1 % (>> the 1e-4-cell rounding of the float32 cell
@@ -85,5 +103,38 @@ __device__ __forceinline__ bool mesh_within(const MeshTables& T, float xf, float
     }
   }
   return false;
+}
+
+// upload-time kernel: classify every voxel (edge v) against distance `dist`.  hd = half diagonal of
+// the voxel inflated by 1 % + an absolute slack: a particle that the float32 index arithmetic of
+// mesh_within assigns to this voxel lies within hd of its centre.
+__global__ void __launch_bounds__(256) k_mesh_classify(MeshTables T, MeshVoxels V, float v, float slack, unsigned char* __restrict__ out) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)V.dims[0] * V.dims[1] * V.dims[2];
+  if (idx >= total) return;
+  const int ix = (int)(idx % V.dims[0]), iy = (int)((idx / V.dims[0]) % V.dims[1]), iz = (int)(idx / ((size_t)V.dims[0] * V.dims[1]));
+  const double cx = (double)V.org[0] + (ix + 0.5) * (double)v, cy = (double)V.org[1] + (iy + 0.5) * (double)v,
+               cz = (double)V.org[2] + (iz + 0.5) * (double)v;
+  const double hd = 0.8660254037844386 * (double)v * 1.01 + (double)slack;
+  const double R = V.dist + hd;
+  const MeshGrid& g = T.g;
+  const int xlo = mt_mesh_cell(cx - R, g.org[0], g.inv_cell, g.dims[0]), xhi = mt_mesh_cell(cx + R, g.org[0], g.inv_cell, g.dims[0]);
+  const int ylo = mt_mesh_cell(cy - R, g.org[1], g.inv_cell, g.dims[1]), yhi = mt_mesh_cell(cy + R, g.org[1], g.inv_cell, g.dims[1]);
+  const int zlo = mt_mesh_cell(cz - R, g.org[2], g.inv_cell, g.dims[2]), zhi = mt_mesh_cell(cz + R, g.org[2], g.inv_cell, g.dims[2]);
+  double dmin2 = 1e300;
+  for (int z = zlo; z <= zhi; ++z)
+    for (int y = ylo; y <= yhi; ++y) {
+      const int rb = (z * g.dims[1] + y) * g.dims[0];
+      const int s = T.cell_start[rb + xlo], e = T.cell_start[rb + xhi + 1];
+      for (int p = s; p < e; ++p) {
+        const double dx = cx - T.verts[3 * (size_t)p], dy = cy - T.verts[3 * (size_t)p + 1], dz = cz - T.verts[3 * (size_t)p + 2];
+        dmin2 = fmin(dmin2, dx * dx + dy * dy + dz * dz);
+      }
+    }
+  const double dmin = sqrt(dmin2);
+  unsigned char k = 2;
+  if (dmin + hd <= V.dist * (1.0 - 1e-9)) k = 0;
+  else if (dmin - hd > V.dist * (1.0 + 1e-9)) k = 1;
+  out[idx] = k;
 }
 #endif

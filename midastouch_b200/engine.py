@@ -68,6 +68,7 @@ class FilterEngine:
         self._a = StepArgs()
         # the codebook query runs on a side stream, concurrently with motion + SE3_NN
         self.overlap_query = True
+        self.fuse_sums = True  # single GPU: weight sums + resampling as one cooperative kernel
         self._side = torch.cuda.Stream(device=self.dev)
         self._ev_table = torch.cuda.Event()
         self._ev_free = torch.cuda.Event()
@@ -140,7 +141,7 @@ class FilterEngine:
         return self.anc[: self.count()]
 
     # ------------------------------------------------------------------ one filter step
-    def _fill(self, odom, u, tn, rot, gt, softmax, prune=True):
+    def _fill(self, odom, u, tn, rot, gt, softmax, prune=True, resample=True):
         a = self._a
         a.d_soa_cur, a.d_soa_next = ptr(self.soa[self.cur]), ptr(self.soa[1 - self.cur])
         a.stride = self.capacity
@@ -150,7 +151,7 @@ class FilterEngine:
         a.d_tn, a.d_rot = ptr(tn), ptr(rot)
         a.sig_t, a.sig_r = self.sig_t, self.sig_r
         a.seed, a.step, a.first_gid = self.seed, self.t, self.rank * (1 << 40)
-        a.softmax, a.u, a.resample = int(bool(softmax)), float(u), 1
+        a.softmax, a.u, a.resample = int(bool(softmax)), float(u), int(bool(resample))
         a.gt = ptr(gt) if gt is not None else None
         a.d_rmse2 = ptr(self.rmse)
         a.rank, a.world = self.rank, self.world
@@ -161,6 +162,7 @@ class FilterEngine:
         a.prune_dist = self.pen_max if (self.prune and prune) else 0.0
         a.d_cb_poses = ptr(self.cb.poses) if self.prune else None
         a.table_ready_event = None
+        a.fuse_sums = int(self.fuse_sums and self.world == 1)
         return a
 
     def step(self, code: torch.Tensor, odom: torch.Tensor, u: float | None = None, tn: torch.Tensor | None = None,
@@ -186,7 +188,7 @@ class FilterEngine:
             gt_h = gt if (gt.device.type == "cpu" and gt.dtype == torch.float32 and gt.is_contiguous()) else gt.detach().float().cpu().contiguous()
         if tn is not None:
             tn, rot = tn.contiguous(), rot.contiguous()
-        a = self._fill(odom16, u, tn, rot, gt_h, softmax, prune)
+        a = self._fill(odom16, u, tn, rot, gt_h, softmax, prune, resample)
         with torch.cuda.device(self.dev):
             s = stream_ptr()
             if self.overlap_query:
