@@ -78,7 +78,7 @@ struct mt_ctx {
   // down-sampled mesh vertices for the drift test (mt_mesh.cuh)
   double* d_mesh_verts;
   float4* d_mesh_verts32;
-  unsigned char* d_mesh_vox;
+  int* d_mesh_vox;
   MeshVoxels vox;
   int* d_mesh_cells;
   MeshGrid mesh;
@@ -393,7 +393,7 @@ extern "C" int mt_mesh_upload(mt_ctx* c, const double* h_vertices, long long V, 
     for (;;) {
       double total = 1;
       for (int k = 0; k < 3; ++k) vx.dims[k] = (int)ceil((hi[k] - lo[k] + 2.0 * (dist + 2.0 * v)) / v) + 1, total *= vx.dims[k];
-      if (total <= 64.0e6) break;
+      if (total <= 48.0e6) break;
       v *= 1.26;
     }
     for (int k = 0; k < 3; ++k) vx.org[k] = (float)(lo[k] - (dist + 2.0 * v));
@@ -401,7 +401,7 @@ extern "C" int mt_mesh_upload(mt_ctx* c, const double* h_vertices, long long V, 
     vx.dist = dist;
     const float vf = 1.0f / vx.inv_v;  // the edge the float32 index arithmetic effectively uses
     const size_t total = (size_t)vx.dims[0] * vx.dims[1] * vx.dims[2];
-    CK(cudaMalloc(&c->d_mesh_vox, total));
+    CK(cudaMalloc(&c->d_mesh_vox, total * sizeof(int)));
     MeshTables T = mesh_of(c);
     T.vox.cls = nullptr;
     // slack: float32 rounding of (x - org) * inv_v, in metres
@@ -1377,37 +1377,73 @@ __global__ void __launch_bounds__(MT_A_BLOCK, MT_A_MINBLOCKS) k_step_a(StepDev p
   }
 }
 
-// queue consumer: blocks of 8 warps pull entries until the queue is empty
+// queue consumer.  Blocks pull eight entries per trip, one per warp: a search whose candidate is
+// close (box of at most ~120 grid rows) is finished by its warp alone; the others (stale hint
+// after a sign flip, no hint) are then served one after the other by the whole block.
+struct NnqEntry {
+  long long i;
+  float key[6];
+  float bd;
+  int bi;
+  bool masked;
+};
+__device__ __forceinline__ void nnq_load(const StepDev& p, const NNTables& T, const MeshTables& Mh, long long i, NnqEntry& q) {
+  float P[3][4];
+  load_pose(p.soa_cur, p.stride, i, P);
+  mt_se3_key(P, q.key);
+  const int stored = p.nn_cur[i];
+  q.i = i;
+  q.bi = nn_index(stored);
+  q.bd = FLT_MAX;
+  q.masked = nn_is_masked(stored);
+  if (q.bi >= 0) {
+    float kh[6];
+    load_key(T.keys_orig, q.bi, kh);
+    q.bd = mt_key_dist(q.key, kh);
+  } else {  // no candidate yet: the mask was not recorded, derive it again
+    q.bi = INT_MAX;
+    q.masked = mt_pose_invalid(P) || (p.prune_dist > 0.0 && !mesh_within(Mh, P[0][3], P[1][3], P[2][3], p.prune_dist));
+  }
+}
 __global__ void __launch_bounds__(256) k_step_nnq(StepDev p, NNTables T, MeshTables Mh) {
   __shared__ unsigned s_e;
+  __shared__ int s_nbig;
+  __shared__ int s_big[8];
   __shared__ float s_bd[8];
   __shared__ int s_bi[8];
   const unsigned qn = *p.qctl;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // few entries: latency matters, every entry gets a whole block; many: throughput matters,
+  // entries with a close candidate get one warp each
+  const bool warp_mode = qn > 4u * gridDim.x;
+  const unsigned take = warp_mode ? 8u : 1u;
   for (;;) {
     __syncthreads();
-    if (threadIdx.x == 0) s_e = atomicAdd(p.qctl + 1, 1u);
+    if (threadIdx.x == 0) s_e = atomicAdd(p.qctl + 1, take), s_nbig = 0;
     __syncthreads();
-    const unsigned e = s_e;
-    if (e >= qn) break;
-    const long long i = p.queue[e];
-    float P[3][4], key[6];
-    load_pose(p.soa_cur, p.stride, i, P);
-    mt_se3_key(P, key);
-    const int stored = p.nn_cur[i];
-    int bi = nn_index(stored);
-    float bd = FLT_MAX;
-    bool masked = nn_is_masked(stored);
-    if (bi >= 0) {
-      float kh[6];
-      load_key(T.keys_orig, bi, kh);
-      bd = mt_key_dist(key, kh);
-    } else {  // no candidate yet: the mask was not recorded, derive it again
-      bi = INT_MAX;
-      masked = mt_pose_invalid(P) || (p.prune_dist > 0.0 && !mesh_within(Mh, P[0][3], P[1][3], P[2][3], p.prune_dist));
+    const unsigned e0 = s_e;
+    if (e0 >= qn) break;
+    if (!warp_mode) {
+      if (threadIdx.x == 0) s_big[0] = (int)e0, s_nbig = 1;
+    } else if (e0 + warp < qn) {
+      NnqEntry q;
+      nnq_load(p, T, Mh, p.queue[e0 + warp], q);
+      if (q.bi != INT_MAX && sqrtf(q.bd) <= 5.f * T.g.h) {
+        const int res = nn_search_coop<1>(T, q.key, q.bd, q.bi, p.flags + 4, nullptr, nullptr);
+        if (lane == 0) p.nn_cur[q.i] = q.masked ? nn_masked(res) : res;
+      } else if (lane == 0) {
+        s_big[atomicAdd(&s_nbig, 1)] = (int)(e0 + warp);
+      }
     }
-    const int res = nn_search_coop<8>(T, key, bd, bi, p.flags + 4, s_bd, s_bi);
-    __syncthreads();  // every thread has read nn_cur[i] before it is overwritten
-    if (threadIdx.x == 0) p.nn_cur[i] = masked ? nn_masked(res) : res;
+    __syncthreads();
+    const int nbig = s_nbig;
+    for (int b = 0; b < nbig; ++b) {
+      NnqEntry q;
+      nnq_load(p, T, Mh, p.queue[s_big[b]], q);
+      const int res = nn_search_coop<8>(T, q.key, q.bd, q.bi, p.flags + 4, s_bd, s_bi);
+      __syncthreads();  // every thread has read nn_cur[i] before it is overwritten
+      if (threadIdx.x == 0) p.nn_cur[q.i] = q.masked ? nn_masked(res) : res;
+    }
   }
 }
 

@@ -27,11 +27,14 @@ MT_HD int mt_mesh_cell(double x, double org, double inv_cell, int dim) {
 }
 
 #if defined(__CUDACC__)
-// Voxel classification for the default invalid_dist (built at upload): 0 = every point of the
-// voxel is within the distance of some vertex, 1 = no point of the voxel is, 2 = undecided (run the
-// search).  Particles on the surface are answered by one byte.
+// Voxel classification for the default invalid_dist (built at upload): -1 = every point of the
+// voxel is within the distance of some vertex, -2 = no point of the voxel is, v >= 0 = undecided,
+// v = the vertex nearest to the voxel centre (tested first; the full search only runs if that one
+// is out of range).  Particles on the surface are answered by one 4-byte load.
+#define MT_VOX_IN (-1)
+#define MT_VOX_OUT (-2)
 struct MeshVoxels {
-  const unsigned char* cls;  // nullptr: not built
+  const int* cls;  // nullptr: not built
   float org[3], inv_v;
   int dims[3];
   double dist;               // the distance the classes were computed for
@@ -67,8 +70,9 @@ __device__ __forceinline__ bool mesh_within(const MeshTables& T, float xf, float
     const float fx = (xf - T.vox.org[0]) * T.vox.inv_v, fy = (yf - T.vox.org[1]) * T.vox.inv_v, fz = (zf - T.vox.org[2]) * T.vox.inv_v;
     if (!(fx >= 0.f && fy >= 0.f && fz >= 0.f && fx < (float)T.vox.dims[0] && fy < (float)T.vox.dims[1] && fz < (float)T.vox.dims[2]))
       return false;  // the voxel grid covers the vertices' bounding box inflated by more than dist
-    const unsigned char k = __ldg(T.vox.cls + ((size_t)(int)fz * T.vox.dims[1] + (int)fy) * T.vox.dims[0] + (int)fx);
-    if (k != 2) return k == 0;
+    const int k = __ldg(T.vox.cls + ((size_t)(int)fz * T.vox.dims[1] + (int)fy) * T.vox.dims[0] + (int)fx);
+    if (k < 0) return k == MT_VOX_IN;
+    if (mesh_vertex_within(T, k, (double)xf, (double)yf, (double)zf, dist)) return true;
   }
   const double x = (double)xf, y = (double)yf, z = (double)zf;
   const MeshGrid& g = T.g;
@@ -108,7 +112,7 @@ __device__ __forceinline__ bool mesh_within(const MeshTables& T, float xf, float
 // upload-time kernel: classify every voxel (edge v) against distance `dist`.  hd = half diagonal of
 // the voxel inflated by 1 % + an absolute slack: a particle that the float32 index arithmetic of
 // mesh_within assigns to this voxel lies within hd of its centre.
-__global__ void __launch_bounds__(256) k_mesh_classify(MeshTables T, MeshVoxels V, float v, float slack, unsigned char* __restrict__ out) {
+__global__ void __launch_bounds__(256) k_mesh_classify(MeshTables T, MeshVoxels V, float v, float slack, int* __restrict__ out) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t total = (size_t)V.dims[0] * V.dims[1] * V.dims[2];
   if (idx >= total) return;
@@ -122,19 +126,21 @@ __global__ void __launch_bounds__(256) k_mesh_classify(MeshTables T, MeshVoxels 
   const int ylo = mt_mesh_cell(cy - R, g.org[1], g.inv_cell, g.dims[1]), yhi = mt_mesh_cell(cy + R, g.org[1], g.inv_cell, g.dims[1]);
   const int zlo = mt_mesh_cell(cz - R, g.org[2], g.inv_cell, g.dims[2]), zhi = mt_mesh_cell(cz + R, g.org[2], g.inv_cell, g.dims[2]);
   double dmin2 = 1e300;
+  int amin = -1;
   for (int z = zlo; z <= zhi; ++z)
     for (int y = ylo; y <= yhi; ++y) {
       const int rb = (z * g.dims[1] + y) * g.dims[0];
       const int s = T.cell_start[rb + xlo], e = T.cell_start[rb + xhi + 1];
       for (int p = s; p < e; ++p) {
         const double dx = cx - T.verts[3 * (size_t)p], dy = cy - T.verts[3 * (size_t)p + 1], dz = cz - T.verts[3 * (size_t)p + 2];
-        dmin2 = fmin(dmin2, dx * dx + dy * dy + dz * dz);
+        const double d2 = dx * dx + dy * dy + dz * dz;
+        if (d2 < dmin2) dmin2 = d2, amin = p;
       }
     }
   const double dmin = sqrt(dmin2);
-  unsigned char k = 2;
-  if (dmin + hd <= V.dist * (1.0 - 1e-9)) k = 0;
-  else if (dmin - hd > V.dist * (1.0 + 1e-9)) k = 1;
+  int k = amin;  // undecided: remember the nearest vertex
+  if (amin < 0 || dmin - hd > V.dist * (1.0 + 1e-9)) k = MT_VOX_OUT;
+  else if (dmin + hd <= V.dist * (1.0 - 1e-9)) k = MT_VOX_IN;
   out[idx] = k;
 }
 #endif

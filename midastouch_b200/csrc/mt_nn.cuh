@@ -307,7 +307,7 @@ __device__ __noinline__ int nn_search_coop(const NNTables& T, const float q[6], 
       if (best_i != INT_MAX && need <= kh + gx && need <= kh + gy && need <= kh + gz) break;  // bound closed
     }
   }
-  if (stats && threadIdx.x == 0) {
+  if (stats && (NW == 1 ? (threadIdx.x & 31) == 0 : threadIdx.x == 0)) {
     atomicAdd(stats, rows);
     atomicMax(stats + 3, rows);
   }

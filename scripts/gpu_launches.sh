@@ -9,3 +9,8 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --c
     python bench.py --steps 30 --warmup 5 --no-cpu > gpurun_out/bench_ncu.log 2>&1
 echo "ncu rc=$?"
 timeout 600 python bench.py --steps 30 --warmup 5 --no-cpu > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -c 1200 gpurun_out/bench.json
+for k in ${KERNELS:-}; do
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:$k -s ${SKIP:-24} -c 1 -f -o gpurun_out/prof_$k \
+     python bench.py --steps 4 --warmup ${WARM:-25} --no-cpu > gpurun_out/ncu_$k.log 2>&1
+  echo "$k rc=$?"
+done
