@@ -29,7 +29,7 @@ M, D = 50_000, 256
 OBJ = "035_power_drill"
 ALGO_BYTES_PER_UPDATE = 208  # whole sweep, SURVEY 8d / DESIGN.md
 A_BYTES_PER_UPDATE = 104     # k_step_a: pose 48 R + 48 W, match index 4 R + 4 W
-T_TRAJ = 64
+T_TRAJ = 256  # frames of the synthetic slide; every measured phase restarts the filter at frame 0
 
 
 def peaks():
@@ -84,7 +84,7 @@ def make_assets(seed=3):
     from midastouch_b200 import synth
 
     obj = synth.make_object(OBJ)
-    cbs = synth.make_codebook(obj, M=M, D=D, seed=seed)
+    cbs = synth.make_codebook(obj, M=M, D=D, seed=seed, embedding="smooth")
     gt, meas = synth.make_trajectory(obj, T=T_TRAJ, seed=seed)
     return obj, cbs, gt, meas
 
@@ -119,12 +119,22 @@ def run_ours(args):
     # particles start on codebook poses (what init_filter + the SE3_NN snap of filter.py:159-160 produce)
     g = torch.Generator().manual_seed(100 + rank)
     sel = torch.randint(0, M, (n,), generator=g)
-    eng.load_particles(cbs.poses.to(dev)[sel.to(dev)], nn_hint=sel.int().to(dev), spatial_sort=not args.no_sort)
+    poses0, hint0 = cbs.poses.to(dev)[sel.to(dev)], sel.int().to(dev)
+
+    def restart():
+        """every measured phase is a fresh filter run: particles spread over the whole codebook"""
+        eng.load_particles(poses0, nn_hint=hint0, spatial_sort=not args.no_sort)
+        eng.t = 0
+        eng.use_n_dev = False
+        eng.ctx.stats(reset=True)
+
+    restart()
 
     odoms = [prepare_odom(torch.inverse(meas[t - 1]) @ meas[t]) for t in range(1, T_TRAJ)]
     gts = [gt[t].float().contiguous() for t in range(T_TRAJ)]
     # tactile codes: pinned host buffers, one per frame (the step's only per-frame tensor input)
-    codes_h = [synth.make_query(cbs, int(sel[t]) if rank == 0 else 0, seed=t).pin_memory() for t in range(T_TRAJ - 1)]
+    # frame t+1's code = smooth embedding of the true pose + noise (what a trained TCN would return)
+    codes_h = [synth.make_pose_query(gt[t + 1], D, seed=3, frame=t).pin_memory() for t in range(T_TRAJ - 1)]
     codes_d = [c.to(dev) for c in codes_h]
     us = torch.rand(4096, generator=torch.Generator().manual_seed(7)).tolist()
     l2flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
@@ -147,6 +157,8 @@ def run_ours(args):
             e.record()  # materialises the cudaEvent_t handle
         return ev
 
+    if args.warmup + args.steps + 1 > T_TRAJ - 1:
+        raise SystemExit(f"--warmup + --steps must stay below {T_TRAJ - 2} (length of the synthetic slide)")
     for t in range(args.warmup):
         one(t, False)
     sync()
@@ -170,6 +182,8 @@ def run_ours(args):
     k_q = sum(e[2].elapsed_time(e[3]) for e in evs) / args.steps
     k_w = sum(e[3].elapsed_time(e[4]) for e in evs) / args.steps   # includes any wait for the side-stream query
     k_b = sum(e[4].elapsed_time(e[5]) for e in evs) / args.steps
+    k_max = {"k_step_a": max(e[1].elapsed_time(e[2]) for e in evs), "k_step_nnq": max(e[2].elapsed_time(e[3]) for e in evs),
+             "k_step_b": max(e[4].elapsed_time(e[5]) for e in evs)}
     total_ms = torch.tensor([sum(ms)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
@@ -180,19 +194,41 @@ def run_ours(args):
     # ---- codebook query kernel alone (it overlaps the motion/NN kernel inside a step)
     q_ms = query_time(eng, codes_d, l2flush, min(args.steps, 20))
 
-    # ---- end to end through the public API: host code + odom in, rmse out, every step
+    # ---- end to end through the public API: every step the tactile code (pinned host) + odometry +
+    # ground truth go host->device and the step's result (rmse, 8 bytes) comes back to the host.  The
+    # read-back is asynchronous into pinned memory and consumed one step later, so the host prepares
+    # step t+1 while the GPU runs step t (the reference's loop reads .item() synchronously instead).
     sync()
+    restart()
+    for t in range(args.warmup):
+        one(t, True)
+    sync()
+    res_pinned = [torch.zeros(2, dtype=torch.float32).pin_memory() for _ in range(2)]
+    res_ev = [torch.cuda.Event() for _ in range(2)]
+    results = []
     t0 = torch.cuda.Event(enable_timing=True)
     t1 = torch.cuda.Event(enable_timing=True)
     t0.record()
     for t in range(args.steps):
-        one(args.warmup + args.steps + t, True)
+        k = args.warmup + t
+        eng.step(codes_h[k], odoms[k], u=us[k % 4096], gt=gts[k + 1])
+        res_pinned[t & 1].copy_(eng.rmse, non_blocking=True)
+        res_ev[t & 1].record()
+        if t:
+            res_ev[(t - 1) & 1].synchronize()
+            results.append(float(res_pinned[(t - 1) & 1][0]))
+    res_ev[(args.steps - 1) & 1].synchronize()
+    results.append(float(res_pinned[(args.steps - 1) & 1][0]))
     t1.record()
     sync()
+    assert len(results) == args.steps and all(r == r for r in results)
     e2e_ms = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e = n * world * args.steps / (float(e2e_ms.item()) * 1e-3)
+
+    # ---- tactile code network (one forward per frame; random weights, 4096-point contact patch)
+    tcn_ms = tcn_time(dev) if rank == 0 else None
 
     if rank == 0:
         peak, how = peaks()
@@ -207,7 +243,9 @@ def run_ours(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 poses / f64 weights+prefix",
             "data": "synthetic (seeded stand-ins for YCB-Slide assets; no datasets offline)",
-            "config": {"workload": f"{OBJ} log 3, N=1e6 particles per GPU, fused motion+SE3_NN+weight+prune+systematic-resample step",
+            "config": {"workload": f"{OBJ} log 3, N=1e6 particles per GPU, fused motion+SE3_NN+weight+prune+systematic-resample step; "
+                                   f"steps {args.warmup}..{args.warmup + args.steps} of a filter run from global initialisation",
+                       "embeddings": "smooth synthetic pose embedding (random Fourier features), query = embedding of the true pose + noise",
                        "particles_per_gpu": n, "codebook_M": M, "embedding_D": D, "embedding_dtype": "f64",
                        "noise": "in-kernel Philox4x32-10", "particle_order": "random" if args.no_sort else "sorted by codebook cell at load",
                        "drift_pruning": "pen_max 2 mm against the 1 mm surface vertex set (density of nontextured.stl[::10])",
@@ -216,16 +254,21 @@ def run_ours(args):
                          "traffic": traffic, "peak_source": how, "kernel": "k_step_a (motion + drift test + hint-graph SE3_NN)",
                          "algorithmic_bytes_per_launch": A_BYTES_PER_UPDATE * n, "avg_launch_ms": k_a,
                          "sweep": {"kernels_ms": {"k_step_a": k_a, "k_step_nnq": k_q, "k_step_sums(+query wait)": k_w, "k_step_b": k_b},
-                                   "algorithmic_bytes_per_step": ALGO_BYTES_PER_UPDATE * n,
+                                   "kernels_ms_max": k_max, "algorithmic_bytes_per_step": ALGO_BYTES_PER_UPDATE * n,
                                    "achieved": ALGO_BYTES_PER_UPDATE * n / (sweep_ms * 1e-3) / 1e9,
                                    "frac": ALGO_BYTES_PER_UPDATE * n / (sweep_ms * 1e-3) / 1e9 / peak},
                          "codebook_query": {"kernel": "k_cosine_rows<double>", "ms": q_ms, "algorithmic_bytes": M * D * 8 + D * 8 + M * 16,
                                             "achieved": (M * D * 8 + D * 8 + M * 16) / (q_ms * 1e-3) / 1e9,
                                             "frac": (M * D * 8 + D * 8 + M * 16) / (q_ms * 1e-3) / 1e9 / peak}},
-            "e2e": {"value": e2e, "unit": "particle-updates/s", "h2d_bytes_per_step": D * 8 + 64 + 64 + 4, "d2h_bytes_per_step": 8},
+            "e2e": {"value": e2e, "unit": "particle-updates/s", "h2d_bytes_per_step": D * 8 + 64 + 64 + 4, "d2h_bytes_per_step": 8,
+                    "readback": "rmse of every step, asynchronous into pinned memory, consumed one step later"},
+            "tcn_forward_ms": tcn_ms,
             "gpu_launches": 6 * args.steps, "clocks": clk.summary(),
-            "engine_stats": {"nn_grid_searches_per_step": stats_loop["nn_fallbacks"] / args.steps,
-                             "on_surface_last_step": stats_loop["on_surface"], "overflow": stats_loop["overflow"]},
+            "filter": {"rmse_t_mm_last_e2e_step": 1e3 * results[-1], "rmse_t_mm_first_e2e_step": 1e3 * results[0],
+                       "step_ms_every_5th": [round(x, 4) for x in ms[::5]]},
+            "engine_stats": {"nn_grid_searches_per_step": stats_loop["nn_fallbacks"] / (args.steps + args.warmup),
+                             "on_surface_last_step": stats_loop["on_surface"], "overflow": stats_loop["overflow"],
+                             "grid_rows_max_one_search": stats_loop["grid_rows_max"]},
         }
         if world == 1 and not args.no_cpu:
             out["cpu_baseline"] = cpu_baseline(budget_s=15.0)
@@ -234,6 +277,53 @@ def run_ours(args):
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def tcn_time(dev, reps=20):
+    """device time of one TCN forward (mt_tcn_forward: MinkLoc3D on one 4096-point cloud), random weights"""
+    import numpy as np
+
+    from midastouch_b200.tcn import TCN
+    import types
+
+    rng = np.random.default_rng(0)
+    m = types.SimpleNamespace(tcn_weights="", model="MinkFPN", num_points=4096, batch_size=100, mink_quantization_size=0.001,
+                              planes="32,64,64", layers="1,1,1", num_top_down=1, conv0_kernel_size=5, feature_size=256, output_dim=256)
+    P = {}
+
+    def conv(name, kvol, cin, cout):
+        w = torch.from_numpy(rng.normal(size=(kvol, cin, cout)).astype("float32") * (2.0 / (kvol * cin)) ** 0.5)
+        P[name] = w if kvol > 1 else w[0]
+
+    def bn(name, c):
+        P[f"{name}.bn.weight"], P[f"{name}.bn.bias"] = torch.ones(c), torch.zeros(c)
+        P[f"{name}.bn.running_mean"], P[f"{name}.bn.running_var"] = torch.zeros(c), torch.ones(c)
+
+    conv("backbone.conv0.kernel", 125, 1, 32), bn("backbone.bn0", 32)
+    inpl = 32
+    for s_, pl in enumerate((32, 64, 64)):
+        conv(f"backbone.convs.{s_}.kernel", 8, inpl, inpl), bn(f"backbone.bn.{s_}", inpl)
+        b = f"backbone.blocks.{s_}.0"
+        conv(f"{b}.conv1.kernel", 27, inpl, pl), bn(f"{b}.norm1", pl), conv(f"{b}.conv2.kernel", 27, pl, pl), bn(f"{b}.norm2", pl)
+        if inpl != pl:
+            conv(f"{b}.downsample.0.kernel", 1, inpl, pl), bn(f"{b}.downsample.1", pl)
+        inpl = pl
+    conv("backbone.conv1x1.0.kernel", 1, 64, 256), conv("backbone.tconvs.0.kernel", 8, 256, 256), conv("backbone.conv1x1.1.kernel", 1, 64, 256)
+    P["pooling.p"] = torch.tensor([3.0])
+    tcn = TCN(types.SimpleNamespace(model=m, train=types.SimpleNamespace(normalize_embeddings=True)), device=dev, weights=P)
+    xy = rng.uniform(-1, 1, size=(4096, 2))
+    z = 0.3 * (xy[:, 0] ** 2 + xy[:, 1] ** 2) - 0.2
+    cloud = torch.from_numpy(np.concatenate([xy, z[:, None]], 1).astype("float32")).to(dev)[None]
+    for _ in range(3):
+        tcn.embed_clouds(cloud)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        tcn.embed_clouds(cloud)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
 
 
 def query_time(eng, codes_d, l2flush, reps):
@@ -275,7 +365,7 @@ def cpu_baseline(budget_s=15.0, n=65536, steps=None):
     t = 0
     while (t_total < budget_s and (steps is None)) or (steps is not None and done < steps):
         odom = torch.inverse(meas[t % (T_TRAJ - 1)]) @ meas[t % (T_TRAJ - 1) + 1]
-        q = synth.make_query(cbs, int(sel[t % n]), seed=t)
+        q = synth.make_pose_query(gt[t % (T_TRAJ - 1) + 1], D, seed=3, frame=t % (T_TRAJ - 1))
         t0 = time.perf_counter()
         tn, rot = O.draw_motion_noise(n, 2e-4, 0.5)
         moved, _ = O.motion_model(poses, odom, tn, rot)                      # motionModel

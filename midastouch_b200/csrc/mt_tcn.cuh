@@ -57,6 +57,7 @@ struct mt_tcn {
   int* d_n;                // [4] active points per level (device)
   int* d_flag;             // max_points scratch (first-child flags -> parent rows)
   float* pool;             // feature scratch
+  double* gem_part;        // max_batch x TCN_GEM_SLICES x 256 GeM partial sums
   size_t pool_floats;
 };
 
@@ -196,35 +197,55 @@ __global__ void __launch_bounds__(256) k_tcn_conv(const unsigned long long* __re
   for (int j = 0; j < 8; ++j) acc[j] = 0.f;
   const int kvol = (MODE == 1) ? 1 : k * k * k;
   const int centre = (k & 1) ? (k >> 1) : 0;
-  for (int i = 0; i < kvol; ++i) {
-    int wi = i;
-    unsigned long long nk;
-    if (MODE == 0) {
-      const int ox = (i % k - centre) * dil, oy = ((i / k) % k - centre) * dil, oz = (i / (k * k) - centre) * dil;
-      nk = tcn_pack(b, x + ox, y + oy, z + oz);
-    } else {
-      const int px = tcn_floor_to(x, 2 * dil), py = tcn_floor_to(y, 2 * dil), pz = tcn_floor_to(z, 2 * dil);
-      wi = ((z - pz) / dil * 2 + (y - py) / dil) * 2 + (x - px) / dil;
-      nk = tcn_pack(b, px, py, pz);
+  for (int i0 = 0; i0 < kvol; i0 += 32) {
+    // the 32 lanes resolve 32 kernel offsets at once (the look-ups are independent memory chains)
+    const int i = i0 + lane;
+    int row = -1, wi = i;
+    if (i < kvol) {
+      unsigned long long nk;
+      if (MODE == 0) {
+        const int ox = (i % k - centre) * dil, oy = ((i / k) % k - centre) * dil, oz = (i / (k * k) - centre) * dil;
+        nk = tcn_pack(b, x + ox, y + oy, z + oz);
+      } else {
+        const int px = tcn_floor_to(x, 2 * dil), py = tcn_floor_to(y, 2 * dil), pz = tcn_floor_to(z, 2 * dil);
+        wi = ((z - pz) / dil * 2 + (y - py) / dil) * 2 + (x - px) / dil;
+        nk = tcn_pack(b, px, py, pz);
+      }
+      row = tcn_lookup(in_tab, nk);
     }
-    const int row = tcn_lookup(in_tab, nk);
-    if (row < 0) continue;  // warp-uniform: all lanes look the same key up
-    const float* __restrict__ Wi = W + (size_t)wi * cin * cout;
-    if (!in_feat) {  // conv0: the reference assigns a dummy feature 1 to every point (tcn.py:131-134)
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (lane + 32 * j < cout) acc[j] += __ldg(Wi + lane + 32 * j);
-      continue;
-    }
-    for (int c0 = 0; c0 < cin; c0 += 32) {
-      const float xv = (c0 + lane < cin) ? __ldg(in_feat + (size_t)row * cin + c0 + lane) : 0.f;
-      const int cn = min(32, cin - c0);
-      for (int t = 0; t < cn; ++t) {
-        const float xs = __shfl_sync(0xffffffffu, xv, t);
-        const float* __restrict__ Wr = Wi + (size_t)(c0 + t) * cout;
+    unsigned found = __ballot_sync(0xffffffffu, row >= 0);
+    while (found) {  // ascending offset order: the summation order is fixed
+      const int src = __ffs(found) - 1;
+      found &= found - 1;
+      const int r = __shfl_sync(0xffffffffu, row, src);
+      const float* __restrict__ Wi = W + (size_t)__shfl_sync(0xffffffffu, wi, src) * cin * cout;
+      if (!in_feat) {  // conv0: the reference assigns a dummy feature 1 to every point (tcn.py:131-134)
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          if (lane + 32 * j < cout) acc[j] = fmaf(xs, __ldg(Wr + lane + 32 * j), acc[j]);
+          if (lane + 32 * j < cout) acc[j] += __ldg(Wi + lane + 32 * j);
+        continue;
+      }
+      for (int c0 = 0; c0 < cin; c0 += 32) {
+        const float xv = (c0 + lane < cin) ? __ldg(in_feat + (size_t)r * cin + c0 + lane) : 0.f;  // zero beyond cin
+        const int cn = min(32, cin - c0);
+        if (cn == 32) {
+#pragma unroll 8
+          for (int t = 0; t < 32; ++t) {  // unrolled: eight rows of W in flight
+            const float xs = __shfl_sync(0xffffffffu, xv, t);
+            const float* __restrict__ Wr = Wi + (size_t)(c0 + t) * cout;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (lane + 32 * j < cout) acc[j] = fmaf(xs, __ldg(Wr + lane + 32 * j), acc[j]);
+          }
+        } else {
+          for (int t = 0; t < cn; ++t) {
+            const float xs = __shfl_sync(0xffffffffu, xv, t);
+            const float* __restrict__ Wr = Wi + (size_t)(c0 + t) * cout;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (lane + 32 * j < cout) acc[j] = fmaf(xs, __ldg(Wr + lane + 32 * j), acc[j]);
+          }
+        }
       }
     }
   }
@@ -243,29 +264,48 @@ __global__ void __launch_bounds__(256) k_tcn_conv(const unsigned long long* __re
 }
 
 // GeM pooling (minkloc.py:84-95) over the points of every batch element + optional L2
-// normalisation (tcn.py:140-143) -> float64 (tcn.py:148).  One block per batch element, one
-// thread per channel; points of a batch element are contiguous (keys are batch-major).
-__global__ void __launch_bounds__(256) k_tcn_gem(const unsigned long long* __restrict__ keys, const int* __restrict__ d_n,
-                                                 const float* __restrict__ feat, int c, float p, float eps, int normalize,
-                                                 double* __restrict__ out) {
-  __shared__ double s_sq[8];
-  __shared__ int s_lo, s_hi;
-  const int n = *d_n, b = blockIdx.x;
-  if (threadIdx.x < 2) {  // first row with batch >= b (+1)
-    const unsigned long long target = (unsigned long long)(b + threadIdx.x);
+// normalisation (tcn.py:140-143) -> float64 (tcn.py:148).  Points of a batch element are contiguous
+// (keys are batch-major).  Pass 1: grid (batch, TCN_GEM_SLICES), thread = channel, every block sums
+// clamp(x)^p over its slice of the points; pass 2: one block per batch element combines the slices in
+// a fixed order.
+#define TCN_GEM_SLICES 64
+__device__ __forceinline__ void tcn_batch_range(const unsigned long long* __restrict__ keys, int n, int b, int& lo_out, int& hi_out) {
+  int r[2];
+  for (int s = 0; s < 2; ++s) {  // first row with batch >= b + s
+    const unsigned long long target = (unsigned long long)(b + s);
     int lo = 0, hi = n;
     while (lo < hi) {
       const int mid = (lo + hi) >> 1;
       if ((keys[mid] >> 54) < target) lo = mid + 1; else hi = mid;
     }
-    if (threadIdx.x == 0) s_lo = lo; else s_hi = lo;
+    r[s] = lo;
   }
-  __syncthreads();
-  const int lo = s_lo, hi = s_hi;
+  lo_out = r[0], hi_out = r[1];
+}
+__global__ void __launch_bounds__(256) k_tcn_gem_partial(const unsigned long long* __restrict__ keys, const int* __restrict__ d_n,
+                                                         const float* __restrict__ feat, int c, float p, float eps,
+                                                         double* __restrict__ part /* batch x slices x c */) {
+  int lo, hi;
+  tcn_batch_range(keys, *d_n, blockIdx.x, lo, hi);
+  const int per = (hi - lo + TCN_GEM_SLICES - 1) / TCN_GEM_SLICES;
+  const int s0 = lo + blockIdx.y * per, s1 = min(s0 + per, hi);
+  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+    double acc = 0.0;
+    for (int r = s0; r < s1; ++r) acc += (double)powf(fmaxf(feat[(size_t)r * c + ch], eps), p);
+    part[((size_t)blockIdx.x * TCN_GEM_SLICES + blockIdx.y) * c + ch] = acc;
+  }
+}
+__global__ void __launch_bounds__(256) k_tcn_gem(const unsigned long long* __restrict__ keys, const int* __restrict__ d_n,
+                                                 const double* __restrict__ part, int c, float p, int normalize,
+                                                 double* __restrict__ out) {
+  __shared__ double s_sq[8];
+  int lo, hi;
+  tcn_batch_range(keys, *d_n, blockIdx.x, lo, hi);
+  const int b = blockIdx.x;
   double acc_total = 0.0;
   for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
     double acc = 0.0;
-    for (int r = lo; r < hi; ++r) acc += (double)powf(fmaxf(feat[(size_t)r * c + ch], eps), p);
+    for (int sl = 0; sl < TCN_GEM_SLICES; ++sl) acc += part[((size_t)b * TCN_GEM_SLICES + sl) * c + ch];
     const double g = (hi > lo) ? pow(acc / (double)(hi - lo), 1.0 / (double)p) : 0.0;
     out[(size_t)b * c + ch] = g;
     acc_total += g * g;
@@ -301,6 +341,7 @@ extern "C" int mt_tcn_create(int device, int max_points, int max_batch, mt_tcn**
   CK(cudaMalloc(&t->d_flag, sizeof(int) * max_points));
   t->pool_floats = (size_t)max_points * 1184;
   CK(cudaMalloc(&t->pool, sizeof(float) * t->pool_floats));
+  CK(cudaMalloc(&t->gem_part, sizeof(double) * (size_t)max_batch * 64 * 256));
   *out = t;
   return MT_OK;
 }
@@ -311,7 +352,7 @@ extern "C" int mt_tcn_destroy(mt_tcn* t) {
   for (int l = 0; l < 4; ++l) cudaFree(t->tab[l].keys), cudaFree(t->tab[l].vals), cudaFree(t->keys[l]);
   for (int i = 0; i < TCN_NCONV; ++i) cudaFree(t->conv[i].w);
   for (int i = 0; i < TCN_NBN; ++i) cudaFree(t->bn[i].scale), cudaFree(t->bn[i].shift);
-  cudaFree(t->d_n), cudaFree(t->d_flag), cudaFree(t->pool);
+  cudaFree(t->d_n), cudaFree(t->d_flag), cudaFree(t->pool), cudaFree(t->gem_part);
   delete t;
   return MT_OK;
 }
@@ -444,7 +485,9 @@ extern "C" int mt_tcn_forward(mt_tcn* t, const unsigned long long* d_keys, int n
   TCN_RUN(tcn_conv_launch(t, 0, TCN_LAT1, -1, t->keys[2], t->d_n + 2, n, t->tab[2], fmap, 1, 4, nullptr, 0, 0, fp, st));
   TCN_RUN(tcn_conv_launch(t, 1, TCN_TCONV, -1, t->keys[2], t->d_n + 2, n, t->tab[3], z, 2, 4, nullptr, 0, 1, fp, st));
 #undef TCN_RUN
-  k_tcn_gem<<<batch, 256, 0, st>>>(t->keys[2], t->d_n + 2, fp, f, t->gem_p, t->gem_eps, normalize, d_out);
+  k_tcn_gem_partial<<<dim3(batch, TCN_GEM_SLICES), 256, 0, st>>>(t->keys[2], t->d_n + 2, fp, f, t->gem_p, t->gem_eps, t->gem_part);
+  CK_LAUNCH();
+  k_tcn_gem<<<batch, 256, 0, st>>>(t->keys[2], t->d_n + 2, t->gem_part, f, t->gem_p, normalize, d_out);
   CK_LAUNCH();
   if (d_counts) CK(cudaMemcpyAsync(d_counts, t->d_n, sizeof(int) * 4, cudaMemcpyDeviceToDevice, st));
   return MT_OK;

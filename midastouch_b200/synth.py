@@ -159,15 +159,41 @@ class SynthCodebook:
     embeddings: torch.Tensor  # (M,D) float64 (build_codebook.py:72-74)
 
 
-def make_codebook(obj: SynthObject, M: int = 50000, D: int = 256, seed: int = 0, cam_dist: float = 0.022) -> SynthCodebook:
+def pose_embedding(poses: np.ndarray, D: int, seed: int = 0, len_t: float = 0.01, kappa: float = 2.0) -> np.ndarray:
+    """smooth positive embedding of sensor poses: random Fourier features of (t / len_t, kappa * z-axis,
+    kappa * x-axis), 1 + cos(.), L2-normalised.  Stands for a trained TCN: codes of nearby / similarly
+    oriented touches are similar (cosine ~1 within ~len_t, ~0.67 far away), which is what lets the
+    filter's weights concentrate the particles."""
+    P = np.asarray(poses, dtype=np.float64).reshape(-1, 4, 4)
+    f = np.concatenate([P[:, :3, 3] / len_t, kappa * P[:, :3, 2], kappa * P[:, :3, 0]], axis=1)
+    rng = np.random.default_rng(seed + 7000)
+    W, b = rng.normal(size=(9, D)), rng.uniform(0, 2 * math.pi, D)
+    E = 1.0 + np.cos(f @ W + b)
+    return E / np.linalg.norm(E, axis=1, keepdims=True)
+
+
+def make_codebook(obj: SynthObject, M: int = 50000, D: int = 256, seed: int = 0, cam_dist: float = 0.022,
+                  embedding: str = "random") -> SynthCodebook:
+    """embedding="random": i.i.d. positive codes (tests / golden vectors); "smooth": ``pose_embedding``."""
     rng = np.random.default_rng(seed + 1000)
     pts, nrm = obj.sample_surface(M, rng)
     T = poses_from_normals(pts, nrm, rng)
     cam = T.copy()
     cam[:, :3, 3] += cam_dist * T[:, :3, 2]
-    E = rng.uniform(0.0, 1.0, (M, D))
-    E /= np.linalg.norm(E, axis=1, keepdims=True)
+    if embedding == "smooth":
+        E = pose_embedding(T, D, seed)
+    else:
+        E = rng.uniform(0.0, 1.0, (M, D))
+        E /= np.linalg.norm(E, axis=1, keepdims=True)
     return SynthCodebook(torch.from_numpy(T).float(), torch.from_numpy(cam).float(), torch.from_numpy(E))
+
+
+def make_pose_query(pose: torch.Tensor, D: int, seed: int = 0, noise: float = 0.05, frame: int = 0) -> torch.Tensor:
+    """tactile code of a touch at ``pose`` under the smooth embedding (+ noise), (1,D) float64."""
+    e = torch.from_numpy(pose_embedding(pose.double().numpy(), D, seed))[0]
+    g = torch.Generator().manual_seed(seed + 4000 + int(frame))
+    q = e + noise * torch.randn(D, generator=g, dtype=torch.float64) / math.sqrt(D)
+    return (q / q.norm())[None]
 
 
 def _noise_tf(n, sig_t, sig_r_deg, rng):
