@@ -71,6 +71,7 @@ struct mt_ctx {
   double* d_esim;  // exp(cos)
   double* d_rnorm; // max(|E_m|, 1e-8), computed by the first query after an upload
   bool rnorm_ready;
+  int query_blocks_per_sm;
   bool cb_ready;
   void* d_scratch;       // grow-on-demand scratch of the cluster / selection entry points
   size_t scratch_bytes;
@@ -272,6 +273,7 @@ extern "C" int mt_codebook_upload(mt_ctx* c, const float* h_keys, const void* d_
   c->d_emb = d_emb;
   c->emb_dtype = emb_dtype;
   c->rnorm_ready = false;
+  c->query_blocks_per_sm = 0;
   c->cb_ready = true;
   return MT_OK;
 }
@@ -679,37 +681,34 @@ __global__ void __launch_bounds__(256) k_row_norms(const T* __restrict__ E, int 
   if (lane == 0) rnorm[row] = fmax(sqrt(nn), 1e-8);
 }
 
-// query -> float64 + its clamped norm (one block)
-template <typename TQ>
-__global__ void __launch_bounds__(256) k_stage_query(const TQ* __restrict__ in, int D, double* __restrict__ out, double* __restrict__ qnorm) {
-  __shared__ double s8[8];
-  double acc = 0.0;
-  for (int i = threadIdx.x; i < D; i += 256) {
-    const double x = (double)in[i];
-    out[i] = x;
-    acc = fma(x, x, acc);
-  }
-  const double t = block_sum_256(acc, s8);
-  if (threadIdx.x == 0) *qnorm = fmax(sqrt(t), 1e-8);
-}
-
 // sim[m] = <q, E_m> / (|q| |E_m|), exp(sim[m]).  Persistent warps, four rows per trip: the query
 // vector is read from shared memory once per four rows, sixteen 16-byte loads are in flight per
 // lane, and the four dot products are reduced with a transposing butterfly (12 shuffles instead
 // of 40).  Traffic: M*D*sizeof(T) + 24*M bytes.
-template <typename T>
-__global__ void __launch_bounds__(256) k_codebook_query(const double* __restrict__ qd, const double* __restrict__ qnorm,
-                                                        const T* __restrict__ E, const double* __restrict__ rnorm, int M, int D,
+template <typename T, typename TQ>
+__global__ void __launch_bounds__(256) k_codebook_query(const TQ* __restrict__ q_in, const T* __restrict__ E,
+                                                        const double* __restrict__ rnorm, int M, int D,
                                                         double* __restrict__ sim, double* __restrict__ esim,
                                                         double* __restrict__ sim2) {
   extern __shared__ double sq[];
-  for (int i = threadIdx.x; i < D; i += blockDim.x) sq[i] = qd[i];
-  __syncthreads();
+  __shared__ double s8q[8];
+  __shared__ double s_qn;
+  {  // every block stages the query as float64 and computes its clamped norm (D values: cheaper than a launch)
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < D; i += blockDim.x) {
+      const double x = (double)q_in[i];
+      sq[i] = x;
+      acc = fma(x, x, acc);
+    }
+    const double t = block_sum_256(acc, s8q);
+    if (threadIdx.x == 0) s_qn = fmax(sqrt(t), 1e-8);
+    __syncthreads();
+  }
   constexpr int W = VecLoad<T>::W;
   const int lane = threadIdx.x & 31;
   const int nvec = D / W;
   const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nw = gridDim.x * (blockDim.x >> 5);
-  const double qn = *qnorm;
+  const double qn = s_qn;
   for (int r0 = 4 * gw; r0 < M; r0 += 4 * nw) {
     const T* e[4];
 #pragma unroll
@@ -790,30 +789,38 @@ extern "C" int mt_codebook_query(mt_ctx* c, const void* d_q, int q_dtype, double
   cudaStream_t st = (cudaStream_t)stream;
   const int D = c->D, M = c->M;
   if (D > MT_MAX_D) return set_err(MT_ERR_ARG, "cosine: D exceeds MT_MAX_D (6144)");
-  if (q_dtype == MT_DTYPE_F32)
-    k_stage_query<float><<<1, 256, 0, st>>>((const float*)d_q, D, c->d_q64, c->d_scal + 7);
-  else if (q_dtype == MT_DTYPE_F64)
-    k_stage_query<double><<<1, 256, 0, st>>>((const double*)d_q, D, c->d_q64, c->d_scal + 7);
-  else
-    return set_err(MT_ERR_ARG, "cosine: bad query dtype");
-  CK_LAUNCH();
+  if (q_dtype != MT_DTYPE_F32 && q_dtype != MT_DTYPE_F64) return set_err(MT_ERR_ARG, "cosine: bad query dtype");
+  const bool e32 = c->emb_dtype == MT_DTYPE_F32, q32 = q_dtype == MT_DTYPE_F32;
+  if (e32 && D % 4) return set_err(MT_ERR_ARG, "cosine: D must be a multiple of 4 for float32 rows");
+  if (!e32 && D % 2) return set_err(MT_ERR_ARG, "cosine: D must be a multiple of 2 for float64 rows");
   if (!c->rnorm_ready) {  // the embeddings are static between uploads: their norms are computed once
-    if (c->emb_dtype == MT_DTYPE_F32)
+    if (e32)
       k_row_norms<float><<<(M + 7) / 8, 256, 0, st>>>((const float*)c->d_emb, M, D, c->d_rnorm);
     else
       k_row_norms<double><<<(M + 7) / 8, 256, 0, st>>>((const double*)c->d_emb, M, D, c->d_rnorm);
     CK_LAUNCH();
     c->rnorm_ready = true;
   }
-  const int grid = std::min((M + 31) / 32, c->sm_count * 8);
   const size_t sh = sizeof(double) * D;
-  if (c->emb_dtype == MT_DTYPE_F32) {
-    if (D % 4) return set_err(MT_ERR_ARG, "cosine: D must be a multiple of 4 for float32 rows");
-    k_codebook_query<float><<<grid, 256, sh, st>>>(c->d_q64, c->d_scal + 7, (const float*)c->d_emb, c->d_rnorm, M, D, c->d_sim, c->d_esim, d_sim_out);
-  } else {
-    if (D % 2) return set_err(MT_ERR_ARG, "cosine: D must be a multiple of 2 for float64 rows");
-    k_codebook_query<double><<<grid, 256, sh, st>>>(c->d_q64, c->d_scal + 7, (const double*)c->d_emb, c->d_rnorm, M, D, c->d_sim, c->d_esim, d_sim_out);
+  if (!c->query_blocks_per_sm) {  // persistent grid = what is resident at once (no tail wave)
+    int occ = 0;
+    if (e32)
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_codebook_query<float, double>, 256, sh);
+    else
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_codebook_query<double, double>, 256, sh);
+    c->query_blocks_per_sm = occ > 0 ? occ : 4;
   }
+  // persistent warps take 4 rows per trip: size the grid so that every warp makes the same number of trips
+  const int resident = c->sm_count * c->query_blocks_per_sm;
+  const int trips_total = (M + 3) / 4;
+  int grid = (trips_total + 7) / 8;
+  for (int k = 2; grid > resident; ++k) grid = ((trips_total + k - 1) / k + 7) / 8;
+  const float* Ef = (const float*)c->d_emb;
+  const double* Ed = (const double*)c->d_emb;
+  if (e32 && q32) k_codebook_query<float, float><<<grid, 256, sh, st>>>((const float*)d_q, Ef, c->d_rnorm, M, D, c->d_sim, c->d_esim, d_sim_out);
+  else if (e32) k_codebook_query<float, double><<<grid, 256, sh, st>>>((const double*)d_q, Ef, c->d_rnorm, M, D, c->d_sim, c->d_esim, d_sim_out);
+  else if (q32) k_codebook_query<double, float><<<grid, 256, sh, st>>>((const float*)d_q, Ed, c->d_rnorm, M, D, c->d_sim, c->d_esim, d_sim_out);
+  else k_codebook_query<double, double><<<grid, 256, sh, st>>>((const double*)d_q, Ed, c->d_rnorm, M, D, c->d_sim, c->d_esim, d_sim_out);
   CK_LAUNCH();
   return MT_OK;
 }
@@ -1676,6 +1683,9 @@ __global__ void __launch_bounds__(256) k_step_b(StepDev p) {
 // on their common boundary), then resamples its chunks.  Saves a launch, the 4 B/particle re-read
 // and the serial last-block scan.
 #define MT_BW_MAX_PER 32
+#ifndef MT_BW_PREFETCH
+#define MT_BW_PREFETCH 0
+#endif
 #define MT_BW_MAX_GRID 1184
 __global__ void __launch_bounds__(256) k_step_bw(StepDev p, unsigned long long* bar, unsigned long long bar_target,
                                                  double* __restrict__ blocktot /* 3 x grid */, int* __restrict__ blockcnt) {
@@ -1742,10 +1752,16 @@ __global__ void __launch_bounds__(256) k_step_bw(StepDev p, unsigned long long* 
     const double base = fmin(run, next_g);
     run += s_part[c - c_lo];
     const double endv = (c + 1 == c_hi) ? next_g : fmin(run, next_g);
+#if MT_BW_PREFETCH
     if (c + 1 < c_hi) step_b_load<true, true>(p, c + 1, n, nxt);  // in flight while this chunk is resampled
+#endif
     __syncthreads();  // s8 / s_cnt of the previous chunk are free
     step_b_chunk<true, true>(p, c, n, S, 0.0, base, endv, s8, s_cnt, cur);
+#if MT_BW_PREFETCH
     cur = nxt;
+#else
+    if (c + 1 < c_hi) step_b_load<true, true>(p, c + 1, n, cur);
+#endif
   }
   if (g == 0) {  // RMSE, drift flag, bookkeeping (what the last block of k_step_sums does)
     __syncthreads();

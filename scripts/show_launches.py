@@ -3,7 +3,7 @@ lines=[l for l in open('/root/repo/gpurun_out/launches.csv') if not l.startswith
 seq=[(x['Kernel Name'].split('(')[0][:28], float(x['Metric Value'].replace(',',''))/1000) for x in csv.DictReader(lines)]
 steps=[]; cur=None
 for n,t in seq:
-    if 'k_to_f64' in n or 'k_stage_query' in n:
+    if 'k_codebook_query' in n:
         if cur: steps.append(cur)
         cur=[]
     if cur is not None: cur.append((n,t))
