@@ -1,0 +1,106 @@
+"""The loop of ``midastouch/filter/filter.py:131-233`` without the GUI / image networks: tactile codes
+come from a callable (the TCN, or precomputed codes), everything else is the reference's sequence
+
+    t>0: odom = inv(meas[prev]) @ meas[idx]; particles = pf.motionModel(particles, odom)      (154-155)
+    t=0: particles = pf.init_filter(gt[idx], N); poses = codebook.SE3_NN(poses)[0]             (159-160)
+    rmse = particle_rmse(particles, gt[idx])                                                     (164)
+    weights = pf.get_similarity(code, codebook.SE3_NN(poses)[2])                              (170-173)
+    particles, drifted = pf.remove_invalid_particles(particles); drifted -> re-project        (176-179)
+    cluster_poses, cluster_stds = pf.get_cluster_centers(particles, "quat_avg")               (184-186)
+    particles = pf.annealing(particles, mean(cluster_stds)); particles = pf.resampler(...)    (189-190)
+
+with two deliberate differences: the frame index follows a fixed schedule instead of wall-clock pacing
+(134-139; reproducible), and DBSCAN re-clustering every 50 frames (182-183) is not run (labels stay 0).
+``filter_stats`` has the reference's keys (99-116).  ``run_filter_engine`` is the same loop on the
+resident FilterEngine (fixed N, systematic resampling, everything on the GPU)."""
+from __future__ import annotations
+
+import time
+
+import torch
+
+from .engine import FilterEngine
+from .particle_filter import Particles, particle_filter, particle_rmse
+
+
+def _new_stats(cfg, pf, codebook, traj_size, init_particles):
+    return {"rmse_t": [], "rmse_r": [], "time": [], "traj_size": traj_size, "avg_time": None, "total_time": 0,
+            "cluster_poses": [], "cluster_stds": [], "obj_name": cfg.expt.obj_model, "tree_size": len(codebook),
+            "noise_ratio": cfg.expt.params.noise_ratio, "init_noise": pf.init_noise, "init_particles": init_particles,
+            "num_particles": [], "log_id": str(cfg.expt.log_id).zfill(2), "trial_id": 0}
+
+
+def run_filter(cfg, pf: particle_filter, codebook, code_fn, gt_p: torch.Tensor, meas_p: torch.Tensor, schedule=None,
+               softmax: bool = True, floor: int = 1000, resample: str | None = None) -> dict:
+    """drop-in classes, reference order.  code_fn(idx) -> (1,D) tactile code.  gt_p / meas_p: (T,4,4) CUDA."""
+    N = int(cfg.expt.params.num_particles)
+    resample = resample or getattr(cfg.expt.params, "resample", "weighted_random")
+    schedule = list(range(gt_p.shape[0])) if schedule is None else list(schedule)
+    stats = _new_stats(cfg, pf, codebook, len(schedule), N)
+    prev_idx, particles = 0, None
+    for idx in schedule:
+        t0 = time.time()
+        code = code_fn(idx)
+        if prev_idx > 0:
+            odom = torch.inverse(meas_p[prev_idx]) @ meas_p[idx]
+            particles = pf.motionModel(particles, odom)
+        else:  # the reference re-initialises until the previous frame index was > 0 (filter.py:152,230)
+            particles = pf.init_filter(gt_p[idx], N)
+            particles.poses, _, _ = codebook.SE3_NN(particles.poses)
+        rmse_t, rmse_r = particle_rmse(particles, gt_p[idx])
+        stats["rmse_t"].append(rmse_t.item())
+        stats["rmse_r"].append(rmse_r.item())
+        _, _, nn_codes = codebook.SE3_NN(particles.poses)
+        particles.weights = pf.get_similarity(code, nn_codes, softmax=softmax)
+        particles, drifted = pf.remove_invalid_particles(particles)
+        if drifted:
+            particles.poses, _, _ = codebook.SE3_NN(particles.poses)
+        cluster_poses, cluster_stds = pf.get_cluster_centers(particles, method="quat_avg")
+        particles = pf.annealing(particles, torch.mean(cluster_stds), floor=floor)
+        particles = pf.resampler(particles, resample=resample)
+        stats["cluster_poses"].append(cluster_poses)
+        stats["cluster_stds"].append(cluster_stds)
+        stats["num_particles"].append(len(particles))
+        stats["time"].append(time.time() - t0)
+        stats["total_time"] = sum(stats["time"])
+        prev_idx = idx
+    stats["avg_time"] = stats["total_time"] / max(len(schedule), 1)
+    return stats
+
+
+def run_filter_engine(cfg, pf: particle_filter, codebook, code_fn, gt_p: torch.Tensor, meas_p: torch.Tensor, schedule=None,
+                      softmax: bool = True, seed: int = 0) -> dict:
+    """same loop on the resident engine: one ``FilterEngine.step`` per frame (motion + SE3_NN + weights +
+    prune + systematic resampling), particle count fixed, no host synchronisation inside the loop (the
+    RMSE values are read back once at the end)."""
+    N = int(cfg.expt.params.num_particles)
+    schedule = list(range(gt_p.shape[0])) if schedule is None else list(schedule)
+    stats = _new_stats(cfg, pf, codebook, len(schedule), N)
+    eng = FilterEngine(codebook, capacity=N, sig_t=pf.motion_noise["sig_t"], sig_r=pf.motion_noise["sig_r"], seed=seed,
+                       mesh_vertices=pf.mesh_vertices_ds, pen_max=pf.pen_max)
+    gt_h, meas_h = gt_p.detach().float().cpu(), meas_p.detach().float().cpu()
+    rm = torch.zeros((len(schedule), 2), dtype=torch.float32, device=gt_p.device)
+    prev_idx = 0
+    t_start = time.time()
+    for k, idx in enumerate(schedule):
+        code = code_fn(idx)
+        if prev_idx > 0:
+            odom = torch.inverse(meas_h[prev_idx]) @ meas_h[idx]
+            eng.step(code, odom, gt=gt_h[idx], softmax=softmax)
+        else:
+            parts = pf.init_filter(gt_p[idx], N)
+            eng.load_particles(parts.poses)
+            eng.snap_to_codebook()
+            # frame without motion: weights + resampling only (identity odometry, no noise)
+            z = torch.zeros((N, 3), dtype=torch.float32, device=gt_p.device)
+            eng.step(code, torch.eye(4), tn=z, rot=z, gt=gt_h[idx], softmax=softmax)
+        rm[k].copy_(eng.rmse)
+        stats["num_particles"].append(N)
+        prev_idx = idx
+    rm = rm.cpu()
+    stats["rmse_t"], stats["rmse_r"] = rm[:, 0].tolist(), rm[:, 1].tolist()
+    stats["total_time"] = time.time() - t_start
+    stats["avg_time"] = stats["total_time"] / max(len(schedule), 1)
+    stats["time"] = [stats["avg_time"]] * len(schedule)
+    stats["engine"] = eng
+    return stats

@@ -713,3 +713,35 @@ def test_cpu_tensor_rejected(mt, box):
     pf = mt.pf.particle_filter(synth_cfg(), box.vertices)
     with pytest.raises(mt.lib.MidasError):
         pf.get_similarity(torch.rand(1, 8, dtype=torch.float64), torch.rand(4, 8, dtype=torch.float64))
+
+
+# ----------------------------------------------------------------------------- the loop (filter.py:131-233)
+def test_filter_loop_dropin_and_engine_converge(mt, dev, box):
+    """both forms of the loop -- the reference's sequence of drop-in calls and the resident engine --
+    localise a sliding touch on the sugar box: translation RMSE falls from the global initialisation
+    (~ object scale) to millimetres; filter_stats carries the reference's keys."""
+    from midastouch_b200.config import compose
+    from midastouch_b200.filter_loop import run_filter, run_filter_engine
+
+    cfg = compose(overrides=["expt.params.num_particles=20000", "expt.params.resample=low_var"])
+    cbs = synth.make_codebook(box, M=20000, D=64, seed=4, embedding="smooth")
+    cb = mt.tt.tactile_tree(cbs.poses, cbs.cam_poses, cbs.embeddings)
+    cb.to_device(dev)
+    pf = mt.pf.particle_filter(cfg, box.vertices, downsample=1)
+    gt, meas = synth.make_trajectory(box, T=80, seed=4)
+    code_fn = lambda idx: synth.make_pose_query(gt[idx], 64, seed=4, frame=idx)  # noqa: E731
+    torch.manual_seed(0)
+    st = run_filter(cfg, pf, cb, lambda i: code_fn(i).to(dev), gt.to(dev), meas.to(dev), floor=5000)
+    for k in ("rmse_t", "rmse_r", "time", "traj_size", "avg_time", "total_time", "cluster_poses", "cluster_stds", "obj_name",
+              "tree_size", "noise_ratio", "init_noise", "init_particles", "num_particles", "log_id", "trial_id"):
+        assert k in st, k
+    assert st["traj_size"] == 80 and st["tree_size"] == 20000 and st["log_id"] == "00"
+    assert st["rmse_t"][0] > 0.03 and st["rmse_t"][-1] < 0.012, (st["rmse_t"][0], st["rmse_t"][-1])
+    assert 5000 <= st["num_particles"][-1] <= 20000 and st["cluster_poses"][-1].shape == (1, 4, 4)
+    torch.manual_seed(0)
+    pf2 = mt.pf.particle_filter(cfg, box.vertices, downsample=1)
+    # the engine keeps N fixed (no annealing = less selection pressure): it needs ~70 frames where the
+    # reference sequence needs ~45
+    se = run_filter_engine(cfg, pf2, cb, code_fn, gt.to(dev), meas.to(dev))
+    assert se["rmse_t"][0] > 0.03 and se["rmse_t"][-1] < 0.012, (se["rmse_t"][0], se["rmse_t"][-1])
+    assert se["engine"].ctx.stats()["overflow"] == 0
