@@ -1157,12 +1157,12 @@ __device__ __forceinline__ void draw_or_load_noise(const float* __restrict__ tn,
   }
 }
 
-__device__ __forceinline__ void apply_motion(const float P[3][4], const Affine& odom, const float t[3], const float r[3], float out[3][4], int euler_mode = 0) {
+__device__ __forceinline__ void apply_motion(const float P[3][4], const Affine& odom, const float t[3], const float r[3], float out[3][4], int euler_mode = 0, int fast = 0) {
   float Tn[3][4], G[3][4];
   if (euler_mode)
     mt_noise_affine_extrinsic(t, r, Tn);
   else
-    mt_noise_affine(t, r, Tn);
+    mt_noise_affine(t, r, Tn, fast);
   mt_compose(odom.m, Tn, G);  // noisyOdom = odom @ Tn   (particle_filter.py:345)
   mt_compose(P, G, out);      // pose @ noisyOdom         (particle_filter.py:374)
 }
@@ -1177,7 +1177,7 @@ __global__ void __launch_bounds__(256) k_motion(const float4* __restrict__ in, f
   float P[3][4], t[3], r[3], O[3][4];
   load_pose(in, stride, i, P);
   draw_or_load_noise(tn, rot, i, sig_t, sig_r, seed, step, first_gid + (uint64_t)i, t, r);
-  apply_motion(P, odom, t, r, O, euler_mode);
+  apply_motion(P, odom, t, r, O, euler_mode, tn == nullptr);
   store_pose(out, stride, i, O);
   if (invalid && mt_pose_invalid(O)) atomicAdd(invalid, 1);
 }
@@ -1352,7 +1352,7 @@ __global__ void __launch_bounds__(MT_A_BLOCK, MT_A_MINBLOCKS) k_step_a(StepDev p
     const int hint = nn_index(p.nn_cur[i]);
     nn_prefetch(T, hint);
     draw_or_load_noise(p.tn, p.rot, i, p.sig_t, p.sig_r, p.seed, p.step, p.first_gid + (uint64_t)i, t, r);
-    apply_motion(P, p.odom, t, r, O);
+    apply_motion(P, p.odom, t, r, O, 0, p.tn == nullptr);
     store_pose(p.soa_cur, p.stride, i, O);
     mt_se3_key(O, key);
     const bool invalid = mt_pose_invalid(O);

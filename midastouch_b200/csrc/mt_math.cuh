@@ -56,15 +56,24 @@ MT_HD void mt_compose(const float A[3][4], const float B[3][4], float C[3][4]) {
 
 // Rn = Rz(a0) Ry(a1) Rx(a2), angles = deg2rad(rot_deg) in float32
 // (euler_angles_to_matrix(.., "ZYX"), pose.py:215-269; deg2rad at particle_filter.py:336).
-MT_HD void mt_noise_affine(const float tn[3], const float rot_deg[3], float Tn[3][4]) {
+// fast != 0 (device, in-kernel noise only): SFU sine / cosine -- the angles are drawn noise of a
+// fraction of a degree, where __sincosf is accurate to ~1e-7 absolute.
+MT_HD void mt_noise_affine(const float tn[3], const float rot_deg[3], float Tn[3][4], int fast = 0) {
   const float d2r = 0.017453292519943295f;  // torch.deg2rad: x * (pi/180) in float32
   float a0 = rot_deg[0] * d2r, a1 = rot_deg[1] * d2r, a2 = rot_deg[2] * d2r;
   float cz, sz, cy, sy, cx, sx;
 #if defined(__CUDA_ARCH__)
-  sincosf(a0, &sz, &cz);
-  sincosf(a1, &sy, &cy);
-  sincosf(a2, &sx, &cx);
+  if (fast) {
+    __sincosf(a0, &sz, &cz);
+    __sincosf(a1, &sy, &cy);
+    __sincosf(a2, &sx, &cx);
+  } else {
+    sincosf(a0, &sz, &cz);
+    sincosf(a1, &sy, &cy);
+    sincosf(a2, &sx, &cx);
+  }
 #else
+  (void)fast;
   sz = sinf(a0); cz = cosf(a0); sy = sinf(a1); cy = cosf(a1); sx = sinf(a2); cx = cosf(a2);
 #endif
   // (Rz Ry) first, then times Rx -- matrices[0] @ matrices[1] @ matrices[2]
@@ -247,13 +256,32 @@ MT_HD void mt_box_muller(uint32_t a, uint32_t b, float* n0, float* n1) {
   *n1 = r * s;
 }
 
-// six N(0,1) draws for particle `gid` of filter step `step`: (tn[3], rot[3])
+// 21-bit uniform in (0,1): six of them come out of ONE Philox4x32-10 call (128 bits)
+MT_HD float mt_u01_21(uint32_t x) { return ((float)(x & 0x1FFFFFu) + 0.5f) * (1.0f / 2097152.0f); }
+
+// six N(0,1) draws for particle `gid` of filter step `step`: (tn[3], rot[3]).  One Philox call keyed by
+// (seed; gid, step); the 128 output bits are cut into six 21-bit uniforms (Box-Muller tails reach
+// 5.4 sigma, far beyond what a 1e6-particle cloud resolves).
 MT_HD void mt_motion_normals(uint64_t seed, uint64_t step, uint64_t gid, float tn[3], float rot[3]) {
-  mt_u4 c0 = {(uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)step, 0u};
-  mt_u4 c1 = {(uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)step, 1u};
+  mt_u4 c0 = {(uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)step, (uint32_t)(step >> 32)};
   mt_u4 a = mt_philox(c0, (uint32_t)seed, (uint32_t)(seed >> 32));
-  mt_u4 b = mt_philox(c1, (uint32_t)seed, (uint32_t)(seed >> 32));
-  mt_box_muller(a.x, a.y, &tn[0], &tn[1]);
-  mt_box_muller(a.z, a.w, &tn[2], &rot[0]);
-  mt_box_muller(b.x, b.y, &rot[1], &rot[2]);
+  const uint64_t lo = ((uint64_t)a.y << 32) | a.x, hi = ((uint64_t)a.w << 32) | a.z;
+  const uint32_t u0 = (uint32_t)lo, u1 = (uint32_t)(lo >> 21), u2 = (uint32_t)(lo >> 42);
+  const uint32_t u3 = (uint32_t)hi, u4 = (uint32_t)(hi >> 21), u5 = (uint32_t)(hi >> 42);
+  float n[6];
+  const uint32_t ua[3] = {u0, u2, u4}, ub[3] = {u1, u3, u5};
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+#if defined(__CUDA_ARCH__)
+    const float r = sqrtf(-2.0f * __logf(mt_u01_21(ua[k])));
+    float s, c;
+    __sincosf(6.283185307179586f * mt_u01_21(ub[k]), &s, &c);
+#else
+    const float r = sqrtf(-2.0f * logf(mt_u01_21(ua[k])));
+    const float ang = 6.283185307179586f * mt_u01_21(ub[k]);
+    const float s = sinf(ang), c = cosf(ang);
+#endif
+    n[2 * k] = r * c, n[2 * k + 1] = r * s;
+  }
+  tn[0] = n[0], tn[1] = n[1], tn[2] = n[2], rot[0] = n[3], rot[1] = n[4], rot[2] = n[5];
 }
