@@ -31,6 +31,23 @@ def prepare_odom(odom) -> "Odom16":
     return Odom16(*[float(x) for x in vals])
 
 
+def rebalance_plan(counts, rank: int):
+    """Particles are globally ordered rank-major.  Given the current per-rank counts, return
+    (send_counts, recv_counts, targets) that move the shard boundaries to an even split while keeping
+    the global order: rank r sends to rank s the overlap of its current range with s's target range."""
+    G, total = len(counts), int(sum(counts))
+    targets = [total // G + (1 if r < total % G else 0) for r in range(G)]
+    cur_off = [sum(counts[:r]) for r in range(G)]
+    tgt_off = [sum(targets[:r]) for r in range(G)]
+
+    def overlap(a0, a1, b0, b1):
+        return max(0, min(a1, b1) - max(a0, b0))
+
+    send = [overlap(cur_off[rank], cur_off[rank] + counts[rank], tgt_off[s], tgt_off[s] + targets[s]) for s in range(G)]
+    recv = [overlap(cur_off[s], cur_off[s] + counts[s], tgt_off[rank], tgt_off[rank] + targets[rank]) for s in range(G)]
+    return send, recv, targets
+
+
 class FilterEngine:
     def __init__(self, codebook: tactile_tree, capacity: int, sig_t: float = 2e-4, sig_r: float = 0.5,
                  seed: int = 0, rank: int = 0, world: int = 1, group=None, n_global: int | None = None,
@@ -68,6 +85,7 @@ class FilterEngine:
         self._a = StepArgs()
         # the codebook query runs on a side stream, concurrently with motion + SE3_NN
         self.overlap_query = True
+        self.rebalance_every = 64  # sharded runs: even the shards out every this many steps (0 = never)
         self.fuse_sums = True  # single GPU: weight sums + resampling as one cooperative kernel
         self._side = torch.cuda.Stream(device=self.dev)
         self._ev_table = torch.cuda.Event()
@@ -211,9 +229,42 @@ class FilterEngine:
             self.cur = 1 - self.cur
             if self.world > 1:
                 self.use_n_dev = True
-                # children per GPU drift by O(sqrt) per step; keep the host bound safe
+                # children per GPU drift slowly; keep the host-side bound (grid size) safe and even the
+                # shards out before the bound reaches the capacity
                 self.n = min(self.capacity, self.n + max(64, self.n // 1024))
+                if self.rebalance_every and (self.t + 1) % self.rebalance_every == 0:
+                    self.rebalance()
         self.t += 1
+
+    def rebalance(self):
+        """sharded runs: children follow their parents, so a GPU whose particles carry more weight
+        accumulates particles (slowly: weights are within a factor e).  This evens the shards out again
+        with one all-to-all of 52 B per moved particle (poses + matches); global order is preserved.
+        Synchronises with the host (reads the device-side counts)."""
+        if self.world == 1:
+            return
+        import torch.distributed as dist
+
+        n = self.count()
+        counts = torch.zeros(self.world, dtype=torch.int64, device=self.dev)
+        dist.all_gather_into_tensor(counts, self.n_dev[self.cur].reshape(1), group=self.group)
+        counts = counts.cpu().tolist()
+        send, recv, targets = rebalance_plan(counts, self.rank)
+        if counts == targets:
+            return
+        soa, nn = self.soa[self.cur], self.nn[self.cur]
+        rows = torch.cat([soa[0, :n], soa[1, :n], soa[2, :n], nn[:n].view(torch.float32).reshape(n, 1)], dim=1).contiguous()  # (n,13)
+        out = torch.empty((sum(recv), 13), dtype=torch.float32, device=self.dev)
+        dist.all_to_all_single(out, rows, output_split_sizes=recv, input_split_sizes=send, group=self.group)
+        m = out.shape[0]
+        if m > self.capacity:
+            raise MidasError("rebalance: shard exceeds the engine capacity")
+        for r in range(3):
+            soa[r, :m] = out[:, 4 * r:4 * r + 4]
+        nn[:m] = out[:, 12].contiguous().view(torch.int32)
+        self.n = m
+        self.n_dev[self.cur].fill_(m)
+        self.use_n_dev = True
 
     def _allgather_sums(self):
         import torch.distributed as dist

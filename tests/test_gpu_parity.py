@@ -745,3 +745,18 @@ def test_filter_loop_dropin_and_engine_converge(mt, dev, box):
     se = run_filter_engine(cfg, pf2, cb, code_fn, gt.to(dev), meas.to(dev))
     assert se["rmse_t"][0] > 0.03 and se["rmse_t"][-1] < 0.012, (se["rmse_t"][0], se["rmse_t"][-1])
     assert se["engine"].ctx.stats()["overflow"] == 0
+
+
+def test_sharded_engine_matches_single_gpu():
+    """2 GPUs (skipped on a 1-GPU box): the sharded step reproduces the single-GPU children exactly and
+    rebalance() preserves the global particle sequence (scripts/multigpu_check.py under torchrun)."""
+    import os
+    import subprocess
+    import sys
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29533", os.path.join(root, "scripts", "multigpu_check.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]

@@ -79,3 +79,29 @@ def test_two_rank_slot_ownership_matches_oracle(tmp_path, N, u):
     assert bool((res["w"][res["merged"][filled]] > 0).all())
     assert sum(res["children"]) == int(filled.sum()) or sum(res["children"]) == N
     assert abs(res["children"][0] - N / 2) < 0.05 * N  # near-flat weights: children stay balanced
+
+
+def test_rebalance_plan_preserves_order_and_evens_out():
+    from midastouch_b200.engine import rebalance_plan
+
+    for counts in ([10, 0, 5, 9], [1050774, 987000, 990000, 972226], [3], [0, 7], [5, 5, 5, 5]):
+        G, total = len(counts), sum(counts)
+        plans = [rebalance_plan(counts, r) for r in range(G)]
+        targets = plans[0][2]
+        assert sum(targets) == total and max(targets) - min(targets) <= 1
+        for r in range(G):
+            send, recv, _ = plans[r]
+            assert sum(send) == counts[r] and sum(recv) == targets[r]
+            for s_ in range(G):
+                assert send[s_] == plans[s_][1][r]  # what r sends to s is what s expects from r
+        # simulate the all-to-all on global indices: order must be preserved
+        glob = iter(range(total))
+        held = [[next(glob) for _ in range(c)] for c in counts]
+        new = [[] for _ in range(G)]
+        for r in range(G):
+            off = 0
+            for s_ in range(G):
+                new[s_].append((r, held[r][off:off + plans[r][0][s_]]))
+                off += plans[r][0][s_]
+        flat = [x for s_ in range(G) for _, chunk in sorted(new[s_]) for x in chunk]
+        assert flat == list(range(total))
