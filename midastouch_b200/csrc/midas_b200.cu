@@ -1946,13 +1946,13 @@ extern "C" int mt_step_b(mt_ctx* c, const mt_step_args* a, void* stream) {
   if (step_fused(c, a)) {
     if (a->table_ready_event) CK(cudaStreamWaitEvent(st, (cudaEvent_t)a->table_ready_event, 0));
     const int grid = std::min(std::min(d.nchunks, c->sm_count * c->bw_blocks_per_sm), MT_BW_MAX_GRID);
-    c->bar_target += (unsigned long long)grid;
     unsigned long long* bar = c->d_bar;
-    unsigned long long target = c->bar_target;
+    unsigned long long target = c->bar_target + (unsigned long long)grid;  // the barrier counter is monotone
     double* bw = c->d_bw;
     int* bwc = c->d_bwcnt;
     void* args[] = {&d, &bar, &target, &bw, &bwc};
     CK(cudaLaunchCooperativeKernel((const void*)k_step_bw, dim3(grid), dim3(256), args, 0, st));
+    c->bar_target = target;  // only once the launch was accepted
     return MT_OK;
   }
   k_step_b<true, true><<<d.nchunks, MT_CHUNK, 0, st>>>(d);
