@@ -1683,6 +1683,7 @@ __global__ void __launch_bounds__(256) k_step_b(StepDev p) {
 // on their common boundary), then resamples its chunks.  Saves a launch, the 4 B/particle re-read
 // and the serial last-block scan.
 #define MT_BW_MAX_PER 32
+#define MT_BW_FAST_PER 10  // chunks per block whose weights stay in shared memory (30 KB)
 #ifndef MT_BW_PREFETCH
 #define MT_BW_PREFETCH 0
 #endif
@@ -1694,30 +1695,44 @@ __global__ void __launch_bounds__(256) k_step_bw(StepDev p, unsigned long long* 
   __shared__ double s_part[MT_BW_MAX_PER];
   __shared__ double s_tot[MT_BW_MAX_GRID];
   __shared__ double s_bc[3];
+  __shared__ double s_e[MT_BW_FAST_PER * MT_CHUNK];  // weight of every particle of the block's chunks
+  __shared__ int s_nn[MT_BW_FAST_PER * MT_CHUNK];    // and its match (phase 2 does not go back to memory for them)
   const int G = gridDim.x, g = blockIdx.x;
   const long long n = p.n_in ? *p.n_in : p.n;
   const int nwarps = (int)((n + 31) >> 5);
   const int per = (p.nchunks + G - 1) / G;
   const int c_lo = g * per, c_hi = min(c_lo + per, p.nchunks);
-  // ---- phase 1
+  // ---- phase 1: weights of this block's chunks.  Up to MT_BW_FAST_PER chunks keep (match, weight) of
+  // every particle in shared memory for phase 2; the look-ups are issued four chunks at a time so that
+  // their DRAM / L2 latencies overlap.
+  const bool cached = per <= MT_BW_FAST_PER;
   double tot = 0.0, ra = 0.0, rb = 0.0;
   int cnt = 0;
-  for (int c = c_lo; c < c_hi; ++c) {
-    const long long i = (long long)c * MT_CHUNK + threadIdx.x;
-    double e = 0.0;
-    if (i < n) {
-      const int stored = p.nn_cur[i];
-      e = nn_is_masked(stored) ? 0.0 : __ldg(p.wtab + nn_index(stored));
+  for (int c0 = c_lo; c0 < c_hi; c0 += 4) {
+    int st4[4];
+    double e4[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const long long i = (long long)(c0 + k) * MT_CHUNK + threadIdx.x;
+      st4[k] = (c0 + k < c_hi && i < n) ? p.nn_cur[i] : -1;
     }
-    const double se = block_sum_256(e, s8);
-    if (threadIdx.x == 0) {
-      s_part[c - c_lo] = se;
-      tot += se;
-      for (int j = 0; j < 8; ++j) {  // kernel A's per-warp partials of this chunk (fixed order)
-        const int gw = 8 * c + j;
-        if (gw < nwarps) {
-          cnt += p.wcnt[gw];
-          if (p.has_gt) ra += p.wrm[2 * gw], rb += p.wrm[2 * gw + 1];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) e4[k] = (st4[k] >= 0) ? __ldg(p.wtab + st4[k]) : 0.0;  // masked (< -1) and absent (-1): 0
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int c = c0 + k;
+      if (c >= c_hi) break;
+      if (cached) s_e[(c - c_lo) * MT_CHUNK + threadIdx.x] = e4[k], s_nn[(c - c_lo) * MT_CHUNK + threadIdx.x] = nn_index(st4[k]);
+      const double se = block_sum_256(e4[k], s8);
+      if (threadIdx.x == 0) {
+        s_part[c - c_lo] = se;
+        tot += se;
+        for (int j = 0; j < 8; ++j) {  // kernel A's per-warp partials of this chunk (fixed order)
+          const int gw = 8 * c + j;
+          if (gw < nwarps) {
+            cnt += p.wcnt[gw];
+            if (p.has_gt) ra += p.wrm[2 * gw], rb += p.wrm[2 * gw + 1];
+          }
         }
       }
     }
@@ -1772,22 +1787,21 @@ __global__ void __launch_bounds__(256) k_step_bw(StepDev p, unsigned long long* 
   __syncthreads();
   const double base_g = s_bc[0], next_g = s_bc[1], S = s_bc[2];
   double run = base_g;
-  ChunkIn cur, nxt;
-  if (c_lo < c_hi) step_b_load<true, true>(p, c_lo, n, cur);
   for (int c = c_lo; c < c_hi; ++c) {
     const double base = fmin(run, next_g);
     run += s_part[c - c_lo];
     const double endv = (c + 1 == c_hi) ? next_g : fmin(run, next_g);
-#if MT_BW_PREFETCH
-    if (c + 1 < c_hi) step_b_load<true, true>(p, c + 1, n, nxt);  // in flight while this chunk is resampled
-#endif
+    ChunkIn cur;
+    if (cached) {  // only the pose comes from memory, and it is not needed before the scatter
+      const long long i = (long long)c * MT_CHUNK + threadIdx.x;
+      cur.nn = s_nn[(c - c_lo) * MT_CHUNK + threadIdx.x];
+      cur.e = s_e[(c - c_lo) * MT_CHUNK + threadIdx.x];
+      if (i < n) load_pose(p.soa_cur, p.stride, i, cur.P);
+    } else {
+      step_b_load<true, true>(p, c, n, cur);
+    }
     __syncthreads();  // s8 / s_cnt of the previous chunk are free
     step_b_chunk<true, true>(p, c, n, S, 0.0, base, endv, s8, s_cnt, cur);
-#if MT_BW_PREFETCH
-    cur = nxt;
-#else
-    if (c + 1 < c_hi) step_b_load<true, true>(p, c + 1, n, cur);
-#endif
   }
   if (g == 0) {  // RMSE, drift flag, bookkeeping (what the last block of k_step_sums does)
     __syncthreads();
