@@ -1384,7 +1384,7 @@ __global__ void __launch_bounds__(MT_A_BLOCK, MT_A_MINBLOCKS) k_step_a(StepDev p
   }
 }
 
-// queue consumer.  Blocks pull eight entries per trip, one per warp: a search whose candidate is
+// queue consumer.  In warp mode blocks pull MT_NNQ_WARPS entries per trip, one per warp: a search whose candidate is
 // close (box of at most ~120 grid rows) is finished by its warp alone; the others (stale hint
 // after a sign flip, no hint) are then served one after the other by the whole block.
 struct NnqEntry {
@@ -1412,18 +1412,19 @@ __device__ __forceinline__ void nnq_load(const StepDev& p, const NNTables& T, co
     q.masked = mt_pose_invalid(P) || (p.prune_dist > 0.0 && !mesh_within(Mh, P[0][3], P[1][3], P[2][3], p.prune_dist));
   }
 }
-__global__ void __launch_bounds__(256) k_step_nnq(StepDev p, NNTables T, MeshTables Mh) {
+#define MT_NNQ_WARPS 4
+__global__ void __launch_bounds__(32 * MT_NNQ_WARPS) k_step_nnq(StepDev p, NNTables T, MeshTables Mh) {
   __shared__ unsigned s_e;
   __shared__ int s_nbig;
-  __shared__ int s_big[8];
-  __shared__ float s_bd[8];
-  __shared__ int s_bi[8];
+  __shared__ int s_big[MT_NNQ_WARPS];
+  __shared__ float s_bd[MT_NNQ_WARPS];
+  __shared__ int s_bi[MT_NNQ_WARPS];
   const unsigned qn = *p.qctl;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // few entries: latency matters, every entry gets a whole block; many: throughput matters,
   // entries with a close candidate get one warp each
   const bool warp_mode = qn > 4u * gridDim.x;
-  const unsigned take = warp_mode ? 8u : 1u;
+  const unsigned take = warp_mode ? (unsigned)MT_NNQ_WARPS : 1u;
   for (;;) {
     __syncthreads();
     if (threadIdx.x == 0) s_e = atomicAdd(p.qctl + 1, take), s_nbig = 0;
@@ -1447,7 +1448,7 @@ __global__ void __launch_bounds__(256) k_step_nnq(StepDev p, NNTables T, MeshTab
     for (int b = 0; b < nbig; ++b) {
       NnqEntry q;
       nnq_load(p, T, Mh, p.queue[s_big[b]], q);
-      const int res = nn_search_coop<8>(T, q.key, q.bd, q.bi, p.flags + 4, s_bd, s_bi);
+      const int res = nn_search_coop<MT_NNQ_WARPS>(T, q.key, q.bd, q.bi, p.flags + 4, s_bd, s_bi);
       __syncthreads();  // every thread has read nn_cur[i] before it is overwritten
       if (threadIdx.x == 0) p.nn_cur[q.i] = q.masked ? nn_masked(res) : res;
     }
@@ -1684,9 +1685,6 @@ __global__ void __launch_bounds__(256) k_step_b(StepDev p) {
 // and the serial last-block scan.
 #define MT_BW_MAX_PER 32
 #define MT_BW_FAST_PER 10  // chunks per block whose weights stay in shared memory (30 KB)
-#ifndef MT_BW_PREFETCH
-#define MT_BW_PREFETCH 0
-#endif
 #define MT_BW_MAX_GRID 1184
 __global__ void __launch_bounds__(256) k_step_bw(StepDev p, unsigned long long* bar, unsigned long long bar_target,
                                                  double* __restrict__ blocktot /* 3 x grid */, int* __restrict__ blockcnt) {
@@ -1932,7 +1930,7 @@ extern "C" int mt_step_a(mt_ctx* c, const mt_step_args* a, void* stream) {
   k_step_a<<<(unsigned)((a->n + MT_A_BLOCK - 1) / MT_A_BLOCK), MT_A_BLOCK, 0, st>>>(d, tables_of(c), mesh_of(c));
   CK_LAUNCH();
   if (c->timing[1]) CK(cudaEventRecord(c->timing[1], st));
-  k_step_nnq<<<c->sm_count * 4, 256, 0, st>>>(d, tables_of(c), mesh_of(c));
+  k_step_nnq<<<c->sm_count * 8, 32 * MT_NNQ_WARPS, 0, st>>>(d, tables_of(c), mesh_of(c));
   CK_LAUNCH();
   if (c->timing[2]) CK(cudaEventRecord(c->timing[2], st));
   if (!step_fused(c, a)) {  // otherwise the sums are folded into mt_step_b's kernel

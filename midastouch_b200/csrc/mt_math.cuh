@@ -237,25 +237,6 @@ MT_HD mt_u4 mt_philox(mt_u4 c, uint32_t k0, uint32_t k1) {
   return c;
 }
 
-MT_HD float mt_u01(uint32_t x) { return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f); }
-
-MT_HD void mt_box_muller(uint32_t a, uint32_t b, float* n0, float* n1) {
-#if defined(__CUDA_ARCH__)
-  // SFU versions: the argument ranges ((0,1) and [0, 2 pi)) are where __logf / __sincosf are
-  // accurate to ~1e-6 absolute, far below the sampling noise of the filter
-  float r = sqrtf(-2.0f * __logf(mt_u01(a)));
-  float ang = 6.283185307179586f * mt_u01(b);
-  float s, c;
-  __sincosf(ang, &s, &c);
-#else
-  float r = sqrtf(-2.0f * logf(mt_u01(a)));
-  float ang = 6.283185307179586f * mt_u01(b);
-  float s = sinf(ang), c = cosf(ang);
-#endif
-  *n0 = r * c;
-  *n1 = r * s;
-}
-
 // 21-bit uniform in (0,1): six of them come out of ONE Philox4x32-10 call (128 bits)
 MT_HD float mt_u01_21(uint32_t x) { return ((float)(x & 0x1FFFFFu) + 0.5f) * (1.0f / 2097152.0f); }
 

@@ -55,7 +55,6 @@ struct mt_tcn {
   TcnTable tab[4];         // level 0..3 (tensor stride 1,2,4,8)
   unsigned long long* keys[4];
   int* d_n;                // [4] active points per level (device)
-  int* d_flag;             // max_points scratch (first-child flags -> parent rows)
   float* pool;             // feature scratch
   double* gem_part;        // max_batch x TCN_GEM_SLICES x 256 GeM partial sums
   size_t pool_floats;
@@ -338,7 +337,6 @@ extern "C" int mt_tcn_create(int device, int max_points, int max_batch, mt_tcn**
     CK(cudaMalloc(&t->keys[l], sizeof(unsigned long long) * max_points));
   }
   CK(cudaMalloc(&t->d_n, sizeof(int) * 4));
-  CK(cudaMalloc(&t->d_flag, sizeof(int) * max_points));
   t->pool_floats = (size_t)max_points * 1184;
   CK(cudaMalloc(&t->pool, sizeof(float) * t->pool_floats));
   CK(cudaMalloc(&t->gem_part, sizeof(double) * (size_t)max_batch * 64 * 256));
@@ -352,7 +350,7 @@ extern "C" int mt_tcn_destroy(mt_tcn* t) {
   for (int l = 0; l < 4; ++l) cudaFree(t->tab[l].keys), cudaFree(t->tab[l].vals), cudaFree(t->keys[l]);
   for (int i = 0; i < TCN_NCONV; ++i) cudaFree(t->conv[i].w);
   for (int i = 0; i < TCN_NBN; ++i) cudaFree(t->bn[i].scale), cudaFree(t->bn[i].shift);
-  cudaFree(t->d_n), cudaFree(t->d_flag), cudaFree(t->pool), cudaFree(t->gem_part);
+  cudaFree(t->d_n), cudaFree(t->pool), cudaFree(t->gem_part);
   delete t;
   return MT_OK;
 }
