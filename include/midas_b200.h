@@ -93,6 +93,10 @@ int mt_prune_aos(mt_ctx* ctx, const float* d_poses, long long n, double invalid_
  * per-particle weights of filter.py:170-173 by table lookup).  d_q: (D,) in q_dtype.
  * d_sim_out (nullable): (M,) float64 copy of the table. */
 int mt_codebook_query(mt_ctx* ctx, const void* d_q, int q_dtype, double* d_sim_out, void* stream);
+/* nq queries at once against the uploaded codebook: d_out[q*M + m] = cos(Q_q, E_m), float32
+ * (the batched form of get_similarity, eval/single_touch_test.py:35-73).  tcgen05 tensor-core
+ * GEMM with TMEM accumulators, 3xTF32 split operands (~1e-6 relative).  d_Q: (nq, D) float32. */
+int mt_codebook_query_batched(mt_ctx* ctx, const float* d_Q, int nq, float* d_out, void* stream);
 /* general form: cos(q, T_n) for an explicit (rows, D) target matrix
  * (get_similarity(queries, targets), particle_filter.py:449-457). */
 int mt_cosine_rows(mt_ctx* ctx, const void* d_q, int q_dtype, const void* d_targets, int t_dtype, long long rows,

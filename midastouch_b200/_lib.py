@@ -11,7 +11,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MIDAS_B200_LIB") or os.path.join(_HERE, "libmidas_b200.so")  # override: A/B builds only
 SOURCES = [os.path.join(_HERE, "csrc", "midas_b200.cu")]
-HEADERS = [os.path.join(_HERE, "csrc", "mt_math.cuh"), os.path.join(_HERE, "csrc", "mt_nn.cuh"), os.path.join(_HERE, "csrc", "mt_mesh.cuh"), os.path.join(_HERE, "csrc", "mt_tcn.cuh"), os.path.join(_HERE, "csrc", "mt_cluster.cuh"), os.path.join(_HERE, "..", "include", "midas_b200.h")]
+HEADERS = [os.path.join(_HERE, "csrc", "mt_math.cuh"), os.path.join(_HERE, "csrc", "mt_nn.cuh"), os.path.join(_HERE, "csrc", "mt_mesh.cuh"), os.path.join(_HERE, "csrc", "mt_tcn.cuh"), os.path.join(_HERE, "csrc", "mt_cluster.cuh"), os.path.join(_HERE, "csrc", "mt_gemm_tc.cuh"), os.path.join(_HERE, "..", "include", "midas_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -63,6 +63,7 @@ _SIGS = {
     "mt_mesh_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_double]),
     "mt_prune_aos": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mt_codebook_query": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "mt_codebook_query_batched": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "mt_cosine_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p]),
     "mt_cosine_batched": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p]),
     "mt_softmax_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]),

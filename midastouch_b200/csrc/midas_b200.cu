@@ -2026,6 +2026,40 @@ extern "C" int mt_resample_systematic(mt_ctx* c, const double* d_w, long long n,
   return MT_OK;
 }
 
+// ------------------------------------------------------------------------- batched codebook query (tensor cores)
+#include "mt_gemm_tc.cuh"
+
+extern "C" int mt_codebook_query_batched(mt_ctx* c, const float* d_Q, int nq, float* d_out, void* stream) {
+  if (!c || !c->cb_ready || !c->d_emb) return set_err(MT_ERR_STATE, "mt_codebook_query_batched: no codebook");
+  if (!d_Q || !d_out || nq <= 0) return set_err(MT_ERR_ARG, "mt_codebook_query_batched: bad argument");
+  CK(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int M = c->M, D = c->D;
+  const bool e32 = c->emb_dtype == MT_DTYPE_F32;
+  if (!c->rnorm_ready) {
+    if (e32)
+      k_row_norms<float><<<(M + 7) / 8, 256, 0, st>>>((const float*)c->d_emb, M, D, c->d_rnorm);
+    else
+      k_row_norms<double><<<(M + 7) / 8, 256, 0, st>>>((const double*)c->d_emb, M, D, c->d_rnorm);
+    CK_LAUNCH();
+    c->rnorm_ready = true;
+  }
+  const size_t sh = sizeof(float) * 4 * TC_TILE_FLOATS;  // 64 KB: A/B tiles, big + small parts
+  static bool attr_set = false;
+  if (!attr_set) {
+    CK(cudaFuncSetAttribute(k_codebook_gemm_tc<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+    CK(cudaFuncSetAttribute(k_codebook_gemm_tc<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+    attr_set = true;
+  }
+  dim3 grid((M + TC_BM - 1) / TC_BM, (nq + TC_BN - 1) / TC_BN);
+  if (e32)
+    k_codebook_gemm_tc<float><<<grid, 128, sh, st>>>((const float*)c->d_emb, c->d_rnorm, M, D, d_Q, nq, d_out);
+  else
+    k_codebook_gemm_tc<double><<<grid, 128, sh, st>>>((const double*)c->d_emb, c->d_rnorm, M, D, d_Q, nq, d_out);
+  CK_LAUNCH();
+  return MT_OK;
+}
+
 // ------------------------------------------------------------------------- cluster centres / annealing
 #include "mt_cluster.cuh"
 

@@ -83,6 +83,16 @@ class tactile_tree(torch.nn.Module):
             call("mt_codebook_query", self.ctx.h, ptr(code), dtype_code(code), ptr(out), stream_ptr())
         return out
 
+    def query_batched(self, codes: torch.Tensor) -> torch.Tensor:
+        """cos(codes_q, E_m) for a batch of codes: (nq, D) -> (nq, M) float32, on the tensor cores
+        (tcgen05 / TMEM, 3xTF32; the eval script's M x M retrieval, single_touch_test.py:35-73)."""
+        require_cuda(codes, "codes")
+        q = torch.atleast_2d(codes).to(torch.float32).contiguous()
+        out = torch.empty((q.shape[0], self.tree_size), dtype=torch.float32, device=q.device)
+        with torch.cuda.device(q.device):
+            call("mt_codebook_query_batched", self.ctx.h, ptr(q), q.shape[0], ptr(out), stream_ptr())
+        return out
+
     def _gather(self, table: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
         n = idx.shape[0]
         row = table[0].numel() * (2 if table.dtype == torch.float64 else 1)

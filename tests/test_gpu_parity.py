@@ -296,6 +296,30 @@ def test_cosine_batched(mt, dev):
     assert torch.allclose(out.cpu().double(), ref, rtol=1e-5, atol=0)
 
 
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_codebook_query_batched_tensor_core(mt, dev, box, dtype):
+    """tcgen05 / TMEM GEMM (3xTF32): nq codes against the whole codebook, within 1e-5 of the float64
+    cosine; ragged sizes (M, nq not multiples of the 128 x 128 tile, D not a multiple of 32)."""
+    g = torch.Generator().manual_seed(5)
+    for M, D, nq in ((1000, 256, 70), (4133, 200, 300)):
+        poses = torch.eye(4)[None].repeat(M, 1, 1)
+        poses[:, :3, 3] = torch.rand(M, 3, generator=g) * 0.05
+        emb = torch.rand(M, D, dtype=torch.float64, generator=g)
+        emb[3] *= 1e-3  # a short row: the norm matters
+        cb = mt.tt.tactile_tree(poses, poses, emb.to(dtype))
+        cb.to_device(dev)
+        Q = torch.rand(nq, D, generator=g)
+        Q[1] = emb[7].float()
+        out = cb.query_batched(Q.to(dev)).cpu().double()
+        ref = torch.nn.functional.cosine_similarity(Q.double()[:, None, :], emb.to(dtype).double()[None], dim=2)
+        assert out.shape == (nq, M)
+        err = ((out - ref).abs() / ref.abs().clamp_min(1e-12)).max()
+        assert float(err) < 1e-5, float(err)
+        # and the single-query kernel agrees with row 0
+        one = cb.query(Q[0].double().to(dev)).cpu()
+        assert torch.allclose(out[0], one, rtol=1e-5, atol=0)
+
+
 # ----------------------------------------------------------------------------- resampling
 @pytest.mark.parametrize("name", ["soft", "raw", "masked", "peaked"])
 @pytest.mark.parametrize("seq", [0, 1])
