@@ -2036,6 +2036,7 @@ extern "C" int mt_codebook_query_batched(mt_ctx* c, const float* d_Q, int nq, fl
   cudaStream_t st = (cudaStream_t)stream;
   const int M = c->M, D = c->D;
   const bool e32 = c->emb_dtype == MT_DTYPE_F32;
+  if (D % 4) return set_err(MT_ERR_ARG, "mt_codebook_query_batched: D must be a multiple of 4 (16-byte rows)");
   if (!c->rnorm_ready) {
     if (e32)
       k_row_norms<float><<<(M + 7) / 8, 256, 0, st>>>((const float*)c->d_emb, M, D, c->d_rnorm);
