@@ -179,75 +179,97 @@ __global__ void k_tcn_untag(TcnTable t) {
 //           centre = k/2 for odd k, 0 for even k (regular, strided-down and 1x1 convolutions)
 //   MODE 1: transposed k=2,s=2: out[p] = in[parent(p)] W[i(p - parent(p))], dil = stride of p
 // epilogue: * scale + shift (BatchNorm eval) -> + residual -> ReLU
-template <int MODE>
+template <int MODE, int WPP>  // WPP warps per output point: the input channels are split between them
 __global__ void __launch_bounds__(256) k_tcn_conv(const unsigned long long* __restrict__ out_keys, const int* __restrict__ d_nout,
                                                   TcnTable in_tab, const float* __restrict__ in_feat, int cin,
                                                   const float* __restrict__ W, int cout, int k, int dil,
                                                   const float* __restrict__ scale, const float* __restrict__ shift,
                                                   const float* __restrict__ residual, int relu, int accumulate,
                                                   float* __restrict__ out_feat) {
-  const int lane = threadIdx.x & 31;
-  const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (p >= *d_nout) return;
-  int b, x, y, z;
-  tcn_unpack(out_keys[p], b, x, y, z);
+  constexpr int PPB = 8 / WPP;  // points per 256-thread block
+  __shared__ float s_acc[WPP > 1 ? 8 : 1][256];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int part = warp % WPP;  // which slice of the input channels this warp multiplies
+  const int p = blockIdx.x * PPB + warp / WPP;
+  const bool live = p < *d_nout;
   float acc[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-  const int kvol = (MODE == 1) ? 1 : k * k * k;
-  const int centre = (k & 1) ? (k >> 1) : 0;
-  for (int i0 = 0; i0 < kvol; i0 += 32) {
-    // the 32 lanes resolve 32 kernel offsets at once (the look-ups are independent memory chains)
-    const int i = i0 + lane;
-    int row = -1, wi = i;
-    if (i < kvol) {
-      unsigned long long nk;
-      if (MODE == 0) {
-        const int ox = (i % k - centre) * dil, oy = ((i / k) % k - centre) * dil, oz = (i / (k * k) - centre) * dil;
-        nk = tcn_pack(b, x + ox, y + oy, z + oz);
-      } else {
-        const int px = tcn_floor_to(x, 2 * dil), py = tcn_floor_to(y, 2 * dil), pz = tcn_floor_to(z, 2 * dil);
-        wi = ((z - pz) / dil * 2 + (y - py) / dil) * 2 + (x - px) / dil;
-        nk = tcn_pack(b, px, py, pz);
-      }
-      row = tcn_lookup(in_tab, nk);
-    }
-    unsigned found = __ballot_sync(0xffffffffu, row >= 0);
-    while (found) {  // ascending offset order: the summation order is fixed
-      const int src = __ffs(found) - 1;
-      found &= found - 1;
-      const int r = __shfl_sync(0xffffffffu, row, src);
-      const float* __restrict__ Wi = W + (size_t)__shfl_sync(0xffffffffu, wi, src) * cin * cout;
-      if (!in_feat) {  // conv0: the reference assigns a dummy feature 1 to every point (tcn.py:131-134)
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (lane + 32 * j < cout) acc[j] += __ldg(Wi + lane + 32 * j);
-        continue;
-      }
-      for (int c0 = 0; c0 < cin; c0 += 32) {
-        const float xv = (c0 + lane < cin) ? __ldg(in_feat + (size_t)r * cin + c0 + lane) : 0.f;  // zero beyond cin
-        const int cn = min(32, cin - c0);
-        if (cn == 32) {
-#pragma unroll 8
-          for (int t = 0; t < 32; ++t) {  // unrolled: eight rows of W in flight
-            const float xs = __shfl_sync(0xffffffffu, xv, t);
-            const float* __restrict__ Wr = Wi + (size_t)(c0 + t) * cout;
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              if (lane + 32 * j < cout) acc[j] = fmaf(xs, __ldg(Wr + lane + 32 * j), acc[j]);
-          }
+  if (live) {
+    int b, x, y, z;
+    tcn_unpack(out_keys[p], b, x, y, z);
+    const int kvol = (MODE == 1) ? 1 : k * k * k;
+    const int centre = (k & 1) ? (k >> 1) : 0;
+    const int cslice = (cin + WPP - 1) / WPP, cbeg = part * cslice, cend = min(cin, cbeg + cslice);
+    for (int i0 = 0; i0 < kvol; i0 += 32) {
+      // the 32 lanes resolve 32 kernel offsets at once (the look-ups are independent memory chains)
+      const int i = i0 + lane;
+      int row = -1, wi = i;
+      if (i < kvol) {
+        unsigned long long nk;
+        if (MODE == 0) {
+          const int ox = (i % k - centre) * dil, oy = ((i / k) % k - centre) * dil, oz = (i / (k * k) - centre) * dil;
+          nk = tcn_pack(b, x + ox, y + oy, z + oz);
         } else {
-          for (int t = 0; t < cn; ++t) {
-            const float xs = __shfl_sync(0xffffffffu, xv, t);
-            const float* __restrict__ Wr = Wi + (size_t)(c0 + t) * cout;
+          const int px = tcn_floor_to(x, 2 * dil), py = tcn_floor_to(y, 2 * dil), pz = tcn_floor_to(z, 2 * dil);
+          wi = ((z - pz) / dil * 2 + (y - py) / dil) * 2 + (x - px) / dil;
+          nk = tcn_pack(b, px, py, pz);
+        }
+        row = tcn_lookup(in_tab, nk);
+      }
+      unsigned found = __ballot_sync(0xffffffffu, row >= 0);
+      while (found) {  // ascending offset order: the summation order is fixed
+        const int src = __ffs(found) - 1;
+        found &= found - 1;
+        const int r = __shfl_sync(0xffffffffu, row, src);
+        const float* __restrict__ Wi = W + (size_t)__shfl_sync(0xffffffffu, wi, src) * cin * cout;
+        if (!in_feat) {  // conv0: the reference assigns a dummy feature 1 to every point (tcn.py:131-134)
+          if (part == 0) {
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-              if (lane + 32 * j < cout) acc[j] = fmaf(xs, __ldg(Wr + lane + 32 * j), acc[j]);
+              if (lane + 32 * j < cout) acc[j] += __ldg(Wi + lane + 32 * j);
+          }
+          continue;
+        }
+        for (int c0 = cbeg; c0 < cend; c0 += 32) {
+          const float xv = (c0 + lane < cend) ? __ldg(in_feat + (size_t)r * cin + c0 + lane) : 0.f;
+          const int cn = min(32, cend - c0);
+          if (cn == 32) {
+#pragma unroll 8
+            for (int t = 0; t < 32; ++t) {  // unrolled: eight rows of W in flight
+              const float xs = __shfl_sync(0xffffffffu, xv, t);
+              const float* __restrict__ Wr = Wi + (size_t)(c0 + t) * cout;
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                if (lane + 32 * j < cout) acc[j] = fmaf(xs, __ldg(Wr + lane + 32 * j), acc[j]);
+            }
+          } else {
+#pragma unroll 4
+            for (int t = 0; t < cn; ++t) {
+              const float xs = __shfl_sync(0xffffffffu, xv, t);
+              const float* __restrict__ Wr = Wi + (size_t)(c0 + t) * cout;
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                if (lane + 32 * j < cout) acc[j] = fmaf(xs, __ldg(Wr + lane + 32 * j), acc[j]);
+            }
           }
         }
       }
     }
   }
+  if (WPP > 1) {  // combine the channel slices in a fixed order
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s_acc[warp][lane + 32 * j] = acc[j];
+    __syncthreads();
+    if (part != 0) return;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float v = 0.f;
+      for (int q = 0; q < WPP; ++q) v += s_acc[warp + q][lane + 32 * j];
+      acc[j] = v;
+    }
+  }
+  if (!live) return;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int c = lane + 32 * j;
@@ -406,11 +428,18 @@ static int tcn_conv_launch(mt_tcn* t, int mode, int conv_id, int bn_id, const un
     if (!t->bn[bn_id].scale || t->bn[bn_id].c != c.cout) return set_err(MT_ERR_STATE, "mt_tcn_forward: BatchNorm missing / wrong width");
     sc = t->bn[bn_id].scale, sh = t->bn[bn_id].shift;
   }
-  const unsigned grid = (unsigned)((nmax + 7) / 8);
-  if (mode == 0)
-    k_tcn_conv<0><<<grid, 256, 0, st>>>(out_keys, d_nout, in_tab, in_feat, c.cin, c.w, c.cout, k, dil, sc, sh, residual, relu, accumulate, out_feat);
+  // few points and many channels: four warps per point split the input channels (shorter FMA chains);
+  // conv0 (one input feature) keeps a warp per point
+  const bool split = in_feat != nullptr && c.cin >= 32;
+  const unsigned grid = (unsigned)(split ? (nmax + 1) / 2 : (nmax + 7) / 8);
+  if (mode == 0 && split)
+    k_tcn_conv<0, 4><<<grid, 256, 0, st>>>(out_keys, d_nout, in_tab, in_feat, c.cin, c.w, c.cout, k, dil, sc, sh, residual, relu, accumulate, out_feat);
+  else if (mode == 0)
+    k_tcn_conv<0, 1><<<grid, 256, 0, st>>>(out_keys, d_nout, in_tab, in_feat, c.cin, c.w, c.cout, k, dil, sc, sh, residual, relu, accumulate, out_feat);
+  else if (split)
+    k_tcn_conv<1, 4><<<grid, 256, 0, st>>>(out_keys, d_nout, in_tab, in_feat, c.cin, c.w, c.cout, k, dil, sc, sh, residual, relu, accumulate, out_feat);
   else
-    k_tcn_conv<1><<<grid, 256, 0, st>>>(out_keys, d_nout, in_tab, in_feat, c.cin, c.w, c.cout, k, dil, sc, sh, residual, relu, accumulate, out_feat);
+    k_tcn_conv<1, 1><<<grid, 256, 0, st>>>(out_keys, d_nout, in_tab, in_feat, c.cin, c.w, c.cout, k, dil, sc, sh, residual, relu, accumulate, out_feat);
   CK_LAUNCH();
   return MT_OK;
 }
