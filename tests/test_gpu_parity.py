@@ -784,3 +784,39 @@ def test_sharded_engine_matches_single_gpu():
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                         "--master-port", "29533", os.path.join(root, "scripts", "multigpu_check.py")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("name,M", [("cotter-pin", 20000), ("025_mug", 30000), ("035_power_drill", 50000)])
+def test_engine_on_other_objects(mt, dev, name, M):
+    """the other BASELINE.json objects (tiny McMaster part, curved mug, L-shaped drill): one engine step
+    from codebook poses, exact SE3_NN of the moved poses and ancestors vs the oracle on a subsample."""
+    obj = synth.make_object(name)
+    cbs = synth.make_codebook(obj, M=M, D=32, seed=6, embedding="smooth")
+    cb = mt.tt.tactile_tree(cbs.poses, cbs.cam_poses, cbs.embeddings)
+    cb.to_device(dev)
+    N = 60000
+    g = torch.Generator().manual_seed(8)
+    sel = torch.randint(0, M, (N,), generator=g)
+    poses = cbs.poses[sel]
+    gt, meas = synth.make_trajectory(obj, T=6, seed=6, step=1e-4 if name == "cotter-pin" else 2.5e-4)
+    sig_t = 1e-4 if name == "cotter-pin" else 2e-4
+    tn = sig_t * torch.randn(N, 3, generator=g)
+    rot = 0.5 * torch.randn(N, 3, generator=g)
+    q = synth.make_pose_query(gt[1], 32, seed=6, frame=1)
+    odom = torch.inverse(meas[0]) @ meas[1]
+    eng = mt.eng.FilterEngine(cb, capacity=N, sig_t=sig_t, mesh_vertices=obj.vertices, pen_max=0.002)
+    eng.load_particles(poses.to(dev), nn_hint=sel.int().to(dev))
+    eng.step(q, odom, u=0.77, tn=tn.to(dev), rot=rot.to(dev), resample=False)
+    moved = eng.poses()
+    nn = eng.nn_idx().cpu().long()
+    keys_cb = cb.logmap_pose.cpu().numpy()
+    sub = torch.randperm(N, generator=g)[:8000]
+    gk = mt.tt.R3_SE3(moved[sub.to(dev)]).cpu().numpy()
+    assert np.array_equal(nn[sub].numpy(), O.nn_exact(keys_cb, gk, k=16))
+    w = eng.weights().cpu()
+    assert abs(float(w.sum()) - 1.0) < 1e-12
+    eng2 = mt.eng.FilterEngine(cb, capacity=N, sig_t=sig_t, mesh_vertices=obj.vertices, pen_max=0.002)
+    eng2.load_particles(poses.to(dev))
+    eng2.step(q, odom, u=0.77, tn=tn.to(dev), rot=rot.to(dev))
+    assert torch.equal(eng2.ancestors().cpu().long(), O.low_var_indices(w, 0.77))
+    assert cb.ctx.stats()["overflow"] == 0
