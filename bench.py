@@ -189,6 +189,7 @@ def run_ours(args):
     RUN = T_TRAJ - 6  # frames of one filter run; longer benchmarks restart the filter (untimed) and slide again
 
     for t in range(args.warmup):
+        l2flush.zero_()  # (also warms the flush itself: its first call allocates)
         one(t, False)
     sync()
     # ---- device-resident timing: per-step events, L2 flushed between steps (untimed); the library

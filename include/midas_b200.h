@@ -67,7 +67,8 @@ int mt_codebook_rank(mt_ctx* ctx, int32_t* d_rank, void* stream);
 int mt_ctx_set_timing_events(mt_ctx* ctx, void* const* events4);
 /* status / statistics words of the context (synchronises).  h_out8[MT_STAT_*]; reset != 0
  * clears the cumulative slots (0..4, 7). */
-#define MT_STAT_OVERFLOW 0      /* children did not fit the destination buffer (sharded steps) */
+#define MT_STAT_OVERFLOW 0      /* 1: children did not fit the destination buffer (sharded steps);
+                                   2: a peer's weight sum never arrived (fused sharded step timed out) */
 #define MT_STAT_RESAMPLE_SKIP 1 /* a resampling saw all-zero / NaN weights and kept the particles */
 #define MT_STAT_INVALID_POSES 2 /* poses check_quats would prune (cumulative) */
 #define MT_STAT_NN_FALLBACKS 3  /* queries that left the hint graph for the grid search (cumulative) */
@@ -202,6 +203,18 @@ typedef struct mt_step_args {
    * valid after mt_step_b in that mode. */
   int fuse_sums;
 } mt_step_args;
+
+/* ---- sharded runs without a collective call ---------------------------------------------------
+ * Every context owns a small exchange buffer.  mt_dist_export writes its CUDA IPC handle (64 bytes,
+ * host) -- exchange the handles between the ranks (e.g. torch.distributed.all_gather) -- and
+ * mt_dist_import(rank, world, handles[world][64]) maps the peers' buffers.  A step with fuse_sums != 0
+ * then runs sums + exchange + resampling as ONE cooperative kernel per GPU: each GPU stores its weight
+ * sum into its peers' buffers over NVLink and spins on its own buffer for theirs. */
+int mt_dist_export(mt_ctx* ctx, void* h_handle64);
+int mt_dist_import(mt_ctx* ctx, int rank, int world, const void* h_handles);
+/* *h_fused = 1 when mt_step_a/mt_step_b will run this step in the fused form (sums + exchange + resampling in
+ * one cooperative kernel; a sharded caller then skips its all-gather of the weight sums), else 0 */
+int mt_step_is_fused(mt_ctx* ctx, const mt_step_args* a, int* h_fused);
 
 /* kernel A: motion + key + exact NN + weight lookup + deterministic weight sums */
 int mt_step_a(mt_ctx* ctx, const mt_step_args* a, void* stream);

@@ -27,6 +27,12 @@
 #include "mt_mesh.cuh"
 
 #define MT_MAX_D 6144  // query staged in 48 KB of shared memory as float64
+#define MT_MAX_WORLD 16
+// exchange buffer of the sharded fused step, double-buffered by step parity
+struct Xchg {
+  double sums[2][MT_MAX_WORLD];
+  unsigned long long seq[2][MT_MAX_WORLD];
+};
 #define MT_CHUNK 256  // particles per chunk == threads per block of the sweep kernels
 
 // nn_cur / nn_next hold the codebook match of every particle; a particle whose weight was
@@ -101,6 +107,13 @@ struct mt_ctx {
   double* d_bw;       // 3 x MT_BW_MAX_GRID block totals (weights, rmse_t, rmse_r)
   int* d_bwcnt;       // MT_BW_MAX_GRID on-surface counts
   int bw_blocks_per_sm;
+  // sharded fused step: every GPU writes its weight sum straight into its peers' exchange buffers over
+  // NVLink (CUDA IPC mappings) -- no collective call between the two phases of k_step_bw
+  struct Xchg* d_xchg;        // own exchange buffer (peer-mapped by the other ranks)
+  struct Xchg** d_peers;      // device array: peers[r] = rank r's buffer as seen from this GPU
+  struct Xchg* h_peers[MT_MAX_WORLD];
+  int peers_world;            // 0: not imported
+  unsigned long long xchg_count;  // fused sharded steps launched so far (same on every rank)
   double* d_q64;      // staged query, float64, MT_MAX_D entries
   double* d_scal;     // [0] local weight sum, [1] max, [2] min, [3] softmax denom, [4..7] spare
   unsigned int* d_ticket;
@@ -137,6 +150,9 @@ extern "C" int mt_ctx_create(int device, size_t capacity, int M, int D, mt_ctx**
   CK(cudaMemset(c->d_qctl, 0, sizeof(unsigned int) * 4));
   CK(cudaMalloc(&c->d_bar, sizeof(unsigned long long)));
   CK(cudaMemset(c->d_bar, 0, sizeof(unsigned long long)));
+  CK(cudaMalloc(&c->d_xchg, sizeof(Xchg)));
+  CK(cudaMemset(c->d_xchg, 0, sizeof(Xchg)));
+  CK(cudaMalloc(&c->d_peers, sizeof(Xchg*) * MT_MAX_WORLD));
   CK(cudaMalloc(&c->d_bw, sizeof(double) * 3 * 1184));
   CK(cudaMalloc(&c->d_bwcnt, sizeof(int) * 1184));
   CK(cudaMalloc(&c->d_prefix, sizeof(double) * (c->chunk_cap + 1)));
@@ -177,6 +193,10 @@ extern "C" int mt_ctx_destroy(mt_ctx* c) {
   cudaFree(c->d_scratch);
   cudaFree(c->d_qctl);
   cudaFree(c->d_bar);
+  for (int r = 0; r < c->peers_world; ++r)
+    if (c->h_peers[r] && c->h_peers[r] != c->d_xchg) cudaIpcCloseMemHandle(c->h_peers[r]);
+  cudaFree(c->d_xchg);
+  cudaFree(c->d_peers);
   cudaFree(c->d_bw);
   cudaFree(c->d_bwcnt);
   cudaFree(c->d_scal);
@@ -1303,6 +1323,8 @@ struct StepDev {
   int rank, world;
   long long n_global;
   const double* shard_sums;
+  Xchg* const* peers;          // sharded fused step: peer exchange buffers (nullptr otherwise)
+  unsigned long long xseq;     // sequence number of this step's exchange (same on every rank)
   long long* n_out;
   const long long* n_in;  // device-resident particle count (nullable): overrides n
   double prune_dist;      // > 0: drift test against the mesh (remove_invalid_particles)
@@ -1783,12 +1805,55 @@ __global__ void __launch_bounds__(256) k_step_bw(StepDev p, unsigned long long* 
     }
   }
   __syncthreads();
-  const double base_g = s_bc[0], next_g = s_bc[1], S = s_bc[2];
+  double base_g = s_bc[0], next_g = s_bc[1], S = s_bc[2], A = 0.0;
+  if (p.world > 1) {
+    // sharded: this GPU's total goes straight into every peer's exchange buffer (remote stores over
+    // NVLink), then every block waits for all the totals of this step to have arrived locally
+    __shared__ double s_x[2];
+    const int par = (int)(p.xseq & 1);
+    if (g == 0 && threadIdx.x < p.world) {
+      Xchg* peer = p.peers[threadIdx.x];
+      peer->sums[par][p.rank] = S;
+      __threadfence_system();
+      *(volatile unsigned long long*)&peer->seq[par][p.rank] = p.xseq;
+    }
+    if (threadIdx.x == 0) {
+      Xchg* own = p.peers[p.rank];
+      double tot = 0.0, off = 0.0;
+      bool ok = true;
+      for (int r = 0; r < p.world; ++r) {
+        unsigned long long t0 = 0;
+        int spins = 0;
+        while (*(volatile unsigned long long*)&own->seq[par][r] != p.xseq) {
+          if ((++spins & 1023) == 0) {  // a peer that never arrives (10 s) is flagged instead of hanging the GPU
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            if (!t0) t0 = t;
+            if (t - t0 > 10000000000ull) {
+              ok = false;
+              break;
+            }
+          }
+        }
+        __threadfence_system();
+        if (r == p.rank) off = tot;
+        tot += *(volatile double*)&own->sums[par][r];  // sequential, identical on every GPU
+      }
+      if (!ok) p.flags[0] = 2;
+      s_x[0] = off, s_x[1] = tot;
+    }
+    __syncthreads();
+    A = s_x[0];
+    S = s_x[1];
+    base_g += A, next_g += A;
+  }
   double run = base_g;
   for (int c = c_lo; c < c_hi; ++c) {
     const double base = fmin(run, next_g);
     run += s_part[c - c_lo];
-    const double endv = (c + 1 == c_hi) ? next_g : fmin(run, next_g);
+    // the block's last chunk, or the chunk holding the shard's last particle (sharded runs size the grid
+    // from a host-side bound), ends exactly on the block boundary
+    const double endv = (c + 1 == c_hi || (long long)(c + 1) * MT_CHUNK >= n) ? next_g : fmin(run, next_g);
     ChunkIn cur;
     if (cached) {  // only the pose comes from memory, and it is not needed before the scatter
       const long long i = (long long)c * MT_CHUNK + threadIdx.x;
@@ -1799,7 +1864,7 @@ __global__ void __launch_bounds__(256) k_step_bw(StepDev p, unsigned long long* 
       step_b_load<true, true>(p, c, n, cur);
     }
     __syncthreads();  // s8 / s_cnt of the previous chunk are free
-    step_b_chunk<true, true>(p, c, n, S, 0.0, base, endv, s8, s_cnt, cur);
+    step_b_chunk<true, true>(p, c, n, S, A, base, endv, s8, s_cnt, cur);
   }
   if (g == 0) {  // RMSE, drift flag, bookkeeping (what the last block of k_step_sums does)
     __syncthreads();
@@ -1820,8 +1885,8 @@ __global__ void __launch_bounds__(256) k_step_bw(StepDev p, unsigned long long* 
         p.rmse2[0] = (float)sqrt(sa / (double)n);
         p.rmse2[1] = (float)sqrt(sb / (double)n);
       }
-      p.prefix[p.nchunks] = S;
-      p.scal[0] = S;
+      p.prefix[p.nchunks] = s_bc[2];  // this GPU's weight sum
+      p.scal[0] = s_bc[2];
       p.flags[6] = s_on;
       p.flags[5] = (p.prune_dist > 0.0 && s_on == 0);
       p.flags[3] += (int)p.qctl[0];
@@ -1882,6 +1947,8 @@ static int fill_step(mt_ctx* c, const mt_step_args* a, StepDev* d) {
   d->world = a->world > 1 ? a->world : 1;
   d->n_global = a->world > 1 ? a->n_global : a->n;
   d->shard_sums = a->d_shard_sums;
+  d->peers = (c->peers_world == d->world && d->world > 1) ? c->d_peers : nullptr;
+  d->xseq = c->xchg_count + 1;
   d->n_out = a->d_n_out;
   d->n_in = a->d_n_in;
   d->prune_dist = (c->mesh_ready && a->prune_dist > 0.0) ? a->prune_dist : 0.0;
@@ -1901,10 +1968,46 @@ static int fill_step(mt_ctx* c, const mt_step_args* a, StepDev* d) {
   return MT_OK;
 }
 
+extern "C" int mt_dist_export(mt_ctx* c, void* h_handle64) {
+  if (!c || !h_handle64) return set_err(MT_ERR_ARG, "mt_dist_export: null");
+  CK(cudaSetDevice(c->device));
+  cudaIpcMemHandle_t h;
+  CK(cudaIpcGetMemHandle(&h, c->d_xchg));
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(h_handle64, &h, 64);
+  return MT_OK;
+}
+
+extern "C" int mt_dist_import(mt_ctx* c, int rank, int world, const void* h_handles) {
+  if (!c || !h_handles || world < 2 || world > MT_MAX_WORLD || rank < 0 || rank >= world)
+    return set_err(MT_ERR_ARG, "mt_dist_import: bad argument (2 <= world <= 16)");
+  CK(cudaSetDevice(c->device));
+  for (int r = 0; r < c->peers_world; ++r) {  // re-import: drop the previous mappings
+    if (c->h_peers[r] && c->h_peers[r] != c->d_xchg) cudaIpcCloseMemHandle(c->h_peers[r]);
+    c->h_peers[r] = nullptr;
+  }
+  c->peers_world = 0;
+  for (int r = 0; r < world; ++r) {
+    if (r == rank) {
+      c->h_peers[r] = c->d_xchg;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char*)h_handles + 64 * r, 64);
+    void* ptr = nullptr;
+    CK(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    c->h_peers[r] = (Xchg*)ptr;
+  }
+  CK(cudaMemcpy(c->d_peers, c->h_peers, sizeof(Xchg*) * world, cudaMemcpyHostToDevice));
+  c->peers_world = world;
+  return MT_OK;
+}
+
 // single GPU, resampling requested, few enough chunks per block: k_step_sums + k_step_b run as one
 // persistent cooperative kernel (k_step_bw)
 static bool step_fused(mt_ctx* c, const mt_step_args* a) {
-  if (!a->fuse_sums || a->world > 1 || !a->resample) return false;
+  if (!a->fuse_sums || !a->resample) return false;
+  if (a->world > 1 && c->peers_world != a->world) return false;  // sharded: needs mt_dist_import
   if (c->bw_blocks_per_sm == 0) {
     int coop = 0, occ = 0;
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->device);
@@ -1912,8 +2015,17 @@ static bool step_fused(mt_ctx* c, const mt_step_args* a) {
     c->bw_blocks_per_sm = (coop && occ > 0) ? std::min(occ, 4) : -1;
   }
   if (c->bw_blocks_per_sm < 0) return false;
-  const int grid = std::min(std::min((int)nchunks_of(a->n), c->sm_count * c->bw_blocks_per_sm), MT_BW_MAX_GRID);
-  return (nchunks_of(a->n) + grid - 1) / grid <= MT_BW_MAX_PER;
+  // sharded: every rank must take the same decision, so it is taken on the capacity (equal on all ranks,
+  // and chunks per block only grow with the particle count), not on this rank's current count
+  const long long nb = a->world > 1 ? std::max(a->stride, a->n) : a->n;
+  const int grid = std::min(std::min((int)nchunks_of(nb), c->sm_count * c->bw_blocks_per_sm), MT_BW_MAX_GRID);
+  return (nchunks_of(nb) + grid - 1) / grid <= MT_BW_MAX_PER;
+}
+
+extern "C" int mt_step_is_fused(mt_ctx* c, const mt_step_args* a, int* h_fused) {
+  if (!c || !a || !h_fused) return set_err(MT_ERR_ARG, "mt_step_is_fused: null");
+  *h_fused = step_fused(c, a) ? 1 : 0;
+  return MT_OK;
 }
 
 extern "C" int mt_step_a(mt_ctx* c, const mt_step_args* a, void* stream) {
@@ -1953,7 +2065,8 @@ extern "C" int mt_step_b(mt_ctx* c, const mt_step_args* a, void* stream) {
   int r = fill_step(c, a, &d);
   if (r) return r;
   if (!a->d_soa_cur || !a->d_soa_next || !a->d_nn_cur || !a->d_nn_next) return set_err(MT_ERR_ARG, "mt_step_b: null particle buffers");
-  if (a->world > 1 && (!a->d_shard_sums || a->n_global <= 0)) return set_err(MT_ERR_ARG, "mt_step_b: sharded step needs shard sums");
+  if (a->world > 1 && a->n_global <= 0) return set_err(MT_ERR_ARG, "mt_step_b: sharded step needs n_global");
+  if (a->world > 1 && !step_fused(c, a) && !a->d_shard_sums) return set_err(MT_ERR_ARG, "mt_step_b: sharded step needs shard sums");
   cudaStream_t st = (cudaStream_t)stream;
   if (step_fused(c, a)) {
     if (a->table_ready_event) CK(cudaStreamWaitEvent(st, (cudaEvent_t)a->table_ready_event, 0));
@@ -1965,6 +2078,7 @@ extern "C" int mt_step_b(mt_ctx* c, const mt_step_args* a, void* stream) {
     void* args[] = {&d, &bar, &target, &bw, &bwc};
     CK(cudaLaunchCooperativeKernel((const void*)k_step_bw, dim3(grid), dim3(256), args, 0, st));
     c->bar_target = target;  // only once the launch was accepted
+    if (d.world > 1) c->xchg_count += 1;
     return MT_OK;
   }
   k_step_b<true, true><<<d.nchunks, MT_CHUNK, 0, st>>>(d);

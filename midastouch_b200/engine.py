@@ -91,6 +91,37 @@ class FilterEngine:
         self._ev_table = torch.cuda.Event()
         self._ev_free = torch.cuda.Event()
         self._rng = torch.Generator().manual_seed(self.seed)
+        # sharded: map the peers' exchange buffers so that the weight sums travel inside the fused kernel
+        self.peer_exchange = False
+        if self.world > 1:
+            self.connect_peers()
+
+    def connect_peers(self) -> bool:
+        """sharded runs: exchange the CUDA IPC handles of the contexts' exchange buffers (one 64-byte
+        all-gather, once) and map them; afterwards a step is codebook query + kernel A + ONE cooperative
+        kernel per GPU that stores its weight sum into the peers' buffers over NVLink -- no collective on
+        the data path.  Returns False (and keeps the all-gather path) when peer mapping is unavailable."""
+        import torch.distributed as dist
+        import warnings
+
+        if not (dist.is_available() and dist.is_initialized()):
+            return False
+        mine = (C.c_ubyte * 64)()
+        call("mt_dist_export", self.ctx.h, mine)
+        local = torch.frombuffer(bytearray(mine), dtype=torch.uint8).to(self.dev)
+        allh = torch.zeros(self.world * 64, dtype=torch.uint8, device=self.dev)
+        dist.all_gather_into_tensor(allh, local, group=self.group)
+        buf = (C.c_ubyte * (64 * self.world)).from_buffer_copy(bytes(allh.cpu().numpy().tobytes()))
+        ok = torch.ones(1, dtype=torch.int32, device=self.dev)
+        try:
+            with torch.cuda.device(self.dev):
+                call("mt_dist_import", self.ctx.h, self.rank, self.world, buf)
+        except MidasError as e:
+            warnings.warn(f"peer exchange unavailable, using the all-gather path: {e}")
+            ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)  # all ranks take the same path
+        self.peer_exchange = bool(ok.item())
+        return self.peer_exchange
 
     # ------------------------------------------------------------------ state in / out
     def load_particles(self, poses: torch.Tensor, nn_hint: torch.Tensor | None = None, spatial_sort: bool = False):
@@ -180,7 +211,7 @@ class FilterEngine:
         a.prune_dist = self.pen_max if (self.prune and prune) else 0.0
         a.d_cb_poses = ptr(self.cb.poses) if self.prune else None
         a.table_ready_event = None
-        a.fuse_sums = int(self.fuse_sums and self.world == 1)
+        a.fuse_sums = int(self.fuse_sums and (self.world == 1 or (self.peer_exchange and resample)))
         return a
 
     def step(self, code: torch.Tensor, odom: torch.Tensor, u: float | None = None, tn: torch.Tensor | None = None,
@@ -222,7 +253,10 @@ class FilterEngine:
                 call("mt_codebook_query", self.ctx.h, ptr(q), dtype_code(q), 0, s)
             call("mt_step_a", self.ctx.h, C.byref(a), s)
             if self.world > 1:
-                self._allgather_sums()
+                fused = C.c_int(0)
+                call("mt_step_is_fused", self.ctx.h, C.byref(a), C.byref(fused))
+                if not fused.value:
+                    self._allgather_sums()
             if resample:
                 call("mt_step_b", self.ctx.h, C.byref(a), s)
         if resample:

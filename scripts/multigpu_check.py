@@ -26,27 +26,51 @@ tn = 2e-4 * torch.randn(N, 3, generator=g); rot = 0.5 * torch.randn(N, 3, genera
 q = synth.make_pose_query(gt[1], 64, seed=4, frame=1)
 odom = torch.inverse(meas[0]) @ meas[1]
 lo, hi = rank * N // world, (rank + 1) * N // world
-eng = FilterEngine(cb, capacity=int(1.5 * (hi - lo)), rank=rank, world=world, n_global=N, mesh_vertices=box.vertices)
-eng.rebalance_every = 0
-eng.load_particles(poses[lo:hi].to(dev))
-eng.step(q, odom, u=0.37, tn=tn[lo:hi].to(dev), rot=rot[lo:hi].to(dev))
-n_loc = eng.count()
-mine = torch.cat([eng.poses().reshape(n_loc, 16), eng.nn_idx().float().reshape(n_loc, 1)], 1)
-cnt = torch.zeros(world, dtype=torch.int64, device=dev)
-dist.all_gather_into_tensor(cnt, torch.tensor([n_loc], device=dev))
-parts = [torch.zeros((int(c), 17), device=dev) for c in cnt.tolist()]
-dist.all_gather(parts, mine)
-full = torch.cat(parts)
+
+
+def gather_state(e):
+    n_loc = e.count()
+    mine = torch.cat([e.poses().reshape(n_loc, 16), e.nn_idx().float().reshape(n_loc, 1)], 1)
+    cnt = torch.zeros(world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(cnt, torch.tensor([n_loc], device=dev))
+    parts = [torch.zeros((int(c), 17), device=dev) for c in cnt.tolist()]
+    dist.all_gather(parts, mine)
+    return torch.cat(parts), cnt.tolist()
+
+
 ok = True
-if rank == 0:
-    ref = FilterEngine(cb, capacity=N, mesh_vertices=box.vertices)
-    ref.fuse_sums = False
-    ref.load_particles(poses.to(dev))
-    ref.step(q, odom, u=0.37, tn=tn.to(dev), rot=rot.to(dev))
-    want = torch.cat([ref.poses().reshape(N, 16), ref.nn_idx().float().reshape(N, 1)], 1)
-    same = full.shape == want.shape and torch.equal(full, want)
-    print("children per rank", cnt.tolist(), "| sharded == single GPU:", same)
-    ok &= bool(same)
+# single-GPU engine (every rank runs its own copy), stepped with the same noise and offsets
+ref = FilterEngine(cb, capacity=N, mesh_vertices=box.vertices)
+ref.load_particles(poses.to(dev))
+STEPS = 4
+noise = [(2e-4 * torch.randn(N, 3, generator=g), 0.5 * torch.randn(N, 3, generator=g)) for _ in range(STEPS)]
+us = [0.37, 0.11, 0.93, 0.5]
+want = []
+for k in range(STEPS):
+    ref.step(q, odom, u=us[k], tn=noise[k][0].to(dev), rot=noise[k][1].to(dev))
+    want.append(torch.cat([ref.poses().reshape(N, 16), ref.nn_idx().float().reshape(N, 1)], 1))
+full = None
+for mode in ("peer", "allgather"):
+    eng = FilterEngine(cb, capacity=int(1.5 * (hi - lo)), rank=rank, world=world, n_global=N, mesh_vertices=box.vertices)
+    if mode == "peer" and not eng.peer_exchange:
+        if rank == 0:
+            print("peer exchange unavailable on this box")
+        ok = False
+    if mode == "allgather":
+        eng.peer_exchange = False
+    eng.rebalance_every = 0
+    eng.load_particles(poses[lo:hi].to(dev))
+    counts = [hi_ - lo_ for lo_, hi_ in [(r * N // world, (r + 1) * N // world) for r in range(world)]]
+    for k in range(STEPS):
+        off = sum(counts[:rank])
+        n_loc = counts[rank]
+        eng.step(q, odom, u=us[k], tn=noise[k][0][off:off + n_loc].to(dev), rot=noise[k][1][off:off + n_loc].to(dev))
+        full, counts = gather_state(eng)
+        same = full.shape == want[k].shape and torch.equal(full, want[k])
+        st = eng.ctx.stats()
+        if rank == 0:
+            print(f"[{mode}] step {k}: children per rank {counts} | sharded == single GPU: {same} | overflow flag {st['overflow']}")
+        ok &= bool(same) and st['overflow'] == 0
 # skew the shards artificially, then rebalance
 eng.rebalance()
 n2 = eng.count()
