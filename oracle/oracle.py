@@ -117,16 +117,41 @@ def r3_se3(poses: torch.Tensor, w: float = 0.01) -> torch.Tensor:
     return torch.cat(((1.0 - w) * poses[:, :3, 3], w * so3_log_map(poses[:, :3, :3])), dim=1)
 
 
+def fma_f32(a: np.ndarray, b: np.ndarray, c: np.ndarray) -> np.ndarray:
+    """correctly rounded float32 fma(a, b, c) = round(a*b + c) (what fmaf / FFMA compute).
+    a*b is exact in float64; the float64 sum may round, and rounding that to float32 could then land on
+    the wrong side of a float32 midpoint (double rounding), so the TwoSum residual decides such ties."""
+    a64, b64, c64 = (np.asarray(x, dtype=np.float32).astype(np.float64) for x in (a, b, c))
+    t = a64 * b64
+    s = t + c64
+    bb = s - t
+    e = (t - (s - bb)) + (c64 - bb)  # s + e == t + c exactly
+    r = s.astype(np.float32)
+    diff = s - r.astype(np.float64)
+    with np.errstate(invalid="ignore"):
+        r2 = np.nextafter(r, np.where(diff > 0, np.float32(np.inf), np.float32(-np.inf)).astype(np.float32))
+        mid = (diff != 0) & np.isfinite(r2) & (np.abs(diff) == np.abs(r2.astype(np.float64) - s))
+        # only when s is exactly a float32 midpoint can the residual change the result: it breaks the tie
+        toward_r2 = mid & (((e > 0) & (r2 > r)) | ((e < 0) & (r2 < r)))
+    out = np.where(toward_r2, r2, r)
+    return out.astype(np.float32)
+
+
 def l2_sq_f32(keys: np.ndarray, q: np.ndarray) -> np.ndarray:
-    """squared L2 in float32 with the fixed operation order the CUDA kernels use:
-    ((((d0^2 + d1^2) + d2^2) + d3^2) + d4^2) + d5^2, every op rounded to float32.
+    """squared L2 in float32 with the fixed operation order the CUDA kernels use (mt_math.cuh mt_key_dist):
+    lo = fma(d4, d4, fma(d2, d2, d0*d0)), hi = fma(d5, d5, fma(d3, d3, d1*d1)), result = lo + hi, with
+    d_k = key_k - q_k; every operation correctly rounded to float32.
     keys (M,6) f32, q (6,) or (N,6) f32 broadcasting against keys."""
     d = (keys.astype(np.float32) - q.astype(np.float32)).astype(np.float32)
-    s = (d * d).astype(np.float32)
-    acc = s[..., 0]
-    for k in range(1, s.shape[-1]):
-        acc = (acc + s[..., k]).astype(np.float32)
-    return acc
+    if d.shape[-1] != 6:
+        raise ValueError("l2_sq_f32: 6-D keys")
+    lo = (d[..., 0] * d[..., 0]).astype(np.float32)
+    hi = (d[..., 1] * d[..., 1]).astype(np.float32)
+    lo = fma_f32(d[..., 2], d[..., 2], lo)
+    hi = fma_f32(d[..., 3], d[..., 3], hi)
+    lo = fma_f32(d[..., 4], d[..., 4], lo)
+    hi = fma_f32(d[..., 5], d[..., 5], hi)
+    return (lo + hi).astype(np.float32)
 
 
 def nn_brute(keys: np.ndarray, queries: np.ndarray, chunk: int = 512) -> np.ndarray:

@@ -176,3 +176,31 @@ def test_filter_step_table_equals_gather_dot():
     assert torch.equal(a["nn_idx"], b["nn_idx"]) and torch.equal(a["anc"], b["anc"])
     assert torch.allclose(a["weights"], b["weights"], rtol=1e-12)
     assert (a["anc"][1:] >= a["anc"][:-1]).all()
+
+
+def test_fma_f32_is_correctly_rounded():
+    """oracle.fma_f32 (the float32 fma behind l2_sq_f32) against exact rational arithmetic, including
+    crafted cases where the float64 intermediate lands exactly on a float32 midpoint (double rounding)."""
+    from fractions import Fraction
+
+    def exact(a, b, c):
+        v = Fraction(float(a)) * Fraction(float(b)) + Fraction(float(c))
+        # round-to-nearest-even to float32 via two candidate neighbours
+        f = np.float32(float(v))  # float(v) is correctly rounded to f64; may double-round -> check neighbours
+        cands = {f, np.nextafter(f, np.float32(np.inf)), np.nextafter(f, np.float32(-np.inf))}
+        best = min(cands, key=lambda x: (abs(Fraction(float(x)) - v), int(np.float32(x).view(np.uint32)) & 1))
+        return np.float32(best)
+
+    rng = np.random.default_rng(5)
+    a = rng.standard_normal(4000).astype(np.float32)
+    b = rng.standard_normal(4000).astype(np.float32)
+    c = (rng.standard_normal(4000) * 10.0 ** rng.integers(-6, 3, 4000)).astype(np.float32)
+    # midpoint traps: c = 1, a*b = 2^-24 + tiny  (1 + 2^-24 is the midpoint between 1 and 1 + 2^-23)
+    ta = np.array([2.0 ** -12, 2.0 ** -12, 2.0 ** -12 * (1 + 2.0 ** -23), 2.0 ** -12 * (1 - 2.0 ** -23)], dtype=np.float32)
+    tb = np.array([2.0 ** -12, 2.0 ** -12 * (1 + 2.0 ** -23), 2.0 ** -12 * (1 + 2.0 ** -23), 2.0 ** -12], dtype=np.float32)
+    tc = np.array([1.0, 1.0, 1.0, 1.0], dtype=np.float32)
+    a, b, c = np.concatenate([a, ta]), np.concatenate([b, tb]), np.concatenate([c, tc])
+    got = O.fma_f32(a, b, c)
+    want = np.array([exact(x, y, z) for x, y, z in zip(a, b, c)], dtype=np.float32)
+    assert np.array_equal(got, want)
+    assert got[-3] == np.float32(1.0 + 2.0 ** -23) and got[-4] == np.float32(1.0)  # tie-to-even vs residual above
