@@ -47,13 +47,14 @@ int mt_ctx_create(int device, size_t capacity, int M, int D, mt_ctx** out);
 int mt_ctx_destroy(mt_ctx* ctx);
 
 /* ---- codebook: tactile_tree.__init__ / init_tree (tactile_tree.py:13-41) ---------- */
-/* h_keys: (M,6) float32 R3_SE3 keys on the HOST (a uniform grid over the translation
- * part replaces the nanoflann tree); d_emb: (M,D) embeddings on the device in emb_dtype
+/* h_keys: (M,6) float32 R3_SE3 keys on the HOST (a per-key neighbour graph plus a 32-ary
+ * bounding-box hierarchy over the keys in 6-D Morton order replace the nanoflann tree); d_emb: (M,D) embeddings on the device in emb_dtype
  * (the reference stores float64, build_codebook.py:72-74).  The library keeps the pointer,
  * it does not copy the embeddings; their row norms are cached by the first query, so call
  * mt_codebook_upload again if the embeddings change. */
 int mt_codebook_upload(mt_ctx* ctx, const float* h_keys, const void* d_emb, int emb_dtype);
-/* key grid introspection (tests): cell size, dims[3], number of occupied cells */
+/* search index introspection (tests): Morton cell edge, dims = {leaves, level-1 nodes, level-2 nodes},
+ * occupied = leaves (32 keys each) */
 int mt_codebook_grid_info(mt_ctx* ctx, float* h, int dims[3], int* occupied);
 
 /* neighbour-graph introspection (tests): device pointer to the (M, k, 8) float32 table
@@ -71,9 +72,9 @@ int mt_ctx_set_timing_events(mt_ctx* ctx, void* const* events4);
                                    2: a peer's weight sum never arrived (fused sharded step timed out) */
 #define MT_STAT_RESAMPLE_SKIP 1 /* a resampling saw all-zero / NaN weights and kept the particles */
 #define MT_STAT_INVALID_POSES 2 /* poses check_quats would prune (cumulative) */
-#define MT_STAT_NN_FALLBACKS 3  /* queries that left the hint graph for the grid search (cumulative) */
-#define MT_STAT_GRID_ROWS 4     /* grid rows visited by those searches (cumulative) */
-#define MT_STAT_GRID_ROWS_MAX 7 /* most rows visited by a single search */
+#define MT_STAT_NN_FALLBACKS 3  /* queries that left the hint graph for the box-hierarchy search (cumulative) */
+#define MT_STAT_GRID_ROWS 4     /* leaves (32 keys each) visited by those searches (cumulative) */
+#define MT_STAT_GRID_ROWS_MAX 7 /* most leaves visited by a single search */
 #define MT_STAT_DRIFTED 5       /* last mt_step_a: every particle failed the drift test */
 #define MT_STAT_ON_SURFACE 6    /* last mt_step_a: particles that passed the drift test */
 int mt_ctx_stats(mt_ctx* ctx, long long* h_out8, int reset);

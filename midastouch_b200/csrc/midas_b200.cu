@@ -67,10 +67,9 @@ struct mt_ctx {
   float4* d_keys_orig;    // M x 2 float4 (k0..k3 | k4,k5,0,0), original order
   float4* d_keys_sorted;  // same, sorted by grid cell
   int* d_sorted_orig;     // scratch: partner index per key during upload
-  int* d_cell_start;      // ncells + 1
+  float4* d_bvh;          // boxes of the search index: leaves | level 1 | level 2 (3 float4 each)
   float4* d_nbr;          // M x MT_NBR_K x 2 float4 neighbour lists (mt_nn.cuh)
-  GridParams grid;
-  int occupied;
+  BvhParams bvh;
   const void* d_emb;
   int emb_dtype;
   double* d_sim;   // cos(q, E_m)
@@ -174,7 +173,7 @@ extern "C" int mt_ctx_destroy(mt_ctx* c) {
   cudaFree(c->d_keys_orig);
   cudaFree(c->d_keys_sorted);
   cudaFree(c->d_sorted_orig);
-  cudaFree(c->d_cell_start);
+  cudaFree(c->d_bvh);
   cudaFree(c->d_nbr);
   cudaFree(c->d_mesh_verts);
   cudaFree(c->d_mesh_verts32);
@@ -213,62 +212,35 @@ extern "C" int mt_codebook_upload(mt_ctx* c, const float* h_keys, const void* d_
   if (emb_dtype != MT_DTYPE_F32 && emb_dtype != MT_DTYPE_F64) return set_err(MT_ERR_ARG, "mt_codebook_upload: dtype");
   CK(cudaSetDevice(c->device));
   const int M = c->M;
-  float lo[3], hi[3];
-  for (int k = 0; k < 3; ++k) lo[k] = FLT_MAX, hi[k] = -FLT_MAX;
+  // ---- search index: 6-D Morton order, leaves of 32 keys, two levels of 32-ary boxes (mt_nn.cuh)
+  float lo[6], hi[6];
+  for (int k = 0; k < 6; ++k) lo[k] = FLT_MAX, hi[k] = -FLT_MAX;
   for (int m = 0; m < M; ++m)
-    for (int k = 0; k < 3; ++k) {
+    for (int k = 0; k < 6; ++k) {
       float v = h_keys[6 * m + k];
       if (!(v == v)) return set_err(MT_ERR_ARG, "mt_codebook_upload: NaN key");
       lo[k] = std::min(lo[k], v);
       hi[k] = std::max(hi[k], v);
     }
-  float ext[3], maxext = 0.f;
-  for (int k = 0; k < 3; ++k) ext[k] = hi[k] - lo[k], maxext = std::max(maxext, ext[k]);
-  if (maxext <= 0.f) maxext = 1e-3f;
-  // cell size: shrink until <= 4 keys per occupied cell on average (keys lie on a surface),
-  // bounded by 4M cells in the box.
-  std::vector<long long> ids(M);
-  float best_h = maxext;
-  int best_dims[3] = {1, 1, 1};
-  int best_occ = 1;
-  for (float h = maxext / 2.f; h > maxext * 1e-4f; h /= 1.5f) {
-    int dims[3];
-    double total = 1;
-    for (int k = 0; k < 3; ++k) dims[k] = (int)floorf(ext[k] / h) + 1, total *= dims[k];
-    if (total > 4.0e6) break;
-    float inv_h = 1.0f / h;
-    for (int m = 0; m < M; ++m) {
-      int x = mt_cell_coord(h_keys[6 * m], lo[0], inv_h, dims[0]);
-      int y = mt_cell_coord(h_keys[6 * m + 1], lo[1], inv_h, dims[1]);
-      int z = mt_cell_coord(h_keys[6 * m + 2], lo[2], inv_h, dims[2]);
-      ids[m] = ((long long)z * dims[1] + y) * dims[0] + x;
-    }
-    std::vector<long long> s(ids);
-    std::sort(s.begin(), s.end());
-    int occ = (int)(std::unique(s.begin(), s.end()) - s.begin());
-    best_h = h;
-    best_occ = occ;
-    for (int k = 0; k < 3; ++k) best_dims[k] = dims[k];
-    if ((double)M / occ <= 4.0) break;
-  }
-  GridParams g;
-  for (int k = 0; k < 3; ++k) g.org[k] = lo[k], g.dims[k] = best_dims[k];
-  g.h = best_h;
-  g.inv_h = 1.0f / best_h;
-  const long long ncell = (long long)g.dims[0] * g.dims[1] * g.dims[2];
-  std::vector<int> cell(M);
+  float maxext = 0.f;
+  for (int k = 0; k < 6; ++k) maxext = std::max(maxext, hi[k] - lo[k]);
+  if (!(maxext > 0.f) || !(maxext <= FLT_MAX)) maxext = 1e-3f;
+  const float cell = maxext / 1023.f;  // the same cell edge in every coordinate: Morton cells are cubes
+  std::vector<unsigned long long> code(M);
   for (int m = 0; m < M; ++m) {
-    int x = mt_cell_coord(h_keys[6 * m], g.org[0], g.inv_h, g.dims[0]);
-    int y = mt_cell_coord(h_keys[6 * m + 1], g.org[1], g.inv_h, g.dims[1]);
-    int z = mt_cell_coord(h_keys[6 * m + 2], g.org[2], g.inv_h, g.dims[2]);
-    cell[m] = (int)(((long long)z * g.dims[1] + y) * g.dims[0] + x);
+    unsigned long long cd = 0;
+    unsigned qk[6];
+    for (int k = 0; k < 6; ++k) {
+      float f = floorf((h_keys[6 * m + k] - lo[k]) / cell);
+      qk[k] = (f < 0.f) ? 0u : (f > 1023.f ? 1023u : (unsigned)f);
+    }
+    for (int bit = 9; bit >= 0; --bit)
+      for (int k = 0; k < 6; ++k) cd = (cd << 1) | ((qk[k] >> bit) & 1u);
+    code[m] = cd;
   }
   std::vector<int> order(M);
   std::iota(order.begin(), order.end(), 0);
-  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cell[a] < cell[b]; });
-  std::vector<int> start(ncell + 1, 0);
-  for (int m = 0; m < M; ++m) start[cell[m] + 1]++;
-  for (long long i = 0; i < ncell; ++i) start[i + 1] += start[i];
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return code[a] < code[b]; });
   std::vector<float> ko(8 * (size_t)M, 0.f), ks(8 * (size_t)M, 0.f);
   for (int m = 0; m < M; ++m)
     for (int k = 0; k < 6; ++k) {
@@ -276,9 +248,33 @@ extern "C" int mt_codebook_upload(mt_ctx* c, const float* h_keys, const void* d_
       ks[8 * (size_t)m + k] = h_keys[6 * order[m] + k];
     }
   for (int m = 0; m < M; ++m) memcpy(&ks[8 * (size_t)m + 6], &order[m], sizeof(int));  // original index rides in the padding
-  if (c->d_cell_start) cudaFree(c->d_cell_start), c->d_cell_start = nullptr;
-  CK(cudaMalloc(&c->d_cell_start, sizeof(int) * (ncell + 1)));
-  CK(cudaMemcpy(c->d_cell_start, start.data(), sizeof(int) * (ncell + 1), cudaMemcpyHostToDevice));
+  BvhParams bp;
+  bp.n_leaf = (M + 31) / 32, bp.n_l1 = (bp.n_leaf + 31) / 32, bp.n_l2 = (bp.n_l1 + 31) / 32, bp.cell = cell;
+  // boxes: 12 floats per node = lo[6] | hi[6]
+  auto make_level = [](const std::vector<float>& child, int n_child, int n_node) {
+    std::vector<float> out(12 * (size_t)n_node);
+    for (int j = 0; j < n_node; ++j) {
+      float* o = &out[12 * (size_t)j];
+      for (int k = 0; k < 6; ++k) o[k] = FLT_MAX, o[6 + k] = -FLT_MAX;
+      for (int ch = 32 * j; ch < std::min(32 * j + 32, n_child); ++ch)
+        for (int k = 0; k < 6; ++k) {
+          o[k] = std::min(o[k], child[12 * (size_t)ch + k]);
+          o[6 + k] = std::max(o[6 + k], child[12 * (size_t)ch + 6 + k]);
+        }
+    }
+    return out;
+  };
+  std::vector<float> pts(12 * (size_t)M);  // a key is a degenerate box
+  for (int m = 0; m < M; ++m)
+    for (int k = 0; k < 6; ++k) pts[12 * (size_t)m + k] = pts[12 * (size_t)m + 6 + k] = ks[8 * (size_t)m + k];
+  const std::vector<float> leaf = make_level(pts, M, bp.n_leaf);
+  const std::vector<float> l1 = make_level(leaf, bp.n_leaf, bp.n_l1);
+  const std::vector<float> l2 = make_level(l1, bp.n_l1, bp.n_l2);
+  if (c->d_bvh) cudaFree(c->d_bvh), c->d_bvh = nullptr;
+  CK(cudaMalloc(&c->d_bvh, sizeof(float) * 12 * ((size_t)bp.n_leaf + bp.n_l1 + bp.n_l2)));
+  CK(cudaMemcpy(c->d_bvh, leaf.data(), sizeof(float) * leaf.size(), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(c->d_bvh + 3 * (size_t)bp.n_leaf, l1.data(), sizeof(float) * l1.size(), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(c->d_bvh + 3 * ((size_t)bp.n_leaf + bp.n_l1), l2.data(), sizeof(float) * l2.size(), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(c->d_keys_orig, ko.data(), sizeof(float) * 8 * M, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(c->d_keys_sorted, ks.data(), sizeof(float) * 8 * M, cudaMemcpyHostToDevice));
   k_build_nbr<false><<<(M + 7) / 8, 256>>>(c->d_keys_orig, M, c->d_nbr, nullptr);
@@ -288,8 +284,7 @@ extern "C" int mt_codebook_upload(mt_ctx* c, const float* h_keys, const void* d_
   k_set_partner<<<(M + 255) / 256, 256>>>(c->d_keys_orig, M, c->d_sorted_orig, c->d_nbr);
   CK_LAUNCH();
   CK(cudaDeviceSynchronize());
-  c->grid = g;
-  c->occupied = best_occ;
+  c->bvh = bp;
   c->d_emb = d_emb;
   c->emb_dtype = emb_dtype;
   c->rnorm_ready = false;
@@ -300,10 +295,9 @@ extern "C" int mt_codebook_upload(mt_ctx* c, const float* h_keys, const void* d_
 
 extern "C" int mt_codebook_grid_info(mt_ctx* c, float* h, int dims[3], int* occupied) {
   if (!c || !c->cb_ready) return set_err(MT_ERR_STATE, "mt_codebook_grid_info: no codebook");
-  if (h) *h = c->grid.h;
-  if (dims)
-    for (int k = 0; k < 3; ++k) dims[k] = c->grid.dims[k];
-  if (occupied) *occupied = c->occupied;
+  if (h) *h = c->bvh.cell;
+  if (dims) dims[0] = c->bvh.n_leaf, dims[1] = c->bvh.n_l1, dims[2] = c->bvh.n_l2;
+  if (occupied) *occupied = c->bvh.n_leaf;
   return MT_OK;
 }
 
@@ -1093,9 +1087,11 @@ static NNTables tables_of(mt_ctx* c) {
   NNTables T;
   T.keys_orig = c->d_keys_orig;
   T.keys_sorted = c->d_keys_sorted;
-  T.cell_start = c->d_cell_start;
+  T.bvh_leaf = c->d_bvh;
+  T.bvh_l1 = c->d_bvh + 3 * (size_t)c->bvh.n_leaf;
+  T.bvh_l2 = c->d_bvh + 3 * ((size_t)c->bvh.n_leaf + c->bvh.n_l1);
   T.nbr = c->d_nbr;
-  T.g = c->grid;
+  T.b = c->bvh;
   T.M = c->M;
   return T;
 }
@@ -1352,7 +1348,7 @@ struct StepDev {
 //               particle to a queue.  Per-warp RMSE / on-surface partials.
 //               HBM per particle: read 48 B pose + 4 B hint (+ 24 B noise when supplied),
 //               write 48 B + 4 B.  Keys / neighbour lists / mesh grid are L2-resident.
-//  k_step_nnq   the queue, one warp per entry (grid search, mt_nn.cuh): the long-tailed work is
+//  k_step_nnq   the queue, one warp per entry (box-hierarchy search, mt_nn.cuh): the long-tailed work is
 //               spread over the whole GPU instead of stalling the warp that found it.
 //  k_step_sums  weight lookup w = table[match] (4 B / particle), deterministic float64 chunk
 //               sums, and in the last block the chunk prefix for kernel B, the RMSE and the
@@ -1383,7 +1379,15 @@ __global__ void __launch_bounds__(MT_A_BLOCK, MT_A_MINBLOCKS) k_step_a(StepDev p
     if (p.prune_dist > 0.0) on_surface = mesh_within(Mh, O[0][3], O[1][3], O[2][3], p.prune_dist);
     float bd;
     int bi;
+#ifdef MT_SCAN_HIST
+    int slen;
+    todo = !nn_hint_search(T, key, hint, bd, bi, slen);
+    atomicAdd(&g_scan_hist[0][slen], 1ull);
+    const int wmax = __reduce_max_sync(__activemask(), slen);
+    if (lane == (__ffs(__activemask()) - 1)) atomicAdd(&g_scan_hist[1][wmax], 1ull);
+#else
     todo = !nn_hint_search(T, key, hint, bd, bi);
+#endif
     if (bi == INT_MAX) bi = -1;  // no usable hint
     // masked: weights *= m (particle_filter.py:398-401); a particle without any candidate yet
     // (-1) has its mask re-derived by k_step_nnq
@@ -1406,9 +1410,8 @@ __global__ void __launch_bounds__(MT_A_BLOCK, MT_A_MINBLOCKS) k_step_a(StepDev p
   }
 }
 
-// queue consumer.  In warp mode blocks pull MT_NNQ_WARPS entries per trip, one per warp: a search whose candidate is
-// close (box of at most ~120 grid rows) is finished by its warp alone; the others (stale hint
-// after a sign flip, no hint) are then served one after the other by the whole block.
+// queue consumer: one warp per entry, best-first search through the box hierarchy (nn_bvh_search) seeded with the
+// candidate the hint scan left behind.
 struct NnqEntry {
   long long i;
   float key[6];
@@ -1436,44 +1439,30 @@ __device__ __forceinline__ void nnq_load(const StepDev& p, const NNTables& T, co
 }
 #define MT_NNQ_WARPS 4
 __global__ void __launch_bounds__(32 * MT_NNQ_WARPS) k_step_nnq(StepDev p, NNTables T, MeshTables Mh) {
-  __shared__ unsigned s_e;
-  __shared__ int s_nbig;
-  __shared__ int s_big[MT_NNQ_WARPS];
-  __shared__ float s_bd[MT_NNQ_WARPS];
-  __shared__ int s_bi[MT_NNQ_WARPS];
   const unsigned qn = *p.qctl;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  // few entries: latency matters, every entry gets a whole block; many: throughput matters,
-  // entries with a close candidate get one warp each
-  const bool warp_mode = qn > 4u * gridDim.x;
-  const unsigned take = warp_mode ? (unsigned)MT_NNQ_WARPS : 1u;
-  for (;;) {
-    __syncthreads();
-    if (threadIdx.x == 0) s_e = atomicAdd(p.qctl + 1, take), s_nbig = 0;
-    __syncthreads();
-    const unsigned e0 = s_e;
-    if (e0 >= qn) break;
-    if (!warp_mode) {
-      if (threadIdx.x == 0) s_big[0] = (int)e0, s_nbig = 1;
-    } else if (e0 + warp < qn) {
-      NnqEntry q;
-      nnq_load(p, T, Mh, p.queue[e0 + warp], q);
-      if (q.bi != INT_MAX && sqrtf(q.bd) <= 5.f * T.g.h) {
-        const int res = nn_search_coop<1>(T, q.key, q.bd, q.bi, p.flags + 4, nullptr, nullptr);
-        if (lane == 0) p.nn_cur[q.i] = q.masked ? nn_masked(res) : res;
-      } else if (lane == 0) {
-        s_big[atomicAdd(&s_nbig, 1)] = (int)(e0 + warp);
-      }
+  const int lane = threadIdx.x & 31;
+  if (qn == 0) return;
+  {
+    // the search index (boxes 0.1 MB + Morton-ordered keys 32 B each) was last touched a step ago: pull it into
+    // L2 with one prefetch per 128-byte line, spread over the grid, so that the dependent rounds of the searches
+    // below pay L2 latency instead of DRAM latency
+    const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, gsz = (size_t)gridDim.x * blockDim.x;
+    const size_t box_lines = ((size_t)(T.b.n_leaf + T.b.n_l1 + T.b.n_l2) * 48 + 127) / 128;
+    const size_t key_lines = ((size_t)T.M * 32 + 127) / 128;
+    for (size_t l = gtid; l < box_lines + key_lines; l += gsz) {
+      const char* a = (l < box_lines) ? (const char*)T.bvh_leaf + 128 * l : (const char*)T.keys_sorted + 128 * (l - box_lines);
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
     }
-    __syncthreads();
-    const int nbig = s_nbig;
-    for (int b = 0; b < nbig; ++b) {
-      NnqEntry q;
-      nnq_load(p, T, Mh, p.queue[s_big[b]], q);
-      const int res = nn_search_coop<MT_NNQ_WARPS>(T, q.key, q.bd, q.bi, p.flags + 4, s_bd, s_bi);
-      __syncthreads();  // every thread has read nn_cur[i] before it is overwritten
-      if (threadIdx.x == 0) p.nn_cur[q.i] = q.masked ? nn_masked(res) : res;
-    }
+  }
+  for (;;) {  // every warp pulls one entry at a time
+    unsigned e = 0;
+    if (lane == 0) e = atomicAdd(p.qctl + 1, 1u);
+    e = __shfl_sync(0xffffffffu, e, 0);
+    if (e >= qn) break;
+    NnqEntry q;
+    nnq_load(p, T, Mh, p.queue[e], q);
+    const int res = nn_bvh_search(T, q.key, q.bd, q.bi, p.flags + 4);
+    if (lane == 0) p.nn_cur[q.i] = q.masked ? nn_masked(res) : res;
   }
 }
 
@@ -2022,6 +2011,17 @@ static bool step_fused(mt_ctx* c, const mt_step_args* a) {
   return (nchunks_of(nb) + grid - 1) / grid <= MT_BW_MAX_PER;
 }
 
+#ifdef MT_SCAN_HIST
+extern "C" int mt_debug_scan_hist(unsigned long long* h_out132, int reset) {
+  CK(cudaMemcpyFromSymbol(h_out132, g_scan_hist, sizeof(unsigned long long) * 132));
+  if (reset) {
+    static unsigned long long z[132];
+    CK(cudaMemcpyToSymbol(g_scan_hist, z, sizeof(z)));
+  }
+  return MT_OK;
+}
+#endif
+
 extern "C" int mt_step_is_fused(mt_ctx* c, const mt_step_args* a, int* h_fused) {
   if (!c || !a || !h_fused) return set_err(MT_ERR_ARG, "mt_step_is_fused: null");
   *h_fused = step_fused(c, a) ? 1 : 0;
@@ -2042,7 +2042,7 @@ extern "C" int mt_step_a(mt_ctx* c, const mt_step_args* a, void* stream) {
   k_step_a<<<(unsigned)((a->n + MT_A_BLOCK - 1) / MT_A_BLOCK), MT_A_BLOCK, 0, st>>>(d, tables_of(c), mesh_of(c));
   CK_LAUNCH();
   if (c->timing[1]) CK(cudaEventRecord(c->timing[1], st));
-  k_step_nnq<<<c->sm_count * 8, 32 * MT_NNQ_WARPS, 0, st>>>(d, tables_of(c), mesh_of(c));
+  k_step_nnq<<<c->sm_count * 12, 32 * MT_NNQ_WARPS, 0, st>>>(d, tables_of(c), mesh_of(c));
   CK_LAUNCH();
   if (c->timing[2]) CK(cudaEventRecord(c->timing[2], st));
   if (!step_fused(c, a)) {  // otherwise the sums are folded into mt_step_b's kernel

@@ -34,19 +34,23 @@
 #endif
 #define MT_NBR_K 64  // neighbours per key (the build kernel keeps two per lane)
 
-struct GridParams {
-  float org[3];
-  float inv_h, h;
-  int dims[3];
+// Search index of the fallback path: the keys in 6-D Morton order, 32 consecutive keys per leaf, and two
+// levels of 32-ary inner nodes above the leaves; every node stores its axis-aligned bounding box in all six
+// key coordinates (12 floats = 3 float4: lo0..lo3 | lo4,lo5,hi0,hi1 | hi2..hi5).
+struct BvhParams {
+  int n_leaf, n_l1, n_l2;
+  float cell;  // Morton cell edge (diagnostic)
 };
 
 #if defined(__CUDACC__)
 struct NNTables {
   const float4* keys_orig;    // M x 2 float4 (k0..k3 | k4,k5,partner bits,delta_0), original order
-  const float4* keys_sorted;  // M x 2 float4 (k0..k3 | k4,k5,original index bits,0), sorted by grid cell
-  const int* cell_start;      // ncells + 1
+  const float4* keys_sorted;  // M x 2 float4 (k0..k3 | k4,k5,original index bits,0), 6-D Morton order
+  const float4* bvh_leaf;     // n_leaf x 3 float4
+  const float4* bvh_l1;       // n_l1 x 3 float4 (node j covers leaves 32j .. 32j+31)
+  const float4* bvh_l2;       // n_l2 x 3 float4 (node j covers level-1 nodes 32j .. 32j+31)
   const float4* nbr;          // M x MT_NBR_K x 2 float4: (k0..k3 | k4,k5,delta,idx bits)
-  GridParams g;
+  BvhParams b;
   int M;
 };
 #endif
@@ -130,7 +134,21 @@ __device__ __forceinline__ void nn_prefetch(const NNTables& T, int hint) {
 
 // (1) one thread per query.  false -> needs the grid search (best_* = best so far, or
 // FLT_MAX / INT_MAX when there was no usable hint).
-__device__ __forceinline__ bool nn_hint_search(const NNTables& T, const float q[6], int hint, float& best_d, int& best_i) {
+#ifdef MT_SCAN_HIST
+__device__ unsigned long long g_scan_hist[2][66];  // [0] per particle, [1] max over the warp; index = entries read
+__device__ int g_scan_len;
+#define MT_SCAN_RET(n, v) do { mt_scan_len = (n); return (v); } while (0)
+#else
+#define MT_SCAN_RET(n, v) return (v)
+#endif
+__device__ __forceinline__ bool nn_hint_search(const NNTables& T, const float q[6], int hint, float& best_d, int& best_i
+#ifdef MT_SCAN_HIST
+                                               , int& mt_scan_len
+#endif
+) {
+#ifdef MT_SCAN_HIST
+  mt_scan_len = 0;
+#endif
   if (hint < 0 || hint >= T.M) {
     best_d = FLT_MAX;
     best_i = INT_MAX;
@@ -152,21 +170,21 @@ __device__ __forceinline__ bool nn_hint_search(const NNTables& T, const float q[
   }
   const float dh = sqrtf(best_d);
   float lim = mt_hint_limit(dh, best_d);
-  if (delta0 > lim) return true;  // nearest other key of the centre is already out of reach
+  if (delta0 > lim) MT_SCAN_RET(0, true);  // nearest other key of the centre is already out of reach
   const float4* __restrict__ L = T.nbr + (size_t)hint * (2 * MT_NBR_K);
 #pragma unroll 1
   for (int j = 0; j < MT_NBR_K; j += 2) {
     // two entries (64 contiguous bytes) per trip: both in flight together
     const float4 a0 = __ldg(L + 2 * j), b0 = __ldg(L + 2 * j + 1);
     const float4 a1 = __ldg(L + 2 * j + 2), b1 = __ldg(L + 2 * j + 3);
-    if (b0.z > lim) return true;
+    if (b0.z > lim) MT_SCAN_RET(j + 1, true);
     {
       const float k[6] = {a0.x, a0.y, a0.z, a0.w, b0.x, b0.y};
       const float d = mt_key_dist(q, k);
       const int idx = __float_as_int(b0.w);
       if (mt_better(d, idx, best_d, best_i)) best_d = d, best_i = idx, lim = mt_hint_limit(dh, d);
     }
-    if (b1.z > lim) return true;
+    if (b1.z > lim) MT_SCAN_RET(j + 2, true);
     {
       const float k[6] = {a1.x, a1.y, a1.z, a1.w, b1.x, b1.y};
       const float d = mt_key_dist(q, k);
@@ -174,7 +192,7 @@ __device__ __forceinline__ bool nn_hint_search(const NNTables& T, const float q[
       if (mt_better(d, idx, best_d, best_i)) best_d = d, best_i = idx, lim = mt_hint_limit(dh, d);
     }
   }
-  return false;
+  MT_SCAN_RET(65, false);
 }
 
 // warp-wide (best_d, best_i) = lexicographic min over lanes
@@ -187,135 +205,106 @@ __device__ __forceinline__ void warp_best(float& d, int& i) {
   }
 }
 
-// (2a) all 32 lanes: scan the cells [xlo..xhi] x [ylo..yhi] x [zlo..zhi].  q / best_* are
-// warp-uniform on entry and on exit.
-__device__ void nn_warp_scan_box(const NNTables& T, const float q[6], int xlo, int xhi, int ylo, int yhi, int zlo,
-                                 int zhi, bool prune, float& best_d, int& best_i, int wid = 0, int nw = 1) {
-  const int lane = threadIdx.x & 31;
-  const GridParams& g = T.g;
-  const int ny = yhi - ylo + 1;
-  const int nrows = ny * (zhi - zlo + 1);
-  const float slack = 1e-3f * g.h;  // cell edges recomputed in float32 are off by ulps
-  for (int r0 = 32 * wid; r0 < nrows; r0 += 32 * nw) {  // row batches are dealt round-robin to the nw warps
-    const int r = r0 + lane;
-    int s = 0, cnt = 0;
-    if (r < nrows) {
-      const int z = zlo + r / ny, y = ylo + r % ny;
-      bool skip = false;
-      if (prune && z > 0 && z < g.dims[2] - 1 && y > 0 && y < g.dims[1] - 1) {
-        // translation lower bound of row (y,z); 0 when q is inside the slab
-        const float z0 = g.org[2] + z * g.h, y0 = g.org[1] + y * g.h;
-        const float dz = fmaxf(fmaxf(z0 - q[2], q[2] - (z0 + g.h)) - slack, 0.f);
-        const float dy = fmaxf(fmaxf(y0 - q[1], q[1] - (y0 + g.h)) - slack, 0.f);
-        skip = (dz * dz + dy * dy) * 0.998f > best_d;
-      }
-      if (!skip) {
-        const int rb = (z * g.dims[1] + y) * g.dims[0];
-        s = __ldg(T.cell_start + rb + xlo);
-        cnt = __ldg(T.cell_start + rb + xhi + 1) - s;
-      }
-    }
-    int incl = cnt;
+// squared distance from q to the box of a node: a lower bound of the distance to every key below it
+__device__ __forceinline__ float bvh_lower_bound(const float4* __restrict__ node, const float q[6]) {
+  const float4 a = __ldg(node), b = __ldg(node + 1), c = __ldg(node + 2);
+  const float lo[6] = {a.x, a.y, a.z, a.w, b.x, b.y}, hi[6] = {b.z, b.w, c.x, c.y, c.z, c.w};
+  float acc = 0.f;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int t = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += t;
-    }
-    const int excl = incl - cnt;
-    const int total = __shfl_sync(0xffffffffu, incl, 31);
-    float ld = FLT_MAX;
-    int li = INT_MAX;
-    for (int t0 = 0; t0 < total; t0 += 32) {
-      const int t = t0 + lane;
-      int lo = 0;  // smallest lane whose inclusive count exceeds t
-#pragma unroll
-      for (int step = 16; step > 0; step >>= 1) {
-        const int v = __shfl_sync(0xffffffffu, incl, lo + step - 1);
-        if (v <= t) lo += step;
-      }
-      lo &= 31;
-      const int e_lo = __shfl_sync(0xffffffffu, excl, lo);
-      const int s_lo = __shfl_sync(0xffffffffu, s, lo);
-      if (t < total) {
-        const int p = s_lo + (t - e_lo);
-        float k[6];
-        const int o = load_key(T.keys_sorted, p, k);
-        const float d = mt_key_dist(q, k);
-        if (mt_better(d, o, ld, li)) ld = d, li = o;
-      }
-    }
-    warp_best(ld, li);
-    if (mt_better(ld, li, best_d, best_i)) best_d = ld, best_i = li;
+  for (int k = 0; k < 6; ++k) {
+    const float d = fmaxf(fmaxf(lo[k] - q[k], q[k] - hi[k]), 0.f);
+    acc = fmaf(d, d, acc);
   }
+  return acc;
 }
 
-// (2) NW warps, one query: exact nearest key given an optional candidate (best_i == INT_MAX:
-// none).  NW == 1: the 32 lanes of a warp (no block synchronisation); NW > 1: a whole block of
-// NW warps, row batches dealt round-robin, results combined through shared memory (s_bd/s_bi:
-// NW entries each; every thread of the block must call with the same arguments).
-// A box of +-k cells around the query's cell contains every key within k*h of the query in each
-// coordinate, so once sqrt(best_d) <= k*h the candidate is proven.  With a reasonably close
-// candidate the box follows from it directly; otherwise (stale hint after a rotation-vector
-// sign flip, no hint at all) boxes of growing k are scanned until the bound closes -- the work
-// then depends on the true nearest distance, not on the quality of the hint.
-// stats (nullable): [0] += rows visited, [3] = max rows visited by one query.
-template <int NW>
-__device__ __forceinline__ void nn_combine(float& bd, int& bi, float* s_bd, int* s_bi) {
-  if (NW == 1) return;
-  const int w = threadIdx.x >> 5;
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) s_bd[w] = bd, s_bi[w] = bi;
-  __syncthreads();
-#pragma unroll
-  for (int k = 0; k < NW; ++k)
-    if (mt_better(s_bd[k], s_bi[k], bd, bi)) bd = s_bd[k], bi = s_bi[k];
+// warp-uniform pick of the smallest remaining bound: returns its lane (bounds are >= 0, so their bit
+// patterns order like the floats) and the bound itself; the picked lane's entry is set to +Inf.
+__device__ __forceinline__ int bvh_pick(float& lb, float& picked) {
+  const unsigned bits = __float_as_uint(lb);
+  const unsigned m = __reduce_min_sync(0xffffffffu, bits);
+  const int who = __ffs(__ballot_sync(0xffffffffu, bits == m)) - 1;
+  picked = __uint_as_float(m);
+  if ((int)(threadIdx.x & 31) == who) lb = __int_as_float(0x7f800000);
+  return who;
 }
 
-template <int NW>
-__device__ __noinline__ int nn_search_coop(const NNTables& T, const float q[6], float best_d, int best_i, int* stats,
-                                           float* s_bd, int* s_bi) {
-  const GridParams& g = T.g;
+// (2) all 32 lanes of a warp, one query (q / best_* warp-uniform): exact nearest key given an optional
+// candidate (best_i == INT_MAX: none).  Best-first descent through the three levels: the lanes evaluate the
+// bounds of up to 32 siblings at once, the warp then visits them in order of increasing bound and stops a
+// level as soon as the smallest remaining bound exceeds the best distance found so far (bounds are scaled
+// by 0.9999 before the comparison: float32 rounding of the bound must never hide a key, and a key at exactly
+// the best distance with a lower index still has to be seen).  A leaf is one coalesced 1 KB read: 32 keys,
+// one per lane.  The work depends on how many boxes the ball (q, sqrt(best)) touches in all six coordinates --
+// also for queries far off the key manifold, which a translation-only grid cannot prune.
+// stats (nullable): [0] += leaves visited, [3] = max leaves visited by one query.
+#define MT_BVH_BATCH 4
+__device__ __noinline__ int nn_bvh_search(const NNTables& T, const float q[6], float best_d, int best_i, int* stats) {
   if (!(q[0] == q[0]) || !(q[1] == q[1]) || !(q[2] == q[2]) || !(q[3] == q[3]) || !(q[4] == q[4]) || !(q[5] == q[5]))
     return 0;  // NaN query: np.argmin semantics
-  const int wid = (NW == 1) ? 0 : (threadIdx.x >> 5);
-  const int cx = mt_cell_coord(q[0], g.org[0], g.inv_h, g.dims[0]);
-  const int cy = mt_cell_coord(q[1], g.org[1], g.inv_h, g.dims[1]);
-  const int cz = mt_cell_coord(q[2], g.org[2], g.inv_h, g.dims[2]);
-  int rows = 0;
-  if (best_i != INT_MAX && sqrtf(best_d) <= 12.f * g.h) {
-    const float r = sqrtf(best_d) * 1.0001f + 1e-12f;
-    const int ylo = mt_cell_coord(q[1] - r, g.org[1], g.inv_h, g.dims[1]), yhi = mt_cell_coord(q[1] + r, g.org[1], g.inv_h, g.dims[1]);
-    const int zlo = mt_cell_coord(q[2] - r, g.org[2], g.inv_h, g.dims[2]), zhi = mt_cell_coord(q[2] + r, g.org[2], g.inv_h, g.dims[2]);
-    nn_warp_scan_box(T, q, mt_cell_coord(q[0] - r, g.org[0], g.inv_h, g.dims[0]),
-                     mt_cell_coord(q[0] + r, g.org[0], g.inv_h, g.dims[0]), ylo, yhi, zlo, zhi, true, best_d, best_i, wid, NW);
-    nn_combine<NW>(best_d, best_i, s_bd, s_bi);
-    rows = (yhi - ylo + 1) * (zhi - zlo + 1);
-  } else {
-    // a query outside the grid is `gap` away from the clamped cell it is assigned to: keys within
-    // D of it lie within (D - gap)/h cells of that cell in this coordinate
-    const float gx = fmaxf(fmaxf(g.org[0] - q[0], q[0] - (g.org[0] + g.dims[0] * g.h)), 0.f);
-    const float gy = fmaxf(fmaxf(g.org[1] - q[1], q[1] - (g.org[1] + g.dims[1] * g.h)), 0.f);
-    const float gz = fmaxf(fmaxf(g.org[2] - q[2], q[2] - (g.org[2] + g.dims[2] * g.h)), 0.f);
-    const int kmax = max(g.dims[0], max(g.dims[1], g.dims[2]));
-    for (int k = 2;; k += max(1, k >> 1)) {
-      const int ylo = max(cy - k, 0), yhi = min(cy + k, g.dims[1] - 1), zlo = max(cz - k, 0), zhi = min(cz + k, g.dims[2] - 1);
-      nn_warp_scan_box(T, q, max(cx - k, 0), min(cx + k, g.dims[0] - 1), ylo, yhi, zlo, zhi, true, best_d, best_i, wid, NW);
-      nn_combine<NW>(best_d, best_i, s_bd, s_bi);
-      rows += (yhi - ylo + 1) * (zhi - zlo + 1);
-      if (k >= kmax) break;  // whole grid scanned
-      const float need = sqrtf(best_d) * 1.001f, kh = k * g.h;
-      if (best_i != INT_MAX && need <= kh + gx && need <= kh + gy && need <= kh + gz) break;  // bound closed
+  const int lane = threadIdx.x & 31;
+  const float INF = __int_as_float(0x7f800000);
+  if (best_i == INT_MAX) best_d = FLT_MAX;
+  int leaves = 0;
+  for (int c2 = 0; c2 < T.b.n_l2; c2 += 32) {
+    float lb2 = (c2 + lane < T.b.n_l2) ? bvh_lower_bound(T.bvh_l2 + 3 * (size_t)(c2 + lane), q) : INF;
+    for (;;) {
+      float v2;
+      const int w2 = bvh_pick(lb2, v2);
+      if (!(v2 * 0.9999f <= best_d)) break;
+      const int i1 = 32 * (c2 + w2) + lane;
+      float lb1 = (i1 < T.b.n_l1) ? bvh_lower_bound(T.bvh_l1 + 3 * (size_t)i1, q) : INF;
+      for (;;) {
+        float v1;
+        const int w1 = bvh_pick(lb1, v1);
+        if (!(v1 * 0.9999f <= best_d)) break;
+        const int il = 32 * (32 * (c2 + w2) + w1) + lane;
+        float lbl = (il < T.b.n_leaf) ? bvh_lower_bound(T.bvh_leaf + 3 * (size_t)il, q) : INF;
+        for (;;) {
+          // up to MT_BVH_BATCH qualifying leaves per round: their keys are fetched together (one memory
+          // latency instead of one per leaf) and reduced once
+          int base[MT_BVH_BATCH];
+          int nb = 0;
+#pragma unroll
+          for (int bq = 0; bq < MT_BVH_BATCH; ++bq) {
+            base[bq] = -1;
+            if (nb == bq) {  // the previous pick qualified
+              float vl;
+              const int wl = bvh_pick(lbl, vl);
+              if (vl * 0.9999f <= best_d) base[bq] = 32 * (32 * (32 * (c2 + w2) + w1) + wl), ++nb;
+            }
+          }
+          if (nb == 0) break;
+          float d = INF;
+          int o = INT_MAX;
+#pragma unroll
+          for (int bq = 0; bq < MT_BVH_BATCH; ++bq) {
+            const int pidx = base[bq] + lane;
+            if (base[bq] >= 0 && pidx < T.M) {
+              float k[6];
+              const int ob = load_key(T.keys_sorted, pidx, k);
+              float db = mt_key_dist(q, k);
+              if (!(db == db)) db = INF;  // Inf query coordinates: Inf - Inf
+              if (mt_better(db, ob, d, o)) d = db, o = ob;
+            }
+          }
+          warp_best(d, o);
+          if (o != INT_MAX && mt_better(d, o, best_d, best_i)) best_d = d, best_i = o;
+          leaves += nb;
+          if (nb < MT_BVH_BATCH) break;  // the last pick did not qualify: nothing left at this level
+        }
+      }
     }
   }
-  if (stats && (NW == 1 ? (threadIdx.x & 31) == 0 : threadIdx.x == 0)) {
-    atomicAdd(stats, rows);
-    atomicMax(stats + 3, rows);
+  if (stats && lane == 0) {
+    atomicAdd(stats, leaves);
+    atomicMax(stats + 3, leaves);
   }
   return best_i == INT_MAX ? 0 : best_i;  // Inf query: every distance is Inf/NaN
 }
 
 __device__ __forceinline__ int nn_search_warp(const NNTables& T, const float q[6], float best_d, int best_i) {
-  return nn_search_coop<1>(T, q, best_d, best_i, nullptr, nullptr, nullptr);
+  return nn_bvh_search(T, q, best_d, best_i, nullptr);
 }
 
 // Driver used by every kernel that assigns neighbours: each thread first tries the hint
@@ -324,7 +313,12 @@ __device__ __forceinline__ int nn_search_warp(const NNTables& T, const float q[6
 __device__ __forceinline__ int nn_assign(const NNTables& T, bool active, const float q[6], int hint, int* fallback_counter) {
   float bd = FLT_MAX;
   int bi = INT_MAX;
+#ifdef MT_SCAN_HIST
+  int slen_unused;
+  const bool todo = active && !nn_hint_search(T, q, hint, bd, bi, slen_unused);
+#else
   const bool todo = active && !nn_hint_search(T, q, hint, bd, bi);
+#endif
   unsigned m = __ballot_sync(0xffffffffu, todo);
   if (m && fallback_counter && (threadIdx.x & 31) == 0) atomicAdd(fallback_counter, __popc(m));
   while (m) {
