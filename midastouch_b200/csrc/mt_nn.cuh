@@ -14,10 +14,10 @@
 //     Rotation vectors flip sign at angle pi, so a pose that was matched to key h can jump
 //     2*pi*w away from it in key space; keys within 0.35 rad of pi therefore carry a
 //     "partner" (the key nearest to their antipodal image) which is tried as the centre too.
-//  2. grid search (one warp per query): uniform grid over the translation part of the
-//     keys, keys sorted by cell; lanes evaluate candidates of all rows of the search box
-//     in parallel (flattened with a warp prefix sum), rows whose translation lower bound
-//     exceeds the best distance are skipped.
+//  2. box-hierarchy search (one warp per query): the keys in 6-D Morton order, leaves of 32
+//     keys and two 32-ary levels of bounding boxes (all six coordinates) above them; the
+//     lanes evaluate the bounds of 32 siblings at once and the warp descends best-first until
+//     no remaining box can hold a key as close as the best one found.
 //
 // Float32 rounding: computed distances carry a relative error < 1e-6; every pruning
 // test is inflated by 1e-5 (relative) so that no candidate that could win or tie under the
@@ -132,7 +132,7 @@ __device__ __forceinline__ void nn_prefetch(const NNTables& T, int hint) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(L + 16));
 }
 
-// (1) one thread per query.  false -> needs the grid search (best_* = best so far, or
+// (1) one thread per query.  false -> needs the box-hierarchy search (best_* = best so far, or
 // FLT_MAX / INT_MAX when there was no usable hint).
 #ifdef MT_SCAN_HIST
 __device__ unsigned long long g_scan_hist[2][66];  // [0] per particle, [1] max over the warp; index = entries read

@@ -1,8 +1,8 @@
 """Drop-in for ``midastouch/tactile_tree/tactile_tree.py`` (reference lines 13-77).
 
 Same class name, constructor, attributes and methods; PyTorch tensors in and out.
-The nanoflann k-d tree (tactile_tree.py:34-41) is replaced by a uniform grid over the
-translation part of the 6-D keys held inside the CUDA library, searched exactly
+The nanoflann k-d tree (tactile_tree.py:34-41) is replaced by a per-key neighbour graph
+and a 6-D bounding-box hierarchy held inside the CUDA library, searched exactly
 (``mt_nn_assign``).  Extra, additive API for the fast path: ``SE3_NN_idx`` (indices
 only) and ``query`` (cos(q, E_m) for every row in one pass).
 """
