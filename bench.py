@@ -170,7 +170,7 @@ def run_ours(args):
     eng = FilterEngine(cb, capacity=cap, sig_t=2e-4, sig_r=0.5, seed=1234, rank=rank, world=world, n_global=n * world,
                        mesh_vertices=obj.vertices, pen_max=0.002)
     # particles start on codebook poses (what init_filter + the SE3_NN snap of filter.py:159-160 produce)
-    g = torch.Generator().manual_seed(100 + rank)
+    g = torch.Generator().manual_seed(100 + (0 if os.environ.get("MT_BENCH_SAME_SEED") else rank))
     sel = torch.randint(0, M, (n,), generator=g)
     poses0, hint0 = cbs.poses.to(dev)[sel.to(dev)], sel.int().to(dev)
 
@@ -254,8 +254,14 @@ def run_ours(args):
     k_max = {"k_step_a": max(e[1].elapsed_time(e[2]) for e in evs), "k_step_nnq": max(e[2].elapsed_time(e[3]) for e in evs),
              "k_step_b": max(e[4].elapsed_time(e[5]) for e in evs)}
     total_ms = torch.tensor([sum(ms)], dtype=torch.float64, device=dev)
+    per_rank = None
     if world > 1:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+        mine = torch.tensor([k_a, k_q, k_w + k_b, sum(ms) / args.steps, float(eng.count())], dtype=torch.float64, device=dev)
+        allr = torch.zeros(world * 5, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(allr, mine)
+        per_rank = [{"k_step_a_ms": r[0], "k_step_nnq_ms": r[1], "k_step_bw_ms (incl. waiting for the peers)": r[2], "step_ms": r[3],
+                     "particles_at_end": int(r[4])} for r in allr.reshape(world, 5).tolist()]
     total_ms = float(total_ms.item())
     value = n * world * args.steps / (total_ms * 1e-3)
     stats_loop = eng.ctx.stats(reset=True)
@@ -339,6 +345,7 @@ def run_ours(args):
             "gpu_launches": (4 if world == 1 else 5) * args.steps, "clocks": clk.summary(),
             "filter": {"rmse_t_mm_last_e2e_step": 1e3 * results[-1], "rmse_t_mm_first_e2e_step": 1e3 * results[0],
                        "step_ms_every_5th": [round(x, 4) for x in ms[::5]]},
+            "per_rank": per_rank,
             "engine_stats": {"nn_grid_searches_per_step": stats_loop["nn_fallbacks"] / (args.steps + args.warmup),
                              "on_surface_last_step": stats_loop["on_surface"], "overflow": stats_loop["overflow"],
                              "grid_rows_max_one_search": stats_loop["grid_rows_max"]},

@@ -213,6 +213,9 @@ typedef struct mt_step_args {
  * sum into its peers' buffers over NVLink and spins on its own buffer for theirs. */
 int mt_dist_export(mt_ctx* ctx, void* h_handle64);
 int mt_dist_import(mt_ctx* ctx, int rank, int world, const void* h_handles);
+/* diagnostics of the last fused sharded step (synchronises): %globaltimer (ns) of block 0 at the end of the local
+ * phase, after its sums were sent, and after all peers' sums had arrived */
+int mt_dist_debug(mt_ctx* ctx, unsigned long long* h_out3);
 /* *h_fused = 1 when mt_step_a/mt_step_b will run this step in the fused form (sums + exchange + resampling in
  * one cooperative kernel; a sharded caller then skips its all-gather of the weight sums), else 0 */
 int mt_step_is_fused(mt_ctx* ctx, const mt_step_args* a, int* h_fused);

@@ -28,10 +28,12 @@
 
 #define MT_MAX_D 6144  // query staged in 48 KB of shared memory as float64
 #define MT_MAX_WORLD 16
-// exchange buffer of the sharded fused step, double-buffered by step parity
+// exchange buffer of the sharded fused step, double-buffered by step parity.  A weight sum travels as two
+// self-validating 64-bit words, (low half of the double << 32 | seq) and (high half << 32 | seq), seq = the low 32
+// bits of the exchange counter: every 8-byte store is atomic, so a reader that sees the expected seq in both
+// words has the value -- no fence on either side.
 struct Xchg {
-  double sums[2][MT_MAX_WORLD];
-  unsigned long long seq[2][MT_MAX_WORLD];
+  unsigned long long w[2][MT_MAX_WORLD][2];
 };
 #define MT_CHUNK 256  // particles per chunk == threads per block of the sweep kernels
 
@@ -113,6 +115,7 @@ struct mt_ctx {
   struct Xchg* h_peers[MT_MAX_WORLD];
   int peers_world;            // 0: not imported
   unsigned long long xchg_count;  // fused sharded steps launched so far (same on every rank)
+  unsigned long long* d_xdbg;     // last exchange: globaltimer at barrier exit / sums sent / all sums received (block 0)
   double* d_q64;      // staged query, float64, MT_MAX_D entries
   double* d_scal;     // [0] local weight sum, [1] max, [2] min, [3] softmax denom, [4..7] spare
   unsigned int* d_ticket;
@@ -152,6 +155,8 @@ extern "C" int mt_ctx_create(int device, size_t capacity, int M, int D, mt_ctx**
   CK(cudaMalloc(&c->d_xchg, sizeof(Xchg)));
   CK(cudaMemset(c->d_xchg, 0, sizeof(Xchg)));
   CK(cudaMalloc(&c->d_peers, sizeof(Xchg*) * MT_MAX_WORLD));
+  CK(cudaMalloc(&c->d_xdbg, sizeof(unsigned long long) * 4));
+  CK(cudaMemset(c->d_xdbg, 0, sizeof(unsigned long long) * 4));
   CK(cudaMalloc(&c->d_bw, sizeof(double) * 3 * 1184));
   CK(cudaMalloc(&c->d_bwcnt, sizeof(int) * 1184));
   CK(cudaMalloc(&c->d_prefix, sizeof(double) * (c->chunk_cap + 1)));
@@ -196,6 +201,7 @@ extern "C" int mt_ctx_destroy(mt_ctx* c) {
     if (c->h_peers[r] && c->h_peers[r] != c->d_xchg) cudaIpcCloseMemHandle(c->h_peers[r]);
   cudaFree(c->d_xchg);
   cudaFree(c->d_peers);
+  cudaFree(c->d_xdbg);
   cudaFree(c->d_bw);
   cudaFree(c->d_bwcnt);
   cudaFree(c->d_scal);
@@ -1321,6 +1327,7 @@ struct StepDev {
   const double* shard_sums;
   Xchg* const* peers;          // sharded fused step: peer exchange buffers (nullptr otherwise)
   unsigned long long xseq;     // sequence number of this step's exchange (same on every rank)
+  unsigned long long* xdbg;    // timestamps of the exchange (diagnostics)
   long long* n_out;
   const long long* n_in;  // device-resident particle count (nullable): overrides n
   double prune_dist;      // > 0: drift test against the mesh (remove_invalid_particles)
@@ -1580,7 +1587,8 @@ __device__ __forceinline__ void step_b_load(const StepDev& p, const int c, const
 
 template <bool FROM_TABLE, bool SCATTER>
 __device__ __forceinline__ void step_b_chunk(const StepDev& p, const int c, const long long n, const double S, const double A,
-                                             const double base, const double endv, double* s8, long long* s_cnt, ChunkIn& in) {
+                                             const double base, const double endv, double* s8, long long* s_cnt, ChunkIn& in,
+                                             const long long slot_base_in = -1) {
   const long long i = (long long)c * MT_CHUNK + threadIdx.x;
   const bool valid = i < n;
   const int nn = in.nn;
@@ -1612,7 +1620,8 @@ __device__ __forceinline__ void step_b_chunk(const StepDev& p, const int c, cons
   }
   s_cnt[threadIdx.x + 1] = cnt;
   __syncthreads();
-  const long long slot_base = (bad || p.world == 1) ? 0 : mt_count_below(A / S, N, dN, off);
+  // first slot of this shard (sharded runs); callers that loop over chunks pass it in
+  const long long slot_base = (bad || p.world == 1) ? 0 : (slot_base_in >= 0 ? slot_base_in : mt_count_below(A / S, N, dN, off));
   if (valid && i == n - 1 && p.n_out) *p.n_out = cnt - slot_base;
   long long prev = s_cnt[threadIdx.x];
   long long kids = valid ? (cnt - prev) : 0;
@@ -1800,20 +1809,34 @@ __global__ void __launch_bounds__(256) k_step_bw(StepDev p, unsigned long long* 
     // NVLink), then every block waits for all the totals of this step to have arrived locally
     __shared__ double s_x[2];
     const int par = (int)(p.xseq & 1);
+    const unsigned seq = (unsigned)p.xseq;
+    if (g == 0 && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(p.xdbg[0]));
+    {  // while the sums travel: pull the poses of this block's first chunk towards L2
+      const long long i0 = (long long)c_lo * MT_CHUNK + threadIdx.x;
+      if (c_lo < c_hi && i0 < n) {
+#pragma unroll
+        for (int r = 0; r < 3; ++r) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.soa_cur + (size_t)r * p.stride + i0));
+      }
+    }
     if (g == 0 && threadIdx.x < p.world) {
       Xchg* peer = p.peers[threadIdx.x];
-      peer->sums[par][p.rank] = S;
-      __threadfence_system();
-      *(volatile unsigned long long*)&peer->seq[par][p.rank] = p.xseq;
+      const unsigned long long bits = (unsigned long long)__double_as_longlong(S);
+      volatile unsigned long long* dst = peer->w[par][p.rank];
+      dst[0] = (bits << 32) | seq;
+      dst[1] = (bits & 0xffffffff00000000ull) | seq;
+      if (threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(p.xdbg[1]));
     }
     if (threadIdx.x == 0) {
       Xchg* own = p.peers[p.rank];
       double tot = 0.0, off = 0.0;
       bool ok = true;
       for (int r = 0; r < p.world; ++r) {
-        unsigned long long t0 = 0;
+        volatile unsigned long long* src = own->w[par][r];
+        unsigned long long t0 = 0, w0, w1;
         int spins = 0;
-        while (*(volatile unsigned long long*)&own->seq[par][r] != p.xseq) {
+        for (;;) {
+          w0 = src[0], w1 = src[1];
+          if ((unsigned)w0 == seq && (unsigned)w1 == seq) break;
           if ((++spins & 1023) == 0) {  // a peer that never arrives (10 s) is flagged instead of hanging the GPU
             unsigned long long t;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -1824,17 +1847,22 @@ __global__ void __launch_bounds__(256) k_step_bw(StepDev p, unsigned long long* 
             }
           }
         }
-        __threadfence_system();
         if (r == p.rank) off = tot;
-        tot += *(volatile double*)&own->sums[par][r];  // sequential, identical on every GPU
+        tot += __longlong_as_double((long long)((w0 >> 32) | (w1 & 0xffffffff00000000ull)));  // sequential, identical on every GPU
       }
       if (!ok) p.flags[0] = 2;
+      if (g == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(p.xdbg[2]));
       s_x[0] = off, s_x[1] = tot;
     }
     __syncthreads();
     A = s_x[0];
     S = s_x[1];
     base_g += A, next_g += A;
+  }
+  long long slot_base = 0;
+  if (p.world > 1 && S > 0.0 && S <= DBL_MAX) {
+    const long long N = p.n_global;
+    slot_base = mt_count_below(A / S, N, (double)N, (double)(p.u / (float)N));
   }
   double run = base_g;
   for (int c = c_lo; c < c_hi; ++c) {
@@ -1853,7 +1881,7 @@ __global__ void __launch_bounds__(256) k_step_bw(StepDev p, unsigned long long* 
       step_b_load<true, true>(p, c, n, cur);
     }
     __syncthreads();  // s8 / s_cnt of the previous chunk are free
-    step_b_chunk<true, true>(p, c, n, S, A, base, endv, s8, s_cnt, cur);
+    step_b_chunk<true, true>(p, c, n, S, A, base, endv, s8, s_cnt, cur, slot_base);
   }
   if (g == 0) {  // RMSE, drift flag, bookkeeping (what the last block of k_step_sums does)
     __syncthreads();
@@ -1938,6 +1966,7 @@ static int fill_step(mt_ctx* c, const mt_step_args* a, StepDev* d) {
   d->shard_sums = a->d_shard_sums;
   d->peers = (c->peers_world == d->world && d->world > 1) ? c->d_peers : nullptr;
   d->xseq = c->xchg_count + 1;
+  d->xdbg = c->d_xdbg;
   d->n_out = a->d_n_out;
   d->n_in = a->d_n_in;
   d->prune_dist = (c->mesh_ready && a->prune_dist > 0.0) ? a->prune_dist : 0.0;
@@ -2021,6 +2050,13 @@ extern "C" int mt_debug_scan_hist(unsigned long long* h_out132, int reset) {
   return MT_OK;
 }
 #endif
+
+extern "C" int mt_dist_debug(mt_ctx* c, unsigned long long* h_out3) {
+  if (!c || !h_out3) return set_err(MT_ERR_ARG, "mt_dist_debug: null");
+  CK(cudaSetDevice(c->device));
+  CK(cudaMemcpy(h_out3, c->d_xdbg, sizeof(unsigned long long) * 3, cudaMemcpyDeviceToHost));
+  return MT_OK;
+}
 
 extern "C" int mt_step_is_fused(mt_ctx* c, const mt_step_args* a, int* h_fused) {
   if (!c || !a || !h_fused) return set_err(MT_ERR_ARG, "mt_step_is_fused: null");

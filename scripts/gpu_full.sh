@@ -14,7 +14,7 @@ timeout 600 python bench.py --no-sort --no-cpu > gpurun_out/bench_nosort.json 2>
 timeout 600 python bench.py --impl reference --steps 20 --warmup 2 > gpurun_out/bench_reference.json 2>> gpurun_out/bench.err; echo "reference rc=$?"; tail -c 1500 gpurun_out/bench_reference.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 30 --warmup 5 --no-cpu > gpurun_out/bench_ncu.log 2>&1; echo "ncu launches rc=$?"
-for k in k_step_a k_step_nnq k_step_bw k_codebook_query k_codebook_gemm_tc; do
+for k in k_step_a k_step_nnq k_step_bw; do
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:$k -s 30 -c 1 -f -o gpurun_out/prof_$k \
      python bench.py --steps 4 --warmup 30 --no-cpu > gpurun_out/ncu_$k.log 2>&1
   echo "$k rc=$?"
