@@ -1706,7 +1706,7 @@ __global__ void __launch_bounds__(256) k_step_b(StepDev p) {
 #define MT_BW_MAX_PER 32
 #define MT_BW_FAST_PER 10  // chunks per block whose weights stay in shared memory (30 KB)
 #define MT_BW_MAX_GRID 1184
-__global__ void __launch_bounds__(256) k_step_bw(StepDev p, unsigned long long* bar, unsigned long long bar_target,
+__global__ void __launch_bounds__(256, 4) k_step_bw(StepDev p, unsigned long long* bar, unsigned long long bar_target,
                                                  double* __restrict__ blocktot /* 3 x grid */, int* __restrict__ blockcnt) {
   __shared__ double s8[8];
   __shared__ long long s_cnt[MT_CHUNK + 1];

@@ -174,10 +174,17 @@ __device__ __forceinline__ bool nn_hint_search(const NNTables& T, const float q[
   const float4* __restrict__ L = T.nbr + (size_t)hint * (2 * MT_NBR_K);
 #pragma unroll 1
   for (int j = 0; j < MT_NBR_K; j += 2) {
-    // two entries (64 contiguous bytes) per trip: both in flight together
+    // two entries (64 contiguous bytes) per trip, all four loads in flight together.  The exit test is made to
+    // depend on all of them (+ 0 * x, exact for the finite keys of a codebook): otherwise ptxas sinks three of
+    // the loads below the first test and every trip pays two dependent cache latencies instead of one.
     const float4 a0 = __ldg(L + 2 * j), b0 = __ldg(L + 2 * j + 1);
     const float4 a1 = __ldg(L + 2 * j + 2), b1 = __ldg(L + 2 * j + 3);
+#ifndef MT_SCAN_PLAIN_LOADS
+    const float dz0 = fmaf(0.0f, a0.x, fmaf(0.0f, a1.x, fmaf(0.0f, b1.x, b0.z)));
+    if (dz0 > lim) MT_SCAN_RET(j + 1, true);
+#else
     if (b0.z > lim) MT_SCAN_RET(j + 1, true);
+#endif
     {
       const float k[6] = {a0.x, a0.y, a0.z, a0.w, b0.x, b0.y};
       const float d = mt_key_dist(q, k);
