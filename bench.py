@@ -84,33 +84,44 @@ class ClockSampler:
     def __init__(self, index):
         self.rows, self.stop, self.max, self.err = [], False, None, None
         self.index = index
+        self.h = None
         self.th = threading.Thread(target=self.run, daemon=True)
-
-    def run(self):
-        try:
+        try:  # NVML is initialised here, outside the timed region (it takes tens of ms, the region may be shorter)
             import pynvml
 
             pynvml.nvmlInit()
-            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
-            self.max = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
-            while not self.stop:
-                self.rows.append((pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM),
-                                  pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)))
-                time.sleep(0.01)
-            return
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
         except Exception as e:  # noqa: BLE001
-            self.err = str(e)
-        try:  # fallback: poll nvidia-smi
-            q = ["nvidia-smi", "-i", str(self.index), "--format=csv,noheader,nounits",
-                 "--query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.active"]
-            while True:
+            self.err, self.h = str(e), None
+        self.err_init = self.err
+
+    def sample_now(self):
+        """one sample taken synchronously by the caller (from inside the timed loop: the GPU is busy with the queued
+        steps while the host asks)"""
+        try:
+            if self.h is not None:
+                self.rows.append((self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM),
+                                  self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)))
+            else:
+                q = ["nvidia-smi", "-i", str(self.index), "--format=csv,noheader,nounits",
+                     "--query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.active"]
                 out = subprocess.run(q, capture_output=True, text=True, timeout=5).stdout.strip().split(",")
                 self.rows.append((int(out[0]), int(out[2].strip(), 16)))
                 self.max = int(out[1])
-                if self.stop:
-                    break
+            return True
         except Exception as e:  # noqa: BLE001
-            self.err = f"{self.err}; {e}"
+            self.err = f"{self.err_init}; {e}"
+            return False
+
+    def run(self):
+        while not self.stop:
+            ok = self.sample_now()
+            if not ok:
+                time.sleep(0.05)
+            elif self.h is not None:
+                time.sleep(0.002)  # (nvidia-smi itself takes ~50 ms per sample)
 
     def __enter__(self):
         self.th.start()
@@ -244,6 +255,8 @@ def run_ours(args):
             e[0].record()
             eng.step(codes_d[(args.warmup + t) % RUN], odoms[(args.warmup + t) % RUN], u=us[(args.warmup + t) % 4096])
             e[5].record()
+            if t == args.steps // 2 and clk.h is not None:
+                clk.sample_now()  # at least one sample from the middle of the region (the GPU runs the queued steps)
         sync()
     call("mt_ctx_set_timing_events", eng.ctx.h, None)
     ms = [e[0].elapsed_time(e[5]) for e in evs]
