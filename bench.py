@@ -339,7 +339,7 @@ def run_ours(args):
                                    f"steps {args.warmup}..{args.warmup + args.steps} of a filter run from global initialisation",
                        "embeddings": "smooth synthetic pose embedding (random Fourier features), query = embedding of the true pose + noise",
                        "particles_per_gpu": n, "codebook_M": M, "embedding_D": D, "embedding_dtype": "f64",
-                       "noise": "in-kernel Philox4x32-10", "particle_order": "random" if args.no_sort else "sorted by codebook cell at load",
+                       "noise": "in-kernel Philox4x32-10", "particle_order": "random" if args.no_sort else "sorted by the 6-D Morton rank of the matched codebook key at load",
                        "drift_pruning": "pen_max 2 mm against the 1 mm surface vertex set (density of nontextured.stl[::10])",
                        "l2": "flushed (256 MiB write + read-back) before every timed step", "parallelism": f"particles sharded x{world}"},
             "roofline": {"bound": "hbm", "achieved": a_gbs, "peak": peak, "unit": "GB/s", "frac": a_gbs / peak,

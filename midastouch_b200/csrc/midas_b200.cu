@@ -219,63 +219,13 @@ extern "C" int mt_codebook_upload(mt_ctx* c, const float* h_keys, const void* d_
   CK(cudaSetDevice(c->device));
   const int M = c->M;
   // ---- search index: 6-D Morton order, leaves of 32 keys, two levels of 32-ary boxes (mt_nn.cuh)
-  float lo[6], hi[6];
-  for (int k = 0; k < 6; ++k) lo[k] = FLT_MAX, hi[k] = -FLT_MAX;
+  MtBvhHost bvh;
+  if (!mt_bvh_build(h_keys, M, bvh)) return set_err(MT_ERR_ARG, "mt_codebook_upload: NaN key");
+  const BvhParams bp = bvh.bp;
+  const std::vector<float>&ks = bvh.keys_sorted, &leaf = bvh.leaf, &l1 = bvh.l1, &l2 = bvh.l2;
+  std::vector<float> ko(8 * (size_t)M, 0.f);
   for (int m = 0; m < M; ++m)
-    for (int k = 0; k < 6; ++k) {
-      float v = h_keys[6 * m + k];
-      if (!(v == v)) return set_err(MT_ERR_ARG, "mt_codebook_upload: NaN key");
-      lo[k] = std::min(lo[k], v);
-      hi[k] = std::max(hi[k], v);
-    }
-  float maxext = 0.f;
-  for (int k = 0; k < 6; ++k) maxext = std::max(maxext, hi[k] - lo[k]);
-  if (!(maxext > 0.f) || !(maxext <= FLT_MAX)) maxext = 1e-3f;
-  const float cell = maxext / 1023.f;  // the same cell edge in every coordinate: Morton cells are cubes
-  std::vector<unsigned long long> code(M);
-  for (int m = 0; m < M; ++m) {
-    unsigned long long cd = 0;
-    unsigned qk[6];
-    for (int k = 0; k < 6; ++k) {
-      float f = floorf((h_keys[6 * m + k] - lo[k]) / cell);
-      qk[k] = (f < 0.f) ? 0u : (f > 1023.f ? 1023u : (unsigned)f);
-    }
-    for (int bit = 9; bit >= 0; --bit)
-      for (int k = 0; k < 6; ++k) cd = (cd << 1) | ((qk[k] >> bit) & 1u);
-    code[m] = cd;
-  }
-  std::vector<int> order(M);
-  std::iota(order.begin(), order.end(), 0);
-  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return code[a] < code[b]; });
-  std::vector<float> ko(8 * (size_t)M, 0.f), ks(8 * (size_t)M, 0.f);
-  for (int m = 0; m < M; ++m)
-    for (int k = 0; k < 6; ++k) {
-      ko[8 * (size_t)m + k] = h_keys[6 * m + k];
-      ks[8 * (size_t)m + k] = h_keys[6 * order[m] + k];
-    }
-  for (int m = 0; m < M; ++m) memcpy(&ks[8 * (size_t)m + 6], &order[m], sizeof(int));  // original index rides in the padding
-  BvhParams bp;
-  bp.n_leaf = (M + 31) / 32, bp.n_l1 = (bp.n_leaf + 31) / 32, bp.n_l2 = (bp.n_l1 + 31) / 32, bp.cell = cell;
-  // boxes: 12 floats per node = lo[6] | hi[6]
-  auto make_level = [](const std::vector<float>& child, int n_child, int n_node) {
-    std::vector<float> out(12 * (size_t)n_node);
-    for (int j = 0; j < n_node; ++j) {
-      float* o = &out[12 * (size_t)j];
-      for (int k = 0; k < 6; ++k) o[k] = FLT_MAX, o[6 + k] = -FLT_MAX;
-      for (int ch = 32 * j; ch < std::min(32 * j + 32, n_child); ++ch)
-        for (int k = 0; k < 6; ++k) {
-          o[k] = std::min(o[k], child[12 * (size_t)ch + k]);
-          o[6 + k] = std::max(o[6 + k], child[12 * (size_t)ch + 6 + k]);
-        }
-    }
-    return out;
-  };
-  std::vector<float> pts(12 * (size_t)M);  // a key is a degenerate box
-  for (int m = 0; m < M; ++m)
-    for (int k = 0; k < 6; ++k) pts[12 * (size_t)m + k] = pts[12 * (size_t)m + 6 + k] = ks[8 * (size_t)m + k];
-  const std::vector<float> leaf = make_level(pts, M, bp.n_leaf);
-  const std::vector<float> l1 = make_level(leaf, bp.n_leaf, bp.n_l1);
-  const std::vector<float> l2 = make_level(l1, bp.n_l1, bp.n_l2);
+    for (int k = 0; k < 6; ++k) ko[8 * (size_t)m + k] = h_keys[6 * m + k];
   if (c->d_bvh) cudaFree(c->d_bvh), c->d_bvh = nullptr;
   CK(cudaMalloc(&c->d_bvh, sizeof(float) * 12 * ((size_t)bp.n_leaf + bp.n_l1 + bp.n_l2)));
   CK(cudaMemcpy(c->d_bvh, leaf.data(), sizeof(float) * leaf.size(), cudaMemcpyHostToDevice));

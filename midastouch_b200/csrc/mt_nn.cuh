@@ -111,6 +111,118 @@ MT_HD bool mt_hint_scan(const float q[6], const float kh[6], int hint, const flo
   return false;
 }
 
+// squared distance from q to an axis-aligned box (lo[6] | hi[6]): a lower bound of the distance from q to
+// every key inside it.  Shared by the device search and its host restatement below.
+MT_HD float mt_box_lower_bound(const float box[12], const float q[6]) {
+  float acc = 0.f;
+  for (int k = 0; k < 6; ++k) {
+    const float d = fmaxf(fmaxf(box[k] - q[k], q[k] - box[6 + k]), 0.f);
+    acc = fmaf(d, d, acc);
+  }
+  return acc;
+}
+// a node is visited when its bound, shrunk against float32 rounding, does not exceed the best distance so far
+// (<=, not <: a key at exactly the best distance with a lower index must still be seen)
+MT_HD bool mt_box_may_hold(float bound, float best_d) { return bound * 0.9999f <= best_d; }
+
+#include <algorithm>
+#include <numeric>
+#include <vector>
+// Host side of the search index (mt_codebook_upload): 6-D Morton order, leaves of 32 keys, two 32-ary levels.
+struct MtBvhHost {
+  BvhParams bp;
+  std::vector<int> order;             // order[j] = original index of the j-th key in Morton order
+  std::vector<float> keys_sorted;     // M x 8 floats: key, original index bits, 0
+  std::vector<float> leaf, l1, l2;    // 12 floats per node
+};
+inline bool mt_bvh_build(const float* h_keys, int M, MtBvhHost& out) {
+  float lo[6], hi[6];
+  for (int k = 0; k < 6; ++k) lo[k] = FLT_MAX, hi[k] = -FLT_MAX;
+  for (int m = 0; m < M; ++m)
+    for (int k = 0; k < 6; ++k) {
+      const float v = h_keys[6 * m + k];
+      if (!(v == v)) return false;  // NaN key
+      lo[k] = std::min(lo[k], v);
+      hi[k] = std::max(hi[k], v);
+    }
+  float maxext = 0.f;
+  for (int k = 0; k < 6; ++k) maxext = std::max(maxext, hi[k] - lo[k]);
+  if (!(maxext > 0.f) || !(maxext <= FLT_MAX)) maxext = 1e-3f;
+  const float cell = maxext / 1023.f;  // the same cell edge in every coordinate: Morton cells are cubes
+  std::vector<unsigned long long> code(M);
+  for (int m = 0; m < M; ++m) {
+    unsigned long long cd = 0;
+    unsigned qk[6];
+    for (int k = 0; k < 6; ++k) {
+      const float f = floorf((h_keys[6 * m + k] - lo[k]) / cell);
+      qk[k] = (f < 0.f) ? 0u : (f > 1023.f ? 1023u : (unsigned)f);
+    }
+    for (int bit = 9; bit >= 0; --bit)
+      for (int k = 0; k < 6; ++k) cd = (cd << 1) | ((qk[k] >> bit) & 1u);
+    code[m] = cd;
+  }
+  out.order.resize(M);
+  std::iota(out.order.begin(), out.order.end(), 0);
+  std::stable_sort(out.order.begin(), out.order.end(), [&](int a, int b) { return code[a] < code[b]; });
+  out.keys_sorted.assign(8 * (size_t)M, 0.f);
+  for (int m = 0; m < M; ++m) {
+    for (int k = 0; k < 6; ++k) out.keys_sorted[8 * (size_t)m + k] = h_keys[6 * (size_t)out.order[m] + k];
+    memcpy(&out.keys_sorted[8 * (size_t)m + 6], &out.order[m], sizeof(int));  // original index rides in the padding
+  }
+  BvhParams& bp = out.bp;
+  bp.n_leaf = (M + 31) / 32, bp.n_l1 = (bp.n_leaf + 31) / 32, bp.n_l2 = (bp.n_l1 + 31) / 32, bp.cell = cell;
+  auto make_level = [](const std::vector<float>& child, int n_child, int n_node) {
+    std::vector<float> o(12 * (size_t)n_node);
+    for (int j = 0; j < n_node; ++j) {
+      float* b = &o[12 * (size_t)j];
+      for (int k = 0; k < 6; ++k) b[k] = FLT_MAX, b[6 + k] = -FLT_MAX;
+      for (int ch = 32 * j; ch < std::min(32 * j + 32, n_child); ++ch)
+        for (int k = 0; k < 6; ++k) {
+          b[k] = std::min(b[k], child[12 * (size_t)ch + k]);
+          b[6 + k] = std::max(b[6 + k], child[12 * (size_t)ch + 6 + k]);
+        }
+    }
+    return o;
+  };
+  std::vector<float> pts(12 * (size_t)M);  // a key is a degenerate box
+  for (int m = 0; m < M; ++m)
+    for (int k = 0; k < 6; ++k) pts[12 * (size_t)m + k] = pts[12 * (size_t)m + 6 + k] = out.keys_sorted[8 * (size_t)m + k];
+  out.leaf = make_level(pts, M, bp.n_leaf);
+  out.l1 = make_level(out.leaf, bp.n_leaf, bp.n_l1);
+  out.l2 = make_level(out.l1, bp.n_l1, bp.n_l2);
+  return true;
+}
+#if !defined(__CUDACC__)
+// (host test harness only) Host restatement of nn_bvh_search (same pruning rule, plain nested loops): returns the index, *visited = leaves
+// whose keys were evaluated.  seed_i < 0: no candidate.
+inline int mt_bvh_search_host(const MtBvhHost& B, int M, const float q[6], float seed_d, int seed_i, int* visited) {
+  for (int k = 0; k < 6; ++k)
+    if (!(q[k] == q[k])) return 0;  // NaN query: np.argmin semantics
+  float best_d = seed_i < 0 ? FLT_MAX : seed_d;
+  int best_i = seed_i < 0 ? INT_MAX : seed_i, leaves = 0;
+  for (int n2 = 0; n2 < B.bp.n_l2; ++n2) {
+    if (!mt_box_may_hold(mt_box_lower_bound(&B.l2[12 * (size_t)n2], q), best_d)) continue;
+    for (int n1 = 32 * n2; n1 < std::min(32 * n2 + 32, B.bp.n_l1); ++n1) {
+      if (!mt_box_may_hold(mt_box_lower_bound(&B.l1[12 * (size_t)n1], q), best_d)) continue;
+      for (int nl = 32 * n1; nl < std::min(32 * n1 + 32, B.bp.n_leaf); ++nl) {
+        if (!mt_box_may_hold(mt_box_lower_bound(&B.leaf[12 * (size_t)nl], q), best_d)) continue;
+        ++leaves;
+        for (int p = 32 * nl; p < std::min(32 * nl + 32, M); ++p) {
+          const float* k = &B.keys_sorted[8 * (size_t)p];
+          float d = mt_key_dist(q, k);
+          if (!(d == d)) continue;  // Inf query coordinates
+          int o;
+          memcpy(&o, k + 6, sizeof(int));
+          if (mt_better(d, o, best_d, best_i)) best_d = d, best_i = o;
+        }
+      }
+    }
+  }
+  if (visited) *visited = leaves;
+  return best_i == INT_MAX ? 0 : best_i;
+}
+#endif
+
 #if defined(__CUDACC__)
 // ------------------------------------------------------------------------- device side
 __device__ __forceinline__ int load_key(const float4* __restrict__ t, int i, float k[6], float* extra = nullptr) {
@@ -212,17 +324,11 @@ __device__ __forceinline__ void warp_best(float& d, int& i) {
   }
 }
 
-// squared distance from q to the box of a node: a lower bound of the distance to every key below it
+// bound of one node (3 float4 = lo[6] | hi[6])
 __device__ __forceinline__ float bvh_lower_bound(const float4* __restrict__ node, const float q[6]) {
   const float4 a = __ldg(node), b = __ldg(node + 1), c = __ldg(node + 2);
-  const float lo[6] = {a.x, a.y, a.z, a.w, b.x, b.y}, hi[6] = {b.z, b.w, c.x, c.y, c.z, c.w};
-  float acc = 0.f;
-#pragma unroll
-  for (int k = 0; k < 6; ++k) {
-    const float d = fmaxf(fmaxf(lo[k] - q[k], q[k] - hi[k]), 0.f);
-    acc = fmaf(d, d, acc);
-  }
-  return acc;
+  const float box[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+  return mt_box_lower_bound(box, q);
 }
 
 // warp-uniform pick of the smallest remaining bound: returns its lane (bounds are >= 0, so their bit
@@ -258,13 +364,13 @@ __device__ __noinline__ int nn_bvh_search(const NNTables& T, const float q[6], f
     for (;;) {
       float v2;
       const int w2 = bvh_pick(lb2, v2);
-      if (!(v2 * 0.9999f <= best_d)) break;
+      if (!mt_box_may_hold(v2, best_d)) break;
       const int i1 = 32 * (c2 + w2) + lane;
       float lb1 = (i1 < T.b.n_l1) ? bvh_lower_bound(T.bvh_l1 + 3 * (size_t)i1, q) : INF;
       for (;;) {
         float v1;
         const int w1 = bvh_pick(lb1, v1);
-        if (!(v1 * 0.9999f <= best_d)) break;
+        if (!mt_box_may_hold(v1, best_d)) break;
         const int il = 32 * (32 * (c2 + w2) + w1) + lane;
         float lbl = (il < T.b.n_leaf) ? bvh_lower_bound(T.bvh_leaf + 3 * (size_t)il, q) : INF;
         for (;;) {
@@ -278,7 +384,7 @@ __device__ __noinline__ int nn_bvh_search(const NNTables& T, const float q[6], f
             if (nb == bq) {  // the previous pick qualified
               float vl;
               const int wl = bvh_pick(lbl, vl);
-              if (vl * 0.9999f <= best_d) base[bq] = 32 * (32 * (32 * (c2 + w2) + w1) + wl), ++nb;
+              if (mt_box_may_hold(vl, best_d)) base[bq] = 32 * (32 * (32 * (c2 + w2) + w1) + wl), ++nb;
             }
           }
           if (nb == 0) break;

@@ -104,4 +104,18 @@ void h_so3_to_quat(const float* aos, long long n, float* out4) {
     mt_so3_to_quat(P, out4 + 4 * i);
   }
 }
+// search index of the fallback path (mt_nn.cuh): build on the host exactly as mt_codebook_upload does, then run
+// the host restatement of the box-hierarchy search for n queries.  seeds: candidate index per query or -1.
+int h_bvh_search(const float* keys, long long M, const float* q, long long n, const int* seeds, int* idx, int* visited,
+                 int* dims3) {
+  MtBvhHost B;
+  if (!mt_bvh_build(keys, (int)M, B)) return -1;
+  dims3[0] = B.bp.n_leaf, dims3[1] = B.bp.n_l1, dims3[2] = B.bp.n_l2;
+  for (long long i = 0; i < n; ++i) {
+    const int s = seeds ? seeds[i] : -1;
+    const float sd = s >= 0 ? mt_key_dist(q + 6 * i, keys + 6 * (long long)s) : 0.f;
+    idx[i] = mt_bvh_search_host(B, (int)M, q + 6 * i, sd, s, visited + i);
+  }
+  return 0;
+}
 }

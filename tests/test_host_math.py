@@ -192,3 +192,47 @@ def test_so3_to_quaternion_matches_oracle(H):
     H.h_so3_to_quat(P(T), ctypes.c_longlong(600), P(q))
     ref = O.so3_to_quaternion(torch.from_numpy(T[:, :3, :3].copy())).numpy()
     assert np.abs(q - ref).max() < 2e-6
+
+
+def test_box_hierarchy_search_is_exact(H):
+    """the fallback search index (6-D Morton order, boxes of 32 keys, two 32-ary levels; mt_nn.cuh) built and
+    searched on the host with the pruning rule the CUDA kernel uses: exact argmin (ties -> lowest index) for
+    queries on the key manifold, far off it, outside the bounding box, with and without a seed candidate, with
+    duplicate keys, and np.argmin semantics for NaN queries -- while visiting a small part of the leaves."""
+    rng = np.random.default_rng(11)
+    M = 6000
+    # keys on a curved 3-D manifold embedded in 6-D (position on a thin rod, normal direction, yaw), like a codebook
+    u, th, yaw = rng.uniform(0, 0.03, M), rng.uniform(0, 2 * np.pi, M), rng.uniform(-np.pi, np.pi, M)
+    keys = np.stack([u, 0.0015 * np.cos(th), 0.0015 * np.sin(th), 0.01 * th, 0.01 * yaw, 0.005 * np.sin(yaw + th)], 1).astype(np.float32)
+    keys[100] = keys[7]          # duplicates: the lower index must win
+    keys[5000] = keys[7]
+    near = keys[rng.integers(0, M, 600)] + rng.normal(0, 2e-4, (600, 6)).astype(np.float32)
+    far = keys[rng.integers(0, M, 600)] + rng.normal(0, 8e-3, (600, 6)).astype(np.float32)
+    outside = (rng.uniform(-0.3, 0.3, (100, 6))).astype(np.float32)
+    exact = keys[[7, 100, 5000, 42]].copy()
+    q = np.ascontiguousarray(np.concatenate([near, far, outside, exact]).astype(np.float32))
+    n = q.shape[0]
+    want = O.nn_brute(keys, q)
+    assert want[-4] == 7 and want[-3] == 7 and want[-2] == 7
+    dims = np.zeros(3, dtype=np.int32)
+    for seeded in (False, True):
+        seeds = rng.integers(0, M, n).astype(np.int32) if seeded else np.full(n, -1, dtype=np.int32)
+        idx, vis = np.zeros(n, dtype=np.int32), np.zeros(n, dtype=np.int32)
+        rc = H.h_bvh_search(P(keys), ctypes.c_longlong(M), P(q), ctypes.c_longlong(n), P(seeds), P(idx), P(vis), P(dims))
+        assert rc == 0 and tuple(dims) == ((M + 31) // 32, ((M + 31) // 32 + 31) // 32, 1)
+        assert np.array_equal(idx, want)
+        assert vis.mean() < dims[0] / 3  # (this host loop is not best-first: an upper bound of the kernel's work)
+    # a good seed (the true neighbour) leaves only the verification
+    idx, vis = np.zeros(n, dtype=np.int32), np.zeros(n, dtype=np.int32)
+    H.h_bvh_search(P(keys), ctypes.c_longlong(M), P(q), ctypes.c_longlong(n), P(want.astype(np.int32)), P(idx), P(vis), P(dims))
+    assert vis[:600].mean() < 8 and vis[600:1200].mean() < 25  # verification only: a handful of leaves
+    assert np.array_equal(idx, want)
+    # NaN query -> index 0 (np.argmin of all-NaN distances); NaN key -> build refuses
+    qn = q[:2].copy()
+    qn[0, 3] = np.nan
+    idx2, vis2 = np.zeros(2, dtype=np.int32), np.zeros(2, dtype=np.int32)
+    H.h_bvh_search(P(keys), ctypes.c_longlong(M), P(qn), ctypes.c_longlong(2), P(np.full(2, -1, dtype=np.int32)), P(idx2), P(vis2), P(dims))
+    assert idx2[0] == 0 and idx2[1] == want[1]
+    bad = keys.copy()
+    bad[3, 2] = np.nan
+    assert H.h_bvh_search(P(bad), ctypes.c_longlong(M), P(q), ctypes.c_longlong(1), P(np.full(1, -1, dtype=np.int32)), P(idx2), P(vis2), P(dims)) == -1
