@@ -1411,15 +1411,19 @@ __global__ void __launch_bounds__(32 * MT_NNQ_WARPS) k_step_nnq(StepDev p, NNTab
       asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
     }
   }
-  for (;;) {  // every warp pulls one entry at a time
-    unsigned e = 0;
-    if (lane == 0) e = atomicAdd(p.qctl + 1, 1u);
-    e = __shfl_sync(0xffffffffu, e, 0);
-    if (e >= qn) break;
+  // the first entry of every warp is assigned statically (one per block first, so that they spread over the SMs):
+  // with the usual few hundred entries nobody touches the shared counter -- thousands of warps opening with an
+  // atomic on one address serialised in L2 and were most of this kernel's duration.  Further entries are pulled.
+  const unsigned W = gridDim.x * MT_NNQ_WARPS;
+  unsigned e = (threadIdx.x >> 5) * gridDim.x + blockIdx.x;
+  while (e < qn) {
     NnqEntry q;
     nnq_load(p, T, Mh, p.queue[e], q);
     const int res = nn_bvh_search(T, q.key, q.bd, q.bi, p.flags + 4);
     if (lane == 0) p.nn_cur[q.i] = q.masked ? nn_masked(res) : res;
+    if (qn <= W) break;
+    if (lane == 0) e = W + atomicAdd(p.qctl + 1, 1u);
+    e = __shfl_sync(0xffffffffu, e, 0);
   }
 }
 
