@@ -820,3 +820,35 @@ def test_engine_on_other_objects(mt, dev, name, M):
     eng2.step(q, odom, u=0.77, tn=tn.to(dev), rot=rot.to(dev))
     assert torch.equal(eng2.ancestors().cpu().long(), O.low_var_indices(w, 0.77))
     assert cb.ctx.stats()["overflow"] == 0
+
+
+def test_engine_heavy_fallback_is_exact(mt, dev):
+    """thin rod (cotter-pin stand-in): after a few steps the particles' rotations have drifted off the key
+    manifold, a large share of the hint scans is inconclusive and the box-hierarchy search carries the load.
+    The matches must still be the exact nearest keys, and the hierarchy must prune (a search that visited
+    every leaf would also be exact)."""
+    obj = synth.make_object("cotter-pin")
+    M, N, D = 20000, 40000, 32
+    cbs = synth.make_codebook(obj, M=M, D=D, seed=9, embedding="smooth")
+    cb = mt.tt.tactile_tree(cbs.poses, cbs.cam_poses, cbs.embeddings)
+    cb.to_device(dev)
+    g = torch.Generator().manual_seed(9)
+    sel = torch.randint(0, M, (N,), generator=g)
+    gt, meas = synth.make_trajectory(obj, T=16, seed=9, step=1e-4)
+    eng = mt.eng.FilterEngine(cb, capacity=N, sig_t=1e-4, seed=3, mesh_vertices=obj.vertices, pen_max=0.002)
+    eng.load_particles(cbs.poses[sel].to(dev), nn_hint=sel.int().to(dev), spatial_sort=True)
+    cb.ctx.stats(reset=True)
+    for t in range(12):
+        q = synth.make_pose_query(gt[t + 1], D, seed=9, frame=t)
+        eng.step(q, torch.inverse(meas[t]) @ meas[t + 1], u=0.1 + 0.07 * t)
+    q = synth.make_pose_query(gt[13], D, seed=9, frame=12)
+    eng.step(q, torch.inverse(meas[12]) @ meas[13], u=0.5, resample=False)
+    st = cb.ctx.stats()
+    moved, nn = eng.poses(), eng.nn_idx().cpu().long().numpy()
+    sub = torch.randperm(N, generator=g)[:6000]
+    gk = mt.tt.R3_SE3(moved[sub.to(dev)]).cpu().numpy()
+    assert np.array_equal(nn[sub.numpy()], O.nn_exact(cb.logmap_pose.cpu().numpy(), gk, k=32))
+    n_leaf = cb.ctx.grid_info()[1][0]
+    assert st["nn_fallbacks"] > N // 4, st       # the fallback path really was exercised (13 steps x N particles)
+    assert 0 < st["grid_rows_max"] < (3 * n_leaf) // 4, (st, n_leaf)
+    assert st["overflow"] == 0
