@@ -220,7 +220,7 @@ extern "C" int mt_codebook_upload(mt_ctx* c, const float* h_keys, const void* d_
   const int M = c->M;
   // ---- search index: 6-D Morton order, leaves of 32 keys, two levels of 32-ary boxes (mt_nn.cuh)
   MtBvhHost bvh;
-  if (!mt_bvh_build(h_keys, M, bvh)) return set_err(MT_ERR_ARG, "mt_codebook_upload: NaN key");
+  if (!mt_bvh_build(h_keys, M, bvh)) return set_err(MT_ERR_ARG, "mt_codebook_upload: NaN or Inf key");
   const BvhParams bp = bvh.bp;
   const std::vector<float>&ks = bvh.keys_sorted, &leaf = bvh.leaf, &l1 = bvh.l1, &l2 = bvh.l2;
   std::vector<float> ko(8 * (size_t)M, 0.f);

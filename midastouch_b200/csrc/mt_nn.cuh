@@ -141,7 +141,7 @@ inline bool mt_bvh_build(const float* h_keys, int M, MtBvhHost& out) {
   for (int m = 0; m < M; ++m)
     for (int k = 0; k < 6; ++k) {
       const float v = h_keys[6 * m + k];
-      if (!(v == v)) return false;  // NaN key
+      if (!(fabsf(v) <= FLT_MAX)) return false;  // NaN / Inf key (the scans rely on finite keys: 0 * x == 0)
       lo[k] = std::min(lo[k], v);
       hi[k] = std::max(hi[k], v);
     }
