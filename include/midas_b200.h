@@ -153,6 +153,15 @@ int mt_rmse(mt_ctx* ctx, const float* d_soa, long long stride, long long n, cons
  * NaN weights, 237-241); the ancestors are then the identity. */
 int mt_resample_systematic(mt_ctx* ctx, const double* d_w, long long n, float u, int seq, int32_t* d_anc,
                            int* d_status, void* stream);
+
+/* ---- resampler("weighted_random") (particle_filter.py:243-250) -------------------- */
+/* n_draws independent categorical draws with replacement from n float64 weights (the reference's
+ * WeightedRandomSampler / torch.multinomial(replacement=True)): d_idx[j] = first i with C_i > u_j * sum(w),
+ * C the inclusive float64 prefix of the weights, u_j a 53-bit uniform from Philox4x32-10 keyed by
+ * (seed; j, stream_id).  Items of zero weight are never drawn.  d_cdf_scratch: (n,) float64 work space owned by
+ * the caller.  d_status as for mt_resample_systematic (indices are then the identity). */
+int mt_resample_multinomial(mt_ctx* ctx, const double* d_w, long long n, long long n_draws, uint64_t seed,
+                            uint64_t stream_id, double* d_cdf_scratch, int32_t* d_idx, int* d_status, void* stream);
 int mt_gather_soa(const float* d_soa_in, long long stride_in, const int32_t* d_anc, long long n, float* d_soa_out,
                   long long stride_out, void* stream);
 int mt_gather_f64(const double* d_in, const int32_t* d_anc, long long n, double* d_out, void* stream);

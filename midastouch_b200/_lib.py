@@ -76,6 +76,8 @@ _SIGS = {
                             C.c_float, C.c_float, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_int, C.c_void_p]),
     "mt_rmse": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mt_resample_systematic": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mt_resample_multinomial": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong, C.c_uint64, C.c_uint64, C.c_void_p,
+                                          C.c_void_p, C.c_void_p, C.c_void_p]),
     "mt_gather_soa": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_void_p]),
     "mt_gather_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]),
     "mt_cluster_centers": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -2130,6 +2130,82 @@ extern "C" int mt_resample_systematic(mt_ctx* c, const double* d_w, long long n,
   return MT_OK;
 }
 
+// ------------------------------------------------------------------------- multinomial resampling
+// resampler(..., "weighted_random") (particle_filter.py:243-250: WeightedRandomSampler = torch.multinomial with
+// replacement): n_draws independent categorical draws.  The inclusive CDF is built with the chunk prefix of
+// k_weight_sums plus a strictly sequential sum inside each 256-chunk (so it is monotone and an item of zero weight
+// adds exactly nothing -- pruned particles can never be drawn), pinned to the next chunk's base at its end.
+__global__ void __launch_bounds__(256) k_cdf_chunks(StepDev p, double* __restrict__ cdf) {
+  __shared__ double s_w[MT_CHUNK];
+  const int c = blockIdx.x;
+  const long long i = (long long)c * MT_CHUNK + threadIdx.x;
+  s_w[threadIdx.x] = (i < p.n) ? p.wsrc[i] : 0.0;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double run = p.prefix[c];
+    const double cap = p.prefix[c + 1];  // == the next chunk's base
+    int last_pos = -1;
+    for (int k = 0; k < MT_CHUNK; ++k) {
+      if (s_w[k] > 0.0) last_pos = k;
+      run += s_w[k];
+      s_w[k] = fmin(run, cap);
+    }
+    // the chunk ends exactly on the next chunk's base, and it gets there on its last item of positive weight:
+    // the CDF is flat across every zero-weight item, also across chunk boundaries
+    if (last_pos >= 0)
+      for (int k = last_pos; k < MT_CHUNK; ++k) s_w[k] = cap;
+  }
+  __syncthreads();
+  if (i < p.n) cdf[i] = s_w[threadIdx.x];
+}
+
+__global__ void k_multinomial(StepDev p, const double* __restrict__ cdf, long long n_draws, int32_t* __restrict__ idx) {
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_draws) return;
+  const double S = p.prefix[p.nchunks];
+  if (!(S > 0.0) || !(S <= DBL_MAX)) {  // all-zero / NaN / Inf weights: the caller keeps the particles (237-241)
+    if (j == 0) p.flags[1] = 1;
+    idx[j] = (int32_t)(j < p.n ? j : p.n - 1);
+    return;
+  }
+  const mt_u4 ctr = {(uint32_t)j, (uint32_t)((uint64_t)j >> 32), (uint32_t)p.step, (uint32_t)(p.step >> 32)};
+  const mt_u4 r = mt_philox(ctr, (uint32_t)p.seed, (uint32_t)(p.seed >> 32));
+  idx[j] = (int32_t)mt_cdf_draw(cdf, p.n, S, mt_u01_53(r.x, r.y));
+}
+
+extern "C" int mt_resample_multinomial(mt_ctx* c, const double* d_w, long long n, long long n_draws, uint64_t seed,
+                                       uint64_t stream_id, double* d_cdf_scratch, int32_t* d_idx, int* d_status, void* stream) {
+  if (!c || !d_w || !d_idx || !d_cdf_scratch || n <= 0 || n_draws <= 0)
+    return set_err(MT_ERR_ARG, "mt_resample_multinomial: bad argument");
+  if ((size_t)n > c->cap) return set_err(MT_ERR_CAPACITY, "mt_resample_multinomial: n exceeds context capacity");
+  if (n > 0x7fffffffLL) return set_err(MT_ERR_ARG, "mt_resample_multinomial: indices are int32");
+  cudaStream_t st = (cudaStream_t)stream;
+  StepDev d;
+  memset(&d, 0, sizeof(d));
+  d.n = n;
+  d.n_global = n;
+  d.stride = n;
+  d.world = 1;
+  d.wsrc = d_w;
+  d.seed = seed;
+  d.step = stream_id;
+  d.part = c->d_part;
+  d.prefix = c->d_prefix;
+  d.scal = c->d_scal + 4;
+  d.ticket = c->d_ticket;
+  d.flags = c->d_flags;
+  d.nchunks = (int)nchunks_of(n);
+  CK(cudaMemsetAsync(c->d_flags + 1, 0, sizeof(int), st));
+  k_weight_sums<<<d.nchunks, MT_CHUNK, 0, st>>>(d);
+  CK_LAUNCH();
+  k_cdf_chunks<<<d.nchunks, MT_CHUNK, 0, st>>>(d, d_cdf_scratch);
+  CK_LAUNCH();
+  k_multinomial<<<(unsigned)((n_draws + 255) / 256), 256, 0, st>>>(d, d_cdf_scratch, n_draws, d_idx);
+  CK_LAUNCH();
+  if (d_status) CK(cudaMemcpyAsync(d_status, c->d_flags + 1, sizeof(int), cudaMemcpyDeviceToDevice, st));
+  return MT_OK;
+}
+
 // ------------------------------------------------------------------------- batched codebook query (tensor cores)
 #include "mt_gemm_tc.cuh"
 

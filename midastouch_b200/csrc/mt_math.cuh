@@ -258,6 +258,38 @@ MT_HD mt_u4 mt_philox(mt_u4 c, uint32_t k0, uint32_t k1) {
   return c;
 }
 
+// 53-bit uniform in [0,1) from two 32-bit words
+MT_HD double mt_u01_53(uint32_t a, uint32_t b) {
+  return (double)((((uint64_t)a >> 5) << 26) | ((uint64_t)b >> 6)) * (1.0 / 9007199254740992.0);
+}
+// first index i in [0,n) with C[i] > t (n when there is none); C non-decreasing
+MT_HD long long mt_upper_bound(const double* C, long long n, double t) {
+  long long lo = 0, hi = n;
+  while (lo < hi) {
+    const long long mid = (lo + hi) >> 1;
+    if (C[mid] > t) hi = mid;
+    else lo = mid + 1;
+  }
+  return lo;
+}
+// categorical draw from an un-normalised inclusive CDF (C[n-1] <= S): u in [0,1) -> first i with C[i] > u*S.
+// Items of zero weight (C[i] == C[i-1]) are never returned.
+MT_HD long long mt_cdf_draw(const double* C, long long n, double S, double u) {
+  double t = u * S;
+  long long r = mt_upper_bound(C, n, t);
+  if (r >= n) {  // u*S rounded up to (or past) the last CDF value: the last item of positive weight
+    const double top = C[n - 1];
+    long long lo = 0, hi = n - 1;  // first index that attains the maximum
+    while (lo < hi) {
+      const long long mid = (lo + hi) >> 1;
+      if (C[mid] >= top) hi = mid;
+      else lo = mid + 1;
+    }
+    r = lo;
+  }
+  return r;
+}
+
 // 21-bit uniform in (0,1): six of them come out of ONE Philox4x32-10 call (128 bits)
 MT_HD float mt_u01_21(uint32_t x) { return ((float)(x & 0x1FFFFFu) + 0.5f) * (1.0f / 2097152.0f); }
 

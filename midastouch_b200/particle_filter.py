@@ -3,10 +3,10 @@
 Same names (``Particles``, ``particle_filter``, ``particle_rmse``, ``torch_delete``),
 argument meaning and error behaviour; PyTorch CUDA tensors in and out; the arithmetic runs
 in libmidas_b200 (sm_100a).  Differences, all additive or documented in DESIGN.md:
-  * ``resampler`` default stays "weighted_random" like the reference (that mode is
-    ``torch.multinomial`` -- a library call, kept as such); "low_var" is the CUDA systematic
-    resampler; "low_var_batch" is served by the same kernel (its N x N formulation has an
-    off-by-one at particle_filter.py:279 that is not reproduced).
+  * ``resampler`` default stays "weighted_random" like the reference (``torch.multinomial`` there;
+    here N categorical draws in the library, Philox-keyed -- same distribution, not the same random
+    stream); "low_var" is the CUDA systematic resampler; "low_var_batch" is served by the same kernel
+    (its N x N formulation has an off-by-one at particle_filter.py:279 that is not reproduced).
   * the mesh is given as a vertex array (or .npy path): trimesh is not a dependency.
 """
 from __future__ import annotations
@@ -166,10 +166,22 @@ class particle_filter:
         nSamples = len(particles)
         require_cuda(particles.poses, "particle poses")
         if resample == "weighted_random":
-            norm_weights = particles.weights / torch.sum(particles.weights)
-            if torch.all(norm_weights == 0) or torch.any(torch.isnan(norm_weights)):
-                return particles
-            idxs = torch.multinomial(norm_weights, nSamples, replacement=True)
+            # WeightedRandomSampler(weights, N, replacement=True) == N categorical draws (243-250); drawn in the
+            # library (Philox4x32-10 keyed by a seed taken from torch's default generator, so torch.manual_seed
+            # still makes a run reproducible)
+            dev = particles.poses.device
+            w = particles.weights.to(torch.float64).contiguous()
+            seed = int(torch.randint(0, 2**62, (1,)).item())
+            ctx = _ctx_for(dev, nSamples)
+            idx32 = torch.empty(nSamples, dtype=torch.int32, device=dev)
+            scratch = torch.empty(nSamples, dtype=torch.float64, device=dev)
+            status = torch.zeros(1, dtype=torch.int32, device=dev)
+            with torch.cuda.device(dev):
+                call("mt_resample_multinomial", ctx.h, ptr(w), nSamples, nSamples, seed, 0, ptr(scratch), ptr(idx32), ptr(status),
+                     stream_ptr())
+            if int(status.item()):
+                return particles  # all-zero / NaN weights: the reference returns the input (237-241)
+            idxs = idx32.long()
             return Particles(particles.poses[idxs, :, :], particles.weights[idxs], particles.labels[idxs])
         if resample not in ("low_var", "low_var_batch"):
             raise MidasError(f"unknown resample mode {resample!r}")

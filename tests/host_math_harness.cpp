@@ -118,4 +118,15 @@ int h_bvh_search(const float* keys, long long M, const float* q, long long n, co
   }
   return 0;
 }
+// categorical draws from an inclusive CDF (mt_cdf_draw) with the uniforms the kernel would use
+void h_cdf_draws(const double* C, long long n, double S, unsigned long long seed, unsigned long long stream_id, long long n_draws,
+                 int* idx, double* u_out) {
+  for (long long j = 0; j < n_draws; ++j) {
+    const mt_u4 ctr = {(uint32_t)j, (uint32_t)((uint64_t)j >> 32), (uint32_t)stream_id, (uint32_t)(stream_id >> 32)};
+    const mt_u4 r = mt_philox(ctr, (uint32_t)seed, (uint32_t)(seed >> 32));
+    const double u = mt_u01_53(r.x, r.y);
+    if (u_out) u_out[j] = u;
+    idx[j] = (int)mt_cdf_draw(C, n, S, u);
+  }
+}
 }

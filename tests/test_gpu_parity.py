@@ -61,6 +61,23 @@ def T(a):
     return torch.from_numpy(np.asarray(a))
 
 
+def philox_u01_53(seed: int, stream_id: int, n: int) -> np.ndarray:
+    """numpy model of the library's per-draw uniform: Philox4x32-10 with counter (j, j >> 32, stream lo, stream hi)
+    and key (seed lo, seed hi); u = ((x >> 5) << 26 | (y >> 6)) * 2^-53 (mt_math.cuh mt_philox / mt_u01_53; pinned
+    against the C source in tests/test_host_math.py::test_categorical_draw_from_cdf)."""
+    j = np.arange(n, dtype=np.uint64)
+    c = [j & np.uint64(0xFFFFFFFF), j >> np.uint64(32), np.full(n, stream_id & 0xFFFFFFFF, dtype=np.uint64),
+         np.full(n, (stream_id >> 32) & 0xFFFFFFFF, dtype=np.uint64)]
+    k0, k1 = np.uint64(seed & 0xFFFFFFFF), np.uint64((seed >> 32) & 0xFFFFFFFF)
+    M0, M1, MASK = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0, p1 = M0 * c[0], M1 * c[2]
+        c = [((p1 >> np.uint64(32)) ^ c[1] ^ k0) & MASK, p1 & MASK, ((p0 >> np.uint64(32)) ^ c[3] ^ k1) & MASK, p0 & MASK]
+        k0, k1 = (k0 + np.uint64(0x9E3779B9)) & MASK, (k1 + np.uint64(0xBB67AE85)) & MASK
+    bits = ((c[0] >> np.uint64(5)) << np.uint64(26)) | (c[1] >> np.uint64(6))
+    return bits.astype(np.float64) * (1.0 / 9007199254740992.0)
+
+
 # ----------------------------------------------------------------------------- layout
 def test_aos_soa_roundtrip(mt, dev):
     p = torch.randn(1000, 4, 4, device=dev)
@@ -852,3 +869,61 @@ def test_engine_heavy_fallback_is_exact(mt, dev):
     assert st["nn_fallbacks"] > N // 4, st       # the fallback path really was exercised (13 steps x N particles)
     assert 0 < st["grid_rows_max"] < (3 * n_leaf) // 4, (st, n_leaf)
     assert st["overflow"] == 0
+
+
+def test_weighted_random_resampler(mt, dev, box):
+    """resampler(..., "weighted_random") (the reference's default, particle_filter.py:243-250: N draws with
+    replacement ~ weights): same distribution (the random stream is the library's Philox, not torch's), zero-weight
+    particles are never drawn, reproducible under torch.manual_seed, guards as in the reference, and the draws
+    equal the host model of the same arithmetic for a fixed seed."""
+    pf = mt.pf.particle_filter(synth_cfg(), box.vertices)
+    n = 200000
+    g = torch.Generator().manual_seed(12)
+    w = torch.rand(n, generator=g, dtype=torch.float64)
+    w[torch.rand(n, generator=g) < 0.3] = 0.0
+    w[-5:] = 0.0
+    poses = torch.eye(4).repeat(n, 1, 1)
+    poses[:, 0, 3] = torch.arange(n, dtype=torch.float32)
+    labels = torch.arange(n, dtype=torch.float32)
+    P = mt.pf.Particles(poses.to(dev), w.to(dev), labels.to(dev))
+    torch.manual_seed(5)
+    out = pf.resampler(P)  # default mode
+    idx = out.labels.long().cpu()
+    assert len(out) == n and torch.equal(out.poses[:, 0, 3].cpu(), idx.float()) and torch.equal(out.weights.cpu(), w[idx])
+    assert bool((w[idx] > 0).all())
+    # counts per block of 400 consecutive particles against their expectation (~400 draws each -> normal z-scores)
+    counts = torch.bincount(idx // 400, minlength=n // 400).double()
+    exp = (n * w / w.sum()).reshape(-1, 400).sum(1)
+    z = (counts - exp) / exp.sqrt()
+    assert float(z.abs().max()) < 5.0 and abs(float(z.mean())) < 0.15 and abs(float(z.std()) - 1.0) < 0.15
+    torch.manual_seed(5)
+    again = pf.resampler(P)
+    assert torch.equal(again.labels, out.labels)
+    other = pf.resampler(P)
+    assert not torch.equal(other.labels, out.labels)
+    # guards (237-241)
+    z0 = pf.resampler(mt.pf.Particles(P.poses, torch.zeros_like(P.weights), P.labels))
+    assert torch.equal(z0.poses, P.poses)
+    wn = P.weights.clone()
+    wn[5] = float("nan")
+    z1 = pf.resampler(mt.pf.Particles(P.poses, wn, P.labels))
+    assert torch.equal(z1.poses, P.poses)
+    one = pf.resampler(mt.pf.Particles(P.poses[:1], P.weights[:1] + 1.0, P.labels[:1]))
+    assert len(one) == 1 and torch.equal(one.poses, P.poses[:1])
+    # C ABI against the host model of the same draw: sequential float64 CDF, u = Philox(seed; j, stream), first C_i > u*S
+    m = 70000
+    ctx = mt.pf._ctx_for(dev, m)
+    wd = w[:m].to(dev).contiguous()
+    idx32 = torch.empty(m, dtype=torch.int32, device=dev)
+    scratch = torch.empty(m, dtype=torch.float64, device=dev)
+    mt.lib.call("mt_resample_multinomial", ctx.h, wd.data_ptr(), m, m, 99, 7, scratch.data_ptr(), idx32.data_ptr(), None, mt.lib.stream_ptr())
+    cdf = scratch.cpu().numpy()
+    assert np.all(np.diff(cdf) >= 0) and np.all((np.diff(cdf) == 0) == (w[1:m].numpy() == 0))
+    assert np.allclose(cdf, np.cumsum(w[:m].numpy()), rtol=1e-12)
+    sp = C.c_void_p()
+    mt.lib.call("mt_step_local_sum_ptr", ctx.h, C.byref(sp))
+    S = float(mt.eng._device_double_view(sp.value + 4 * 8, dev).item())  # the total the resamplers normalise by
+    assert cdf[-1] <= S and abs(S - cdf[-1]) <= 1e-12 * S
+    u = philox_u01_53(99, 7, m)
+    want = np.searchsorted(cdf, u * S, side="right")
+    assert want.max() < m and np.array_equal(idx32.cpu().numpy(), want.astype(np.int32))

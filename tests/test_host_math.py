@@ -236,3 +236,37 @@ def test_box_hierarchy_search_is_exact(H):
     bad = keys.copy()
     bad[3, 2] = np.nan
     assert H.h_bvh_search(P(bad), ctypes.c_longlong(M), P(q), ctypes.c_longlong(1), P(np.full(1, -1, dtype=np.int32)), P(idx2), P(vis2), P(dims)) == -1
+
+
+def test_categorical_draw_from_cdf(H):
+    """mt_cdf_draw / mt_u01_53 (the multinomial resampler's per-draw arithmetic): equals
+    searchsorted(C, u*S, side='right'), never returns an item of zero weight, handles u*S landing on or
+    beyond the last CDF value, and the 53-bit uniforms are in [0,1) and uniform."""
+    rng = np.random.default_rng(2)
+    n = 5000
+    w = rng.random(n)
+    w[rng.random(n) < 0.3] = 0.0
+    w[-7:] = 0.0                       # trailing zero-weight items
+    C = np.cumsum(w)
+    S = float(C[-1])
+    nd = 200000
+    idx, u = np.zeros(nd, dtype=np.int32), np.zeros(nd)
+    H.h_cdf_draws(P(C), ctypes.c_longlong(n), ctypes.c_double(S), ctypes.c_ulonglong(1234), ctypes.c_ulonglong(0),
+                  ctypes.c_longlong(nd), P(idx), P(u))
+    assert (u >= 0).all() and (u < 1).all() and abs(u.mean() - 0.5) < 5e-3 and abs(np.mean(u < 0.1) - 0.1) < 5e-3
+    from test_gpu_parity import philox_u01_53  # the numpy model the GPU test uses: pinned to the C source here
+    assert np.array_equal(u, philox_u01_53(1234, 0, nd))
+    want = np.searchsorted(C, u * S, side="right")
+    assert np.array_equal(idx, np.minimum(want, n - 8))  # (u*S == S cannot pick a trailing zero-weight item)
+    assert (w[idx] > 0).all()
+    counts = np.bincount(idx, minlength=n)
+    z = (counts - nd * w / S) / np.sqrt(np.maximum(nd * w / S, 1e-9))
+    assert np.abs(z[w > 0]).max() < 6.0
+    # a CDF whose top is below S (chunk clamping): draws beyond it fall on the last item of positive weight
+    idx2 = np.zeros(4, dtype=np.int32)
+    H.h_cdf_draws(P(C), ctypes.c_longlong(n), ctypes.c_double(S * (1 + 1e-3)), ctypes.c_ulonglong(5), ctypes.c_ulonglong(1),
+                  ctypes.c_longlong(4), P(idx2), None)
+    assert (w[idx2] > 0).all()
+    one = np.array([3.0])
+    H.h_cdf_draws(P(one), ctypes.c_longlong(1), ctypes.c_double(3.0), ctypes.c_ulonglong(5), ctypes.c_ulonglong(1), ctypes.c_longlong(4), P(idx2), None)
+    assert (idx2 == 0).all()
