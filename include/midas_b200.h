@@ -66,8 +66,9 @@ int mt_codebook_rank(mt_ctx* ctx, int32_t* d_rank, void* stream);
 /* instrumentation: four cudaEvent_t (before k_step_a, after it, after k_step_nnq, after
  * k_step_sums) recorded on the step's stream by every following mt_step_a; NULL switches it off. */
 int mt_ctx_set_timing_events(mt_ctx* ctx, void* const* events4);
-/* status / statistics words of the context (synchronises).  h_out8[MT_STAT_*]; reset != 0
- * clears the cumulative slots (0..4, 7). */
+/* status / statistics words of the context (synchronises).  h_out[MT_STAT_*], MT_STAT_COUNT entries;
+ * reset != 0 clears the cumulative slots (0..4, 7..). */
+#define MT_STAT_COUNT 16
 #define MT_STAT_OVERFLOW 0      /* 1: children did not fit the destination buffer (sharded steps);
                                    2: a peer's weight sum never arrived (fused sharded step timed out) */
 #define MT_STAT_RESAMPLE_SKIP 1 /* a resampling saw all-zero / NaN weights and kept the particles */
@@ -77,7 +78,8 @@ int mt_ctx_set_timing_events(mt_ctx* ctx, void* const* events4);
 #define MT_STAT_GRID_ROWS_MAX 7 /* most leaves visited by a single search */
 #define MT_STAT_DRIFTED 5       /* last mt_step_a: every particle failed the drift test */
 #define MT_STAT_ON_SURFACE 6    /* last mt_step_a: particles that passed the drift test */
-int mt_ctx_stats(mt_ctx* ctx, long long* h_out8, int reset);
+#define MT_STAT_MESH_DEFERRED 8 /* drift tests whose voxel was undecided and that ran the vertex search (cumulative) */
+int mt_ctx_stats(mt_ctx* ctx, long long* h_out, int reset);
 
 /* ---- mesh: particle_filter.__init__ (particle_filter.py:108-110) ------------------- */
 /* h_vertices: (V,3) float64 down-sampled mesh vertices (mesh.vertices[::10]) on the HOST; a

@@ -101,8 +101,9 @@ struct mt_ctx {
   double* d_wpart;    // per-warp weight sums of kernel A (32 particles each)
   double* d_wrm;      // 2 x warp_cap rmse partials of kernel A
   int* d_wcnt;        // per-warp count of particles that passed the drift test
+  int* d_queue2;      // drift tests left for the grid search
   int* d_queue;       // particles whose hint-graph search was not conclusive (kernel A -> A2)
-  unsigned int* d_qctl;  // [0] queue length, [1] queue head
+  unsigned int* d_qctl;  // [0] searches queued, [1] queue head, [3] deferred drift tests queued
   unsigned long long* d_bar;  // grid barrier of k_step_bw (monotone counter)
   unsigned long long bar_target;
   double* d_bw;       // 3 x MT_BW_MAX_GRID block totals (weights, rmse_t, rmse_r)
@@ -148,6 +149,7 @@ extern "C" int mt_ctx_create(int device, size_t capacity, int M, int D, mt_ctx**
   CK(cudaMalloc(&c->d_wrm, sizeof(double) * 2 * c->warp_cap));
   CK(cudaMalloc(&c->d_wcnt, sizeof(int) * c->warp_cap));
   CK(cudaMalloc(&c->d_queue, sizeof(int) * (capacity + 32)));
+  CK(cudaMalloc(&c->d_queue2, sizeof(int) * (capacity + 32)));
   CK(cudaMalloc(&c->d_qctl, sizeof(unsigned int) * 4));
   CK(cudaMemset(c->d_qctl, 0, sizeof(unsigned int) * 4));
   CK(cudaMalloc(&c->d_bar, sizeof(unsigned long long)));
@@ -164,9 +166,9 @@ extern "C" int mt_ctx_create(int device, size_t capacity, int M, int D, mt_ctx**
   CK(cudaMalloc(&c->d_scal, sizeof(double) * 8));
   CK(cudaMalloc(&c->d_q64, sizeof(double) * MT_MAX_D));
   CK(cudaMalloc(&c->d_ticket, sizeof(unsigned int) * 4));
-  CK(cudaMalloc(&c->d_flags, sizeof(int) * 8));
+  CK(cudaMalloc(&c->d_flags, sizeof(int) * MT_STAT_COUNT));
   CK(cudaMemset(c->d_ticket, 0, sizeof(unsigned int) * 4));
-  CK(cudaMemset(c->d_flags, 0, sizeof(int) * 8));
+  CK(cudaMemset(c->d_flags, 0, sizeof(int) * MT_STAT_COUNT));
   CK(cudaMemset(c->d_scal, 0, sizeof(double) * 8));
   *out = c;
   return MT_OK;
@@ -194,6 +196,7 @@ extern "C" int mt_ctx_destroy(mt_ctx* c) {
   cudaFree(c->d_wrm);
   cudaFree(c->d_wcnt);
   cudaFree(c->d_queue);
+  cudaFree(c->d_queue2);
   cudaFree(c->d_scratch);
   cudaFree(c->d_qctl);
   cudaFree(c->d_bar);
@@ -278,16 +281,16 @@ extern "C" int mt_ctx_set_timing_events(mt_ctx* c, void* const* events4) {
   return MT_OK;
 }
 
-extern "C" int mt_ctx_stats(mt_ctx* c, long long* h_out8, int reset) {
+extern "C" int mt_ctx_stats(mt_ctx* c, long long* h_out, int reset) {
   if (!c) return set_err(MT_ERR_ARG, "mt_ctx_stats: null context");
   CK(cudaSetDevice(c->device));
-  int f[8];
+  int f[MT_STAT_COUNT];
   CK(cudaMemcpy(f, c->d_flags, sizeof(f), cudaMemcpyDeviceToHost));
-  if (h_out8)
-    for (int k = 0; k < 8; ++k) h_out8[k] = f[k];
+  if (h_out)
+    for (int k = 0; k < MT_STAT_COUNT; ++k) h_out[k] = f[k];
   if (reset) {
     CK(cudaMemset(c->d_flags, 0, 5 * sizeof(int)));
-    CK(cudaMemset(c->d_flags + 7, 0, sizeof(int)));
+    CK(cudaMemset(c->d_flags + 7, 0, (MT_STAT_COUNT - 7) * sizeof(int)));
   }
   return MT_OK;
 }
@@ -539,6 +542,16 @@ struct VecLoad<float> {
     float4 v = __ldg(reinterpret_cast<const float4*>(p));
     o[0] = v.x, o[1] = v.y, o[2] = v.z, o[3] = v.w;
   }
+  // the codebook query reads every embedding once per frame: streamed past the resident tables
+  __device__ static void ld_stream(const float* p, double* o) {
+#if MT_L2_HINTS
+    float4 v;
+    asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(mt_pol_stream()));
+    o[0] = v.x, o[1] = v.y, o[2] = v.z, o[3] = v.w;
+#else
+    ld(p, o);
+#endif
+  }
 };
 template <>
 struct VecLoad<double> {
@@ -546,6 +559,13 @@ struct VecLoad<double> {
   __device__ static void ld(const double* p, double* o) {
     double2 v = __ldg(reinterpret_cast<const double2*>(p));
     o[0] = v.x, o[1] = v.y;
+  }
+  __device__ static void ld_stream(const double* p, double* o) {
+#if MT_L2_HINTS
+    asm volatile("ld.global.nc.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(o[0]), "=d"(o[1]) : "l"(p), "l"(mt_pol_stream()));
+#else
+    ld(p, o);
+#endif
   }
 };
 
@@ -690,7 +710,7 @@ __global__ void __launch_bounds__(256) k_codebook_query(const TQ* __restrict__ q
 #pragma unroll
       for (int u = 0; u < 4; ++u)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) VecLoad<T>::ld(e[j] + (size_t)(v + 32 * u) * W, x[u][j]);
+        for (int j = 0; j < 4; ++j) VecLoad<T>::ld_stream(e[j] + (size_t)(v + 32 * u) * W, x[u][j]);
 #pragma unroll
       for (int u = 0; u < 4; ++u)
 #pragma unroll
@@ -703,7 +723,7 @@ __global__ void __launch_bounds__(256) k_codebook_query(const TQ* __restrict__ q
     for (; v < nvec; v += 32) {
       double x[4][W];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) VecLoad<T>::ld(e[j] + (size_t)v * W, x[j]);
+      for (int j = 0; j < 4; ++j) VecLoad<T>::ld_stream(e[j] + (size_t)v * W, x[j]);
 #pragma unroll
       for (int k = 0; k < W; ++k) {
         const double qv = sq[v * W + k];
@@ -964,6 +984,19 @@ __device__ __forceinline__ void store_pose(float4* __restrict__ soa, long long s
   soa[i] = make_float4(P[0][0], P[0][1], P[0][2], P[0][3]);
   soa[stride + i] = make_float4(P[1][0], P[1][1], P[1][2], P[1][3]);
   soa[2 * stride + i] = make_float4(P[2][0], P[2][1], P[2][2], P[2][3]);
+}
+
+// the step kernels touch every particle once per launch: streamed (L2 evict_first) so that the tables stay resident
+__device__ __forceinline__ void load_pose_stream(const float4* __restrict__ soa, long long stride, long long i, float P[3][4]) {
+  float4 a = mt_lds(soa + i), b = mt_lds(soa + stride + i), c = mt_lds(soa + 2 * stride + i);
+  P[0][0] = a.x, P[0][1] = a.y, P[0][2] = a.z, P[0][3] = a.w;
+  P[1][0] = b.x, P[1][1] = b.y, P[1][2] = b.z, P[1][3] = b.w;
+  P[2][0] = c.x, P[2][1] = c.y, P[2][2] = c.z, P[2][3] = c.w;
+}
+__device__ __forceinline__ void store_pose_stream(float4* __restrict__ soa, long long stride, long long i, const float P[3][4]) {
+  mt_sts(soa + i, make_float4(P[0][0], P[0][1], P[0][2], P[0][3]));
+  mt_sts(soa + stride + i, make_float4(P[1][0], P[1][1], P[1][2], P[1][3]));
+  mt_sts(soa + 2 * stride + i, make_float4(P[2][0], P[2][1], P[2][2], P[2][3]));
 }
 
 __global__ void k_aos_to_soa(const float4* __restrict__ aos, long long n, float4* __restrict__ soa, long long stride) {
@@ -1290,7 +1323,9 @@ struct StepDev {
   double* wrm;
   int* wcnt;
   int* queue;
-  unsigned int* qctl;
+  int* queue2;          // drift tests that need the grid search (k_step_meshq -> k_step_meshq2)
+  long long queue_cap;  // entries in `queue` (searches grow from the front, deferred drift tests from the back)
+  unsigned int* qctl;   // [0] searches queued, [1] queue head, [2] drift tests left for the grid search, [3] drift tests queued
   double* scal;
   unsigned int* ticket;
   int* flags;
@@ -1310,53 +1345,99 @@ struct StepDev {
 //  k_step_sums  weight lookup w = table[match] (4 B / particle), deterministic float64 chunk
 //               sums, and in the last block the chunk prefix for kernel B, the RMSE and the
 //               drift flag.
+#ifndef MT_A_BLOCK
 #define MT_A_BLOCK 64
-#ifndef MT_A_MINBLOCKS
-#define MT_A_MINBLOCKS 20  // 48 registers: 40 warps per SM measured ~6 % faster than 32 warps at 64 registers
 #endif
+#ifndef MT_A_MINBLOCKS
+#define MT_A_MINBLOCKS 16  // 64 registers (the pipelined scan keeps two trips of list entries in registers)
+#endif
+#ifndef MT_STREAM_HINTS
+#define MT_STREAM_HINTS 0
+#endif
+#ifndef MT_MESH_DEFER
+#define MT_MESH_DEFER 1  // undecided voxels of the drift test go to the queue instead of stalling their warp
+#endif
+// queue entries: particle index | what is left to do for it
+#define MT_Q_NN 0x20000000    // the hint-graph search was not conclusive: box-hierarchy search
+#define MT_Q_MESH 0x40000000  // the voxel class was "undecided": vertex search of the drift test
+#define MT_Q_INDEX 0x1fffffff
 __global__ void __launch_bounds__(MT_A_BLOCK, MT_A_MINBLOCKS) k_step_a(StepDev p, NNTables T, MeshTables Mh) {
   const long long i = (long long)blockIdx.x * MT_A_BLOCK + threadIdx.x;
   const long long n = p.n_in ? *p.n_in : p.n;
   const bool valid = i < n;
   const int lane = threadIdx.x & 31;
   double et2 = 0.0, ang2 = 0.0;
-  bool on_surface = valid, todo = false;
+  bool on_surface = valid;
+  int todo = 0;
   if (valid) {
     float P[3][4], t[3], r[3], O[3][4], key[6];
-    load_pose(p.soa_cur, p.stride, i, P);
-    const int hint = nn_index(p.nn_cur[i]);
+#if MT_STREAM_HINTS
+    {  // the particle arrays are touched once per kernel: streaming loads / stores leave L1 to the neighbour lists
+      const float4 a = __ldcs(p.soa_cur + i), b = __ldcs(p.soa_cur + p.stride + i), c = __ldcs(p.soa_cur + 2 * p.stride + i);
+      P[0][0] = a.x, P[0][1] = a.y, P[0][2] = a.z, P[0][3] = a.w;
+      P[1][0] = b.x, P[1][1] = b.y, P[1][2] = b.z, P[1][3] = b.w;
+      P[2][0] = c.x, P[2][1] = c.y, P[2][2] = c.z, P[2][3] = c.w;
+    }
+    const int hint = nn_index(__ldcs(p.nn_cur + i));
+#else
+    load_pose_stream(p.soa_cur, p.stride, i, P);
+    const int hint = nn_index(mt_lds(p.nn_cur + i));
+#endif
     nn_prefetch(T, hint);
     draw_or_load_noise(p.tn, p.rot, i, p.sig_t, p.sig_r, p.seed, p.step, p.first_gid + (uint64_t)i, t, r);
     apply_motion(P, p.odom, t, r, O, 0, p.tn == nullptr);
-    store_pose(p.soa_cur, p.stride, i, O);
+    // drift test: the voxel class is one dependent 4-byte load; it is requested here so that it travels while
+    // the key is computed
+    int mcls = 1, mk = -1;
+    if (p.prune_dist > 0.0) mcls = mesh_voxel_class(Mh, O[0][3], O[1][3], O[2][3], p.prune_dist, &mk);
+#if MT_STREAM_HINTS
+    __stcs(p.soa_cur + i, make_float4(O[0][0], O[0][1], O[0][2], O[0][3]));
+    __stcs(p.soa_cur + p.stride + i, make_float4(O[1][0], O[1][1], O[1][2], O[1][3]));
+    __stcs(p.soa_cur + 2 * p.stride + i, make_float4(O[2][0], O[2][1], O[2][2], O[2][3]));
+#else
+    store_pose_stream(p.soa_cur, p.stride, i, O);
+#endif
     mt_se3_key(O, key);
     const bool invalid = mt_pose_invalid(O);
     if (invalid) atomicAdd(p.flags + 2, 1);  // check_quats would delete the particle (particle_filter.py:347-357)
     if (p.has_gt) rmse_terms(p.gt, O, et2, ang2);
-    if (p.prune_dist > 0.0) on_surface = mesh_within(Mh, O[0][3], O[1][3], O[2][3], p.prune_dist);
+#if MT_MESH_DEFER
+    on_surface = mcls != 0;  // undecided: counted as on the surface until the queue consumer has looked
+    if (mcls >= 2) todo |= MT_Q_MESH;
+#else
+    on_surface = (mcls >= 2) ? mesh_within_search(Mh, O[0][3], O[1][3], O[2][3], p.prune_dist, mcls == 2 ? mk : -1) : (mcls == 1);
+#endif
     float bd;
     int bi;
 #ifdef MT_SCAN_HIST
     int slen;
-    todo = !nn_hint_search(T, key, hint, bd, bi, slen);
+    if (!nn_hint_search(T, key, hint, bd, bi, slen)) todo |= MT_Q_NN;
     atomicAdd(&g_scan_hist[0][slen], 1ull);
     const int wmax = __reduce_max_sync(__activemask(), slen);
     if (lane == (__ffs(__activemask()) - 1)) atomicAdd(&g_scan_hist[1][wmax], 1ull);
 #else
-    todo = !nn_hint_search(T, key, hint, bd, bi);
+    if (!nn_hint_search(T, key, hint, bd, bi)) todo |= MT_Q_NN;
 #endif
     if (bi == INT_MAX) bi = -1;  // no usable hint
     // masked: weights *= m (particle_filter.py:398-401); a particle without any candidate yet
     // (-1) has its mask re-derived by k_step_nnq
-    p.nn_cur[i] = (bi >= 0 && (!on_surface || invalid)) ? nn_masked(bi) : bi;
+    mt_sts(p.nn_cur + i, (bi >= 0 && (!on_surface || invalid)) ? nn_masked(bi) : bi);
   }
-  // queue the inconclusive searches (one atomic per warp)
-  const unsigned qm = __ballot_sync(0xffffffffu, todo);
-  if (qm) {
-    unsigned base = 0;
-    if (lane == 0) base = atomicAdd(p.qctl, (unsigned)__popc(qm));
+  // queue what is left (one atomic per warp and queue).  Searches go to the front of the queue array (one warp
+  // per entry later on), drift tests that need nothing else to its back (one thread per entry).
+  const unsigned nm = __ballot_sync(0xffffffffu, (todo & MT_Q_NN) != 0);
+  const unsigned mm = __ballot_sync(0xffffffffu, todo == MT_Q_MESH);
+  if (nm | mm) {
+    unsigned base = 0, mbase = 0;
+    if (lane == 0) {
+      if (nm) base = atomicAdd(p.qctl, (unsigned)__popc(nm));
+      if (mm) mbase = atomicAdd(p.qctl + 3, (unsigned)__popc(mm));
+    }
     base = __shfl_sync(0xffffffffu, base, 0);
-    if (todo) p.queue[base + __popc(qm & ((1u << lane) - 1))] = (int)i;
+    mbase = __shfl_sync(0xffffffffu, mbase, 0);
+    const unsigned below = (1u << lane) - 1;
+    if (todo & MT_Q_NN) p.queue[base + __popc(nm & below)] = (int)i | todo;
+    else if (todo) p.queue[p.queue_cap - 1 - (mbase + __popc(mm & below))] = (int)i;
   }
   const long long gw = i >> 5;  // global warp = 32 consecutive particles
   const unsigned on = __ballot_sync(0xffffffffu, on_surface);
@@ -1367,8 +1448,137 @@ __global__ void __launch_bounds__(MT_A_BLOCK, MT_A_MINBLOCKS) k_step_a(StepDev p
   }
 }
 
-// queue consumer: one warp per entry, best-first search through the box hierarchy (nn_bvh_search) seeded with the
-// candidate the hint scan left behind.
+// k_step_a with the neighbour lists staged in shared memory.  Particles keep the order of their codebook match
+// (FilterEngine.load_particles sorts them once, systematic resampling preserves the order), so a block of 256
+// consecutive particles holds a handful of distinct hints in contiguous runs.  Every run gets a slot: the key record
+// of its hint plus the first MT_A_STAGE entries of the hint's list (1 KB), copied global -> shared with cp.async
+// right after the hints are known and in flight during the motion arithmetic.  The scans then read shared memory
+// (a broadcast when the lanes share a slot) instead of chasing cache lines through L1 / L2 / DRAM: the long-scoreboard
+// stalls on the list loads were 55 % of the old kernel's stall samples.  Runs beyond MT_A_SLOTS, list entries beyond
+// the staged head and the lists of near-pi partners are read from global memory as before.
+#ifndef MT_A_SMEM
+#define MT_A_SMEM 0
+#endif
+#define MT_AS_BLOCK 256
+#ifndef MT_AS_MINBLOCKS
+#define MT_AS_MINBLOCKS 5
+#endif
+#ifndef MT_A_SLOTS
+#define MT_A_SLOTS 32
+#endif
+#define MT_A_STAGE 32
+#define MT_A_SLOT_F4 (2 + 2 * MT_A_STAGE)
+#define MT_A_TAB_LOG2 7
+#define MT_A_TAB (1 << MT_A_TAB_LOG2)
+__device__ __forceinline__ void mt_cp_async16(void* smem_dst, const void* gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__global__ void __launch_bounds__(MT_AS_BLOCK, MT_AS_MINBLOCKS) k_step_a_s(StepDev p, NNTables T, MeshTables Mh) {
+  __shared__ float4 s_list[MT_A_SLOTS][MT_A_SLOT_F4];
+  __shared__ int s_tab[MT_A_TAB];       // open-addressed set of the block's distinct hints
+  __shared__ int s_tab_slot[MT_A_TAB];  // slot of the hint stored at that position
+  __shared__ int s_slot_hint[MT_A_SLOTS];
+  __shared__ int s_count;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long i = (long long)blockIdx.x * MT_AS_BLOCK + tid;
+  const long long n = p.n_in ? *p.n_in : p.n;
+  const bool valid = i < n;
+  int hint = valid ? nn_index(mt_lds(p.nn_cur + i)) : -1;
+  if (hint >= T.M) hint = -1;
+  if (tid < MT_A_TAB) s_tab[tid] = -1;
+  if (tid == 0) s_count = 0;
+  float P[3][4];
+  if (valid) load_pose_stream(p.soa_cur, p.stride, i, P);
+  __syncthreads();
+  // distinct hints of the block -> slots (neighbouring particles share their few hints, in no particular order)
+  int pos = -1;
+  if (hint >= 0) {
+    unsigned h = ((unsigned)hint * 2654435761u) >> (32 - MT_A_TAB_LOG2);
+    for (int probe = 0; probe < MT_A_TAB; ++probe, h = (h + 1) & (MT_A_TAB - 1)) {
+      const int old = atomicCAS(&s_tab[h], -1, hint);
+      if (old == -1) {  // this thread inserted the hint: it names the slot
+        const int sl = atomicAdd(&s_count, 1);
+        s_tab_slot[h] = sl;
+        if (sl < MT_A_SLOTS) s_slot_hint[sl] = hint;
+        pos = (int)h;
+        break;
+      }
+      if (old == hint) {
+        pos = (int)h;
+        break;
+      }
+    }
+  }
+  __syncthreads();
+  int slot = pos >= 0 ? s_tab_slot[pos] : -1;
+  if (slot >= MT_A_SLOTS) slot = -1;
+  const int nslots = min(s_count, MT_A_SLOTS);
+  for (int sl = warp; sl < nslots; sl += MT_AS_BLOCK / 32) {
+    const int h = s_slot_hint[sl];
+    const float4* key = T.keys_orig + 2 * (size_t)h;
+    const float4* lst = T.nbr + (size_t)h * (2 * MT_NBR_K);
+#pragma unroll
+    for (int c = lane; c < MT_A_SLOT_F4; c += 32) mt_cp_async16(&s_list[sl][c], c < 2 ? key + c : lst + (c - 2));
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  if (slot < 0) nn_prefetch(T, hint);
+
+  double et2 = 0.0, ang2 = 0.0;
+  bool on_surface = valid, invalid = false;
+  int todo = 0;
+  float key[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (valid) {
+    float t[3], r[3], O[3][4];
+    draw_or_load_noise(p.tn, p.rot, i, p.sig_t, p.sig_r, p.seed, p.step, p.first_gid + (uint64_t)i, t, r);
+    apply_motion(P, p.odom, t, r, O, 0, p.tn == nullptr);
+    int mcls = 1, mk = -1;
+    if (p.prune_dist > 0.0) mcls = mesh_voxel_class(Mh, O[0][3], O[1][3], O[2][3], p.prune_dist, &mk);
+    store_pose_stream(p.soa_cur, p.stride, i, O);
+    mt_se3_key(O, key);
+    invalid = mt_pose_invalid(O);
+    if (invalid) atomicAdd(p.flags + 2, 1);  // check_quats would delete the particle (particle_filter.py:347-357)
+    if (p.has_gt) rmse_terms(p.gt, O, et2, ang2);
+    on_surface = mcls != 0;  // undecided: counted as on the surface until the queue consumer has looked
+    if (mcls >= 2) todo |= MT_Q_MESH;
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  if (valid) {
+    float bd;
+    int bi;
+    bool done;
+    if (slot >= 0) done = nn_hint_search_staged(T, s_list[slot], MT_A_STAGE, key, hint, bd, bi);
+    else done = nn_hint_search(T, key, hint, bd, bi);
+    if (!done) todo |= MT_Q_NN;
+    if (bi == INT_MAX) bi = -1;  // no usable hint
+    mt_sts(p.nn_cur + i, (bi >= 0 && (!on_surface || invalid)) ? nn_masked(bi) : bi);
+  }
+  const unsigned nm = __ballot_sync(0xffffffffu, (todo & MT_Q_NN) != 0);
+  const unsigned mm = __ballot_sync(0xffffffffu, todo == MT_Q_MESH);
+  if (nm | mm) {
+    unsigned base = 0, mbase = 0;
+    if (lane == 0) {
+      if (nm) base = atomicAdd(p.qctl, (unsigned)__popc(nm));
+      if (mm) mbase = atomicAdd(p.qctl + 3, (unsigned)__popc(mm));
+    }
+    base = __shfl_sync(0xffffffffu, base, 0);
+    mbase = __shfl_sync(0xffffffffu, mbase, 0);
+    const unsigned below = (1u << lane) - 1;
+    if (todo & MT_Q_NN) p.queue[base + __popc(nm & below)] = (int)i | todo;
+    else if (todo) p.queue[p.queue_cap - 1 - (mbase + __popc(mm & below))] = (int)i;
+  }
+  const long long gw = i >> 5;
+  const unsigned on = __ballot_sync(0xffffffffu, on_surface);
+  if (p.has_gt) et2 = warp_sum(et2), ang2 = warp_sum(ang2);
+  if (lane == 0 && gw < ((n + 31) >> 5)) {
+    p.wcnt[gw] = __popc(on);
+    if (p.has_gt) p.wrm[2 * gw] = et2, p.wrm[2 * gw + 1] = ang2;
+  }
+}
+
+// queue consumer: one warp per entry.  MT_Q_NN: best-first search through the box hierarchy (nn_bvh_search)
+// seeded with the candidate the hint scan left behind.  MT_Q_MESH: the vertex search of the drift test.
 struct NnqEntry {
   long long i;
   float key[6];
@@ -1376,7 +1586,8 @@ struct NnqEntry {
   int bi;
   bool masked;
 };
-__device__ __forceinline__ void nnq_load(const StepDev& p, const NNTables& T, const MeshTables& Mh, long long i, NnqEntry& q) {
+__device__ __forceinline__ void nnq_load(const StepDev& p, const NNTables& T, const MeshTables& Mh, int raw, NnqEntry& q) {
+  const long long i = raw & MT_Q_INDEX;
   float P[3][4];
   load_pose(p.soa_cur, p.stride, i, P);
   mt_se3_key(P, q.key);
@@ -1389,17 +1600,71 @@ __device__ __forceinline__ void nnq_load(const StepDev& p, const NNTables& T, co
     float kh[6];
     load_key(T.keys_orig, q.bi, kh);
     q.bd = mt_key_dist(q.key, kh);
-  } else {  // no candidate yet: the mask was not recorded, derive it again
+  } else {
     q.bi = INT_MAX;
-    q.masked = mt_pose_invalid(P) || (p.prune_dist > 0.0 && !mesh_within(Mh, P[0][3], P[1][3], P[2][3], p.prune_dist));
   }
+  if (raw & MT_Q_MESH) {  // provisionally on the surface: look now
+    const bool on = mesh_within_warp(Mh, P[0][3], P[1][3], P[2][3], p.prune_dist);
+    if (!on) {
+      q.masked = true;
+      if ((threadIdx.x & 31) == 0) atomicSub(p.wcnt + (i >> 5), 1);
+    }
+  } else if (stored == -1) {  // no candidate yet: the mask was not recorded, derive it again
+    q.masked = mt_pose_invalid(P) || (p.prune_dist > 0.0 && !mesh_within_warp(Mh, P[0][3], P[1][3], P[2][3], p.prune_dist));
+  }
+  if (stored == -1 && (raw & MT_Q_MESH)) q.masked = q.masked || mt_pose_invalid(P);
 }
 #define MT_NNQ_WARPS 4
-__global__ void __launch_bounds__(32 * MT_NNQ_WARPS) k_step_nnq(StepDev p, NNTables T, MeshTables Mh) {
-  const unsigned qn = *p.qctl;
+// Deferred drift tests (voxel class "undecided" in k_step_a): the vertex search of remove_invalid_particles.  The
+// particle was counted as on the surface; a failed test takes that back.
+//   k_step_meshq   one thread per entry: the two quick certificates (mesh_quick) settle ~3/4 of the entries with one
+//                  vertex load; the rest is compacted into a second list
+//   k_step_meshq2  one warp per entry of that list: grid search, the lanes over the candidate vertices
+__device__ __forceinline__ void mesh_mark_off(const StepDev& p, long long i) {
+  const int stored = p.nn_cur[i];
+  if (stored >= 0) p.nn_cur[i] = nn_masked(stored);
+  atomicSub(p.wcnt + (i >> 5), 1);
+}
+__global__ void __launch_bounds__(256) k_step_meshq(StepDev p, MeshTables Mh) {
+  const unsigned mn = p.qctl[3];
   const int lane = threadIdx.x & 31;
-  if (qn == 0) return;
-  {
+  const unsigned span = gridDim.x * blockDim.x;
+  for (unsigned e0 = blockIdx.x * blockDim.x + threadIdx.x - lane; e0 < mn; e0 += span) {  // whole warps stay in the loop
+    const unsigned e = e0 + lane;
+    int res = 1;  // 1 within, 0 not within, 2 grid search
+    long long i = 0;
+    if (e < mn) {
+      i = p.queue[p.queue_cap - 1 - e];
+      const float x = p.soa_cur[i].w, y = p.soa_cur[p.stride + i].w, z = p.soa_cur[2 * p.stride + i].w;
+      int k = -1;
+      const int c = mesh_voxel_class(Mh, x, y, z, p.prune_dist, &k);
+      res = c < 2 ? c : (c == 2 ? mesh_quick(Mh, x, y, z, p.prune_dist, k) : 2);
+      if (res == 0) mesh_mark_off(p, i);
+    }
+    const unsigned m2 = __ballot_sync(0xffffffffu, res == 2);
+    if (m2) {
+      unsigned base = 0;
+      if (lane == 0) base = atomicAdd(p.qctl + 2, (unsigned)__popc(m2));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (res == 2) p.queue2[base + __popc(m2 & ((1u << lane) - 1))] = (int)i;
+    }
+  }
+}
+__global__ void __launch_bounds__(256) k_step_meshq2(StepDev p, MeshTables Mh) {
+  const unsigned n2 = p.qctl[2];
+  const unsigned gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  for (unsigned e = gw; e < n2; e += nw) {
+    const long long i = p.queue2[e];
+    const float x = p.soa_cur[i].w, y = p.soa_cur[p.stride + i].w, z = p.soa_cur[2 * p.stride + i].w;
+    const bool on = mesh_search_warp(Mh, x, y, z, p.prune_dist);
+    if (!on && (threadIdx.x & 31) == 0) mesh_mark_off(p, i);
+  }
+}
+
+__global__ void __launch_bounds__(32 * MT_NNQ_WARPS) k_step_nnq(StepDev p, NNTables T, MeshTables Mh) {
+  const unsigned qn = p.qctl[0];
+  const int lane = threadIdx.x & 31;
+  if (qn) {
     // the search index (boxes 0.1 MB + Morton-ordered keys 32 B each) was last touched a step ago: pull it into
     // L2 with one prefetch per 128-byte line, spread over the grid, so that the dependent rounds of the searches
     // below pay L2 latency instead of DRAM latency
@@ -1418,7 +1683,8 @@ __global__ void __launch_bounds__(32 * MT_NNQ_WARPS) k_step_nnq(StepDev p, NNTab
   unsigned e = (threadIdx.x >> 5) * gridDim.x + blockIdx.x;
   while (e < qn) {
     NnqEntry q;
-    nnq_load(p, T, Mh, p.queue[e], q);
+    const int raw = p.queue[e];
+    nnq_load(p, T, Mh, raw, q);
     const int res = nn_bvh_search(T, q.key, q.bd, q.bi, p.flags + 4);
     if (lane == 0) p.nn_cur[q.i] = q.masked ? nn_masked(res) : res;
     if (qn <= W) break;
@@ -1436,8 +1702,8 @@ __global__ void __launch_bounds__(256) k_step_sums(StepDev p) {
   const int nwarps = (int)((n + 31) >> 5);
   double e = 0.0;
   if (i < n) {
-    const int stored = p.nn_cur[i];
-    e = nn_is_masked(stored) ? 0.0 : __ldg(p.wtab + nn_index(stored));
+    const int stored = mt_lds(p.nn_cur + i);
+    e = nn_is_masked(stored) ? 0.0 : mt_ldk(p.wtab + nn_index(stored));
   }
   const double se = block_sum_256(e, s8);
   __shared__ bool last;
@@ -1480,8 +1746,9 @@ __global__ void __launch_bounds__(256) k_step_sums(StepDev p) {
     }
     p.flags[6] = s_cnt;                               // particles on the surface this step
     p.flags[5] = (p.prune_dist > 0.0 && s_cnt == 0);  // drifted (particle_filter.py:402)
-    p.flags[3] += (int)p.qctl[0];                     // searches that needed the grid (cumulative)
-    p.qctl[0] = 0, p.qctl[1] = 0;
+    p.flags[3] += (int)p.qctl[0];                     // searches that needed the box hierarchy (cumulative)
+    p.flags[MT_STAT_MESH_DEFERRED] += (int)p.qctl[3];
+    p.qctl[0] = 0, p.qctl[1] = 0, p.qctl[2] = 0, p.qctl[3] = 0;
     *p.ticket = 0;
   }
 }
@@ -1529,13 +1796,13 @@ __device__ __forceinline__ void step_b_load(const StepDev& p, const int c, const
   in.e = 0.0;
   if (i < n) {
     if (FROM_TABLE) {
-      const int stored = p.nn_cur[i];
+      const int stored = mt_lds(p.nn_cur + i);
       in.nn = nn_index(stored);
-      in.e = nn_is_masked(stored) ? 0.0 : __ldg(p.wtab + in.nn);
+      in.e = nn_is_masked(stored) ? 0.0 : mt_ldk(p.wtab + in.nn);
     } else {
       in.e = p.wsrc[i];
     }
-    if (SCATTER) load_pose(p.soa_cur, p.stride, i, in.P);
+    if (SCATTER) load_pose_stream(p.soa_cur, p.stride, i, in.P);
   }
 }
 
@@ -1593,10 +1860,10 @@ __device__ __forceinline__ void step_b_chunk(const StepDev& p, const int c, cons
         break;
       }
       if (SCATTER) {
-        store_pose(p.soa_next, p.stride, s, P);
-        if (FROM_TABLE) p.nn_next[s] = nn;
+        store_pose_stream(p.soa_next, p.stride, s, P);
+        if (FROM_TABLE) mt_sts(p.nn_next + s, nn);
       }
-      if (p.anc) p.anc[s] = (int)i;
+      if (p.anc) mt_sts(p.anc + s, (int)i);
     }
   }
   unsigned hm = __ballot_sync(0xffffffffu, heavy);
@@ -1621,10 +1888,10 @@ __device__ __forceinline__ void step_b_chunk(const StepDev& p, const int c, cons
         break;
       }
       if (SCATTER) {
-        store_pose(p.soa_next, p.stride, s, Q);
-        if (FROM_TABLE) p.nn_next[s] = pn;
+        store_pose_stream(p.soa_next, p.stride, s, Q);
+        if (FROM_TABLE) mt_sts(p.nn_next + s, pn);
       }
-      if (p.anc) p.anc[s] = (int)pi;
+      if (p.anc) mt_sts(p.anc + s, (int)pi);
     }
   }
 }
@@ -1686,10 +1953,10 @@ __global__ void __launch_bounds__(256, 4) k_step_bw(StepDev p, unsigned long lon
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const long long i = (long long)(c0 + k) * MT_CHUNK + threadIdx.x;
-      st4[k] = (c0 + k < c_hi && i < n) ? p.nn_cur[i] : -1;
+      st4[k] = (c0 + k < c_hi && i < n) ? mt_lds(p.nn_cur + i) : -1;
     }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) e4[k] = (st4[k] >= 0) ? __ldg(p.wtab + st4[k]) : 0.0;  // masked (< -1) and absent (-1): 0
+    for (int k = 0; k < 4; ++k) e4[k] = (st4[k] >= 0) ? mt_ldk(p.wtab + st4[k]) : 0.0;  // masked (< -1) and absent (-1): 0
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int c = c0 + k;
@@ -1830,7 +2097,7 @@ __global__ void __launch_bounds__(256, 4) k_step_bw(StepDev p, unsigned long lon
       const long long i = (long long)c * MT_CHUNK + threadIdx.x;
       cur.nn = s_nn[(c - c_lo) * MT_CHUNK + threadIdx.x];
       cur.e = s_e[(c - c_lo) * MT_CHUNK + threadIdx.x];
-      if (i < n) load_pose(p.soa_cur, p.stride, i, cur.P);
+      if (i < n) load_pose_stream(p.soa_cur, p.stride, i, cur.P);
     } else {
       step_b_load<true, true>(p, c, n, cur);
     }
@@ -1861,7 +2128,8 @@ __global__ void __launch_bounds__(256, 4) k_step_bw(StepDev p, unsigned long lon
       p.flags[6] = s_on;
       p.flags[5] = (p.prune_dist > 0.0 && s_on == 0);
       p.flags[3] += (int)p.qctl[0];
-      p.qctl[0] = 0, p.qctl[1] = 0;
+      p.flags[MT_STAT_MESH_DEFERRED] += (int)p.qctl[3];
+      p.qctl[0] = 0, p.qctl[1] = 0, p.qctl[2] = 0, p.qctl[3] = 0;
     }
   }
 }
@@ -1893,6 +2161,7 @@ __global__ void k_resample_seq(StepDev p) {
 static int fill_step(mt_ctx* c, const mt_step_args* a, StepDev* d) {
   if (!c || !a) return set_err(MT_ERR_ARG, "step: null argument");
   if (a->n <= 0 || (size_t)a->n > c->cap || a->stride < a->n) return set_err(MT_ERR_CAPACITY, "step: n/stride out of range");
+  if (a->n > 0x1fffffffLL) return set_err(MT_ERR_CAPACITY, "step: at most 2^29 - 1 particles per GPU (queue entries carry two flag bits)");
   memset(d, 0, sizeof(*d));
   d->soa_cur = (float4*)a->d_soa_cur;
   d->soa_next = (float4*)a->d_soa_next;
@@ -1932,6 +2201,8 @@ static int fill_step(mt_ctx* c, const mt_step_args* a, StepDev* d) {
   d->wrm = c->d_wrm;
   d->wcnt = c->d_wcnt;
   d->queue = c->d_queue;
+  d->queue2 = c->d_queue2;
+  d->queue_cap = (long long)c->cap + 32;
   d->qctl = c->d_qctl;
   d->scal = c->d_scal;
   d->ticket = c->d_ticket;
@@ -2029,9 +2300,19 @@ extern "C" int mt_step_a(mt_ctx* c, const mt_step_args* a, void* stream) {
   if (a->prune_dist > 0.0 && !c->mesh_ready) return set_err(MT_ERR_STATE, "mt_step_a: prune_dist given but no mesh uploaded");
   cudaStream_t st = (cudaStream_t)stream;
   if (c->timing[0]) CK(cudaEventRecord(c->timing[0], st));
+#if MT_A_SMEM
+  k_step_a_s<<<(unsigned)((a->n + MT_AS_BLOCK - 1) / MT_AS_BLOCK), MT_AS_BLOCK, 0, st>>>(d, tables_of(c), mesh_of(c));
+#else
   k_step_a<<<(unsigned)((a->n + MT_A_BLOCK - 1) / MT_A_BLOCK), MT_A_BLOCK, 0, st>>>(d, tables_of(c), mesh_of(c));
+#endif
   CK_LAUNCH();
   if (c->timing[1]) CK(cudaEventRecord(c->timing[1], st));
+  if (d.prune_dist > 0.0) {  // (a particle is in at most one of the two queues)
+    k_step_meshq<<<c->sm_count * 4, 256, 0, st>>>(d, mesh_of(c));
+    CK_LAUNCH();
+    k_step_meshq2<<<c->sm_count * 8, 256, 0, st>>>(d, mesh_of(c));
+    CK_LAUNCH();
+  }
   k_step_nnq<<<c->sm_count * 12, 32 * MT_NNQ_WARPS, 0, st>>>(d, tables_of(c), mesh_of(c));
   CK_LAUNCH();
   if (c->timing[2]) CK(cudaEventRecord(c->timing[2], st));

@@ -27,6 +27,77 @@ static inline float mt_nofma_add(float a, float b) { volatile float r = a + b; r
 #define MT_FADD(a, b) mt_nofma_add((a), (b))
 #endif
 
+// ---------------------------------------------------------------- L2 residency hints
+// One filter step streams ~0.5 GB (poses read + written twice, the embeddings once) through a 126 MB L2, while the
+// tables every particle consults (codebook keys, neighbour lists, drift-test voxels and vertices, weight tables)
+// total a few tens of MB of hot lines.  Without hints the stream evicts the tables and every dependent table
+// access of the next kernel pays DRAM latency (measured: 45 % of the L2 requests of k_step_a missed).  Table loads
+// therefore carry an L2 evict_last policy, the streams evict_first.
+#ifndef MT_L2_HINTS
+#define MT_L2_HINTS 1
+#endif
+#if defined(__CUDACC__)
+__device__ __forceinline__ unsigned long long mt_pol_keep() {
+  unsigned long long p;
+  asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ unsigned long long mt_pol_stream() {
+  unsigned long long p;
+  asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+#if MT_L2_HINTS
+// table loads (read-only data path, L2 evict_last)
+__device__ __forceinline__ float4 mt_ldk(const float4* a) {
+  float4 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(a), "l"(mt_pol_keep()));
+  return v;
+}
+__device__ __forceinline__ int mt_ldk(const int* a) {
+  int v;
+  asm volatile("ld.global.nc.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(a), "l"(mt_pol_keep()));
+  return v;
+}
+__device__ __forceinline__ float mt_ldk(const float* a) {
+  float v;
+  asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(a), "l"(mt_pol_keep()));
+  return v;
+}
+__device__ __forceinline__ double mt_ldk(const double* a) {
+  double v;
+  asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(a), "l"(mt_pol_keep()));
+  return v;
+}
+__device__ __forceinline__ void mt_prefetch_keep(const void* a) { asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(a)); }
+// streamed particle arrays (L2 evict_first)
+__device__ __forceinline__ float4 mt_lds(const float4* a) {
+  float4 v;
+  asm volatile("ld.global.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(a), "l"(mt_pol_stream()));
+  return v;
+}
+__device__ __forceinline__ int mt_lds(const int* a) {
+  int v;
+  asm volatile("ld.global.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(a), "l"(mt_pol_stream()));
+  return v;
+}
+__device__ __forceinline__ void mt_sts(float4* a, float4 v) {
+  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(mt_pol_stream()) : "memory");
+}
+__device__ __forceinline__ void mt_sts(int* a, int v) {
+  asm volatile("st.global.L2::cache_hint.s32 [%0], %1, %2;" ::"l"(a), "r"(v), "l"(mt_pol_stream()) : "memory");
+}
+#else
+template <typename T>
+__device__ __forceinline__ T mt_ldk(const T* a) { return __ldg(a); }
+__device__ __forceinline__ void mt_prefetch_keep(const void* a) { asm volatile("prefetch.global.L2 [%0];" ::"l"(a)); }
+template <typename T>
+__device__ __forceinline__ T mt_lds(const T* a) { return *a; }
+template <typename T>
+__device__ __forceinline__ void mt_sts(T* a, T v) { *a = v; }
+#endif
+#endif
+
 struct mt_pose {  // rows of the 3x4 [R|t]; the constant bottom row (0,0,0,1) is implicit
   float r[3][4];
 };

@@ -226,10 +226,28 @@ inline int mt_bvh_search_host(const MtBvhHost& B, int M, const float q[6], float
 #if defined(__CUDACC__)
 // ------------------------------------------------------------------------- device side
 __device__ __forceinline__ int load_key(const float4* __restrict__ t, int i, float k[6], float* extra = nullptr) {
-  float4 a = __ldg(t + 2 * (size_t)i), b = __ldg(t + 2 * (size_t)i + 1);
+  float4 a = mt_ldk(t + 2 * (size_t)i), b = mt_ldk(t + 2 * (size_t)i + 1);
   k[0] = a.x, k[1] = a.y, k[2] = a.z, k[3] = a.w, k[4] = b.x, k[5] = b.y;
   if (extra) *extra = b.w;     // keys_orig: delta_0 = distance to the nearest other key
   return __float_as_int(b.z);  // partner (keys_orig) / original index (keys_sorted)
+}
+
+#ifndef MT_SCAN_PIPE
+#define MT_SCAN_PIPE 1
+#endif
+#ifndef MT_SCAN_PF
+#define MT_SCAN_PF 0
+#endif
+#ifndef MT_PF_INIT_L1
+#define MT_PF_INIT_L1 0
+#endif
+// 16-byte read-only load that the compiler keeps where it is written (see the pipelined scan below)
+__device__ __forceinline__ float4 mt_ldnc(const float4* p) {
+  // (default L2 priority: the lists are 2 KB per key, too many to pin; the streamed particle arrays are evict_first,
+  // so the lists in use still outlive them)
+  float4 v;
+  asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
 }
 
 // Issue as soon as the hint is known (kernel A does it before the motion arithmetic): the
@@ -240,8 +258,13 @@ __device__ __forceinline__ void nn_prefetch(const NNTables& T, int hint) {
   const float4* L = T.nbr + (size_t)hint * (2 * MT_NBR_K);
   asm volatile("prefetch.global.L1 [%0];" ::"l"(T.keys_orig + 2 * (size_t)hint));
   asm volatile("prefetch.global.L1 [%0];" ::"l"(L));
+#if MT_PF_INIT_L1
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(L + 8));
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(L + 16));
+#else
   asm volatile("prefetch.global.L2 [%0];" ::"l"(L + 8));
   asm volatile("prefetch.global.L2 [%0];" ::"l"(L + 16));
+#endif
 }
 
 // (1) one thread per query.  false -> needs the box-hierarchy search (best_* = best so far, or
@@ -284,6 +307,38 @@ __device__ __forceinline__ bool nn_hint_search(const NNTables& T, const float q[
   float lim = mt_hint_limit(dh, best_d);
   if (delta0 > lim) MT_SCAN_RET(0, true);  // nearest other key of the centre is already out of reach
   const float4* __restrict__ L = T.nbr + (size_t)hint * (2 * MT_NBR_K);
+#if MT_SCAN_PIPE
+  // software pipeline: the two entries of trip t+1 are requested before trip t is evaluated, so a trip waits
+  // for loads issued ~40 instructions (x the other resident warps) earlier instead of for loads it has just
+  // issued.  The loads are volatile asm (plain ld.global.nc underneath, i.e. cached in L1 like __ldg) so that
+  // neither NVVM nor ptxas sinks them below the exit tests of the current trip.
+  // Two register sets (x*, y*) alternate between "being evaluated" and "in flight": no moves at the loop end.
+  float4 xa0 = mt_ldnc(L), xb0 = mt_ldnc(L + 1), xa1 = mt_ldnc(L + 2), xb1 = mt_ldnc(L + 3);
+  float4 ya0, yb0, ya1, yb1;
+#define MT_SCAN_ENTRY(A, B, JRET)                                                                       \
+  {                                                                                                     \
+    if (B.z > lim) MT_SCAN_RET(JRET, true);                                                             \
+    const float k[6] = {A.x, A.y, A.z, A.w, B.x, B.y};                                                  \
+    const float d = mt_key_dist(q, k);                                                                  \
+    const int idx = __float_as_int(B.w);                                                                \
+    if (mt_better(d, idx, best_d, best_i)) best_d = d, best_i = idx, lim = mt_hint_limit(dh, d);        \
+  }
+#pragma unroll 1
+  for (int j = 0; j < MT_NBR_K; j += 4) {
+#if MT_SCAN_PF
+    // rolling prefetch, MT_SCAN_PF lines (4 entries each) ahead of the trip being evaluated
+    if (j + 4 * MT_SCAN_PF < MT_NBR_K) asm volatile("prefetch.global.L1 [%0];" ::"l"(L + 2 * (j + 4 * MT_SCAN_PF)));
+#endif
+    ya0 = mt_ldnc(L + 2 * j + 4), yb0 = mt_ldnc(L + 2 * j + 5), ya1 = mt_ldnc(L + 2 * j + 6), yb1 = mt_ldnc(L + 2 * j + 7);
+    MT_SCAN_ENTRY(xa0, xb0, j + 1)
+    MT_SCAN_ENTRY(xa1, xb1, j + 2)
+    const int jn = min(j + 4, MT_NBR_K - 2);  // the last trip re-reads its own entries (L1 hit, never used)
+    xa0 = mt_ldnc(L + 2 * jn), xb0 = mt_ldnc(L + 2 * jn + 1), xa1 = mt_ldnc(L + 2 * jn + 2), xb1 = mt_ldnc(L + 2 * jn + 3);
+    MT_SCAN_ENTRY(ya0, yb0, j + 3)
+    MT_SCAN_ENTRY(ya1, yb1, j + 4)
+  }
+#undef MT_SCAN_ENTRY
+#else
 #pragma unroll 1
   for (int j = 0; j < MT_NBR_K; j += 2) {
     // two entries (64 contiguous bytes) per trip, all four loads in flight together.  The exit test is made to
@@ -311,7 +366,69 @@ __device__ __forceinline__ bool nn_hint_search(const NNTables& T, const float q[
       if (mt_better(d, idx, best_d, best_i)) best_d = d, best_i = idx, lim = mt_hint_limit(dh, d);
     }
   }
+#endif
   MT_SCAN_RET(65, false);
+}
+
+// (1b) the same search with the head of the hint's list staged in shared memory by the caller: S[0..1] = the key
+// record of `hint` (keys_orig layout), S[2 + 2 j], S[3 + 2 j] = list entry j for j < n_staged.  Entries beyond the
+// staged head (and the list of a near-pi partner that replaces the hint as the centre) are read from global memory.
+__device__ __forceinline__ bool nn_hint_search_staged(const NNTables& T, const float4* __restrict__ S, int n_staged,
+                                                      const float q[6], int hint, float& best_d, int& best_i) {
+  const float4 ka = S[0], kb = S[1];
+  const float kh[6] = {ka.x, ka.y, ka.z, ka.w, kb.x, kb.y};
+  const int partner = __float_as_int(kb.z);
+  float delta0 = kb.w;
+  best_d = mt_key_dist(q, kh);
+  best_i = hint;
+  if (!(best_d == best_d)) {
+    best_i = 0;
+    return true;
+  }
+  bool staged = true;
+  if (partner >= 0) {  // near angle pi: the pose may have jumped to the other sign of the axis
+    float kp[6], dp0;
+    load_key(T.keys_orig, partner, kp, &dp0);
+    const float dp = mt_key_dist(q, kp);
+    if (mt_better(dp, partner, best_d, best_i)) best_d = dp, best_i = partner, hint = partner, delta0 = dp0, staged = false;
+  }
+  const float dh = sqrtf(best_d);
+  float lim = mt_hint_limit(dh, best_d);
+  if (delta0 > lim) return true;  // nearest other key of the centre is already out of reach
+  int j = 0;
+  if (staged) {
+#pragma unroll 1
+    for (; j < n_staged; ++j) {
+      const float4 a = S[2 + 2 * j], b = S[3 + 2 * j];
+      if (b.z > lim) return true;
+      const float k[6] = {a.x, a.y, a.z, a.w, b.x, b.y};
+      const float d = mt_key_dist(q, k);
+      const int idx = __float_as_int(b.w);
+      if (mt_better(d, idx, best_d, best_i)) best_d = d, best_i = idx, lim = mt_hint_limit(dh, d);
+    }
+  }
+  const float4* __restrict__ L = T.nbr + (size_t)hint * (2 * MT_NBR_K);
+#pragma unroll 1
+  for (; j < MT_NBR_K; j += 2) {
+    const float4 a0 = __ldg(L + 2 * j), b0 = __ldg(L + 2 * j + 1);
+    const float4 a1 = __ldg(L + 2 * j + 2), b1 = __ldg(L + 2 * j + 3);
+    const float dz0 = fmaf(0.0f, a0.x, fmaf(0.0f, a1.x, fmaf(0.0f, b1.x, b0.z)));
+    if (dz0 > lim) return true;
+    {
+      const float k[6] = {a0.x, a0.y, a0.z, a0.w, b0.x, b0.y};
+      const float d = mt_key_dist(q, k);
+      const int idx = __float_as_int(b0.w);
+      if (mt_better(d, idx, best_d, best_i)) best_d = d, best_i = idx, lim = mt_hint_limit(dh, d);
+    }
+    if (b1.z > lim) return true;
+    {
+      const float k[6] = {a1.x, a1.y, a1.z, a1.w, b1.x, b1.y};
+      const float d = mt_key_dist(q, k);
+      const int idx = __float_as_int(b1.w);
+      if (mt_better(d, idx, best_d, best_i)) best_d = d, best_i = idx, lim = mt_hint_limit(dh, d);
+    }
+  }
+  return false;
 }
 
 // warp-wide (best_d, best_i) = lexicographic min over lanes
@@ -326,7 +443,7 @@ __device__ __forceinline__ void warp_best(float& d, int& i) {
 
 // bound of one node (3 float4 = lo[6] | hi[6])
 __device__ __forceinline__ float bvh_lower_bound(const float4* __restrict__ node, const float q[6]) {
-  const float4 a = __ldg(node), b = __ldg(node + 1), c = __ldg(node + 2);
+  const float4 a = mt_ldk(node), b = mt_ldk(node + 1), c = mt_ldk(node + 2);
   const float box[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
   return mt_box_lower_bound(box, q);
 }
