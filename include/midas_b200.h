@@ -199,8 +199,9 @@ typedef struct mt_step_args {
   long long n_global;
   double* d_shard_sums;
   long long* d_n_out;    /* device (nullable): number of children written on this GPU */
-  const long long* d_n_in; /* device (nullable): particle count read by the kernels instead of n; n is then
-                            * only the upper bound that sizes the grid (no host sync between steps) */
+  const long long* d_n_in; /* device (nullable): particle count read by the kernels instead of n (no host sync
+                            * between steps); the grids then cover `stride` particles and n is informational.
+                            * A count beyond stride raises MT_STAT_OVERFLOW. */
   /* drift pruning (remove_invalid_particles, filter.py:176-179): > 0 zeroes the weight of particles
    * further than this from the uploaded mesh; if all drift, mt_step_b re-projects the particles onto
    * d_cb_poses[(M,4,4) float32 codebook poses, nullable] instead of resampling. */
@@ -230,6 +231,18 @@ int mt_dist_debug(mt_ctx* ctx, unsigned long long* h_out3);
 /* *h_fused = 1 when mt_step_a/mt_step_b will run this step in the fused form (sums + exchange + resampling in
  * one cooperative kernel; a sharded caller then skips its all-gather of the weight sums), else 0 */
 int mt_step_is_fused(mt_ctx* ctx, const mt_step_args* a, int* h_fused);
+
+/* One filter step as ONE call: mt_codebook_query(d_q) concurrently with mt_step_a, then mt_step_b -- the loop body
+ * filter.py:154-190 (motionModel, SE3_NN, get_similarity, remove_invalid_particles, resampler "low_var").
+ * use_graph != 0 (and a step that runs in the fused form, see mt_step_is_fused): the kernels are nodes of a CUDA
+ * graph (query | motion+SE3_NN -> queue consumers -> cooperative resampling kernel) that is instantiated once per
+ * configuration (buffer parity, query pointer, grid sizes) and replayed; only the by-value arguments that change
+ * from step to step are patched.  d_q must then be the same device buffer every step (copy the code into it).
+ * a->table_ready_event is ignored.  Sharded steps (world > 1) need mt_dist_import; without it use
+ * mt_step_a + all-gather + mt_step_b. */
+int mt_step(mt_ctx* ctx, const mt_step_args* a, const void* d_q, int q_dtype, int use_graph, void* stream);
+/* graph replays so far / instantiated graphs held by the context */
+int mt_step_graph_info(mt_ctx* ctx, long long* h_replays, int* h_cached);
 
 /* kernel A: motion + key + exact NN + weight lookup + deterministic weight sums */
 int mt_step_a(mt_ctx* ctx, const mt_step_args* a, void* stream);

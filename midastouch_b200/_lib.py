@@ -59,6 +59,8 @@ _SIGS = {
     "mt_codebook_nbr_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int)]),
     "mt_codebook_rank": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "mt_ctx_set_timing_events": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "mt_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "mt_step_graph_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_longlong), C.POINTER(C.c_int)]),
     "mt_ctx_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_longlong), C.c_int]),
     "mt_mesh_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_double]),
     "mt_prune_aos": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),

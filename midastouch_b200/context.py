@@ -35,6 +35,7 @@ class Context:
         self.capacity, self.M, self.D = int(capacity), int(M), int(D)
         self._h = C.c_void_p()
         call("mt_ctx_create", self.index, C.c_size_t(self.capacity), self.M, self.D, C.byref(self._h))
+        self.generation = 0    # bumped whenever the mt_ctx is re-created (holders of addresses inside it must refresh)
         self._codebook = None  # (keys_host, emb) kept alive / for re-upload on growth
         self._mesh = None      # (vertices_host float64, cell)
 
@@ -60,6 +61,7 @@ class Context:
         self.capacity = int(max(n, 2 * self.capacity))
         self._h = C.c_void_p()
         call("mt_ctx_create", self.index, C.c_size_t(self.capacity), self.M, self.D, C.byref(self._h))
+        self.generation += 1
         if cb is not None:
             self.upload_codebook(*cb)
         if self._mesh is not None:

@@ -121,8 +121,15 @@ struct mt_ctx {
   double* d_scal;     // [0] local weight sum, [1] max, [2] min, [3] softmax denom, [4..7] spare
   unsigned int* d_ticket;
   int* d_flags;  // MT_STAT_* slots (include/midas_b200.h)
+  // mt_step: the codebook query runs on a side stream (or as a parallel branch of the step's CUDA graph)
+  cudaStream_t side;
+  cudaEvent_t ev_fork, ev_join;
+  struct StepGraph* graphs;  // MT_STEP_GRAPHS cached instantiations (one per buffer parity / configuration)
+  int graph_next;
+  unsigned long long graph_replays;
 };
 
+static void step_graphs_free(mt_ctx* c);
 static size_t nchunks_of(long long n) { return (size_t)((n + MT_CHUNK - 1) / MT_CHUNK); }
 
 extern "C" int mt_ctx_create(int device, size_t capacity, int M, int D, mt_ctx** out) {
@@ -170,6 +177,9 @@ extern "C" int mt_ctx_create(int device, size_t capacity, int M, int D, mt_ctx**
   CK(cudaMemset(c->d_ticket, 0, sizeof(unsigned int) * 4));
   CK(cudaMemset(c->d_flags, 0, sizeof(int) * MT_STAT_COUNT));
   CK(cudaMemset(c->d_scal, 0, sizeof(double) * 8));
+  CK(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
   *out = c;
   return MT_OK;
 }
@@ -177,6 +187,10 @@ extern "C" int mt_ctx_create(int device, size_t capacity, int M, int D, mt_ctx**
 extern "C" int mt_ctx_destroy(mt_ctx* c) {
   if (!c) return MT_OK;
   cudaSetDevice(c->device);
+  step_graphs_free(c);
+  if (c->side) cudaStreamDestroy(c->side);
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->ev_join) cudaEventDestroy(c->ev_join);
   cudaFree(c->d_keys_orig);
   cudaFree(c->d_keys_sorted);
   cudaFree(c->d_sorted_orig);
@@ -1332,6 +1346,18 @@ struct StepDev {
   int nchunks;
 };
 
+// particle count seen by the step kernels: the device-resident count when there is one (sharded runs: the host only
+// knows the capacity), clamped to what the grids cover; a count beyond the buffers raises MT_STAT_OVERFLOW
+__device__ __forceinline__ long long step_count(const StepDev& p) {
+  if (!p.n_in) return p.n;
+  long long n = *p.n_in;
+  if (n > p.stride) {
+    n = p.stride;
+    p.flags[0] = 1;
+  }
+  return n < 0 ? 0 : n;
+}
+
 // The measurement half of a step is three kernels (mt_step_a launches them back to back):
 //
 //  k_step_a     one particle per thread, 64-thread blocks, no block-level synchronisation:
@@ -1363,7 +1389,7 @@ struct StepDev {
 #define MT_Q_INDEX 0x1fffffff
 __global__ void __launch_bounds__(MT_A_BLOCK, MT_A_MINBLOCKS) k_step_a(StepDev p, NNTables T, MeshTables Mh) {
   const long long i = (long long)blockIdx.x * MT_A_BLOCK + threadIdx.x;
-  const long long n = p.n_in ? *p.n_in : p.n;
+  const long long n = step_count(p);
   const bool valid = i < n;
   const int lane = threadIdx.x & 31;
   double et2 = 0.0, ang2 = 0.0;
@@ -1482,7 +1508,7 @@ __global__ void __launch_bounds__(MT_AS_BLOCK, MT_AS_MINBLOCKS) k_step_a_s(StepD
   __shared__ int s_count;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long i = (long long)blockIdx.x * MT_AS_BLOCK + tid;
-  const long long n = p.n_in ? *p.n_in : p.n;
+  const long long n = step_count(p);
   const bool valid = i < n;
   int hint = valid ? nn_index(mt_lds(p.nn_cur + i)) : -1;
   if (hint >= T.M) hint = -1;
@@ -1698,7 +1724,7 @@ __global__ void __launch_bounds__(256) k_step_sums(StepDev p) {
   __shared__ double s8[8];
   __shared__ int s_cnt;
   const long long i = (long long)blockIdx.x * MT_CHUNK + threadIdx.x;
-  const long long n = p.n_in ? *p.n_in : p.n;
+  const long long n = step_count(p);
   const int nwarps = (int)((n + 31) >> 5);
   double e = 0.0;
   if (i < n) {
@@ -1901,7 +1927,7 @@ __global__ void __launch_bounds__(256) k_step_b(StepDev p) {
   __shared__ double s8[8];
   __shared__ long long s_cnt[MT_CHUNK + 1];
   const int c = blockIdx.x;
-  const long long n = p.n_in ? *p.n_in : p.n;
+  const long long n = step_count(p);
   // global normaliser and this shard's CDF offset (sequential, identical on every GPU)
   double S = 0.0, A = 0.0;
   if (p.world > 1) {
@@ -1914,6 +1940,7 @@ __global__ void __launch_bounds__(256) k_step_b(StepDev p) {
   }
   const double base = A + p.prefix[c];
   const double endv = (c + 1 == p.nchunks) ? (A + p.prefix[p.nchunks]) : (A + p.prefix[c + 1]);
+  if (n == 0 && c == 0 && threadIdx.x == 0 && p.n_out) *p.n_out = 0;
   ChunkIn in;
   step_b_load<FROM_TABLE, SCATTER>(p, c, n, in);
   step_b_chunk<FROM_TABLE, SCATTER>(p, c, n, S, A, base, endv, s8, s_cnt, in);
@@ -1937,7 +1964,7 @@ __global__ void __launch_bounds__(256, 4) k_step_bw(StepDev p, unsigned long lon
   __shared__ double s_e[MT_BW_FAST_PER * MT_CHUNK];  // weight of every particle of the block's chunks
   __shared__ int s_nn[MT_BW_FAST_PER * MT_CHUNK];    // and its match (phase 2 does not go back to memory for them)
   const int G = gridDim.x, g = blockIdx.x;
-  const long long n = p.n_in ? *p.n_in : p.n;
+  const long long n = step_count(p);
   const int nwarps = (int)((n + 31) >> 5);
   const int per = (p.nchunks + G - 1) / G;
   const int c_lo = g * per, c_hi = min(c_lo + per, p.nchunks);
@@ -2071,7 +2098,10 @@ __global__ void __launch_bounds__(256, 4) k_step_bw(StepDev p, unsigned long lon
         if (r == p.rank) off = tot;
         tot += __longlong_as_double((long long)((w0 >> 32) | (w1 & 0xffffffff00000000ull)));  // sequential, identical on every GPU
       }
-      if (!ok) p.flags[0] = 2;
+      if (!ok) {  // a peer never arrived: S is not trustworthy -> NaN, i.e. the "keep the particles" path of every chunk
+        p.flags[0] = 2;
+        tot = __longlong_as_double(0x7ff8000000000000LL);
+      }
       if (g == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(p.xdbg[2]));
       s_x[0] = off, s_x[1] = tot;
     }
@@ -2123,6 +2153,7 @@ __global__ void __launch_bounds__(256, 4) k_step_bw(StepDev p, unsigned long lon
         p.rmse2[0] = (float)sqrt(sa / (double)n);
         p.rmse2[1] = (float)sqrt(sb / (double)n);
       }
+      if (n == 0 && p.n_out) *p.n_out = 0;  // a shard without particles has no children (nobody owns i == n - 1)
       p.prefix[p.nchunks] = s_bc[2];  // this GPU's weight sum
       p.scal[0] = s_bc[2];
       p.flags[6] = s_on;
@@ -2158,9 +2189,13 @@ __global__ void k_resample_seq(StepDev p) {
   for (long long s = prev; s < N; ++s) p.anc[s] = -1;
 }
 
+// particles the grids must cover: with a device-resident count (d_n_in) the host only knows the capacity
+static long long step_cover(const mt_step_args* a) { return a->d_n_in ? a->stride : a->n; }
+
 static int fill_step(mt_ctx* c, const mt_step_args* a, StepDev* d) {
   if (!c || !a) return set_err(MT_ERR_ARG, "step: null argument");
   if (a->n <= 0 || (size_t)a->n > c->cap || a->stride < a->n) return set_err(MT_ERR_CAPACITY, "step: n/stride out of range");
+  if (a->d_n_in && (size_t)a->stride > c->cap) return set_err(MT_ERR_CAPACITY, "step: with a device-resident count the stride must not exceed the context capacity");
   if (a->n > 0x1fffffffLL) return set_err(MT_ERR_CAPACITY, "step: at most 2^29 - 1 particles per GPU (queue entries carry two flag bits)");
   memset(d, 0, sizeof(*d));
   d->soa_cur = (float4*)a->d_soa_cur;
@@ -2207,7 +2242,7 @@ static int fill_step(mt_ctx* c, const mt_step_args* a, StepDev* d) {
   d->scal = c->d_scal;
   d->ticket = c->d_ticket;
   d->flags = c->d_flags;
-  d->nchunks = (int)nchunks_of(a->n);
+  d->nchunks = (int)nchunks_of(step_cover(a));
   return MT_OK;
 }
 
@@ -2260,7 +2295,7 @@ static bool step_fused(mt_ctx* c, const mt_step_args* a) {
   if (c->bw_blocks_per_sm < 0) return false;
   // sharded: every rank must take the same decision, so it is taken on the capacity (equal on all ranks,
   // and chunks per block only grow with the particle count), not on this rank's current count
-  const long long nb = a->world > 1 ? std::max(a->stride, a->n) : a->n;
+  const long long nb = (a->world > 1 || a->d_n_in) ? std::max(a->stride, a->n) : a->n;
   const int grid = std::min(std::min((int)nchunks_of(nb), c->sm_count * c->bw_blocks_per_sm), MT_BW_MAX_GRID);
   return (nchunks_of(nb) + grid - 1) / grid <= MT_BW_MAX_PER;
 }
@@ -2301,9 +2336,9 @@ extern "C" int mt_step_a(mt_ctx* c, const mt_step_args* a, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (c->timing[0]) CK(cudaEventRecord(c->timing[0], st));
 #if MT_A_SMEM
-  k_step_a_s<<<(unsigned)((a->n + MT_AS_BLOCK - 1) / MT_AS_BLOCK), MT_AS_BLOCK, 0, st>>>(d, tables_of(c), mesh_of(c));
+  k_step_a_s<<<(unsigned)((step_cover(a) + MT_AS_BLOCK - 1) / MT_AS_BLOCK), MT_AS_BLOCK, 0, st>>>(d, tables_of(c), mesh_of(c));
 #else
-  k_step_a<<<(unsigned)((a->n + MT_A_BLOCK - 1) / MT_A_BLOCK), MT_A_BLOCK, 0, st>>>(d, tables_of(c), mesh_of(c));
+  k_step_a<<<(unsigned)((step_cover(a) + MT_A_BLOCK - 1) / MT_A_BLOCK), MT_A_BLOCK, 0, st>>>(d, tables_of(c), mesh_of(c));
 #endif
   CK_LAUNCH();
   if (c->timing[1]) CK(cudaEventRecord(c->timing[1], st));
@@ -2357,9 +2392,216 @@ extern "C" int mt_step_b(mt_ctx* c, const mt_step_args* a, void* stream) {
   return MT_OK;
 }
 
+// ------------------------------------------------------------------------- one call per step, CUDA graph
+// mt_step = codebook query + k_step_a + queue consumers + the cooperative resampling kernel.  Stream form: the query
+// runs on the context's side stream, concurrently with k_step_a.  Graph form: the same kernels as nodes of a CUDA
+// graph (query | a -> {meshq -> meshq2, nnq} -> bw), instantiated once per configuration (buffer parity) and
+// replayed; the by-value kernel arguments that change every step (odometry, noise key, offset, ground truth,
+// barrier / exchange counters) are patched into the instantiated graph with cudaGraphExecKernelNodeSetParams.
+#define MT_STEP_GRAPHS 4
+struct StepGraph {
+  bool valid;
+  unsigned long long key[20];
+  cudaGraph_t graph;
+  cudaGraphExec_t exec;
+  cudaGraphNode_t n_query, n_a, n_meshq, n_meshq2, n_nnq, n_bw;
+  bool has_mesh;
+};
+static void step_graphs_free(mt_ctx* c) {
+  if (!c->graphs) return;
+  for (int k = 0; k < MT_STEP_GRAPHS; ++k)
+    if (c->graphs[k].valid) {
+      cudaGraphExecDestroy(c->graphs[k].exec);
+      cudaGraphDestroy(c->graphs[k].graph);
+    }
+  delete[] c->graphs;
+  c->graphs = nullptr;
+}
+
+struct QueryLaunch {
+  const void* func;
+  int grid;
+  size_t smem;
+  const void* q;
+  const void* E;
+  const double* rnorm;
+  int M, D;
+  double *sim, *esim, *sim2;
+};
+// launch parameters of k_codebook_query for this context (row norms are computed on `st` if they are not cached yet)
+static int query_plan(mt_ctx* c, const void* d_q, int q_dtype, QueryLaunch* Q, cudaStream_t st) {
+  if (!c->cb_ready || !c->d_emb) return set_err(MT_ERR_STATE, "mt_step: no codebook");
+  if (!d_q) return set_err(MT_ERR_ARG, "mt_step: null query");
+  const int D = c->D, M = c->M;
+  if (D > MT_MAX_D) return set_err(MT_ERR_ARG, "cosine: D exceeds MT_MAX_D (6144)");
+  if (q_dtype != MT_DTYPE_F32 && q_dtype != MT_DTYPE_F64) return set_err(MT_ERR_ARG, "cosine: bad query dtype");
+  const bool e32 = c->emb_dtype == MT_DTYPE_F32, q32 = q_dtype == MT_DTYPE_F32;
+  if (e32 && D % 4) return set_err(MT_ERR_ARG, "cosine: D must be a multiple of 4 for float32 rows");
+  if (!e32 && D % 2) return set_err(MT_ERR_ARG, "cosine: D must be a multiple of 2 for float64 rows");
+  if (!c->rnorm_ready) {
+    if (e32)
+      k_row_norms<float><<<(M + 7) / 8, 256, 0, st>>>((const float*)c->d_emb, M, D, c->d_rnorm);
+    else
+      k_row_norms<double><<<(M + 7) / 8, 256, 0, st>>>((const double*)c->d_emb, M, D, c->d_rnorm);
+    CK_LAUNCH();
+    c->rnorm_ready = true;
+  }
+  Q->smem = sizeof(double) * D;
+  Q->func = e32 ? (q32 ? (const void*)k_codebook_query<float, float> : (const void*)k_codebook_query<float, double>)
+                : (q32 ? (const void*)k_codebook_query<double, float> : (const void*)k_codebook_query<double, double>);
+  if (!c->query_blocks_per_sm) {
+    int occ = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, Q->func, 256, Q->smem);
+    c->query_blocks_per_sm = occ > 0 ? occ : 4;
+  }
+  const int resident = c->sm_count * c->query_blocks_per_sm;
+  const int trips_total = (M + 3) / 4;
+  int grid = (trips_total + 7) / 8;
+  for (int k = 2; grid > resident; ++k) grid = ((trips_total + k - 1) / k + 7) / 8;
+  Q->grid = grid;
+  Q->q = d_q, Q->E = c->d_emb, Q->rnorm = c->d_rnorm, Q->M = M, Q->D = D;
+  Q->sim = c->d_sim, Q->esim = c->d_esim, Q->sim2 = nullptr;
+  return MT_OK;
+}
+
+
+extern "C" int mt_step(mt_ctx* c, const mt_step_args* a, const void* d_q, int q_dtype, int use_graph, void* stream) {
+  if (!c || !a) return set_err(MT_ERR_ARG, "mt_step: null argument");
+  CK(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool fused = a->resample && step_fused(c, a);
+  if (a->world > 1 && a->resample && !fused)
+    return set_err(MT_ERR_STATE, "mt_step: sharded steps need mt_dist_import (or mt_step_a + all-gather + mt_step_b)");
+  if (!use_graph || !fused) {
+    CK(cudaEventRecord(c->ev_fork, st));
+    CK(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
+    int r = mt_codebook_query(c, d_q, q_dtype, nullptr, c->side);
+    if (r) return r;
+    CK(cudaEventRecord(c->ev_join, c->side));
+    mt_step_args b = *a;
+    b.table_ready_event = c->ev_join;
+    r = mt_step_a(c, &b, st);
+    if (r) return r;
+    if (a->resample) return mt_step_b(c, &b, st);
+    CK(cudaStreamWaitEvent(st, c->ev_join, 0));
+    return MT_OK;
+  }
+  // ---- graph form
+  StepDev d;
+  int r = fill_step(c, a, &d);
+  if (r) return r;
+  if (!a->d_soa_cur || !a->d_soa_next || !a->d_nn_cur || !a->d_nn_next) return set_err(MT_ERR_ARG, "mt_step: null particle buffers");
+  if ((a->d_tn == nullptr) != (a->d_rot == nullptr)) return set_err(MT_ERR_ARG, "mt_step: tn/rot must both be given");
+  if (a->gt && !a->d_rmse2) return set_err(MT_ERR_ARG, "mt_step: gt without rmse output");
+  if (a->prune_dist > 0.0 && !c->mesh_ready) return set_err(MT_ERR_STATE, "mt_step: prune_dist given but no mesh uploaded");
+  if (a->world > 1 && a->n_global <= 0) return set_err(MT_ERR_ARG, "mt_step: sharded step needs n_global");
+  QueryLaunch Q;
+  r = query_plan(c, d_q, q_dtype, &Q, st);
+  if (r) return r;
+  NNTables T = tables_of(c);
+  MeshTables Mh = mesh_of(c);
+  const long long cover = step_cover(a);
+  const int grid_bw = std::min(std::min((int)nchunks_of(cover), c->sm_count * c->bw_blocks_per_sm), MT_BW_MAX_GRID);
+  unsigned long long* bar = c->d_bar;
+  unsigned long long target = c->bar_target + (unsigned long long)grid_bw;
+  double* bw = c->d_bw;
+  int* bwc = c->d_bwcnt;
+  void* args_q[] = {&Q.q, &Q.E, &Q.rnorm, &Q.M, &Q.D, &Q.sim, &Q.esim, &Q.sim2};
+  void* args_a[] = {&d, &T, &Mh};
+  void* args_m[] = {&d, &Mh};
+  void* args_bw[] = {&d, &bar, &target, &bw, &bwc};
+  const bool has_mesh = d.prune_dist > 0.0;
+#if MT_A_SMEM
+  const void* f_a = (const void*)k_step_a_s;
+  const dim3 grid_a((unsigned)((cover + MT_AS_BLOCK - 1) / MT_AS_BLOCK)), block_a(MT_AS_BLOCK);
+#else
+  const void* f_a = (const void*)k_step_a;
+  const dim3 grid_a((unsigned)((cover + MT_A_BLOCK - 1) / MT_A_BLOCK)), block_a(MT_A_BLOCK);
+#endif
+  // configuration key: everything that is baked into the graph's topology or launch geometry
+  unsigned long long key[20] = {(unsigned long long)a->d_soa_cur, (unsigned long long)a->d_soa_next, (unsigned long long)a->d_nn_cur,
+                                (unsigned long long)a->d_nn_next, (unsigned long long)a->d_anc, (unsigned long long)a->stride,
+                                (unsigned long long)cover, (unsigned long long)has_mesh, (unsigned long long)a->world,
+                                (unsigned long long)d_q, (unsigned long long)q_dtype, (unsigned long long)c->d_emb,
+                                (unsigned long long)c->emb_dtype, (unsigned long long)grid_bw, (unsigned long long)Q.grid,
+                                (unsigned long long)c->M, (unsigned long long)c->D, 0, 0, 0};
+  if (!c->graphs) {
+    c->graphs = new StepGraph[MT_STEP_GRAPHS];
+    memset(c->graphs, 0, sizeof(StepGraph) * MT_STEP_GRAPHS);
+  }
+  StepGraph* G = nullptr;
+  for (int k = 0; k < MT_STEP_GRAPHS; ++k)
+    if (c->graphs[k].valid && !memcmp(c->graphs[k].key, key, sizeof(key))) G = &c->graphs[k];
+  auto kparams = [](const void* f, dim3 g, dim3 b, size_t sm, void** args) {
+    cudaKernelNodeParams p;
+    memset(&p, 0, sizeof(p));
+    p.func = (void*)f, p.gridDim = g, p.blockDim = b, p.sharedMemBytes = (unsigned)sm, p.kernelParams = args, p.extra = nullptr;
+    return p;
+  };
+  cudaKernelNodeParams P_q = kparams(Q.func, dim3(Q.grid), dim3(256), Q.smem, args_q);
+  cudaKernelNodeParams P_a = kparams(f_a, grid_a, block_a, 0, args_a);
+  cudaKernelNodeParams P_m1 = kparams((const void*)k_step_meshq, dim3(c->sm_count * 4), dim3(256), 0, args_m);
+  cudaKernelNodeParams P_m2 = kparams((const void*)k_step_meshq2, dim3(c->sm_count * 8), dim3(256), 0, args_m);
+  cudaKernelNodeParams P_n = kparams((const void*)k_step_nnq, dim3(c->sm_count * 12), dim3(32 * MT_NNQ_WARPS), 0, args_a);
+  cudaKernelNodeParams P_b = kparams((const void*)k_step_bw, dim3(grid_bw), dim3(256), 0, args_bw);
+  if (!G) {
+    G = &c->graphs[c->graph_next];
+    c->graph_next = (c->graph_next + 1) % MT_STEP_GRAPHS;
+    if (G->valid) {
+      cudaGraphExecDestroy(G->exec);
+      cudaGraphDestroy(G->graph);
+      G->valid = false;
+    }
+    CK(cudaGraphCreate(&G->graph, 0));
+    CK(cudaGraphAddKernelNode(&G->n_query, G->graph, nullptr, 0, &P_q));
+    CK(cudaGraphAddKernelNode(&G->n_a, G->graph, nullptr, 0, &P_a));
+    std::vector<cudaGraphNode_t> deps_bw = {G->n_query};
+    if (has_mesh) {
+      CK(cudaGraphAddKernelNode(&G->n_meshq, G->graph, &G->n_a, 1, &P_m1));
+      CK(cudaGraphAddKernelNode(&G->n_meshq2, G->graph, &G->n_meshq, 1, &P_m2));
+      deps_bw.push_back(G->n_meshq2);
+    }
+    CK(cudaGraphAddKernelNode(&G->n_nnq, G->graph, &G->n_a, 1, &P_n));
+    deps_bw.push_back(G->n_nnq);
+    CK(cudaGraphAddKernelNode(&G->n_bw, G->graph, deps_bw.data(), deps_bw.size(), &P_b));
+    cudaKernelNodeAttrValue coop;
+    memset(&coop, 0, sizeof(coop));
+    coop.cooperative = 1;
+    CK(cudaGraphKernelNodeSetAttribute(G->n_bw, cudaKernelNodeAttributeCooperative, &coop));
+    CK(cudaGraphInstantiate(&G->exec, G->graph, 0));
+    memcpy(G->key, key, sizeof(key));
+    G->has_mesh = has_mesh;
+    G->valid = true;
+  } else {
+    CK(cudaGraphExecKernelNodeSetParams(G->exec, G->n_a, &P_a));
+    if (G->has_mesh) {
+      CK(cudaGraphExecKernelNodeSetParams(G->exec, G->n_meshq, &P_m1));
+      CK(cudaGraphExecKernelNodeSetParams(G->exec, G->n_meshq2, &P_m2));
+    }
+    CK(cudaGraphExecKernelNodeSetParams(G->exec, G->n_nnq, &P_n));
+    CK(cudaGraphExecKernelNodeSetParams(G->exec, G->n_bw, &P_b));
+  }
+  CK(cudaGraphLaunch(G->exec, st));
+  c->bar_target = target;
+  if (d.world > 1) c->xchg_count += 1;
+  c->graph_replays += 1;
+  return MT_OK;
+}
+
+extern "C" int mt_step_graph_info(mt_ctx* c, long long* h_replays, int* h_cached) {
+  if (!c) return set_err(MT_ERR_ARG, "mt_step_graph_info: null");
+  if (h_replays) *h_replays = (long long)c->graph_replays;
+  if (h_cached) {
+    int n = 0;
+    for (int k = 0; c->graphs && k < MT_STEP_GRAPHS; ++k) n += c->graphs[k].valid;
+    *h_cached = n;
+  }
+  return MT_OK;
+}
+
 __global__ void k_step_weights(StepDev p, double* __restrict__ w) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (p.n_in ? *p.n_in : p.n)) return;
+  if (i >= step_count(p)) return;
   double S = 0.0;
   if (p.world > 1)
     for (int r = 0; r < p.world; ++r) S += p.shard_sums[r];
@@ -2374,7 +2616,7 @@ extern "C" int mt_step_weights(mt_ctx* c, const mt_step_args* a, double* d_w, vo
   int r = fill_step(c, a, &d);
   if (r) return r;
   if (!d_w || !a->d_nn_cur) return set_err(MT_ERR_ARG, "mt_step_weights: null");
-  k_step_weights<<<(unsigned)((a->n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d, d_w);
+  k_step_weights<<<(unsigned)((step_cover(a) + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d, d_w);
   CK_LAUNCH();
   return MT_OK;
 }

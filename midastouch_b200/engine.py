@@ -59,6 +59,7 @@ class FilterEngine:
         self.capacity = int(capacity)
         codebook.ctx.ensure_capacity(self.capacity)
         self.ctx = codebook.ctx
+        self._ctx_gen = self.ctx.generation  # the engine caches addresses inside the context (see _refresh_ctx)
         self.sig_t, self.sig_r, self.seed = float(sig_t), float(sig_r), int(seed)
         # drift pruning (remove_invalid_particles): needs the down-sampled mesh vertices
         self.pen_max = float(pen_max)
@@ -83,7 +84,9 @@ class FilterEngine:
         call("mt_step_local_sum_ptr", self.ctx.h, C.byref(p))
         self._local_sum_ptr = p.value
         self._a = StepArgs()
-        # the codebook query runs on a side stream, concurrently with motion + SE3_NN
+        # one library call per step; the step's kernels are replayed from a CUDA graph (query | motion + SE3_NN ->
+        # queue consumers -> cooperative resampling kernel) whenever the step runs in its fused form
+        self.use_graph = True
         self.overlap_query = True
         self.rebalance_every = 64  # sharded runs: even the shards out every this many steps (0 = never)
         self.fuse_sums = True  # single GPU: weight sums + resampling as one cooperative kernel
@@ -95,6 +98,23 @@ class FilterEngine:
         self.peer_exchange = False
         if self.world > 1:
             self.connect_peers()
+
+    def _refresh_ctx(self):
+        """The shared context of a codebook is re-created when a later user needs more capacity
+        (Context.ensure_capacity): addresses cached from the old one (local weight sum, peer mappings) are stale.
+        Single GPU: re-query them.  Sharded: the peers hold mappings of the old exchange buffer, which only a collective
+        connect_peers() on every rank can renew -- raise rather than read freed memory."""
+        if self._ctx_gen == self.ctx.generation:
+            return
+        if self.world > 1:
+            raise MidasError("the codebook's context was re-created (a later engine needed more capacity) while a sharded FilterEngine "
+                             "was using it: create the largest engine first, or call connect_peers() on every rank")
+        p = C.c_void_p()
+        call("mt_step_local_sum_ptr", self.ctx.h, C.byref(p))
+        self._local_sum_ptr = p.value
+        if self.prune:
+            pass  # Context.ensure_capacity re-uploads the mesh itself
+        self._ctx_gen = self.ctx.generation
 
     def connect_peers(self) -> bool:
         """sharded runs: exchange the CUDA IPC handles of the contexts' exchange buffers (one 64-byte
@@ -121,6 +141,7 @@ class FilterEngine:
             ok.zero_()
         dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)  # all ranks take the same path
         self.peer_exchange = bool(ok.item())
+        self._ctx_gen = self.ctx.generation
         return self.peer_exchange
 
     # ------------------------------------------------------------------ state in / out
@@ -175,6 +196,7 @@ class FilterEngine:
     def count(self) -> int:
         if self.use_n_dev:
             self.n = int(self.n_dev[self.cur].item())
+            self.check()
         return self.n
 
     def nn_idx(self) -> torch.Tensor:
@@ -224,13 +246,13 @@ class FilterEngine:
         prune: apply remove_invalid_particles (needs mesh_vertices at construction)."""
         if self.n == 0:
             raise MidasError("step: no particles loaded")
+        self._refresh_ctx()
         if u is None:
             u = float(torch.rand(1, generator=self._rng).item())
-        if code.is_cuda:
-            q = code.reshape(-1).contiguous()
-        else:  # H2D of the step's only per-frame input (D*8 bytes)
-            self.q_dev.copy_(code.reshape(-1).to(torch.float64), non_blocking=True)
-            q = self.q_dev
+        # the code goes into the engine's own buffer (H2D for a host tensor: the step's only per-frame tensor input,
+        # D*8 bytes): the step graph is keyed on that address
+        self.q_dev.copy_(code.reshape(-1), non_blocking=True)
+        q = self.q_dev
         odom16 = odom if isinstance(odom, Odom16) else prepare_odom(odom)
         gt_h = None
         if gt is not None:
@@ -240,35 +262,34 @@ class FilterEngine:
         a = self._fill(odom16, u, tn, rot, gt_h, softmax, prune, resample)
         with torch.cuda.device(self.dev):
             s = stream_ptr()
-            if self.overlap_query:
-                main = torch.cuda.current_stream()
-                self._ev_free.record(main)       # the previous step's readers of the weight table are done
-                self._side.wait_event(self._ev_free)
-                q.record_stream(self._side)
-                call("mt_codebook_query", self.ctx.h, ptr(q), dtype_code(q), 0, self._side.cuda_stream)
-                self._ev_table.record(self._side)
-                a.table_ready_event = self._ev_table.cuda_event
-            else:
-                a.table_ready_event = None
-                call("mt_codebook_query", self.ctx.h, ptr(q), dtype_code(q), 0, s)
-            call("mt_step_a", self.ctx.h, C.byref(a), s)
+            fused = C.c_int(1)
             if self.world > 1:
-                fused = C.c_int(0)
                 call("mt_step_is_fused", self.ctx.h, C.byref(a), C.byref(fused))
-                if not fused.value:
-                    self._allgather_sums()
-            if resample:
+            if fused.value or not resample:
+                # query (side stream / graph branch) + motion + SE3_NN + queue consumers + resampling: ONE call
+                call("mt_step", self.ctx.h, C.byref(a), ptr(q), dtype_code(q), int(self.use_graph and resample), s)
+            else:  # peers not mappable: sums -> NCCL all-gather (8 bytes / GPU) -> resampling
+                call("mt_codebook_query", self.ctx.h, ptr(q), dtype_code(q), 0, s)
+                call("mt_step_a", self.ctx.h, C.byref(a), s)
+                self._allgather_sums()
                 call("mt_step_b", self.ctx.h, C.byref(a), s)
         if resample:
             self.cur = 1 - self.cur
             if self.world > 1:
+                # the children of this GPU's parents: the count lives on the device from now on (the grids cover the
+                # whole capacity, an overflow raises MT_STAT_OVERFLOW, checked in count() / rebalance())
                 self.use_n_dev = True
-                # children per GPU drift slowly; keep the host-side bound (grid size) safe and even the
-                # shards out before the bound reaches the capacity
-                self.n = min(self.capacity, self.n + max(64, self.n // 1024))
                 if self.rebalance_every and (self.t + 1) % self.rebalance_every == 0:
                     self.rebalance()
         self.t += 1
+
+    def check(self):
+        """raise if a step overflowed the particle buffers or a peer's weight sum never arrived (synchronises)"""
+        st = self.ctx.stats()
+        if st["overflow"] == 1:
+            raise MidasError("FilterEngine: a shard outgrew the engine capacity (children were dropped); rebalance more often or raise the capacity")
+        if st["overflow"] == 2:
+            raise MidasError("FilterEngine: a peer's weight sum never arrived in the fused exchange (10 s); that step kept its particles")
 
     def rebalance(self):
         """sharded runs: children follow their parents, so a GPU whose particles carry more weight
@@ -279,7 +300,7 @@ class FilterEngine:
             return
         import torch.distributed as dist
 
-        n = self.count()
+        n = self.count()  # (also raises on overflow / exchange time-out)
         counts = torch.zeros(self.world, dtype=torch.int64, device=self.dev)
         dist.all_gather_into_tensor(counts, self.n_dev[self.cur].reshape(1), group=self.group)
         counts = counts.cpu().tolist()

@@ -20,7 +20,22 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("MIDAS_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _ref_root() -> str:
+    """the reference tree when it is present (build container), else the verbatim copies of its two hot-path
+    modules under oracle/_ref (made by oracle/build_ref.py; what travels to the GPU box)"""
+    env = os.environ.get("MIDAS_REFERENCE_ROOT")
+    if env:
+        return env
+    for cand in ("/root/reference", os.path.join(_HERE, "_ref")):
+        if os.path.isfile(os.path.join(cand, "midastouch/modules/particle_filter.py")):
+            return cand
+    return "/root/reference"
+
+
+REF_ROOT = _ref_root()
 
 
 def reference_available() -> bool:
