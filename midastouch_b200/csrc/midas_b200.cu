@@ -87,6 +87,7 @@ struct mt_ctx {
   double* d_mesh_verts;
   float4* d_mesh_verts32;
   int* d_mesh_vox;
+  unsigned* d_mesh_vox2;
   MeshVoxels vox;
   int* d_mesh_cells;
   MeshGrid mesh;
@@ -199,6 +200,7 @@ extern "C" int mt_ctx_destroy(mt_ctx* c) {
   cudaFree(c->d_mesh_verts);
   cudaFree(c->d_mesh_verts32);
   cudaFree(c->d_mesh_vox);
+  cudaFree(c->d_mesh_vox2);
   cudaFree(c->d_mesh_cells);
   cudaFree(c->d_sim);
   cudaFree(c->d_esim);
@@ -361,6 +363,8 @@ extern "C" int mt_mesh_upload(mt_ctx* c, const double* h_vertices, long long V, 
   cudaFree(c->d_mesh_verts32);
   cudaFree(c->d_mesh_cells);
   cudaFree(c->d_mesh_vox);
+  cudaFree(c->d_mesh_vox2);
+  c->d_mesh_vox2 = nullptr;
   c->d_mesh_verts = nullptr, c->d_mesh_verts32 = nullptr, c->d_mesh_cells = nullptr, c->d_mesh_vox = nullptr, c->mesh_ready = false;
   memset(&c->vox, 0, sizeof(c->vox));
   CK(cudaMalloc(&c->d_mesh_verts, sizeof(double) * 3 * V));
@@ -397,8 +401,12 @@ extern "C" int mt_mesh_upload(mt_ctx* c, const double* h_vertices, long long V, 
     const float slack = (float)(4e-7 * (g.coord_max + fabs((double)vx.org[0]) + fabs((double)vx.org[1]) + fabs((double)vx.org[2])) + 1e-9);
     k_mesh_classify<<<(unsigned)((total + 255) / 256), 256>>>(T, vx, vf, slack, c->d_mesh_vox);
     CK_LAUNCH();
+    CK(cudaMalloc(&c->d_mesh_vox2, sizeof(unsigned) * (total / 16 + 1)));
+    k_mesh_pack2<<<(unsigned)((total / 16 + 256) / 256), 256>>>(c->d_mesh_vox, total, c->d_mesh_vox2);
+    CK_LAUNCH();
     CK(cudaDeviceSynchronize());
     vx.cls = c->d_mesh_vox;
+    vx.cls2 = c->d_mesh_vox2;
     c->vox = vx;
   }
   return MT_OK;
@@ -1414,8 +1422,14 @@ __global__ void __launch_bounds__(MT_A_BLOCK, MT_A_MINBLOCKS) k_step_a(StepDev p
     apply_motion(P, p.odom, t, r, O, 0, p.tn == nullptr);
     // drift test: the voxel class is one dependent 4-byte load; it is requested here so that it travels while
     // the key is computed
-    int mcls = 1, mk = -1;
+    int mcls = 1;
+    int mk = -1;
+    (void)mk;
+#if MT_MESH_DEFER && MT_VOX2
+    if (p.prune_dist > 0.0) mcls = mesh_voxel_class2(Mh, O[0][3], O[1][3], O[2][3], p.prune_dist);
+#else
     if (p.prune_dist > 0.0) mcls = mesh_voxel_class(Mh, O[0][3], O[1][3], O[2][3], p.prune_dist, &mk);
+#endif
 #if MT_STREAM_HINTS
     __stcs(p.soa_cur + i, make_float4(O[0][0], O[0][1], O[0][2], O[0][3]));
     __stcs(p.soa_cur + p.stride + i, make_float4(O[1][0], O[1][1], O[1][2], O[1][3]));
@@ -1558,8 +1572,8 @@ __global__ void __launch_bounds__(MT_AS_BLOCK, MT_AS_MINBLOCKS) k_step_a_s(StepD
     float t[3], r[3], O[3][4];
     draw_or_load_noise(p.tn, p.rot, i, p.sig_t, p.sig_r, p.seed, p.step, p.first_gid + (uint64_t)i, t, r);
     apply_motion(P, p.odom, t, r, O, 0, p.tn == nullptr);
-    int mcls = 1, mk = -1;
-    if (p.prune_dist > 0.0) mcls = mesh_voxel_class(Mh, O[0][3], O[1][3], O[2][3], p.prune_dist, &mk);
+    int mcls = 1;
+    if (p.prune_dist > 0.0) mcls = mesh_voxel_class2(Mh, O[0][3], O[1][3], O[2][3], p.prune_dist);
     store_pose_stream(p.soa_cur, p.stride, i, O);
     mt_se3_key(O, key);
     invalid = mt_pose_invalid(O);

@@ -59,6 +59,11 @@ __device__ __forceinline__ int mt_ldk(const int* a) {
   asm volatile("ld.global.nc.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(a), "l"(mt_pol_keep()));
   return v;
 }
+__device__ __forceinline__ unsigned mt_ldk(const unsigned* a) {
+  unsigned v;
+  asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(a), "l"(mt_pol_keep()));
+  return v;
+}
 __device__ __forceinline__ float mt_ldk(const float* a) {
   float v;
   asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(a), "l"(mt_pol_keep()));

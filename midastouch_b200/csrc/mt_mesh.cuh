@@ -7,6 +7,12 @@
 // sequential float64 sum of squared differences, sqrt, compare -- no FMA contraction.
 #pragma once
 #include "mt_math.cuh"
+#ifndef MT_VOX2_KEEP
+#define MT_VOX2_KEEP 0
+#endif
+#ifndef MT_VOX2
+#define MT_VOX2 1
+#endif
 
 struct MeshGrid {
   double org[3];
@@ -35,6 +41,8 @@ MT_HD int mt_mesh_cell(double x, double org, double inv_cell, int dim) {
 #define MT_VOX_OUT (-2)
 struct MeshVoxels {
   const int* cls;  // nullptr: not built
+  const unsigned* cls2;  // the same classes packed 2 bits per voxel (0 = out, 1 = in, 2 = undecided): 1/16 of the bytes,
+                         // small enough to stay in L2 -- what the particle sweep consults (nullptr: not built)
   float org[3], inv_v;
   int dims[3];
   double dist;               // the distance the classes were computed for
@@ -76,6 +84,32 @@ __device__ __forceinline__ int mesh_voxel_class(const MeshTables& T, float xf, f
 }
 
 __device__ __forceinline__ int mesh_quick(const MeshTables& T, float xf, float yf, float zf, double dist, int k);
+// Voxel class from the packed table (particle sweep): 1 = within, 0 = not within, 2 = undecided, 3 = no table.
+__device__ __forceinline__ int mesh_voxel_class2(const MeshTables& T, float xf, float yf, float zf, double dist) {
+  if (!(xf == xf) || !(yf == yf) || !(zf == zf)) return 0;
+  if (!(T.vox.cls2 && dist == T.vox.dist)) return 3;
+  const float fx = (xf - T.vox.org[0]) * T.vox.inv_v, fy = (yf - T.vox.org[1]) * T.vox.inv_v, fz = (zf - T.vox.org[2]) * T.vox.inv_v;
+  if (!(fx >= 0.f && fy >= 0.f && fz >= 0.f && fx < (float)T.vox.dims[0] && fy < (float)T.vox.dims[1] && fz < (float)T.vox.dims[2]))
+    return 0;
+  const size_t idx = ((size_t)(int)fz * T.vox.dims[1] + (int)fy) * T.vox.dims[0] + (int)fx;
+#if MT_VOX2_KEEP
+  return (int)((mt_ldk(T.vox.cls2 + (idx >> 4)) >> (2 * (unsigned)(idx & 15))) & 3u);
+#else
+  return (int)((__ldg(T.vox.cls2 + (idx >> 4)) >> (2 * (unsigned)(idx & 15))) & 3u);
+#endif
+}
+__global__ void __launch_bounds__(256) k_mesh_pack2(const int* __restrict__ cls, size_t total, unsigned* __restrict__ out) {
+  const size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w * 16 >= total) return;
+  unsigned v = 0;
+  for (int k = 0; k < 16; ++k) {
+    const size_t i = w * 16 + k;
+    const int c = i < total ? cls[i] : MT_VOX_OUT;
+    v |= (c == MT_VOX_IN ? 1u : (c == MT_VOX_OUT ? 0u : 2u)) << (2 * k);
+  }
+  out[w] = v;
+}
+
 // the search behind an undecided voxel: the remembered vertex first (k >= 0), then the uniform vertex grid.
 // Vertices are filtered in float32 (squared distance against dist^2 with a relative band that covers the
 // rounding of the float32 copies); only vertices inside the band take the exact float64 test, so the answer

@@ -238,6 +238,7 @@ __device__ __forceinline__ int load_key(const float4* __restrict__ t, int i, flo
 #ifndef MT_SCAN_PF
 #define MT_SCAN_PF 0
 #endif
+
 #ifndef MT_PF_INIT_L1
 #define MT_PF_INIT_L1 0
 #endif

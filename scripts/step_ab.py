@@ -17,6 +17,7 @@ n = int(os.environ.get("AB_N", bench.N_PER_GPU))
 eng = FilterEngine(cb, capacity=n, sig_t=2e-4, sig_r=0.5, seed=1234, mesh_vertices=obj.vertices, pen_max=0.002)
 g = torch.Generator().manual_seed(100)
 sel = torch.randint(0, bench.M, (n,), generator=g)
+eng.use_graph = bool(os.environ.get("AB_GRAPH"))
 eng.load_particles(cbs.poses.to(dev)[sel.to(dev)], nn_hint=sel.int().to(dev), spatial_sort=True)
 odoms = [prepare_odom(torch.inverse(meas[t - 1]) @ meas[t]) for t in range(1, bench.T_TRAJ)]
 codes = [synth.make_pose_query(gt[t + 1], bench.D, seed=3, frame=t).to(dev) for t in range(bench.T_TRAJ - 1)]
@@ -40,7 +41,7 @@ call("mt_ctx_set_timing_events", eng.ctx.h, None)
 def avg(lo, hi, a, b):
     return 1e3 * sum(r[a].elapsed_time(r[b]) for r in rows[lo:hi]) / (hi - lo)
 st = eng.ctx.stats(reset=True)
-out = {"lib": os.path.basename(os.environ.get("MIDAS_B200_LIB", "default"))}
+out = {"lib": os.path.basename(os.environ.get("MIDAS_B200_LIB", "default")), "graph": eng.use_graph}
 for name, (lo, hi) in {"init": (5, 55), "conv": (120, min(170, T))}.items():
     if hi <= lo: continue
     out[name] = {"step": round(avg(lo, hi, 0, 5), 1), "a": round(avg(lo, hi, 1, 2), 1), "nnq": round(avg(lo, hi, 2, 3), 1), "bw": round(avg(lo, hi, 3, 5), 1)}
