@@ -176,7 +176,9 @@ def run_ours(args):
     n = N_PER_GPU
     cap = n + (n // 8 if world > 1 else 0)
     cb.to_device(dev)
-    cb.ctx.ensure_capacity(max(cap, n * world if (world > 1 and rank == 0 and not args.no_shard_check) else cap))
+    # one context for everything this process will run on the codebook (the sharded check's single-GPU engine holds all
+    # world x 1e6 particles on rank 0): sized once, up front
+    cb.ctx.ensure_capacity(max(cap, n + n // 4 if world > 1 else cap, n * world if (world > 1 and rank == 0 and not args.no_shard_check) else cap))
     eng = FilterEngine(cb, capacity=cap, sig_t=2e-4, sig_r=0.5, seed=1234, rank=rank, world=world, n_global=n * world,
                        mesh_vertices=obj.vertices, pen_max=0.002)
     eng.use_graph = not args.no_graph

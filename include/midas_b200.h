@@ -253,11 +253,19 @@ int mt_step_b(mt_ctx* ctx, const mt_step_args* a, void* stream);
 /* normalised float64 weights of the current particles (after mt_step_a) */
 int mt_step_weights(mt_ctx* ctx, const mt_step_args* a, double* d_w, void* stream);
 
-/* ---- get_cluster_centers(method="quat_avg") (particle_filter.py:153-206, pose.py:112-147) ---- */
+/* ---- get_cluster_centers (particle_filter.py:153-206; xyz_quat_averaged pose.py:112-147, log_map_averaged 101-109) ---- */
 /* d_poses (n,4,4) float32, d_weights (n,) float64 (cast to float32 like the reference), d_labels (n,)
- * int32 cluster ids 0..K-1 (negative = ignored).  d_centers (K,4,4), d_stds (K,3) float32. */
+ * int32 cluster ids 0..K-1 (negative = ignored).  method 0 = "quat_avg" (what filter.py:184-186 passes), 1 = "logmap"
+ * (the reference's default: weighted mean of the SE(3) tangents, exponentiated).  d_centers (K,4,4), d_stds (K,3) float32. */
 int mt_cluster_centers(mt_ctx* ctx, const float* d_poses, const double* d_weights, const int32_t* d_labels, long long n, int K,
-                       float* d_centers, float* d_stds, void* stream);
+                       int method, float* d_centers, float* d_stds, void* stream);
+/* ---- cluster_particles(method="euclidean") (particle_filter.py:208-228) -------------------- */
+/* sklearn DBSCAN(eps, min_samples) on the translations of d_poses (n,4,4) float32, with sklearn's semantics: float64
+ * squared distance <= eps^2 (the point itself counts), clusters numbered by their lowest-index core point, border
+ * points to the lowest-numbered cluster in reach, noise -1.  d_labels: (n,) int64.  h_n_clusters (host, nullable):
+ * number of clusters.  Synchronises `stream` (the label propagation iterates until nothing changes). */
+int mt_dbscan(mt_ctx* ctx, const float* d_poses, long long n, double eps, long long min_samples, long long* d_labels,
+              int* h_n_clusters, void* stream);
 /* ---- annealing (particle_filter.py:405-447): order statistics of the weights ---------------- */
 /* the k smallest (largest != 0: largest) of n float64 weights: d_sel (k,) their indices in ascending
  * index order, d_keep (n-k,) the remaining indices in ascending order (either may be NULL).  Ties at

@@ -11,7 +11,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MIDAS_B200_LIB") or os.path.join(_HERE, "libmidas_b200.so")  # override: A/B builds only
 SOURCES = [os.path.join(_HERE, "csrc", "midas_b200.cu")]
-HEADERS = [os.path.join(_HERE, "csrc", "mt_math.cuh"), os.path.join(_HERE, "csrc", "mt_nn.cuh"), os.path.join(_HERE, "csrc", "mt_mesh.cuh"), os.path.join(_HERE, "csrc", "mt_tcn.cuh"), os.path.join(_HERE, "csrc", "mt_cluster.cuh"), os.path.join(_HERE, "csrc", "mt_gemm_tc.cuh"), os.path.join(_HERE, "..", "include", "midas_b200.h")]
+HEADERS = [os.path.join(_HERE, "csrc", "mt_math.cuh"), os.path.join(_HERE, "csrc", "mt_nn.cuh"), os.path.join(_HERE, "csrc", "mt_mesh.cuh"), os.path.join(_HERE, "csrc", "mt_tcn.cuh"), os.path.join(_HERE, "csrc", "mt_cluster.cuh"), os.path.join(_HERE, "csrc", "mt_dbscan.cuh"), os.path.join(_HERE, "csrc", "mt_gemm_tc.cuh"), os.path.join(_HERE, "..", "include", "midas_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -61,6 +61,7 @@ _SIGS = {
     "mt_ctx_set_timing_events": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "mt_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "mt_step_graph_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_longlong), C.POINTER(C.c_int)]),
+    "mt_dbscan": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_double, C.c_longlong, C.c_void_p, C.POINTER(C.c_int), C.c_void_p]),
     "mt_ctx_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_longlong), C.c_int]),
     "mt_mesh_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_double]),
     "mt_prune_aos": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -82,7 +83,7 @@ _SIGS = {
                                           C.c_void_p, C.c_void_p, C.c_void_p]),
     "mt_gather_soa": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_void_p]),
     "mt_gather_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]),
-    "mt_cluster_centers": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mt_cluster_centers": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mt_select_k": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mt_tcn_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "mt_tcn_destroy": (C.c_int, [C.c_void_p]),

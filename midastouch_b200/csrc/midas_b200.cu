@@ -2291,6 +2291,13 @@ extern "C" int mt_dist_import(mt_ctx* c, int rank, int world, const void* h_hand
     c->h_peers[r] = (Xchg*)ptr;
   }
   CK(cudaMemcpy(c->d_peers, c->h_peers, sizeof(Xchg*) * world, cudaMemcpyHostToDevice));
+  // Every rank (re)imports collectively, so the exchange sequence restarts everywhere: counter 0, buffer cleared (a
+  // stale word could otherwise carry a sequence number that becomes valid again).  The caller must put a barrier
+  // between this call and the first sharded step (FilterEngine.connect_peers: the all-reduce of the "ok" flag).
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemset(c->d_xchg, 0, sizeof(Xchg)));
+  CK(cudaDeviceSynchronize());
+  c->xchg_count = 0;
   c->peers_world = world;
   return MT_OK;
 }
@@ -2791,7 +2798,8 @@ static int ensure_scratch(mt_ctx* c, size_t bytes) {
 }
 
 extern "C" int mt_cluster_centers(mt_ctx* c, const float* d_poses, const double* d_weights, const int32_t* d_labels, long long n,
-                                  int K, float* d_centers, float* d_stds, void* stream) {
+                                  int K, int method, float* d_centers, float* d_stds, void* stream) {
+  if (method != 0 && method != 1) return set_err(MT_ERR_ARG, "mt_cluster_centers: method 0 (quat_avg) or 1 (logmap)");
   if (!c || !d_poses || !d_weights || !d_labels || !d_centers || !d_stds || n <= 0 || K <= 0 || K > MT_MAX_CLUSTERS)
     return set_err(MT_ERR_ARG, "mt_cluster_centers: bad argument (1 <= K <= 16)");
   CK(cudaSetDevice(c->device));
@@ -2807,9 +2815,9 @@ extern "C" int mt_cluster_centers(mt_ctx* c, const float* d_poses, const double*
   CK_LAUNCH();
   k_cluster_minmax_final<<<K, 256, 0, st>>>(mpart, nb, K, uniform);
   CK_LAUNCH();
-  k_cluster_moments<<<nb, 256, 0, st>>>((const float4*)d_poses, d_weights, d_labels, n, K, uniform, part);
+  k_cluster_moments<<<nb, 256, 0, st>>>((const float4*)d_poses, d_weights, d_labels, n, K, uniform, part, method);
   CK_LAUNCH();
-  k_cluster_final<<<K, 256, 0, st>>>(part, nb, K, d_centers, d_stds);
+  k_cluster_final<<<K, 256, 0, st>>>(part, nb, K, d_centers, d_stds, method);
   CK_LAUNCH();
   return MT_OK;
 }
@@ -2841,6 +2849,55 @@ extern "C" int mt_select_k(mt_ctx* c, const double* d_w, long long n, long long 
   CK_LAUNCH();
   k_select_scatter<<<nb, 256, 0, st>>>(d_w, n, largest, state, blk, d_sel, d_keep);
   CK_LAUNCH();
+  return MT_OK;
+}
+
+// ------------------------------------------------------------------------- cluster_particles (DBSCAN)
+#include "mt_dbscan.cuh"
+
+extern "C" int mt_dbscan(mt_ctx* c, const float* d_poses, long long n, double eps, long long min_samples, long long* d_labels,
+                         int* h_n_clusters, void* stream) {
+  if (!c || !d_poses || !d_labels || n <= 0 || !(eps > 0.0) || min_samples < 1) return set_err(MT_ERR_ARG, "mt_dbscan: bad argument");
+  if (n > 0x7fffffffLL) return set_err(MT_ERR_ARG, "mt_dbscan: indices are int32");
+  CK(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int N = (int)n, nb = (N + MT_DB_TILE - 1) / MT_DB_TILE;
+  int r = ensure_scratch(c, sizeof(float4) * (size_t)N + 3 * sizeof(int) * (size_t)N + 64);
+  if (r) return r;
+  float4* pts = (float4*)c->d_scratch;
+  int* la = (int*)(pts + N);
+  int* lb = la + N;
+  int* cid = lb + N;
+  int* ctl = cid + N;  // [0] changed, [1] clusters
+  DbTest t;
+  t.eps2 = eps * eps;
+  t.lo2 = (float)(t.eps2 * (1.0 - 1e-4));
+  t.hi2 = (float)(t.eps2 * (1.0 + 1e-4)) + 1e-30f;
+  k_db_points<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_poses, n, pts);
+  CK_LAUNCH();
+  const int ms = (int)std::min<long long>(min_samples, 0x7fffffffLL);
+  k_db_count<<<nb, MT_DB_TILE, 0, st>>>(pts, N, t, ms, la);
+  CK_LAUNCH();
+  for (int it = 0; it < 4096; ++it) {  // label propagation + pointer jumping until a pass changes nothing
+    CK(cudaMemsetAsync(ctl, 0, sizeof(int), st));
+    k_db_propagate<<<nb, MT_DB_TILE, 0, st>>>(pts, N, t, la, lb, ctl);
+    CK_LAUNCH();
+    k_db_jump<<<(N + 255) / 256, 256, 0, st>>>(lb, N);
+    CK_LAUNCH();
+    std::swap(la, lb);
+    int changed = 0;
+    CK(cudaMemcpyAsync(&changed, ctl, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (!changed) break;
+  }
+  k_db_number<<<1, 1024, 0, st>>>(la, N, cid, ctl + 1);
+  CK_LAUNCH();
+  k_db_final<<<nb, MT_DB_TILE, 0, st>>>(pts, N, t, la, cid, d_labels);
+  CK_LAUNCH();
+  if (h_n_clusters) {
+    CK(cudaMemcpyAsync(h_n_clusters, ctl + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+  }
   return MT_OK;
 }
 

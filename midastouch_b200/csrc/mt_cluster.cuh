@@ -46,6 +46,45 @@ MT_HD void mt_so3_to_quat(const float R[3][4], float q[4]) {
   q[0] = w, q[1] = sel[0] / nrm * sh, q[2] = sel[1] / nrm * sh, q[3] = sel[2] / nrm * sh;
 }
 
+// theseus SE3.log_map / SE3.exp_map restated (call sites pose.py:101-109, log_map_averaged): tangent = [v, omega] with
+// omega = Log_SO3(R) (mt_so3_log) and v = V^-1 t,  V^-1 = I - 1/2 [w]x + a [w]x^2,
+// a = (1 - theta sin(theta) / (2 (1 - cos(theta)))) / theta^2  (-> 1/12 for theta -> 0).  float32 like the reference.
+MT_HD void mt_se3_log(const float P[3][4], float out[6]) {
+  float w[3];
+  mt_so3_log(P, w);
+  const float th2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
+  const float th = sqrtf(th2);
+  float a;
+  if (th < 5e-3f) a = 1.f / 12.f + th2 / 720.f;
+  else a = (1.f - 0.5f * th * sinf(th) / (1.f - cosf(th))) / th2;
+  const float t[3] = {P[0][3], P[1][3], P[2][3]};
+  const float c1[3] = {w[1] * t[2] - w[2] * t[1], w[2] * t[0] - w[0] * t[2], w[0] * t[1] - w[1] * t[0]};      // w x t
+  const float c2[3] = {w[1] * c1[2] - w[2] * c1[1], w[2] * c1[0] - w[0] * c1[2], w[0] * c1[1] - w[1] * c1[0]};  // w x (w x t)
+#pragma unroll
+  for (int k = 0; k < 3; ++k) out[k] = t[k] - 0.5f * c1[k] + a * c2[k], out[3 + k] = w[k];
+}
+// exp of a tangent [v, omega] in float64 -> 3x4 [R|t]:  R = I + A [w]x + B [w]x^2,  t = (I + B [w]x + C [w]x^2) v,
+// A = sin(th)/th, B = (1 - cos(th))/th^2, C = (th - sin(th))/th^3
+MT_HD void mt_se3_exp(const double x[6], double T[3][4]) {
+  const double v[3] = {x[0], x[1], x[2]}, w[3] = {x[3], x[4], x[5]};
+  const double th2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2], th = sqrt(th2);
+  double A, B, C;
+  if (th < 1e-6) A = 1.0 - th2 / 6.0, B = 0.5 - th2 / 24.0, C = 1.0 / 6.0 - th2 / 120.0;
+  else A = sin(th) / th, B = (1.0 - cos(th)) / th2, C = (th - sin(th)) / (th2 * th);
+  const double K[3][3] = {{0.0, -w[2], w[1]}, {w[2], 0.0, -w[0]}, {-w[1], w[0], 0.0}};
+  double K2[3][3];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) K2[i][j] = K[i][0] * K[0][j] + K[i][1] * K[1][j] + K[i][2] * K[2][j];
+  for (int i = 0; i < 3; ++i) {
+    double t = 0.0;
+    for (int j = 0; j < 3; ++j) {
+      T[i][j] = (i == j ? 1.0 : 0.0) + A * K[i][j] + B * K2[i][j];
+      t += ((i == j ? 1.0 : 0.0) + B * K[i][j] + C * K2[i][j]) * v[j];
+    }
+    T[i][3] = t;
+  }
+}
+
 #if defined(__CUDACC__)
 // pass 1: per-cluster min / max of the float32-cast weights (block partials)
 __global__ void __launch_bounds__(256) k_cluster_minmax(const double* __restrict__ w, const int* __restrict__ label, long long n, int K,
@@ -91,7 +130,7 @@ __global__ void __launch_bounds__(256) k_cluster_minmax_final(const float* __res
 // pass 2: weighted moments per cluster (block partials, float64)
 __global__ void __launch_bounds__(256) k_cluster_moments(const float4* __restrict__ aos, const double* __restrict__ w,
                                                          const int* __restrict__ label, long long n, int K,
-                                                         const int* __restrict__ uniform, double* __restrict__ part) {
+                                                         const int* __restrict__ uniform, double* __restrict__ part, int method) {
   __shared__ double s8[8];
   const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
   double v[MT_CL_VALS];
@@ -104,13 +143,19 @@ __global__ void __launch_bounds__(256) k_cluster_moments(const float4* __restric
     wf = (float)w[i];  // weights.float() (particle_filter.py:163)
     const float4 a = aos[4 * i], b = aos[4 * i + 1], c = aos[4 * i + 2];
     const float P[3][4] = {{a.x, a.y, a.z, a.w}, {b.x, b.y, b.z, b.w}, {c.x, c.y, c.z, c.w}};
-    float q[4];
-    mt_so3_to_quat(P, q);
-    float e[4] = {q[1], q[2], q[3], q[0]};  // (x, y, z, w)
-    if (e[3] < 0.f) e[0] = -e[0], e[1] = -e[1], e[2] = -e[2], e[3] = -e[3];  // antipodal (pose.py:127)
-    int t = 0;
-    for (int r = 0; r < 4; ++r)
-      for (int s = r; s < 4; ++s) v[t++] = (double)e[r] * (double)e[s];
+    if (method == 1) {  // "logmap": weighted mean of the SE(3) tangents (log_map_averaged, pose.py:101-109)
+      float lg[6];
+      mt_se3_log(P, lg);
+      for (int r = 0; r < 6; ++r) v[r] = (double)lg[r];
+    } else {
+      float q[4];
+      mt_so3_to_quat(P, q);
+      float e[4] = {q[1], q[2], q[3], q[0]};  // (x, y, z, w)
+      if (e[3] < 0.f) e[0] = -e[0], e[1] = -e[1], e[2] = -e[2], e[3] = -e[3];  // antipodal (pose.py:127)
+      int t = 0;
+      for (int r = 0; r < 4; ++r)
+        for (int s = r; s < 4; ++s) v[t++] = (double)e[r] * (double)e[s];
+    }
     v[10] = a.w, v[11] = b.w, v[12] = c.w;
     v[13] = (double)a.w * a.w, v[14] = (double)b.w * b.w, v[15] = (double)c.w * c.w;
     v[16] = 1.0, v[17] = 1.0;
@@ -160,7 +205,7 @@ __device__ void jacobi4_dominant(double A[4][4], double vec[4]) {
 }
 
 __global__ void __launch_bounds__(256) k_cluster_final(const double* __restrict__ part, int nblocks, int K,
-                                                       float* __restrict__ poses /* K x 16 */, float* __restrict__ stds /* K x 3 */) {
+                                                       float* __restrict__ poses /* K x 16 */, float* __restrict__ stds /* K x 3 */, int method) {
   __shared__ double s8[8];
   const int k = blockIdx.x;
   double s[MT_CL_VALS];
@@ -171,6 +216,21 @@ __global__ void __launch_bounds__(256) k_cluster_final(const double* __restrict_
   }
   if (threadIdx.x) return;
   const double W = s[16];
+  const double mx = s[10] / W, my = s[11] / W, mz = s[12] / W;
+  float* P = poses + 16 * k;
+  if (method == 1) {
+    const double avg[6] = {s[0] / W, s[1] / W, s[2] / W, s[3] / W, s[4] / W, s[5] / W};
+    double T[3][4];
+    mt_se3_exp(avg, T);
+    for (int r = 0; r < 3; ++r)
+      for (int c2 = 0; c2 < 4; ++c2) P[4 * r + c2] = (float)T[r][c2];
+    P[12] = P[13] = P[14] = 0.f, P[15] = 1.f;
+    const double cx = (double)P[3], cy = (double)P[7], cz = (double)P[11];
+    stds[3 * k] = (float)sqrt(fmax(s[13] / W - 2 * cx * mx + cx * cx, 0.0));
+    stds[3 * k + 1] = (float)sqrt(fmax(s[14] / W - 2 * cy * my + cy * cy, 0.0));
+    stds[3 * k + 2] = (float)sqrt(fmax(s[15] / W - 2 * cz * mz + cz * cz, 0.0));
+    return;
+  }
   double A[4][4];
   int t = 0;
   for (int r = 0; r < 4; ++r)
@@ -180,8 +240,6 @@ __global__ void __launch_bounds__(256) k_cluster_final(const double* __restrict_
   if (e[3] < 0.0) e[0] = -e[0], e[1] = -e[1], e[2] = -e[2], e[3] = -e[3];  // pose.py:140
   const double nq = sqrt(e[0] * e[0] + e[1] * e[1] + e[2] * e[2] + e[3] * e[3]);
   const double x = e[0] / nq, y = e[1] / nq, z = e[2] / nq, w = e[3] / nq;
-  const double mx = s[10] / W, my = s[11] / W, mz = s[12] / W;
-  float* P = poses + 16 * k;
   P[0] = (float)(1 - 2 * (y * y + z * z)), P[1] = (float)(2 * (x * y - z * w)), P[2] = (float)(2 * (x * z + y * w)), P[3] = (float)mx;
   P[4] = (float)(2 * (x * y + z * w)), P[5] = (float)(1 - 2 * (x * x + z * z)), P[6] = (float)(2 * (y * z - x * w)), P[7] = (float)my;
   P[8] = (float)(2 * (x * z - y * w)), P[9] = (float)(2 * (y * z + x * w)), P[10] = (float)(1 - 2 * (x * x + y * y)), P[11] = (float)mz;

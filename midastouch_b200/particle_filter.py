@@ -158,6 +158,8 @@ class particle_filter:
             call("mt_cosine_rows", ctx.h, ptr(q), dtype_code(q), ptr(targets), dtype_code(targets), n, D, ptr(w), stream_ptr())
             if softmax:
                 call("mt_softmax_f64", ctx.h, ptr(w), n, ptr(w), stream_ptr())
+        if targets.dtype != torch.float64:  # torch.cosine_similarity returns the operands' dtype
+            w = w.to(targets.dtype)
         return w.squeeze()
 
     # ------------------------------------------------------------------ resampling (230-307)
@@ -276,11 +278,11 @@ class particle_filter:
         return sel.long(), keep.long()
 
     def get_cluster_centers(self, _particles: Particles, method: str = "logmap"):
-        """particle_filter.py:153-206 -> (cluster_poses (K,4,4), cluster_stds (K,3)) float32.  The loop
-        calls it with method="quat_avg" (filter.py:184-186); the theseus Lie-algebra average
-        ("logmap") is not implemented."""
-        if method != "quat_avg":
-            raise MidasError("get_cluster_centers: only method='quat_avg' (what filter.py uses) is implemented")
+        """particle_filter.py:153-206 -> (cluster_poses (K,4,4), cluster_stds (K,3)) float32.  method "quat_avg"
+        (what the loop passes, filter.py:184-186): Markley quaternion average; "logmap" (the reference's default):
+        weighted mean of the SE(3) tangents, exponentiated (log_map_averaged, pose.py:101-109)."""
+        if method not in ("quat_avg", "logmap"):
+            raise MidasError(f"get_cluster_centers: unknown method {method!r}")
         particles = copy.copy(_particles)
         poses = particles.poses.reshape(-1, 4, 4)
         require_cuda(poses, "particle poses")
@@ -288,19 +290,37 @@ class particle_filter:
         n = poses.shape[0]
         uniq, inv = torch.unique(particles.labels, return_inverse=True)  # the reference's torch.unique (164)
         K = int(uniq.shape[0])
-        if K > 16:
-            raise MidasError("get_cluster_centers: more than 16 clusters")
         ctx = _ctx_for(poses.device, n)
         w = particles.weights.to(torch.float64).contiguous()
-        lab = inv.to(torch.int32).contiguous()
         centers = torch.empty((K, 4, 4), dtype=torch.float32, device=poses.device)
         stds = torch.empty((K, 3), dtype=torch.float32, device=poses.device)
         with torch.cuda.device(poses.device):
-            call("mt_cluster_centers", ctx.h, ptr(poses), ptr(w), ptr(lab), n, K, ptr(centers), ptr(stds), stream_ptr())
+            for k0 in range(0, K, 16):  # the kernels reduce up to 16 clusters per pass
+                kk = min(16, K - k0)
+                lab = (inv - k0).to(torch.int32)
+                lab = torch.where((lab >= 0) & (lab < kk), lab, torch.full_like(lab, -1)).contiguous()
+                call("mt_cluster_centers", ctx.h, ptr(poses), ptr(w), ptr(lab), n, kk, int(method == "logmap"),
+                     ptr(centers[k0:k0 + kk]), ptr(stds[k0:k0 + kk]), stream_ptr())
         return centers, stds
 
     def cluster_particles(self, _particles: Particles, method: str = "euclidean", eps: float = 1e-2) -> Particles:
-        raise MidasError("cluster_particles: DBSCAN is out of scope (SURVEY 8f rank 4)")
+        """particle_filter.py:208-228: DBSCAN(eps, min_samples = N / 5) on the particle translations, sklearn's
+        semantics (labels int64, noise -1), run in the library (``mt_dbscan``).  method "logmap" (DBSCAN on the
+        theseus SE(3) tangents; no call site in the reference uses it) is not implemented."""
+        if method != "euclidean":
+            raise MidasError("cluster_particles: only method='euclidean' (the value every reference call site uses) is implemented")
+        particles = copy.copy(_particles)
+        poses = particles.poses.reshape(-1, 4, 4)
+        require_cuda(poses, "particle poses")
+        poses = poses.float().contiguous()
+        n = poses.shape[0]
+        min_samples = max(int(n / 5), 1)
+        ctx = _ctx_for(poses.device, n)
+        labels = torch.empty(n, dtype=torch.int64, device=poses.device)
+        with torch.cuda.device(poses.device):
+            call("mt_dbscan", ctx.h, ptr(poses), n, C.c_double(float(eps)), min_samples, ptr(labels), None, stream_ptr())
+        particles.labels = labels
+        return particles
 
 
 def particle_rmse(_particles, gt_pose: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:

@@ -16,7 +16,9 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = os.environ.get("MIDAS_REFERENCE_SRC", "/root/reference")
 DST = os.path.join(ROOT, "oracle", "_ref")
-FILES = ("midastouch/modules/particle_filter.py", "midastouch/modules/pose.py")
+# particle_filter.py / pose.py: the functions the CPU arm times.  filter.py: its loop statements (filter.py:150-190) are
+# extracted as text and executed verbatim on the drop-in classes by tests/test_gpu_reference_loop.py.
+FILES = ("midastouch/modules/particle_filter.py", "midastouch/modules/pose.py", "midastouch/filter/filter.py")
 
 
 def main() -> int:

@@ -154,6 +154,39 @@ def l2_sq_f32(keys: np.ndarray, q: np.ndarray) -> np.ndarray:
     return (lo + hi).astype(np.float32)
 
 
+def l2_sq_f32_sequential(keys: np.ndarray, q: np.ndarray) -> np.ndarray:
+    """squared L2 in float32 accumulated the way nanoflann's L2_Simple_Adaptor does for a 6-D point: a plain left-to-right
+    sum of (a_k - b_k)^2, every operation rounded to float32, no fused multiply-add.  Only used to COUNT how many nearest
+    neighbours would change under that order (the kernels and ``l2_sq_f32`` use two interleaved fma chains)."""
+    d = (keys.astype(np.float32) - q.astype(np.float32)).astype(np.float32)
+    acc = np.zeros(d.shape[:-1], dtype=np.float32)
+    for k in range(6):
+        acc = (acc + (d[..., k] * d[..., k]).astype(np.float32)).astype(np.float32)
+    return acc
+
+
+def nn_order_sensitivity(keys: np.ndarray, queries: np.ndarray, k: int = 4, workers: int = -1):
+    """(#queries whose argmin differs between the two float32 accumulation orders, #queries with a float32 near-tie,
+    indices under each order): the float64 k-d tree proposes the k nearest, both orders re-rank them."""
+    from scipy.spatial import cKDTree
+
+    keys = np.ascontiguousarray(keys, dtype=np.float32)
+    queries = np.ascontiguousarray(queries, dtype=np.float32)
+    tree = cKDTree(keys.astype(np.float64))
+    _, cand = tree.query(queries.astype(np.float64), k=k, workers=workers)
+
+    def pick(d):
+        dmin = d.min(axis=1, keepdims=True)
+        return np.where(d == dmin, cand, np.iinfo(np.int64).max).min(axis=1).astype(np.int64)
+
+    a = pick(l2_sq_f32(keys[cand], queries[:, None, :]))
+    b = pick(l2_sq_f32_sequential(keys[cand], queries[:, None, :]))
+    d64 = ((keys[cand].astype(np.float64) - queries[:, None, :].astype(np.float64)) ** 2).sum(-1)
+    d64.sort(axis=1)
+    near = int(((d64[:, 1] - d64[:, 0]) <= 4e-7 * d64[:, 1]).sum())
+    return int((a != b).sum()), near, a, b
+
+
 def nn_brute(keys: np.ndarray, queries: np.ndarray, chunk: int = 512) -> np.ndarray:
     """exact 1-NN by exhaustive search, ties -> lowest codebook index.  This is the
     semantics of pynanoflann.KDTree(metric="L2").kneighbors(n_neighbors=1)
@@ -437,3 +470,71 @@ def filter_step(poses, odom, tn, rot_deg, cb_keys, cb_emb, q, u, softmax=True, g
             w = torch.softmax(w, dim=0)
     anc = low_var_indices(w, u)
     return dict(moved=moved, keep=keep, nn_idx=nn_idx, weights=w, anc=anc, out_poses=moved[anc.clamp(min=0)])
+
+
+# ------------------------------------------------------------------ SE(3) log / exp (theseus, unpinned)
+def se3_log_map(poses: torch.Tensor) -> torch.Tensor:
+    """th.SE3(tensor=T[:, :3, :]).log_map() (call site pose.py:101-105) restated in closed form, float64:
+    tangent = [V^-1 t, Log_SO3(R)],  V^-1 = I - 1/2 [w]x + a [w]x^2,  a = (1 - th sin th / (2 (1 - cos th))) / th^2."""
+    P = poses.reshape(-1, 4, 4).double()
+    w = so3_log_map(P[:, :3, :3].float()).double()
+    t = P[:, :3, 3]
+    th2 = (w * w).sum(1)
+    th = th2.sqrt()
+    small = th < 5e-3
+    ths = torch.where(small, torch.ones_like(th), th)
+    a = torch.where(small, 1.0 / 12.0 + th2 / 720.0, (1.0 - 0.5 * ths * torch.sin(ths) / (1.0 - torch.cos(ths))) / (ths * ths))
+    c1 = torch.cross(w, t, dim=1)
+    c2 = torch.cross(w, c1, dim=1)
+    return torch.cat([t - 0.5 * c1 + a[:, None] * c2, w], dim=1)
+
+
+def se3_exp_map(x: torch.Tensor) -> torch.Tensor:
+    """th.SE3.exp_map(tangent_vector=x).to_matrix() (pose.py:106-109), float64, one tangent (6,) -> (4,4)."""
+    x = x.double().reshape(6)
+    v, w = x[:3], x[3:]
+    th2 = float((w * w).sum())
+    th = th2 ** 0.5
+    K = torch.tensor([[0.0, -w[2], w[1]], [w[2], 0.0, -w[0]], [-w[1], w[0], 0.0]], dtype=torch.float64)
+    if th < 1e-6:
+        A, B, Cc = 1.0 - th2 / 6.0, 0.5 - th2 / 24.0, 1.0 / 6.0 - th2 / 120.0
+    else:
+        import math
+
+        A, B, Cc = math.sin(th) / th, (1.0 - math.cos(th)) / th2, (th - math.sin(th)) / (th2 * th)
+    eye = torch.eye(3, dtype=torch.float64)
+    T = torch.eye(4, dtype=torch.float64)
+    T[:3, :3] = eye + A * K + B * (K @ K)
+    T[:3, 3] = (eye + B * K + Cc * (K @ K)) @ v
+    return T
+
+
+def log_map_averaged(poses: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    """pose.py:101-109: exp(sum_n w_n log(T_n) / sum w)."""
+    lg = se3_log_map(poses)
+    w = w.double()
+    return se3_exp_map((lg * w[:, None]).sum(0) / w.sum()).float()
+
+
+def cluster_centers_logmap(poses, weights, labels):
+    """get_cluster_centers(method="logmap") (particle_filter.py:153-206) on the restated SE(3) maps."""
+    uniq = torch.unique(labels)
+    centers = torch.zeros((len(uniq), 4, 4))
+    stds = torch.zeros((len(uniq), 3))
+    wf = weights.float()
+    for i, lab in enumerate(uniq):
+        m = labels == lab
+        tp, tw = poses[m], wf[m]
+        if torch.isclose(tw.max() - tw.min(), torch.tensor([0.0])):
+            tw = torch.ones_like(tw)
+        centers[i] = log_map_averaged(tp, tw)
+        stds[i] = torch.sqrt(torch.sum(((tp[:, :3, 3] - centers[i, :3, 3]) ** 2 * tw[:, None]) / tw.sum(), dim=0))
+    return centers, stds
+
+
+def dbscan_labels(poses: torch.Tensor, eps: float = 1e-2) -> torch.Tensor:
+    """cluster_particles(method="euclidean") (particle_filter.py:208-228): sklearn itself is the oracle."""
+    from sklearn.cluster import DBSCAN
+
+    n = poses.shape[0]
+    return torch.from_numpy(DBSCAN(eps=eps, min_samples=int(n / 5)).fit(poses[:, :3, 3].cpu().numpy()).labels_.astype("int64"))
