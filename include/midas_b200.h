@@ -196,7 +196,8 @@ typedef struct mt_step_args {
    * device) holds every rank's weight sum, written by the caller's collective between
    * mt_step_a and mt_step_b; NULL for a single GPU. */
   int rank, world;
-  long long n_global;
+  long long n_global;    /* sharded: particles over all GPUs.  Single GPU: > 0 = number of children to draw (<= stride; the
+                          * particle count changes under annealing, particle_filter.py:405-447), 0 = n */
   double* d_shard_sums;
   long long* d_n_out;    /* device (nullable): number of children written on this GPU */
   const long long* d_n_in; /* device (nullable): particle count read by the kernels instead of n (no host sync

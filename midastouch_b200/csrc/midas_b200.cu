@@ -2234,7 +2234,9 @@ static int fill_step(mt_ctx* c, const mt_step_args* a, StepDev* d) {
   d->rmse2 = a->d_rmse2;
   d->rank = a->world > 1 ? a->rank : 0;
   d->world = a->world > 1 ? a->world : 1;
-  d->n_global = a->world > 1 ? a->n_global : a->n;
+  // single GPU: n_global > 0 sets the number of children to draw (annealing changes the particle count,
+  // particle_filter.py:405-447); 0 keeps it at n
+  d->n_global = (a->world > 1 || a->n_global > 0) ? a->n_global : a->n;
   d->shard_sums = a->d_shard_sums;
   d->peers = (c->peers_world == d->world && d->world > 1) ? c->d_peers : nullptr;
   d->xseq = c->xchg_count + 1;

@@ -18,7 +18,7 @@ import ctypes as C
 import torch
 
 from ._lib import MidasError, StepArgs, call, lib, ptr, stream_ptr
-from .context import aos_to_soa, dtype_code, require_cuda, soa_to_aos
+from .context import aos_to_soa, dtype_code, require_cuda, soa_to_aos  # noqa: F401
 from .tactile_tree import tactile_tree
 
 
@@ -77,6 +77,7 @@ class FilterEngine:
         self.shard_sums = torch.zeros(max(self.world, 1), dtype=torch.float64, device=d)
         self.q_dev = torch.zeros(codebook.embeddings.shape[1], dtype=torch.float64, device=d)
         self.cur = 0
+        self._n_children = 0  # single GPU: children to draw in the next resampling (0 = as many as there are particles)
         self.n = 0  # host-side upper bound of the local particle count
         self.t = 0
         self.use_n_dev = False
@@ -226,7 +227,7 @@ class FilterEngine:
         a.gt = ptr(gt) if gt is not None else None
         a.d_rmse2 = ptr(self.rmse)
         a.rank, a.world = self.rank, self.world
-        a.n_global = int(self.n_global if self.n_global is not None else self.n)
+        a.n_global = int(self.n_global if (self.world > 1 and self.n_global is not None) else self._n_children)
         a.d_shard_sums = ptr(self.shard_sums) if self.world > 1 else None
         a.d_n_out = ptr(self.n_dev[1 - self.cur])
         a.d_n_in = ptr(self.n_dev[self.cur]) if self.use_n_dev else None
@@ -282,6 +283,90 @@ class FilterEngine:
                 if self.rebalance_every and (self.t + 1) % self.rebalance_every == 0:
                     self.rebalance()
         self.t += 1
+
+    # ------------------------------------------------------------------ the reference's loop body, particle count varying
+    def step_loop(self, code, odom, u=None, tn=None, rot=None, gt=None, softmax=True, prune=True, count=0, floor=1000,
+                  cluster_every=50, eps=1e-2):
+        """One iteration of filter.py:154-190 INCLUDING cluster_particles (every `cluster_every`-th call), get_cluster_centers
+        ("quat_avg") and annealing: the particle count shrinks / grows with the cluster variance like the reference's
+        (particle_filter.py:405-447).  Single GPU.  Same kernels as step(); between the weighting and the resampling
+        the cluster moments, the order statistic of the weights (radix select) and -- when growing -- the duplication of
+        the heaviest particles run as library calls; the variance (4 bytes) is read by the host, which takes the
+        annealing decision exactly like the reference (one synchronisation per frame, where the reference has several).
+        Shrinking is done in place: the k lightest particles are marked weightless and the resampler draws n - k
+        children, which is what removing them first gives.  Returns (cluster_poses, cluster_stds)."""
+        if self.world != 1:
+            raise MidasError("step_loop: single GPU")
+        self.step(code, odom, u=0.0, tn=tn, rot=rot, gt=gt, softmax=softmax, resample=False, prune=prune)
+        n = self.n
+        dev = self.dev
+        if not hasattr(self, "labels") or self.labels.shape[0] != self.capacity:
+            self.labels = torch.zeros(self.capacity, dtype=torch.int64, device=dev)
+            self._anneal_var, self._init_particles = None, n
+        w = self.weights()  # normalised float64, 0 for pruned particles
+        aos = soa_to_aos(self.soa[self.cur], n)
+        with torch.cuda.device(dev):
+            s = stream_ptr()
+            if cluster_every and count % cluster_every == 0:  # filter.py:182-183
+                call("mt_dbscan", self.ctx.h, ptr(aos), n, C.c_double(float(eps)), max(int(n / 5), 1), ptr(self.labels), None, s)
+            uniq, inv = torch.unique(self.labels[:n], return_inverse=True)
+            K = int(uniq.shape[0])
+            centers = torch.empty((K, 4, 4), dtype=torch.float32, device=dev)
+            stds = torch.empty((K, 3), dtype=torch.float32, device=dev)
+            for k0 in range(0, K, 16):
+                kk = min(16, K - k0)
+                lab = (inv - k0).to(torch.int32)
+                lab = torch.where((lab >= 0) & (lab < kk), lab, torch.full_like(lab, -1)).contiguous()
+                call("mt_cluster_centers", self.ctx.h, ptr(aos), ptr(w), ptr(lab), n, kk, 0, ptr(centers[k0:k0 + kk]), ptr(stds[k0:k0 + kk]), s)
+        var = float(torch.mean(stds).item())  # the frame's one host read
+        # ---- annealing (particle_filter.py:405-447), decision on the host like the reference
+        n_children = n
+        if self._anneal_var is None:
+            self._anneal_var, self._init_particles = var, n
+        elif var != 0.0:
+            ratio = var / self._anneal_var
+            self._anneal_var = var
+            if ratio < 1:
+                num = min(int((1.0 - ratio) * n), abs(n - floor), n // 3)
+                if num:
+                    sel = torch.empty(num, dtype=torch.int32, device=dev)
+                    with torch.cuda.device(dev):
+                        call("mt_select_k", self.ctx.h, ptr(w), n, num, 0, ptr(sel), None, stream_ptr())
+                    nn = self.nn[self.cur]
+                    v = nn[sel.long()]
+                    nn[sel.long()] = torch.where(v >= 0, -(v + 2), v)  # weightless: the resampler gives them no children
+                    n_children = n - num
+            elif ratio > 1:
+                num = min(int((ratio - 1.0) * n), n // 3)
+                if num and num + n <= self._init_particles and num + n <= self.capacity:
+                    sel = torch.empty(num, dtype=torch.int32, device=dev)
+                    with torch.cuda.device(dev):
+                        call("mt_select_k", self.ctx.h, ptr(w), n, num, 1, ptr(sel), None, stream_ptr())
+                    sl = sel.long()
+                    soa, nn = self.soa[self.cur], self.nn[self.cur]
+                    soa[:, n:n + num] = soa[:, sl]  # Particles.add: duplicates appended in index order
+                    nn[n:n + num] = nn[sl]
+                    self.labels[n:n + num] = self.labels[sl]
+                    n = n + num
+                    n_children = n
+                    self.n = n
+                    self.n_dev[self.cur].fill_(n)
+        if u is None:
+            u = float(torch.rand(1, generator=self._rng).item())
+        # ---- resampling of the annealed set: n_children systematic draws
+        self._n_children = n_children
+        odom16 = odom if isinstance(odom, Odom16) else prepare_odom(odom)
+        a = self._fill(odom16, u, tn, rot, None, softmax, prune, True)
+        a.step = self.t - 1
+        with torch.cuda.device(dev):
+            call("mt_step_b", self.ctx.h, C.byref(a), stream_ptr())
+        self._n_children = 0
+        self.cur = 1 - self.cur
+        anc = self.anc[:n_children].long()
+        self.labels[:n_children] = self.labels[anc]
+        self.n = n_children
+        self.n_dev[self.cur].fill_(n_children)
+        return centers, stds
 
     def check(self):
         """raise if a step overflowed the particle buffers or a peer's weight sum never arrived (synchronises)"""

@@ -9,10 +9,12 @@ come from a callable (the TCN, or precomputed codes), everything else is the ref
     cluster_poses, cluster_stds = pf.get_cluster_centers(particles, "quat_avg")               (184-186)
     particles = pf.annealing(particles, mean(cluster_stds)); particles = pf.resampler(...)    (189-190)
 
-with two deliberate differences: the frame index follows a fixed schedule instead of wall-clock pacing
-(134-139; reproducible), and DBSCAN re-clustering every 50 frames (182-183) is not run (labels stay 0).
-``filter_stats`` has the reference's keys (99-116).  ``run_filter_engine`` is the same loop on the
-resident FilterEngine (fixed N, systematic resampling, everything on the GPU)."""
+    count % 50 == 0: particles = pf.cluster_particles(particles)                                (182-183)
+
+with one deliberate difference: the frame index follows a fixed schedule instead of wall-clock pacing (134-139;
+reproducible).  ``filter_stats`` has the reference's keys (99-116).  ``run_filter_engine`` is the same loop on the
+resident FilterEngine: ``step_loop`` (cluster centres + annealing, varying particle count) or, with anneal=False, the
+fixed-N ``step`` replayed from a CUDA graph."""
 from __future__ import annotations
 
 import time
@@ -37,7 +39,7 @@ def run_filter(cfg, pf: particle_filter, codebook, code_fn, gt_p: torch.Tensor, 
     resample = resample or getattr(cfg.expt.params, "resample", "weighted_random")
     schedule = list(range(gt_p.shape[0])) if schedule is None else list(schedule)
     stats = _new_stats(cfg, pf, codebook, len(schedule), N)
-    prev_idx, particles = 0, None
+    prev_idx, particles, count = 0, None, 0
     for idx in schedule:
         t0 = time.time()
         code = code_fn(idx)
@@ -55,6 +57,8 @@ def run_filter(cfg, pf: particle_filter, codebook, code_fn, gt_p: torch.Tensor, 
         particles, drifted = pf.remove_invalid_particles(particles)
         if drifted:
             particles.poses, _, _ = codebook.SE3_NN(particles.poses)
+        if count % 50 == 0:
+            particles = pf.cluster_particles(particles)
         cluster_poses, cluster_stds = pf.get_cluster_centers(particles, method="quat_avg")
         particles = pf.annealing(particles, torch.mean(cluster_stds), floor=floor)
         particles = pf.resampler(particles, resample=resample)
@@ -64,39 +68,56 @@ def run_filter(cfg, pf: particle_filter, codebook, code_fn, gt_p: torch.Tensor, 
         stats["time"].append(time.time() - t0)
         stats["total_time"] = sum(stats["time"])
         prev_idx = idx
+        count += 1
     stats["avg_time"] = stats["total_time"] / max(len(schedule), 1)
     return stats
 
 
 def run_filter_engine(cfg, pf: particle_filter, codebook, code_fn, gt_p: torch.Tensor, meas_p: torch.Tensor, schedule=None,
-                      softmax: bool = True, seed: int = 0) -> dict:
-    """same loop on the resident engine: one ``FilterEngine.step`` per frame (motion + SE3_NN + weights +
-    prune + systematic resampling), particle count fixed, no host synchronisation inside the loop (the
-    RMSE values are read back once at the end)."""
+                      softmax: bool = True, seed: int = 0, anneal: bool = True, floor: int = 1000, teacher_forced: bool = True) -> dict:
+    """same loop on the resident engine.  anneal=True (default): one ``FilterEngine.step_loop`` per frame = the reference's
+    whole loop body, cluster_particles every 50th frame, cluster centres and annealing included, so the particle count
+    follows the cluster variance like ``run_filter``'s.  teacher_forced: motion noise and the systematic offset are
+    drawn exactly like the drop-in classes draw them (CPU default generator / CUDA generator), which makes the two
+    loops comparable frame by frame; otherwise the engine's in-kernel Philox noise.  anneal=False: fixed particle
+    count, ``FilterEngine.step`` (one CUDA-graph replay per frame, no host synchronisation inside the loop)."""
     N = int(cfg.expt.params.num_particles)
     schedule = list(range(gt_p.shape[0])) if schedule is None else list(schedule)
     stats = _new_stats(cfg, pf, codebook, len(schedule), N)
     eng = FilterEngine(codebook, capacity=N, sig_t=pf.motion_noise["sig_t"], sig_r=pf.motion_noise["sig_r"], seed=seed,
                        mesh_vertices=pf.mesh_vertices_ds, pen_max=pf.pen_max)
+    dev = gt_p.device
     gt_h, meas_h = gt_p.detach().float().cpu(), meas_p.detach().float().cpu()
-    rm = torch.zeros((len(schedule), 2), dtype=torch.float32, device=gt_p.device)
-    prev_idx = 0
+    rm = torch.zeros((len(schedule), 2), dtype=torch.float32, device=dev)
+    prev_idx, count = 0, 0
     t_start = time.time()
     for k, idx in enumerate(schedule):
         code = code_fn(idx)
+        tn = rot = None
         if prev_idx > 0:
             odom = torch.inverse(meas_h[prev_idx]) @ meas_h[idx]
-            eng.step(code, odom, gt=gt_h[idx], softmax=softmax)
+            if teacher_forced:  # the draws of particle_filter.add_noise_to_odom (326-335): translation first, CPU generator
+                n = eng.n
+                tn = torch.normal(mean=0.0, std=pf.motion_noise["sig_t"], size=(n, 3)).to(dev)
+                rot = torch.normal(mean=0.0, std=pf.motion_noise["sig_r"], size=(n, 3)).to(dev)
         else:
             parts = pf.init_filter(gt_p[idx], N)
             eng.load_particles(parts.poses)
             eng.snap_to_codebook()
             # frame without motion: weights + resampling only (identity odometry, no noise)
-            z = torch.zeros((N, 3), dtype=torch.float32, device=gt_p.device)
-            eng.step(code, torch.eye(4), tn=z, rot=z, gt=gt_h[idx], softmax=softmax)
+            odom = torch.eye(4)
+            tn = rot = torch.zeros((N, 3), dtype=torch.float32, device=dev)
+        u = float(torch.rand(1, device=dev).item()) if teacher_forced else None  # particle_filter.py:260
+        if anneal:
+            cluster_poses, cluster_stds = eng.step_loop(code, odom, u=u, tn=tn, rot=rot, gt=gt_h[idx], softmax=softmax, count=count, floor=floor)
+            stats["cluster_poses"].append(cluster_poses)
+            stats["cluster_stds"].append(cluster_stds)
+        else:
+            eng.step(code, odom, u=u, tn=tn, rot=rot, gt=gt_h[idx], softmax=softmax)
         rm[k].copy_(eng.rmse)
-        stats["num_particles"].append(N)
+        stats["num_particles"].append(eng.n)
         prev_idx = idx
+        count += 1
     rm = rm.cpu()
     stats["rmse_t"], stats["rmse_r"] = rm[:, 0].tolist(), rm[:, 1].tolist()
     stats["total_time"] = time.time() - t_start

@@ -779,13 +779,27 @@ def test_filter_loop_dropin_and_engine_converge(mt, dev, box):
     assert st["traj_size"] == 80 and st["tree_size"] == 20000 and st["log_id"] == "00"
     assert st["rmse_t"][0] > 0.03 and st["rmse_t"][-1] < 0.012, (st["rmse_t"][0], st["rmse_t"][-1])
     assert 5000 <= st["num_particles"][-1] <= 20000 and st["cluster_poses"][-1].shape == (1, 4, 4)
+    # the resident engine running the same loop body (cluster centres + annealing, varying particle count), teacher-forced
+    # with the drop-in's own random draws: same particle-count trajectory, same convergence
     torch.manual_seed(0)
-    pf2 = mt.pf.particle_filter(cfg, box.vertices, downsample=1)
-    # the engine keeps N fixed (no annealing = less selection pressure): it needs ~70 frames where the
-    # reference sequence needs ~45
-    se = run_filter_engine(cfg, pf2, cb, code_fn, gt.to(dev), meas.to(dev))
+    torch.cuda.manual_seed(0)
+    st0 = run_filter(cfg, mt.pf.particle_filter(cfg, box.vertices, downsample=1), cb, lambda i: code_fn(i).to(dev), gt.to(dev), meas.to(dev),
+                     floor=5000, resample="low_var")
+    torch.manual_seed(0)
+    torch.cuda.manual_seed(0)
+    se = run_filter_engine(cfg, mt.pf.particle_filter(cfg, box.vertices, downsample=1), cb, code_fn, gt.to(dev), meas.to(dev), floor=5000)
     assert se["rmse_t"][0] > 0.03 and se["rmse_t"][-1] < 0.012, (se["rmse_t"][0], se["rmse_t"][-1])
+    a, b = np.array(st0["num_particles"]), np.array(se["num_particles"])
+    assert a.shape == b.shape and b.min() >= 5000 and b[-1] < 20000
+    assert np.abs(a - b).max() <= 0.02 * 20000, (a.tolist(), b.tolist())  # identical up to rare float64 weight ties
+    first = lambda r: next(i for i, x in enumerate(r) if x < 0.012)  # noqa: E731
+    assert abs(first(st0["rmse_t"]) - first(se["rmse_t"])) <= 3, (first(st0["rmse_t"]), first(se["rmse_t"]))
     assert se["engine"].ctx.stats()["overflow"] == 0
+    # fixed-N form (one CUDA-graph replay per frame, in-kernel noise)
+    torch.manual_seed(0)
+    sf = run_filter_engine(cfg, mt.pf.particle_filter(cfg, box.vertices, downsample=1), cb, code_fn, gt.to(dev), meas.to(dev), anneal=False,
+                           teacher_forced=False)
+    assert sf["rmse_t"][0] > 0.03 and sf["rmse_t"][-1] < 0.012 and set(sf["num_particles"]) == {20000}
 
 
 def test_sharded_engine_matches_single_gpu():
