@@ -11,7 +11,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MIDAS_B200_LIB") or os.path.join(_HERE, "libmidas_b200.so")  # override: A/B builds only
 SOURCES = [os.path.join(_HERE, "csrc", "midas_b200.cu")]
-HEADERS = [os.path.join(_HERE, "csrc", "mt_math.cuh"), os.path.join(_HERE, "csrc", "mt_nn.cuh"), os.path.join(_HERE, "csrc", "mt_mesh.cuh"), os.path.join(_HERE, "csrc", "mt_tcn.cuh"), os.path.join(_HERE, "csrc", "mt_cluster.cuh"), os.path.join(_HERE, "csrc", "mt_dbscan.cuh"), os.path.join(_HERE, "csrc", "mt_gemm_tc.cuh"), os.path.join(_HERE, "..", "include", "midas_b200.h")]
+HEADERS = [os.path.join(_HERE, "csrc", "mt_math.cuh"), os.path.join(_HERE, "csrc", "mt_nn.cuh"), os.path.join(_HERE, "csrc", "mt_mesh.cuh"), os.path.join(_HERE, "csrc", "mt_tcn.cuh"), os.path.join(_HERE, "csrc", "mt_cluster.cuh"), os.path.join(_HERE, "csrc", "mt_dbscan.cuh"), os.path.join(_HERE, "csrc", "mt_gemm_tma.cuh"), os.path.join(_HERE, "..", "include", "midas_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

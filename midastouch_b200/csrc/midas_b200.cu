@@ -10,6 +10,7 @@
 //   k_nn_grid/brute    standalone SE3_NN index search
 //   k_resample_*       systematic resampling of explicit float64 weights
 //   small: converters, gathers, rmse, softmax
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <float.h>
 #include <limits.h>
@@ -122,6 +123,10 @@ struct mt_ctx {
   double* d_scal;     // [0] local weight sum, [1] max, [2] min, [3] softmax denom, [4..7] spare
   unsigned int* d_ticket;
   int* d_flags;  // MT_STAT_* slots (include/midas_b200.h)
+  // batched query: float32 split planes of the codebook (big = TF32-exact part, small = remainder) + their TMA maps
+  float *d_plane_big, *d_plane_small;
+  CUtensorMap tm_a_big, tm_a_small;
+  bool planes_ready;
   // mt_step: the codebook query runs on a side stream (or as a parallel branch of the step's CUDA graph)
   cudaStream_t side;
   cudaEvent_t ev_fork, ev_join;
@@ -197,6 +202,8 @@ extern "C" int mt_ctx_destroy(mt_ctx* c) {
   cudaFree(c->d_sorted_orig);
   cudaFree(c->d_bvh);
   cudaFree(c->d_nbr);
+  cudaFree(c->d_plane_big);
+  cudaFree(c->d_plane_small);
   cudaFree(c->d_mesh_verts);
   cudaFree(c->d_mesh_verts32);
   cudaFree(c->d_mesh_vox);
@@ -263,6 +270,7 @@ extern "C" int mt_codebook_upload(mt_ctx* c, const float* h_keys, const void* d_
   c->d_emb = d_emb;
   c->emb_dtype = emb_dtype;
   c->rnorm_ready = false;
+  c->planes_ready = false;
   c->query_blocks_per_sm = 0;
   c->cb_ready = true;
   return MT_OK;
@@ -2753,8 +2761,9 @@ extern "C" int mt_resample_multinomial(mt_ctx* c, const double* d_w, long long n
 }
 
 // ------------------------------------------------------------------------- batched codebook query (tensor cores)
-#include "mt_gemm_tc.cuh"
+#include "mt_gemm_tma.cuh"
 
+static int ensure_scratch(mt_ctx* c, size_t bytes);
 extern "C" int mt_codebook_query_batched(mt_ctx* c, const float* d_Q, int nq, float* d_out, void* stream) {
   if (!c || !c->cb_ready || !c->d_emb) return set_err(MT_ERR_STATE, "mt_codebook_query_batched: no codebook");
   if (!d_Q || !d_out || nq <= 0) return set_err(MT_ERR_ARG, "mt_codebook_query_batched: bad argument");
@@ -2771,18 +2780,40 @@ extern "C" int mt_codebook_query_batched(mt_ctx* c, const float* d_Q, int nq, fl
     CK_LAUNCH();
     c->rnorm_ready = true;
   }
-  const size_t sh = sizeof(float) * 4 * TC_TILE_FLOATS;  // 64 KB: A/B tiles, big + small parts
+  if (!c->planes_ready) {  // split planes of the codebook: once per upload
+    cudaFree(c->d_plane_big), cudaFree(c->d_plane_small);
+    c->d_plane_big = c->d_plane_small = nullptr;
+    CK(cudaMalloc(&c->d_plane_big, sizeof(float) * (size_t)M * D));
+    CK(cudaMalloc(&c->d_plane_small, sizeof(float) * (size_t)M * D));
+    if (e32)
+      k_split_planes<float><<<(M + 7) / 8, 256, 0, st>>>((const float*)c->d_emb, M, D, c->d_plane_big, c->d_plane_small, nullptr);
+    else
+      k_split_planes<double><<<(M + 7) / 8, 256, 0, st>>>((const double*)c->d_emb, M, D, c->d_plane_big, c->d_plane_small, nullptr);
+    CK_LAUNCH();
+    if (!g2_make_map(&c->tm_a_big, c->d_plane_big, M, D) || !g2_make_map(&c->tm_a_small, c->d_plane_small, M, D))
+      return set_err(MT_ERR_CUDA, "mt_codebook_query_batched: cuTensorMapEncodeTiled failed");
+    c->planes_ready = true;
+  }
+  // planes + norms of the queries (per call)
+  const size_t qbytes = sizeof(float) * (size_t)nq * D;
+  int r = ensure_scratch(c, 2 * qbytes + sizeof(float) * (size_t)nq + 256);
+  if (r) return r;
+  float* q_big = (float*)c->d_scratch;
+  float* q_small = q_big + (size_t)nq * D;
+  float* qinv = q_small + (size_t)nq * D;
+  k_split_planes<float><<<(nq + 7) / 8, 256, 0, st>>>(d_Q, nq, D, q_big, q_small, qinv);
+  CK_LAUNCH();
+  CUtensorMap tm_b_big, tm_b_small;
+  if (!g2_make_map(&tm_b_big, q_big, nq, D) || !g2_make_map(&tm_b_small, q_small, nq, D))
+    return set_err(MT_ERR_CUDA, "mt_codebook_query_batched: cuTensorMapEncodeTiled failed");
   static bool attr_set = false;
   if (!attr_set) {
-    CK(cudaFuncSetAttribute(k_codebook_gemm_tc<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
-    CK(cudaFuncSetAttribute(k_codebook_gemm_tc<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+    CK(cudaFuncSetAttribute(k_codebook_gemm_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_BYTES));
     attr_set = true;
   }
-  dim3 grid((M + TC_BM - 1) / TC_BM, (nq + TC_BN - 1) / TC_BN);
-  if (e32)
-    k_codebook_gemm_tc<float><<<grid, 128, sh, st>>>((const float*)c->d_emb, c->d_rnorm, M, D, d_Q, nq, d_out);
-  else
-    k_codebook_gemm_tc<double><<<grid, 128, sh, st>>>((const double*)c->d_emb, c->d_rnorm, M, D, d_Q, nq, d_out);
+  const int ntiles = ((M + G2_BM - 1) / G2_BM) * ((nq + G2_BN - 1) / G2_BN);
+  k_codebook_gemm_tma<<<std::min(ntiles, c->sm_count), G2_THREADS, G2_SMEM_BYTES, st>>>(c->tm_a_big, c->tm_a_small, tm_b_big, tm_b_small, c->d_rnorm,
+                                                                                       qinv, M, D, nq, d_out);
   CK_LAUNCH();
   return MT_OK;
 }
