@@ -81,7 +81,7 @@ class Context:
         with torch.cuda.device(self.index):
             call("mt_ctx_stats", self._h, out, int(reset))
         return {"overflow": out[0], "resample_skipped": out[1], "invalid_poses": out[2], "nn_fallbacks": out[3],
-                "drifted": out[5], "on_surface": out[6], "grid_rows": out[4], "grid_rows_max": out[7], "mesh_deferred": out[8]}
+                "drifted": out[5], "on_surface": out[6], "grid_rows": out[4], "grid_rows_max": out[7], "mesh_deferred": out[8], "scan_deferred": out[9]}
 
     def grid_info(self):
         h = C.c_float()

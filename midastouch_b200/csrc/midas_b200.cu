@@ -103,6 +103,7 @@ struct mt_ctx {
   double* d_wpart;    // per-warp weight sums of kernel A (32 particles each)
   double* d_wrm;      // 2 x warp_cap rmse partials of kernel A
   int* d_wcnt;        // per-warp count of particles that passed the drift test
+  float4* d_rec;      // records of the scans k_step_a cut short (48 B each, k_step_scanq continues them)
   int* d_queue2;      // drift tests left for the grid search
   int* d_queue;       // particles whose hint-graph search was not conclusive (kernel A -> A2)
   unsigned int* d_qctl;  // [0] searches queued, [1] queue head, [3] deferred drift tests queued
@@ -163,8 +164,9 @@ extern "C" int mt_ctx_create(int device, size_t capacity, int M, int D, mt_ctx**
   CK(cudaMalloc(&c->d_wcnt, sizeof(int) * c->warp_cap));
   CK(cudaMalloc(&c->d_queue, sizeof(int) * (capacity + 32)));
   CK(cudaMalloc(&c->d_queue2, sizeof(int) * (capacity + 32)));
-  CK(cudaMalloc(&c->d_qctl, sizeof(unsigned int) * 4));
-  CK(cudaMemset(c->d_qctl, 0, sizeof(unsigned int) * 4));
+  CK(cudaMalloc(&c->d_rec, sizeof(float4) * 3 * (capacity + 32)));
+  CK(cudaMalloc(&c->d_qctl, sizeof(unsigned int) * 8));
+  CK(cudaMemset(c->d_qctl, 0, sizeof(unsigned int) * 8));
   CK(cudaMalloc(&c->d_bar, sizeof(unsigned long long)));
   CK(cudaMemset(c->d_bar, 0, sizeof(unsigned long long)));
   CK(cudaMalloc(&c->d_xchg, sizeof(Xchg)));
@@ -220,6 +222,7 @@ extern "C" int mt_ctx_destroy(mt_ctx* c) {
   cudaFree(c->d_wcnt);
   cudaFree(c->d_queue);
   cudaFree(c->d_queue2);
+  cudaFree(c->d_rec);
   cudaFree(c->d_scratch);
   cudaFree(c->d_qctl);
   cudaFree(c->d_bar);
@@ -1352,10 +1355,12 @@ struct StepDev {
   double* wpart;
   double* wrm;
   int* wcnt;
+  float4* srec;         // scans cut short in k_step_a, 3 float4 each: key | k4,k5,best_d,dh | best_i,centre,particle,flags
   int* queue;
   int* queue2;          // drift tests that need the grid search (k_step_meshq -> k_step_meshq2)
   long long queue_cap;  // entries in `queue` (searches grow from the front, deferred drift tests from the back)
-  unsigned int* qctl;   // [0] searches queued, [1] queue head, [2] drift tests left for the grid search, [3] drift tests queued
+  unsigned int* qctl;   // [0] searches queued, [1] queue head, [2] drift tests left for the grid search, [3] drift tests queued,
+                        // [4] scans to continue
   double* scal;
   unsigned int* ticket;
   int* flags;
@@ -1393,16 +1398,21 @@ __device__ __forceinline__ long long step_count(const StepDev& p) {
 #ifndef MT_A_MINBLOCKS
 #define MT_A_MINBLOCKS 16  // 64 registers (the pipelined scan keeps two trips of list entries in registers)
 #endif
-#ifndef MT_STREAM_HINTS
-#define MT_STREAM_HINTS 0
-#endif
 #ifndef MT_MESH_DEFER
 #define MT_MESH_DEFER 1  // undecided voxels of the drift test go to the queue instead of stalling their warp
 #endif
 // queue entries: particle index | what is left to do for it
 #define MT_Q_NN 0x20000000    // the hint-graph search was not conclusive: box-hierarchy search
 #define MT_Q_MESH 0x40000000  // the voxel class was "undecided": vertex search of the drift test
-#define MT_Q_INDEX 0x1fffffff
+#define MT_Q_SCAN 0x10000000  // (k_step_a internal) the hint scan was cut at MT_A_SCAN_CAP: k_step_scanq continues it
+#define MT_Q_INDEX 0x0fffffff
+// MT_A_SCAN_CAP < 64 cuts the hint scan of k_step_a after that many list entries and lets k_step_scanq continue the rest on
+// compacted warps.  Measured on the bench workload (drill, 1e6 particles): 42 % of the scans need more than 16 entries,
+// 19 % more than 24 -- the tail is too fat for the second pass to pay (k_step_a + k_step_scanq: 105 us at 16, 102 us at
+// 24, 99 us uncut), so the default leaves the scan whole.
+#ifndef MT_A_SCAN_CAP
+#define MT_A_SCAN_CAP 64
+#endif
 __global__ void __launch_bounds__(MT_A_BLOCK, MT_A_MINBLOCKS) k_step_a(StepDev p, NNTables T, MeshTables Mh) {
   const long long i = (long long)blockIdx.x * MT_A_BLOCK + threadIdx.x;
   const long long n = step_count(p);
@@ -1411,40 +1421,24 @@ __global__ void __launch_bounds__(MT_A_BLOCK, MT_A_MINBLOCKS) k_step_a(StepDev p
   double et2 = 0.0, ang2 = 0.0;
   bool on_surface = valid;
   int todo = 0;
+  float4 sq[3];
   if (valid) {
     float P[3][4], t[3], r[3], O[3][4], key[6];
-#if MT_STREAM_HINTS
-    {  // the particle arrays are touched once per kernel: streaming loads / stores leave L1 to the neighbour lists
-      const float4 a = __ldcs(p.soa_cur + i), b = __ldcs(p.soa_cur + p.stride + i), c = __ldcs(p.soa_cur + 2 * p.stride + i);
-      P[0][0] = a.x, P[0][1] = a.y, P[0][2] = a.z, P[0][3] = a.w;
-      P[1][0] = b.x, P[1][1] = b.y, P[1][2] = b.z, P[1][3] = b.w;
-      P[2][0] = c.x, P[2][1] = c.y, P[2][2] = c.z, P[2][3] = c.w;
-    }
-    const int hint = nn_index(__ldcs(p.nn_cur + i));
-#else
     load_pose_stream(p.soa_cur, p.stride, i, P);
     const int hint = nn_index(mt_lds(p.nn_cur + i));
-#endif
     nn_prefetch(T, hint);
     draw_or_load_noise(p.tn, p.rot, i, p.sig_t, p.sig_r, p.seed, p.step, p.first_gid + (uint64_t)i, t, r);
     apply_motion(P, p.odom, t, r, O, 0, p.tn == nullptr);
     // drift test: the voxel class is one dependent 4-byte load; it is requested here so that it travels while
     // the key is computed
     int mcls = 1;
-    int mk = -1;
-    (void)mk;
+    [[maybe_unused]] int mk = -1;
 #if MT_MESH_DEFER && MT_VOX2
     if (p.prune_dist > 0.0) mcls = mesh_voxel_class2(Mh, O[0][3], O[1][3], O[2][3], p.prune_dist);
 #else
     if (p.prune_dist > 0.0) mcls = mesh_voxel_class(Mh, O[0][3], O[1][3], O[2][3], p.prune_dist, &mk);
 #endif
-#if MT_STREAM_HINTS
-    __stcs(p.soa_cur + i, make_float4(O[0][0], O[0][1], O[0][2], O[0][3]));
-    __stcs(p.soa_cur + p.stride + i, make_float4(O[1][0], O[1][1], O[1][2], O[1][3]));
-    __stcs(p.soa_cur + 2 * p.stride + i, make_float4(O[2][0], O[2][1], O[2][2], O[2][3]));
-#else
     store_pose_stream(p.soa_cur, p.stride, i, O);
-#endif
     mt_se3_key(O, key);
     const bool invalid = mt_pose_invalid(O);
     if (invalid) atomicAdd(p.flags + 2, 1);  // check_quats would delete the particle (particle_filter.py:347-357)
@@ -1455,37 +1449,47 @@ __global__ void __launch_bounds__(MT_A_BLOCK, MT_A_MINBLOCKS) k_step_a(StepDev p
 #else
     on_surface = (mcls >= 2) ? mesh_within_search(Mh, O[0][3], O[1][3], O[2][3], p.prune_dist, mcls == 2 ? mk : -1) : (mcls == 1);
 #endif
-    float bd;
-    int bi;
-#ifdef MT_SCAN_HIST
-    int slen;
-    if (!nn_hint_search(T, key, hint, bd, bi, slen)) todo |= MT_Q_NN;
-    atomicAdd(&g_scan_hist[0][slen], 1ull);
-    const int wmax = __reduce_max_sync(__activemask(), slen);
-    if (lane == (__ffs(__activemask()) - 1)) atomicAdd(&g_scan_hist[1][wmax], 1ull);
-#else
-    if (!nn_hint_search(T, key, hint, bd, bi)) todo |= MT_Q_NN;
-#endif
+    // hint-graph search (optionally cut after MT_A_SCAN_CAP list entries, the rest continued by k_step_scanq)
+    float bd, dh;
+    int bi, centre;
+    int st = nn_hint_begin(T, key, hint, bd, bi, centre, dh);
+    if (st == 0) st = nn_hint_scan(T, key, centre, dh, 0, MT_A_SCAN_CAP, bd, bi);
+    if (st < 0) todo |= MT_Q_NN;  // no usable hint: box-hierarchy search
+    else if (st == 0) todo |= (MT_A_SCAN_CAP < MT_NBR_K) ? MT_Q_SCAN : MT_Q_NN;  // continue the scan / list exhausted
     if (bi == INT_MAX) bi = -1;  // no usable hint
+    const bool masked = !on_surface || invalid;
     // masked: weights *= m (particle_filter.py:398-401); a particle without any candidate yet
     // (-1) has its mask re-derived by k_step_nnq
-    mt_sts(p.nn_cur + i, (bi >= 0 && (!on_surface || invalid)) ? nn_masked(bi) : bi);
+    mt_sts(p.nn_cur + i, (bi >= 0 && masked) ? nn_masked(bi) : bi);
+    if (todo & MT_Q_SCAN) {
+      sq[0] = make_float4(key[0], key[1], key[2], key[3]);
+      sq[1] = make_float4(key[4], key[5], bd, dh);
+      sq[2] = make_float4(__int_as_float(bi), __int_as_float(centre), __int_as_float((int)i),
+                          __int_as_float((masked ? 1 : 0) | ((todo & MT_Q_MESH) ? 2 : 0)));
+    }
   }
-  // queue what is left (one atomic per warp and queue).  Searches go to the front of the queue array (one warp
-  // per entry later on), drift tests that need nothing else to its back (one thread per entry).
+  // queue what is left (one atomic per warp and queue).  Box-hierarchy searches go to the front of the queue array
+  // (one warp per entry later on), drift tests that need nothing else to its back (one thread per entry), scans to be
+  // continued to the record array.
   const unsigned nm = __ballot_sync(0xffffffffu, (todo & MT_Q_NN) != 0);
+  const unsigned sm = __ballot_sync(0xffffffffu, (todo & MT_Q_SCAN) != 0);
   const unsigned mm = __ballot_sync(0xffffffffu, todo == MT_Q_MESH);
-  if (nm | mm) {
-    unsigned base = 0, mbase = 0;
+  if (nm | sm | mm) {
+    unsigned base = 0, sbase = 0, mbase = 0;
     if (lane == 0) {
       if (nm) base = atomicAdd(p.qctl, (unsigned)__popc(nm));
+      if (sm) sbase = atomicAdd(p.qctl + 4, (unsigned)__popc(sm));
       if (mm) mbase = atomicAdd(p.qctl + 3, (unsigned)__popc(mm));
     }
     base = __shfl_sync(0xffffffffu, base, 0);
+    sbase = __shfl_sync(0xffffffffu, sbase, 0);
     mbase = __shfl_sync(0xffffffffu, mbase, 0);
     const unsigned below = (1u << lane) - 1;
-    if (todo & MT_Q_NN) p.queue[base + __popc(nm & below)] = (int)i | todo;
-    else if (todo) p.queue[p.queue_cap - 1 - (mbase + __popc(mm & below))] = (int)i;
+    if (todo & MT_Q_NN) p.queue[base + __popc(nm & below)] = (int)i | (todo & (MT_Q_NN | MT_Q_MESH));
+    else if (todo & MT_Q_SCAN) {
+      float4* r = p.srec + 3 * (size_t)(sbase + __popc(sm & below));
+      r[0] = sq[0], r[1] = sq[1], r[2] = sq[2];
+    } else if (todo) p.queue[p.queue_cap - 1 - (mbase + __popc(mm & below))] = (int)i;
   }
   const long long gw = i >> 5;  // global warp = 32 consecutive particles
   const unsigned on = __ballot_sync(0xffffffffu, on_surface);
@@ -1496,132 +1500,42 @@ __global__ void __launch_bounds__(MT_A_BLOCK, MT_A_MINBLOCKS) k_step_a(StepDev p
   }
 }
 
-// k_step_a with the neighbour lists staged in shared memory.  Particles keep the order of their codebook match
-// (FilterEngine.load_particles sorts them once, systematic resampling preserves the order), so a block of 256
-// consecutive particles holds a handful of distinct hints in contiguous runs.  Every run gets a slot: the key record
-// of its hint plus the first MT_A_STAGE entries of the hint's list (1 KB), copied global -> shared with cp.async
-// right after the hints are known and in flight during the motion arithmetic.  The scans then read shared memory
-// (a broadcast when the lanes share a slot) instead of chasing cache lines through L1 / L2 / DRAM: the long-scoreboard
-// stalls on the list loads were 55 % of the old kernel's stall samples.  Runs beyond MT_A_SLOTS, list entries beyond
-// the staged head and the lists of near-pi partners are read from global memory as before.
-#ifndef MT_A_SMEM
-#define MT_A_SMEM 0
-#endif
-#define MT_AS_BLOCK 256
-#ifndef MT_AS_MINBLOCKS
-#define MT_AS_MINBLOCKS 5
-#endif
-#ifndef MT_A_SLOTS
-#define MT_A_SLOTS 32
-#endif
-#define MT_A_STAGE 32
-#define MT_A_SLOT_F4 (2 + 2 * MT_A_STAGE)
-#define MT_A_TAB_LOG2 7
-#define MT_A_TAB (1 << MT_A_TAB_LOG2)
-__device__ __forceinline__ void mt_cp_async16(void* smem_dst, const void* gmem_src) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
-}
-__global__ void __launch_bounds__(MT_AS_BLOCK, MT_AS_MINBLOCKS) k_step_a_s(StepDev p, NNTables T, MeshTables Mh) {
-  __shared__ float4 s_list[MT_A_SLOTS][MT_A_SLOT_F4];
-  __shared__ int s_tab[MT_A_TAB];       // open-addressed set of the block's distinct hints
-  __shared__ int s_tab_slot[MT_A_TAB];  // slot of the hint stored at that position
-  __shared__ int s_slot_hint[MT_A_SLOTS];
-  __shared__ int s_count;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const long long i = (long long)blockIdx.x * MT_AS_BLOCK + tid;
-  const long long n = step_count(p);
-  const bool valid = i < n;
-  int hint = valid ? nn_index(mt_lds(p.nn_cur + i)) : -1;
-  if (hint >= T.M) hint = -1;
-  if (tid < MT_A_TAB) s_tab[tid] = -1;
-  if (tid == 0) s_count = 0;
-  float P[3][4];
-  if (valid) load_pose_stream(p.soa_cur, p.stride, i, P);
-  __syncthreads();
-  // distinct hints of the block -> slots (neighbouring particles share their few hints, in no particular order)
-  int pos = -1;
-  if (hint >= 0) {
-    unsigned h = ((unsigned)hint * 2654435761u) >> (32 - MT_A_TAB_LOG2);
-    for (int probe = 0; probe < MT_A_TAB; ++probe, h = (h + 1) & (MT_A_TAB - 1)) {
-      const int old = atomicCAS(&s_tab[h], -1, hint);
-      if (old == -1) {  // this thread inserted the hint: it names the slot
-        const int sl = atomicAdd(&s_count, 1);
-        s_tab_slot[h] = sl;
-        if (sl < MT_A_SLOTS) s_slot_hint[sl] = hint;
-        pos = (int)h;
-        break;
-      }
-      if (old == hint) {
-        pos = (int)h;
-        break;
-      }
+// Continuation of the hint-graph scans that k_step_a cut short: one thread per record, on compacted warps whose lanes
+// all still have list entries to read.  Proven -> the match is final (a pending drift test goes to its queue);
+// list exhausted -> box-hierarchy queue, seeded with the best candidate so far.
+__global__ void __launch_bounds__(256) k_step_scanq(StepDev p, NNTables T) {
+  const unsigned ns = p.qctl[4];
+  const int lane = threadIdx.x & 31;
+  const unsigned span = gridDim.x * blockDim.x;
+  for (unsigned e0 = blockIdx.x * blockDim.x + threadIdx.x - lane; e0 < ns; e0 += span) {  // whole warps stay in the loop
+    const unsigned e = e0 + lane;
+    int todo = 0, i = 0;
+    if (e < ns) {
+      const float4 r0 = p.srec[3 * (size_t)e], r1 = p.srec[3 * (size_t)e + 1], r2 = p.srec[3 * (size_t)e + 2];
+      const float key[6] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y};
+      float bd = r1.z;
+      int bi = __float_as_int(r2.x);
+      const int centre = __float_as_int(r2.y), fl = __float_as_int(r2.w);
+      i = __float_as_int(r2.z);
+      const int st = nn_hint_scan(T, key, centre, r1.w, MT_A_SCAN_CAP, MT_NBR_K, bd, bi);
+      p.nn_cur[i] = (fl & 1) ? nn_masked(bi) : bi;
+      if (!st) todo = MT_Q_NN | ((fl & 2) ? MT_Q_MESH : 0);
+      else if (fl & 2) todo = MT_Q_MESH;
     }
-  }
-  __syncthreads();
-  int slot = pos >= 0 ? s_tab_slot[pos] : -1;
-  if (slot >= MT_A_SLOTS) slot = -1;
-  const int nslots = min(s_count, MT_A_SLOTS);
-  for (int sl = warp; sl < nslots; sl += MT_AS_BLOCK / 32) {
-    const int h = s_slot_hint[sl];
-    const float4* key = T.keys_orig + 2 * (size_t)h;
-    const float4* lst = T.nbr + (size_t)h * (2 * MT_NBR_K);
-#pragma unroll
-    for (int c = lane; c < MT_A_SLOT_F4; c += 32) mt_cp_async16(&s_list[sl][c], c < 2 ? key + c : lst + (c - 2));
-  }
-  asm volatile("cp.async.commit_group;" ::: "memory");
-  if (slot < 0) nn_prefetch(T, hint);
-
-  double et2 = 0.0, ang2 = 0.0;
-  bool on_surface = valid, invalid = false;
-  int todo = 0;
-  float key[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  if (valid) {
-    float t[3], r[3], O[3][4];
-    draw_or_load_noise(p.tn, p.rot, i, p.sig_t, p.sig_r, p.seed, p.step, p.first_gid + (uint64_t)i, t, r);
-    apply_motion(P, p.odom, t, r, O, 0, p.tn == nullptr);
-    int mcls = 1;
-    if (p.prune_dist > 0.0) mcls = mesh_voxel_class2(Mh, O[0][3], O[1][3], O[2][3], p.prune_dist);
-    store_pose_stream(p.soa_cur, p.stride, i, O);
-    mt_se3_key(O, key);
-    invalid = mt_pose_invalid(O);
-    if (invalid) atomicAdd(p.flags + 2, 1);  // check_quats would delete the particle (particle_filter.py:347-357)
-    if (p.has_gt) rmse_terms(p.gt, O, et2, ang2);
-    on_surface = mcls != 0;  // undecided: counted as on the surface until the queue consumer has looked
-    if (mcls >= 2) todo |= MT_Q_MESH;
-  }
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-  __syncthreads();
-  if (valid) {
-    float bd;
-    int bi;
-    bool done;
-    if (slot >= 0) done = nn_hint_search_staged(T, s_list[slot], MT_A_STAGE, key, hint, bd, bi);
-    else done = nn_hint_search(T, key, hint, bd, bi);
-    if (!done) todo |= MT_Q_NN;
-    if (bi == INT_MAX) bi = -1;  // no usable hint
-    mt_sts(p.nn_cur + i, (bi >= 0 && (!on_surface || invalid)) ? nn_masked(bi) : bi);
-  }
-  const unsigned nm = __ballot_sync(0xffffffffu, (todo & MT_Q_NN) != 0);
-  const unsigned mm = __ballot_sync(0xffffffffu, todo == MT_Q_MESH);
-  if (nm | mm) {
-    unsigned base = 0, mbase = 0;
-    if (lane == 0) {
-      if (nm) base = atomicAdd(p.qctl, (unsigned)__popc(nm));
-      if (mm) mbase = atomicAdd(p.qctl + 3, (unsigned)__popc(mm));
+    const unsigned nm = __ballot_sync(0xffffffffu, (todo & MT_Q_NN) != 0);
+    const unsigned mm = __ballot_sync(0xffffffffu, todo == MT_Q_MESH);
+    if (nm | mm) {
+      unsigned base = 0, mbase = 0;
+      if (lane == 0) {
+        if (nm) base = atomicAdd(p.qctl, (unsigned)__popc(nm));
+        if (mm) mbase = atomicAdd(p.qctl + 3, (unsigned)__popc(mm));
+      }
+      base = __shfl_sync(0xffffffffu, base, 0);
+      mbase = __shfl_sync(0xffffffffu, mbase, 0);
+      const unsigned below = (1u << lane) - 1;
+      if (todo & MT_Q_NN) p.queue[base + __popc(nm & below)] = i | todo;
+      else if (todo) p.queue[p.queue_cap - 1 - (mbase + __popc(mm & below))] = i;
     }
-    base = __shfl_sync(0xffffffffu, base, 0);
-    mbase = __shfl_sync(0xffffffffu, mbase, 0);
-    const unsigned below = (1u << lane) - 1;
-    if (todo & MT_Q_NN) p.queue[base + __popc(nm & below)] = (int)i | todo;
-    else if (todo) p.queue[p.queue_cap - 1 - (mbase + __popc(mm & below))] = (int)i;
-  }
-  const long long gw = i >> 5;
-  const unsigned on = __ballot_sync(0xffffffffu, on_surface);
-  if (p.has_gt) et2 = warp_sum(et2), ang2 = warp_sum(ang2);
-  if (lane == 0 && gw < ((n + 31) >> 5)) {
-    p.wcnt[gw] = __popc(on);
-    if (p.has_gt) p.wrm[2 * gw] = et2, p.wrm[2 * gw + 1] = ang2;
   }
 }
 
@@ -1796,7 +1710,8 @@ __global__ void __launch_bounds__(256) k_step_sums(StepDev p) {
     p.flags[5] = (p.prune_dist > 0.0 && s_cnt == 0);  // drifted (particle_filter.py:402)
     p.flags[3] += (int)p.qctl[0];                     // searches that needed the box hierarchy (cumulative)
     p.flags[MT_STAT_MESH_DEFERRED] += (int)p.qctl[3];
-    p.qctl[0] = 0, p.qctl[1] = 0, p.qctl[2] = 0, p.qctl[3] = 0;
+    p.flags[MT_STAT_SCAN_DEFERRED] += (int)p.qctl[4];
+    p.qctl[0] = 0, p.qctl[1] = 0, p.qctl[2] = 0, p.qctl[3] = 0, p.qctl[4] = 0;
     *p.ticket = 0;
   }
 }
@@ -2182,7 +2097,9 @@ __global__ void __launch_bounds__(256, 4) k_step_bw(StepDev p, unsigned long lon
       p.flags[5] = (p.prune_dist > 0.0 && s_on == 0);
       p.flags[3] += (int)p.qctl[0];
       p.flags[MT_STAT_MESH_DEFERRED] += (int)p.qctl[3];
-      p.qctl[0] = 0, p.qctl[1] = 0, p.qctl[2] = 0, p.qctl[3] = 0;
+      p.flags[MT_STAT_SCAN_DEFERRED] += (int)p.qctl[4];
+    p.flags[MT_STAT_SCAN_DEFERRED] += (int)p.qctl[4];
+      p.qctl[0] = 0, p.qctl[1] = 0, p.qctl[2] = 0, p.qctl[3] = 0, p.qctl[4] = 0;
     }
   }
 }
@@ -2218,7 +2135,7 @@ static int fill_step(mt_ctx* c, const mt_step_args* a, StepDev* d) {
   if (!c || !a) return set_err(MT_ERR_ARG, "step: null argument");
   if (a->n <= 0 || (size_t)a->n > c->cap || a->stride < a->n) return set_err(MT_ERR_CAPACITY, "step: n/stride out of range");
   if (a->d_n_in && (size_t)a->stride > c->cap) return set_err(MT_ERR_CAPACITY, "step: with a device-resident count the stride must not exceed the context capacity");
-  if (a->n > 0x1fffffffLL) return set_err(MT_ERR_CAPACITY, "step: at most 2^29 - 1 particles per GPU (queue entries carry two flag bits)");
+  if (a->n > 0x0fffffffLL) return set_err(MT_ERR_CAPACITY, "step: at most 2^28 - 1 particles per GPU (queue entries carry flag bits)");
   memset(d, 0, sizeof(*d));
   d->soa_cur = (float4*)a->d_soa_cur;
   d->soa_next = (float4*)a->d_soa_next;
@@ -2259,6 +2176,7 @@ static int fill_step(mt_ctx* c, const mt_step_args* a, StepDev* d) {
   d->wpart = c->d_wpart;
   d->wrm = c->d_wrm;
   d->wcnt = c->d_wcnt;
+  d->srec = c->d_rec;
   d->queue = c->d_queue;
   d->queue2 = c->d_queue2;
   d->queue_cap = (long long)c->cap + 32;
@@ -2331,16 +2249,6 @@ static bool step_fused(mt_ctx* c, const mt_step_args* a) {
   return (nchunks_of(nb) + grid - 1) / grid <= MT_BW_MAX_PER;
 }
 
-#ifdef MT_SCAN_HIST
-extern "C" int mt_debug_scan_hist(unsigned long long* h_out132, int reset) {
-  CK(cudaMemcpyFromSymbol(h_out132, g_scan_hist, sizeof(unsigned long long) * 132));
-  if (reset) {
-    static unsigned long long z[132];
-    CK(cudaMemcpyToSymbol(g_scan_hist, z, sizeof(z)));
-  }
-  return MT_OK;
-}
-#endif
 
 extern "C" int mt_dist_debug(mt_ctx* c, unsigned long long* h_out3) {
   if (!c || !h_out3) return set_err(MT_ERR_ARG, "mt_dist_debug: null");
@@ -2366,12 +2274,12 @@ extern "C" int mt_step_a(mt_ctx* c, const mt_step_args* a, void* stream) {
   if (a->prune_dist > 0.0 && !c->mesh_ready) return set_err(MT_ERR_STATE, "mt_step_a: prune_dist given but no mesh uploaded");
   cudaStream_t st = (cudaStream_t)stream;
   if (c->timing[0]) CK(cudaEventRecord(c->timing[0], st));
-#if MT_A_SMEM
-  k_step_a_s<<<(unsigned)((step_cover(a) + MT_AS_BLOCK - 1) / MT_AS_BLOCK), MT_AS_BLOCK, 0, st>>>(d, tables_of(c), mesh_of(c));
-#else
   k_step_a<<<(unsigned)((step_cover(a) + MT_A_BLOCK - 1) / MT_A_BLOCK), MT_A_BLOCK, 0, st>>>(d, tables_of(c), mesh_of(c));
-#endif
   CK_LAUNCH();
+#if MT_A_SCAN_CAP < MT_NBR_K
+  k_step_scanq<<<c->sm_count * 8, 256, 0, st>>>(d, tables_of(c));
+  CK_LAUNCH();
+#endif
   if (c->timing[1]) CK(cudaEventRecord(c->timing[1], st));
   if (d.prune_dist > 0.0) {  // (a particle is in at most one of the two queues)
     k_step_meshq<<<c->sm_count * 4, 256, 0, st>>>(d, mesh_of(c));
@@ -2435,7 +2343,7 @@ struct StepGraph {
   unsigned long long key[20];
   cudaGraph_t graph;
   cudaGraphExec_t exec;
-  cudaGraphNode_t n_query, n_a, n_meshq, n_meshq2, n_nnq, n_bw;
+  cudaGraphNode_t n_query, n_a, n_s, n_meshq, n_meshq2, n_nnq, n_bw;
   bool has_mesh;
 };
 static void step_graphs_free(mt_ctx* c) {
@@ -2542,13 +2450,9 @@ extern "C" int mt_step(mt_ctx* c, const mt_step_args* a, const void* d_q, int q_
   void* args_m[] = {&d, &Mh};
   void* args_bw[] = {&d, &bar, &target, &bw, &bwc};
   const bool has_mesh = d.prune_dist > 0.0;
-#if MT_A_SMEM
-  const void* f_a = (const void*)k_step_a_s;
-  const dim3 grid_a((unsigned)((cover + MT_AS_BLOCK - 1) / MT_AS_BLOCK)), block_a(MT_AS_BLOCK);
-#else
   const void* f_a = (const void*)k_step_a;
   const dim3 grid_a((unsigned)((cover + MT_A_BLOCK - 1) / MT_A_BLOCK)), block_a(MT_A_BLOCK);
-#endif
+  void* args_s[] = {&d, &T};
   // configuration key: everything that is baked into the graph's topology or launch geometry
   unsigned long long key[20] = {(unsigned long long)a->d_soa_cur, (unsigned long long)a->d_soa_next, (unsigned long long)a->d_nn_cur,
                                 (unsigned long long)a->d_nn_next, (unsigned long long)a->d_anc, (unsigned long long)a->stride,
@@ -2571,6 +2475,7 @@ extern "C" int mt_step(mt_ctx* c, const mt_step_args* a, const void* d_q, int q_
   };
   cudaKernelNodeParams P_q = kparams(Q.func, dim3(Q.grid), dim3(256), Q.smem, args_q);
   cudaKernelNodeParams P_a = kparams(f_a, grid_a, block_a, 0, args_a);
+  cudaKernelNodeParams P_s = kparams((const void*)k_step_scanq, dim3(c->sm_count * 8), dim3(256), 0, args_s);
   cudaKernelNodeParams P_m1 = kparams((const void*)k_step_meshq, dim3(c->sm_count * 4), dim3(256), 0, args_m);
   cudaKernelNodeParams P_m2 = kparams((const void*)k_step_meshq2, dim3(c->sm_count * 8), dim3(256), 0, args_m);
   cudaKernelNodeParams P_n = kparams((const void*)k_step_nnq, dim3(c->sm_count * 12), dim3(32 * MT_NNQ_WARPS), 0, args_a);
@@ -2586,13 +2491,20 @@ extern "C" int mt_step(mt_ctx* c, const mt_step_args* a, const void* d_q, int q_
     CK(cudaGraphCreate(&G->graph, 0));
     CK(cudaGraphAddKernelNode(&G->n_query, G->graph, nullptr, 0, &P_q));
     CK(cudaGraphAddKernelNode(&G->n_a, G->graph, nullptr, 0, &P_a));
+#if MT_A_SCAN_CAP < MT_NBR_K
+    CK(cudaGraphAddKernelNode(&G->n_s, G->graph, &G->n_a, 1, &P_s));
+    cudaGraphNode_t* after_a = &G->n_s;
+#else
+    cudaGraphNode_t* after_a = &G->n_a;
+    (void)P_s;
+#endif
     std::vector<cudaGraphNode_t> deps_bw = {G->n_query};
     if (has_mesh) {
-      CK(cudaGraphAddKernelNode(&G->n_meshq, G->graph, &G->n_a, 1, &P_m1));
+      CK(cudaGraphAddKernelNode(&G->n_meshq, G->graph, after_a, 1, &P_m1));
       CK(cudaGraphAddKernelNode(&G->n_meshq2, G->graph, &G->n_meshq, 1, &P_m2));
       deps_bw.push_back(G->n_meshq2);
     }
-    CK(cudaGraphAddKernelNode(&G->n_nnq, G->graph, &G->n_a, 1, &P_n));
+    CK(cudaGraphAddKernelNode(&G->n_nnq, G->graph, after_a, 1, &P_n));
     deps_bw.push_back(G->n_nnq);
     CK(cudaGraphAddKernelNode(&G->n_bw, G->graph, deps_bw.data(), deps_bw.size(), &P_b));
     cudaKernelNodeAttrValue coop;
@@ -2605,6 +2517,9 @@ extern "C" int mt_step(mt_ctx* c, const mt_step_args* a, const void* d_q, int q_
     G->valid = true;
   } else {
     CK(cudaGraphExecKernelNodeSetParams(G->exec, G->n_a, &P_a));
+#if MT_A_SCAN_CAP < MT_NBR_K
+    CK(cudaGraphExecKernelNodeSetParams(G->exec, G->n_s, &P_s));
+#endif
     if (G->has_mesh) {
       CK(cudaGraphExecKernelNodeSetParams(G->exec, G->n_meshq, &P_m1));
       CK(cudaGraphExecKernelNodeSetParams(G->exec, G->n_meshq2, &P_m2));

@@ -232,16 +232,7 @@ __device__ __forceinline__ int load_key(const float4* __restrict__ t, int i, flo
   return __float_as_int(b.z);  // partner (keys_orig) / original index (keys_sorted)
 }
 
-#ifndef MT_SCAN_PIPE
-#define MT_SCAN_PIPE 1
-#endif
-#ifndef MT_SCAN_PF
-#define MT_SCAN_PF 0
-#endif
 
-#ifndef MT_PF_INIT_L1
-#define MT_PF_INIT_L1 0
-#endif
 // 16-byte read-only load that the compiler keeps where it is written (see the pipelined scan below)
 __device__ __forceinline__ float4 mt_ldnc(const float4* p) {
   // (default L2 priority: the lists are 2 KB per key, too many to pin; the streamed particle arrays are evict_first,
@@ -259,177 +250,81 @@ __device__ __forceinline__ void nn_prefetch(const NNTables& T, int hint) {
   const float4* L = T.nbr + (size_t)hint * (2 * MT_NBR_K);
   asm volatile("prefetch.global.L1 [%0];" ::"l"(T.keys_orig + 2 * (size_t)hint));
   asm volatile("prefetch.global.L1 [%0];" ::"l"(L));
-#if MT_PF_INIT_L1
-  asm volatile("prefetch.global.L1 [%0];" ::"l"(L + 8));
-  asm volatile("prefetch.global.L1 [%0];" ::"l"(L + 16));
-#else
   asm volatile("prefetch.global.L2 [%0];" ::"l"(L + 8));
   asm volatile("prefetch.global.L2 [%0];" ::"l"(L + 16));
-#endif
 }
 
-// (1) one thread per query.  false -> needs the box-hierarchy search (best_* = best so far, or
-// FLT_MAX / INT_MAX when there was no usable hint).
-#ifdef MT_SCAN_HIST
-__device__ unsigned long long g_scan_hist[2][66];  // [0] per particle, [1] max over the warp; index = entries read
-__device__ int g_scan_len;
-#define MT_SCAN_RET(n, v) do { mt_scan_len = (n); return (v); } while (0)
-#else
-#define MT_SCAN_RET(n, v) return (v)
-#endif
-__device__ __forceinline__ bool nn_hint_search(const NNTables& T, const float q[6], int hint, float& best_d, int& best_i
-#ifdef MT_SCAN_HIST
-                                               , int& mt_scan_len
-#endif
-) {
-#ifdef MT_SCAN_HIST
-  mt_scan_len = 0;
-#endif
+// (1) one thread per query, in two parts so that a kernel can cut the scan short and hand the rest to a compacted
+// second pass (the scan lengths are long-tailed; in lockstep a warp pays for its longest lane):
+//   nn_hint_begin  centre = hint or its near-pi partner, best = that key.  1: proven exact already, -1: no usable
+//                  hint (best_i = INT_MAX), 0: scan the centre's list
+//   nn_hint_scan   list entries [j0, j1) (multiples of 4) of the centre.  1: proven exact, 0: reached j1
+// nn_hint_search = begin + scan over the whole list; false -> needs the box-hierarchy search (best_* = best so far).
+__device__ __forceinline__ int nn_hint_begin(const NNTables& T, const float q[6], int hint, float& best_d, int& best_i, int& centre,
+                                             float& dh) {
+  centre = hint;
+  dh = 0.f;
   if (hint < 0 || hint >= T.M) {
     best_d = FLT_MAX;
     best_i = INT_MAX;
-    return false;
+    return -1;
   }
   float kh[6], delta0;
   const int partner = load_key(T.keys_orig, hint, kh, &delta0);
   best_d = mt_key_dist(q, kh);
   best_i = hint;
-  if (!(best_d == best_d)) {
+  if (!(best_d == best_d)) {  // NaN query: np.argmin semantics (first NaN) -> index 0
     best_i = 0;
-    return true;
+    return 1;
   }
   if (partner >= 0) {  // near angle pi: the pose may have jumped to the other sign of the axis
     float kp[6], dp0;
     load_key(T.keys_orig, partner, kp, &dp0);
     const float dp = mt_key_dist(q, kp);
-    if (mt_better(dp, partner, best_d, best_i)) best_d = dp, best_i = partner, hint = partner, delta0 = dp0;
+    if (mt_better(dp, partner, best_d, best_i)) best_d = dp, best_i = partner, centre = partner, delta0 = dp0;
   }
-  const float dh = sqrtf(best_d);
+  dh = sqrtf(best_d);
+  return delta0 > mt_hint_limit(dh, best_d) ? 1 : 0;  // nearest other key of the centre already out of reach?
+}
+
+__device__ __forceinline__ int nn_hint_scan(const NNTables& T, const float q[6], int centre, float dh, int j0, int j1, float& best_d,
+                                            int& best_i) {
   float lim = mt_hint_limit(dh, best_d);
-  if (delta0 > lim) MT_SCAN_RET(0, true);  // nearest other key of the centre is already out of reach
-  const float4* __restrict__ L = T.nbr + (size_t)hint * (2 * MT_NBR_K);
-#if MT_SCAN_PIPE
-  // software pipeline: the two entries of trip t+1 are requested before trip t is evaluated, so a trip waits
-  // for loads issued ~40 instructions (x the other resident warps) earlier instead of for loads it has just
-  // issued.  The loads are volatile asm (plain ld.global.nc underneath, i.e. cached in L1 like __ldg) so that
-  // neither NVVM nor ptxas sinks them below the exit tests of the current trip.
-  // Two register sets (x*, y*) alternate between "being evaluated" and "in flight": no moves at the loop end.
-  float4 xa0 = mt_ldnc(L), xb0 = mt_ldnc(L + 1), xa1 = mt_ldnc(L + 2), xb1 = mt_ldnc(L + 3);
+  const float4* __restrict__ L = T.nbr + (size_t)centre * (2 * MT_NBR_K);
+  // Software pipeline: the two entries of the next half trip are requested before the current ones are evaluated, so
+  // a trip waits for loads issued ~40 instructions (x the other resident warps) earlier.  The loads are volatile asm
+  // (plain ld.global.nc underneath, i.e. cached in L1 like __ldg) so that neither NVVM nor ptxas sinks them below the
+  // exit tests.  Two register sets (x*, y*) alternate between "being evaluated" and "in flight".
+  float4 xa0 = mt_ldnc(L + 2 * j0), xb0 = mt_ldnc(L + 2 * j0 + 1), xa1 = mt_ldnc(L + 2 * j0 + 2), xb1 = mt_ldnc(L + 2 * j0 + 3);
   float4 ya0, yb0, ya1, yb1;
-#define MT_SCAN_ENTRY(A, B, JRET)                                                                       \
+#define MT_SCAN_ENTRY(A, B)                                                                             \
   {                                                                                                     \
-    if (B.z > lim) MT_SCAN_RET(JRET, true);                                                             \
+    if (B.z > lim) return 1;                                                                            \
     const float k[6] = {A.x, A.y, A.z, A.w, B.x, B.y};                                                  \
     const float d = mt_key_dist(q, k);                                                                  \
     const int idx = __float_as_int(B.w);                                                                \
     if (mt_better(d, idx, best_d, best_i)) best_d = d, best_i = idx, lim = mt_hint_limit(dh, d);        \
   }
 #pragma unroll 1
-  for (int j = 0; j < MT_NBR_K; j += 4) {
-#if MT_SCAN_PF
-    // rolling prefetch, MT_SCAN_PF lines (4 entries each) ahead of the trip being evaluated
-    if (j + 4 * MT_SCAN_PF < MT_NBR_K) asm volatile("prefetch.global.L1 [%0];" ::"l"(L + 2 * (j + 4 * MT_SCAN_PF)));
-#endif
+  for (int j = j0; j < j1; j += 4) {
     ya0 = mt_ldnc(L + 2 * j + 4), yb0 = mt_ldnc(L + 2 * j + 5), ya1 = mt_ldnc(L + 2 * j + 6), yb1 = mt_ldnc(L + 2 * j + 7);
-    MT_SCAN_ENTRY(xa0, xb0, j + 1)
-    MT_SCAN_ENTRY(xa1, xb1, j + 2)
-    const int jn = min(j + 4, MT_NBR_K - 2);  // the last trip re-reads its own entries (L1 hit, never used)
+    MT_SCAN_ENTRY(xa0, xb0)
+    MT_SCAN_ENTRY(xa1, xb1)
+    const int jn = min(j + 4, MT_NBR_K - 2);  // past the end of the list: a harmless re-read, never used
     xa0 = mt_ldnc(L + 2 * jn), xb0 = mt_ldnc(L + 2 * jn + 1), xa1 = mt_ldnc(L + 2 * jn + 2), xb1 = mt_ldnc(L + 2 * jn + 3);
-    MT_SCAN_ENTRY(ya0, yb0, j + 3)
-    MT_SCAN_ENTRY(ya1, yb1, j + 4)
+    MT_SCAN_ENTRY(ya0, yb0)
+    MT_SCAN_ENTRY(ya1, yb1)
   }
 #undef MT_SCAN_ENTRY
-#else
-#pragma unroll 1
-  for (int j = 0; j < MT_NBR_K; j += 2) {
-    // two entries (64 contiguous bytes) per trip, all four loads in flight together.  The exit test is made to
-    // depend on all of them (+ 0 * x, exact for the finite keys of a codebook): otherwise ptxas sinks three of
-    // the loads below the first test and every trip pays two dependent cache latencies instead of one.
-    const float4 a0 = __ldg(L + 2 * j), b0 = __ldg(L + 2 * j + 1);
-    const float4 a1 = __ldg(L + 2 * j + 2), b1 = __ldg(L + 2 * j + 3);
-#ifndef MT_SCAN_PLAIN_LOADS
-    const float dz0 = fmaf(0.0f, a0.x, fmaf(0.0f, a1.x, fmaf(0.0f, b1.x, b0.z)));
-    if (dz0 > lim) MT_SCAN_RET(j + 1, true);
-#else
-    if (b0.z > lim) MT_SCAN_RET(j + 1, true);
-#endif
-    {
-      const float k[6] = {a0.x, a0.y, a0.z, a0.w, b0.x, b0.y};
-      const float d = mt_key_dist(q, k);
-      const int idx = __float_as_int(b0.w);
-      if (mt_better(d, idx, best_d, best_i)) best_d = d, best_i = idx, lim = mt_hint_limit(dh, d);
-    }
-    if (b1.z > lim) MT_SCAN_RET(j + 2, true);
-    {
-      const float k[6] = {a1.x, a1.y, a1.z, a1.w, b1.x, b1.y};
-      const float d = mt_key_dist(q, k);
-      const int idx = __float_as_int(b1.w);
-      if (mt_better(d, idx, best_d, best_i)) best_d = d, best_i = idx, lim = mt_hint_limit(dh, d);
-    }
-  }
-#endif
-  MT_SCAN_RET(65, false);
+  return 0;
 }
 
-// (1b) the same search with the head of the hint's list staged in shared memory by the caller: S[0..1] = the key
-// record of `hint` (keys_orig layout), S[2 + 2 j], S[3 + 2 j] = list entry j for j < n_staged.  Entries beyond the
-// staged head (and the list of a near-pi partner that replaces the hint as the centre) are read from global memory.
-__device__ __forceinline__ bool nn_hint_search_staged(const NNTables& T, const float4* __restrict__ S, int n_staged,
-                                                      const float q[6], int hint, float& best_d, int& best_i) {
-  const float4 ka = S[0], kb = S[1];
-  const float kh[6] = {ka.x, ka.y, ka.z, ka.w, kb.x, kb.y};
-  const int partner = __float_as_int(kb.z);
-  float delta0 = kb.w;
-  best_d = mt_key_dist(q, kh);
-  best_i = hint;
-  if (!(best_d == best_d)) {
-    best_i = 0;
-    return true;
-  }
-  bool staged = true;
-  if (partner >= 0) {  // near angle pi: the pose may have jumped to the other sign of the axis
-    float kp[6], dp0;
-    load_key(T.keys_orig, partner, kp, &dp0);
-    const float dp = mt_key_dist(q, kp);
-    if (mt_better(dp, partner, best_d, best_i)) best_d = dp, best_i = partner, hint = partner, delta0 = dp0, staged = false;
-  }
-  const float dh = sqrtf(best_d);
-  float lim = mt_hint_limit(dh, best_d);
-  if (delta0 > lim) return true;  // nearest other key of the centre is already out of reach
-  int j = 0;
-  if (staged) {
-#pragma unroll 1
-    for (; j < n_staged; ++j) {
-      const float4 a = S[2 + 2 * j], b = S[3 + 2 * j];
-      if (b.z > lim) return true;
-      const float k[6] = {a.x, a.y, a.z, a.w, b.x, b.y};
-      const float d = mt_key_dist(q, k);
-      const int idx = __float_as_int(b.w);
-      if (mt_better(d, idx, best_d, best_i)) best_d = d, best_i = idx, lim = mt_hint_limit(dh, d);
-    }
-  }
-  const float4* __restrict__ L = T.nbr + (size_t)hint * (2 * MT_NBR_K);
-#pragma unroll 1
-  for (; j < MT_NBR_K; j += 2) {
-    const float4 a0 = __ldg(L + 2 * j), b0 = __ldg(L + 2 * j + 1);
-    const float4 a1 = __ldg(L + 2 * j + 2), b1 = __ldg(L + 2 * j + 3);
-    const float dz0 = fmaf(0.0f, a0.x, fmaf(0.0f, a1.x, fmaf(0.0f, b1.x, b0.z)));
-    if (dz0 > lim) return true;
-    {
-      const float k[6] = {a0.x, a0.y, a0.z, a0.w, b0.x, b0.y};
-      const float d = mt_key_dist(q, k);
-      const int idx = __float_as_int(b0.w);
-      if (mt_better(d, idx, best_d, best_i)) best_d = d, best_i = idx, lim = mt_hint_limit(dh, d);
-    }
-    if (b1.z > lim) return true;
-    {
-      const float k[6] = {a1.x, a1.y, a1.z, a1.w, b1.x, b1.y};
-      const float d = mt_key_dist(q, k);
-      const int idx = __float_as_int(b1.w);
-      if (mt_better(d, idx, best_d, best_i)) best_d = d, best_i = idx, lim = mt_hint_limit(dh, d);
-    }
-  }
-  return false;
+__device__ __forceinline__ bool nn_hint_search(const NNTables& T, const float q[6], int hint, float& best_d, int& best_i) {
+  int centre;
+  float dh;
+  const int st = nn_hint_begin(T, q, hint, best_d, best_i, centre, dh);
+  if (st) return st > 0;
+  return nn_hint_scan(T, q, centre, dh, 0, MT_NBR_K, best_d, best_i) != 0;
 }
 
 // warp-wide (best_d, best_i) = lexicographic min over lanes
@@ -544,12 +439,7 @@ __device__ __forceinline__ int nn_search_warp(const NNTables& T, const float q[6
 __device__ __forceinline__ int nn_assign(const NNTables& T, bool active, const float q[6], int hint, int* fallback_counter) {
   float bd = FLT_MAX;
   int bi = INT_MAX;
-#ifdef MT_SCAN_HIST
-  int slen_unused;
-  const bool todo = active && !nn_hint_search(T, q, hint, bd, bi, slen_unused);
-#else
   const bool todo = active && !nn_hint_search(T, q, hint, bd, bi);
-#endif
   unsigned m = __ballot_sync(0xffffffffu, todo);
   if (m && fallback_counter && (threadIdx.x & 31) == 0) atomicAdd(fallback_counter, __popc(m));
   while (m) {

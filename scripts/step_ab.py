@@ -48,4 +48,5 @@ for name, (lo, hi) in {"init": (5, 55), "conv": (120, min(170, T))}.items():
 out["fallbacks/step"] = st["nn_fallbacks"] / T
 out["on_surface"] = st["on_surface"]
 out["mesh_deferred/step"] = st["mesh_deferred"] / T
+out["scan_deferred/step"] = st["scan_deferred"] / T
 print(json.dumps(out))
