@@ -3,8 +3,8 @@
 * The reference persists a codebook as a dill pickle of the ``tactile_tree`` nn.Module with its
   pynanoflann tree inside (build_codebook.py:130-137, tactile_tree.py:13-41): unloadable without
   the original environment.  ``convert_pickled_codebook`` reads such a pickle WITHOUT importing
-  midastouch / pynanoflann / theseus (unknown classes are replaced by inert stand-ins that only
-  keep their state) and writes the plain-tensor format below.
+  midastouch / pynanoflann / theseus (only an explicit allow-list of tensor / array rebuild functions is
+  resolved; every other class or callable named by the file becomes an inert stand-in that only keeps its state) and writes the plain-tensor format below.
 * Plain format (``.npz``): ``poses`` (M,4,4) f32, ``cam_poses`` (M,4,4) f32, ``embeddings`` (M,D)
   f64 (dtype preserved), ``keys`` (M,6) f32 R3_SE3 keys when known, ``format`` = "midas-b200-codebook-1".
 * ``extract_poses_sim`` reads ``tactile_data.pkl`` (touch_simulator.py:158-167; pose.py:272-300):
@@ -39,10 +39,28 @@ class _Inert:
 
 
 class _TolerantUnpickler(pickle.Unpickler):
-    SAFE_PREFIXES = ("torch", "numpy", "collections", "builtins", "_codecs", "copyreg", "dill")
+    """Resolves ONLY the callables a tensor / array / ordered-dict pickle needs (an explicit (module, name) allow-list);
+    every other global -- the reference's own classes, pynanoflann, theseus, and anything a hostile file might name
+    (builtins.eval, os.system, ...) -- becomes an inert stand-in that merely stores its state."""
+
+    ALLOWED = {
+        ("collections", "OrderedDict"),
+        ("torch._utils", "_rebuild_tensor_v2"), ("torch._utils", "_rebuild_tensor"), ("torch._utils", "_rebuild_parameter"),
+        ("torch._utils", "_rebuild_parameter_with_state"),
+        ("torch", "FloatStorage"), ("torch", "DoubleStorage"), ("torch", "HalfStorage"), ("torch", "BFloat16Storage"),
+        ("torch", "LongStorage"), ("torch", "IntStorage"), ("torch", "ShortStorage"), ("torch", "CharStorage"),
+        ("torch", "ByteStorage"), ("torch", "BoolStorage"), ("torch", "Size"), ("torch", "device"), ("torch", "float32"),
+        ("torch", "float64"), ("torch", "float16"), ("torch", "int64"), ("torch", "int32"),
+        ("torch.storage", "_load_from_bytes"), ("torch.storage", "UntypedStorage"), ("torch.storage", "TypedStorage"),
+        ("torch.serialization", "_get_layout"),
+        ("numpy.core.multiarray", "_reconstruct"), ("numpy._core.multiarray", "_reconstruct"),
+        ("numpy.core.multiarray", "scalar"), ("numpy._core.multiarray", "scalar"),
+        ("numpy", "ndarray"), ("numpy", "dtype"),
+        ("_codecs", "encode"),
+    }
 
     def find_class(self, module, name):
-        if module.startswith(self.SAFE_PREFIXES):
+        if (module, name) in self.ALLOWED:
             try:
                 return super().find_class(module, name)
             except Exception:  # noqa: BLE001

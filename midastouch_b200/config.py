@@ -12,7 +12,10 @@ import yaml
 CONFIG_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "config")
 
 # PyYAML follows YAML 1.1 where "2e-4" (no dot) is a string; hydra/omegaconf read it as a float
-_loader = yaml.SafeLoader
+class _loader(yaml.SafeLoader):  # a subclass: the process-wide yaml.SafeLoader keeps its own resolvers
+    pass
+
+
 _loader.add_implicit_resolver(
     "tag:yaml.org,2002:float",
     __import__("re").compile(r"^[-+]?(\d+\.?\d*|\.\d+)([eE][-+]?\d+)$"), list("-+0123456789."))

@@ -1891,6 +1891,9 @@ __global__ void __launch_bounds__(256) k_step_b(StepDev p) {
 #define MT_BW_MAX_PER 32
 #define MT_BW_FAST_PER 10  // chunks per block whose weights stay in shared memory (30 KB)
 #define MT_BW_MAX_GRID 1184
+#ifndef MT_BW_PREFETCH
+#define MT_BW_PREFETCH 0
+#endif
 __global__ void __launch_bounds__(256, 4) k_step_bw(StepDev p, unsigned long long* bar, unsigned long long bar_target,
                                                  double* __restrict__ blocktot /* 3 x grid */, int* __restrict__ blockcnt) {
   __shared__ double s8[8];
@@ -2053,6 +2056,15 @@ __global__ void __launch_bounds__(256, 4) k_step_bw(StepDev p, unsigned long lon
     slot_base = mt_count_below(A / S, N, (double)N, (double)(p.u / (float)N));
   }
   double run = base_g;
+#if MT_BW_PREFETCH
+  // the poses of chunk c + 1 are requested before chunk c is scanned and scattered: the block's chunks are a chain of
+  // dependent steps (scan -> slot counts -> scatter), and its next loads travel underneath
+  ChunkIn nxt;
+  if (cached && c_lo < c_hi) {
+    const long long i = (long long)c_lo * MT_CHUNK + threadIdx.x;
+    if (i < n) load_pose_stream(p.soa_cur, p.stride, i, nxt.P);
+  }
+#endif
   for (int c = c_lo; c < c_hi; ++c) {
     const double base = fmin(run, next_g);
     run += s_part[c - c_lo];
@@ -2064,7 +2076,16 @@ __global__ void __launch_bounds__(256, 4) k_step_bw(StepDev p, unsigned long lon
       const long long i = (long long)c * MT_CHUNK + threadIdx.x;
       cur.nn = s_nn[(c - c_lo) * MT_CHUNK + threadIdx.x];
       cur.e = s_e[(c - c_lo) * MT_CHUNK + threadIdx.x];
+#if MT_BW_PREFETCH
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) cur.P[a][b] = nxt.P[a][b];
+      const long long i2 = i + MT_CHUNK;
+      if (c + 1 < c_hi && i2 < n) load_pose_stream(p.soa_cur, p.stride, i2, nxt.P);
+#else
       if (i < n) load_pose_stream(p.soa_cur, p.stride, i, cur.P);
+#endif
     } else {
       step_b_load<true, true>(p, c, n, cur);
     }

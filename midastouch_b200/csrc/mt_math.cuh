@@ -288,12 +288,23 @@ MT_HD double mt_loc(long long k, double dN, double off) {
   return l;
 }
 
+// fl(k / dN), correctly rounded, without a division in the loop: with rN = fl(1 / dN), q = fl(k rN),
+// r = k - q dN (exact in one fma), fl(q + r rN) is the correctly rounded quotient (Markstein's correction step; it
+// needs rN within half an ulp of 1/dN, which the IEEE division gives, and fails only for divisors whose 53-bit
+// significand is all ones -- not an integer particle count).  Checked against the division itself in
+// tests/test_host_math.py.
+MT_HD double mt_div_rn(double k, double dN, double rN) {
+  const double q = k * rN;
+  const double r = fma(-q, dN, k);
+  return fma(r, rN, q);
+}
+
 // loc with the two-pointer semantics of the reference loop (particle_filter.py:295-302):
 // if the last location wraps to ~0 it is assigned to whichever parent owns slot N-2, i.e.
 // it behaves like loc(N-2) for counting.
-MT_HD double mt_loc_mono(long long k, long long N, double dN, double off) {
-  double l = (double)k / dN + off;
-  if (l >= 1.0) l = (k > 0) ? ((double)(k - 1) / dN + off) : (l - 1.0);  // only k = N-1 can wrap
+MT_HD double mt_loc_mono(long long k, long long N, double dN, double rN, double off) {
+  double l = mt_div_rn((double)k, dN, rN) + off;
+  if (l >= 1.0) l = (k > 0) ? (mt_div_rn((double)(k - 1), dN, rN) + off) : (l - 1.0);  // only k = N-1 can wrap
   (void)N;
   return l;
 }
@@ -302,10 +313,11 @@ MT_HD double mt_loc_mono(long long k, long long N, double dN, double off) {
 // whose loc is >= C.  A closed-form guess is corrected with exact comparisons.
 MT_HD long long mt_count_below(double C, long long N, double dN, double off) {
   if (!(C == C)) return 0;  // NaN CDF value owns nothing
+  const double rN = 1.0 / dN;
   double g = ceil((C - off) * dN);
   long long k = (g <= 0.0) ? 0 : (g >= dN ? N : (long long)g);
-  while (k > 0 && !(mt_loc_mono(k - 1, N, dN, off) < C)) --k;
-  while (k < N && (mt_loc_mono(k, N, dN, off) < C)) ++k;
+  while (k > 0 && !(mt_loc_mono(k - 1, N, dN, rN, off) < C)) --k;
+  while (k < N && (mt_loc_mono(k, N, dN, rN, off) < C)) ++k;
   return k;
 }
 

@@ -45,6 +45,11 @@ void h_ancestors_from_cdf(const double* C, long long n, float u, long long* anc)
   }
   for (long long s = prev; s < n; ++s) anc[s] = -1;
 }
+// mt_div_rn(k, dN, 1 / dN) for k = k0 .. k0 + cnt - 1
+void h_div_rn(long long k0, long long cnt, long long n, double* out) {
+  const double dN = (double)n, rN = 1.0 / dN;
+  for (long long k = 0; k < cnt; ++k) out[k] = mt_div_rn((double)(k0 + k), dN, rN);
+}
 void h_locs(long long n, float u, double* out) {
   double dN = (double)n, off = (double)(u / (float)n);
   for (long long k = 0; k < n; ++k) out[k] = mt_loc(k, dN, off);

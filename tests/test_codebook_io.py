@@ -75,3 +75,23 @@ def test_extract_poses_sim(tmp_path):
     assert cam.shape == (7, 4, 4) and cam.dtype == torch.float32
     assert np.allclose(gel[:, :3, :3].numpy(), R.from_quat(d["gelposes"][:, 3:]).as_matrix(), atol=1e-6)
     assert np.allclose(meas[:, :3, 3].numpy(), d["gelposes_meas"][:, :3], atol=1e-6)
+
+
+def test_hostile_pickle_executes_nothing(tmp_path):
+    """the reader resolves an explicit allow-list only: a pickle that names builtins.eval / os.system gets inert objects"""
+    marker = tmp_path / "pwned"
+
+    class Evil:
+        def __reduce__(self):
+            import os
+
+            return (os.system, (f"touch {marker}",))
+
+    class Evil2:
+        def __reduce__(self):
+            return (eval, (f"open({str(marker)!r}, 'w').close()",))
+
+    for raw in (pickle.dumps({"poses": Evil()}), pickle.dumps({"poses": Evil2()})):
+        obj = io_._TolerantUnpickler(__import__("io").BytesIO(raw)).load()
+        assert isinstance(obj["poses"], io_._Inert)
+    assert not marker.exists()

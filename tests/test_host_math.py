@@ -103,6 +103,20 @@ def test_locs_and_counts(H, n):
         assert np.array_equal(anc, O.low_var_indices(w, u).numpy())
 
 
+@pytest.mark.parametrize("n", [1, 2, 3, 7, 1000, 1024, 65536, 999983, 1000000, 1000003, (1 << 24) - 1, 16000000, (1 << 31) - 1])
+def test_division_free_quotient_is_correctly_rounded(H, n):
+    """mt_div_rn(k, N, fl(1/N)) == fl(k / N) bit for bit (the systematic sample locations k/N of particle_filter.py:254-261
+    are computed without a division in the resampling kernel)"""
+    rng = np.random.default_rng(n)
+    starts = [0] if n <= 70000 else [0, n - 50000] + [int(x) for x in rng.integers(0, n - 50000, 6)]
+    for k0 in starts:
+        cnt = min(n, 70000) if k0 == 0 else 50000
+        out = np.empty(cnt, dtype=np.float64)
+        H.h_div_rn(ctypes.c_longlong(k0), ctypes.c_longlong(cnt), ctypes.c_longlong(n), out.ctypes.data_as(ctypes.c_void_p))
+        want = np.arange(k0, k0 + cnt, dtype=np.float64) / np.float64(n)
+        assert np.array_equal(out, want), (n, k0, int((out != want).sum()))
+
+
 def test_philox_normals_statistics(H):
     n = 200000
     out = np.zeros((n, 6), np.float32)
