@@ -2473,6 +2473,7 @@ extern "C" int mt_step(mt_ctx* c, const mt_step_args* a, const void* d_q, int q_
   const bool has_mesh = d.prune_dist > 0.0;
   const void* f_a = (const void*)k_step_a;
   const dim3 grid_a((unsigned)((cover + MT_A_BLOCK - 1) / MT_A_BLOCK)), block_a(MT_A_BLOCK);
+  const size_t smem_a = 0;
   void* args_s[] = {&d, &T};
   // configuration key: everything that is baked into the graph's topology or launch geometry
   unsigned long long key[20] = {(unsigned long long)a->d_soa_cur, (unsigned long long)a->d_soa_next, (unsigned long long)a->d_nn_cur,
@@ -2495,7 +2496,7 @@ extern "C" int mt_step(mt_ctx* c, const mt_step_args* a, const void* d_q, int q_
     return p;
   };
   cudaKernelNodeParams P_q = kparams(Q.func, dim3(Q.grid), dim3(256), Q.smem, args_q);
-  cudaKernelNodeParams P_a = kparams(f_a, grid_a, block_a, 0, args_a);
+  cudaKernelNodeParams P_a = kparams(f_a, grid_a, block_a, smem_a, args_a);
   cudaKernelNodeParams P_s = kparams((const void*)k_step_scanq, dim3(c->sm_count * 8), dim3(256), 0, args_s);
   cudaKernelNodeParams P_m1 = kparams((const void*)k_step_meshq, dim3(c->sm_count * 4), dim3(256), 0, args_m);
   cudaKernelNodeParams P_m2 = kparams((const void*)k_step_meshq2, dim3(c->sm_count * 8), dim3(256), 0, args_m);
