@@ -18,6 +18,7 @@ eng = FilterEngine(cb, capacity=n, sig_t=2e-4, sig_r=0.5, seed=1234, mesh_vertic
 g = torch.Generator().manual_seed(100)
 sel = torch.randint(0, bench.M, (n,), generator=g)
 eng.use_graph = bool(os.environ.get("AB_GRAPH"))
+eng.fuse_sums = not bool(os.environ.get("AB_UNFUSED"))
 eng.load_particles(cbs.poses.to(dev)[sel.to(dev)], nn_hint=sel.int().to(dev), spatial_sort=True)
 odoms = [prepare_odom(torch.inverse(meas[t - 1]) @ meas[t]) for t in range(1, bench.T_TRAJ)]
 codes = [synth.make_pose_query(gt[t + 1], bench.D, seed=3, frame=t).to(dev) for t in range(bench.T_TRAJ - 1)]
