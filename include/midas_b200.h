@@ -230,6 +230,12 @@ int mt_dist_import(mt_ctx* ctx, int rank, int world, const void* h_handles);
 /* diagnostics of the last fused sharded step (synchronises): %globaltimer (ns) of block 0 at the end of the local
  * phase, after its sums were sent, and after all peers' sums had arrived */
 int mt_dist_debug(mt_ctx* ctx, unsigned long long* h_out3);
+/* diagnostics (synchronises): the context's 64-word timestamp buffer.  In a library built with -DMT_TRACE=1 the step
+ * kernels record the earliest block start / latest block end (%globaltimer, ns) in words 8 + 2k / 9 + 2k
+ * (k = 0 k_step_a, 1 k_step_meshq, 2 k_step_meshq2, 3 k_step_nnq, 4 k_step_bw) and k_step_bw its phase boundaries
+ * in words 24..28; h_out64[63] = 1 for such a build, 0 for the shipped one (which records nothing).  reset != 0
+ * re-arms the buffer for the next step. */
+int mt_trace_read(mt_ctx* ctx, unsigned long long* h_out64, int reset);
 /* *h_fused = 1 when mt_step_a/mt_step_b will run this step in the fused form (sums + exchange + resampling in
  * one cooperative kernel; a sharded caller then skips its all-gather of the weight sums), else 0 */
 int mt_step_is_fused(mt_ctx* ctx, const mt_step_args* a, int* h_fused);

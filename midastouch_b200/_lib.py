@@ -94,6 +94,7 @@ _SIGS = {
     "mt_dist_export": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mt_dist_import": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "mt_dist_debug": (C.c_int, [C.c_void_p, C.POINTER(C.c_ulonglong)]),
+    "mt_trace_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_ulonglong), C.c_int]),
     "mt_step_is_fused": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]),
     "mt_step_a": (C.c_int, [C.c_void_p, C.POINTER(StepArgs), C.c_void_p]),
     "mt_step_local_sum_ptr": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),

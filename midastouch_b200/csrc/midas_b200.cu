@@ -172,8 +172,8 @@ extern "C" int mt_ctx_create(int device, size_t capacity, int M, int D, mt_ctx**
   CK(cudaMalloc(&c->d_xchg, sizeof(Xchg)));
   CK(cudaMemset(c->d_xchg, 0, sizeof(Xchg)));
   CK(cudaMalloc(&c->d_peers, sizeof(Xchg*) * MT_MAX_WORLD));
-  CK(cudaMalloc(&c->d_xdbg, sizeof(unsigned long long) * 4));
-  CK(cudaMemset(c->d_xdbg, 0, sizeof(unsigned long long) * 4));
+  CK(cudaMalloc(&c->d_xdbg, sizeof(unsigned long long) * 64));
+  CK(cudaMemset(c->d_xdbg, 0, sizeof(unsigned long long) * 64));
   CK(cudaMalloc(&c->d_bw, sizeof(double) * 3 * 1184));
   CK(cudaMalloc(&c->d_bwcnt, sizeof(int) * 1184));
   CK(cudaMalloc(&c->d_prefix, sizeof(double) * (c->chunk_cap + 1)));
@@ -497,6 +497,27 @@ __device__ __forceinline__ double block_incl_scan_256(double v, double* s8) {
   for (int k = 0; k < MT_CHUNK / 32; ++k)
     if (k < w) carry += s8[k];
   return carry + v;
+}
+
+// The same scan made monotone: float64 rounding can leave a Kogge-Stone prefix of non-negative terms an ulp below
+// its predecessor; a running maximum (exact, associative) on top removes that.  Every block that runs this on the
+// same inputs gets the same bits.
+__device__ __forceinline__ double block_incl_scan_mono_256(double v, double* s8) {
+  v = block_incl_scan_256(v, s8);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v = fmax(v, t);
+  }
+  __syncthreads();
+  if (lane == 31) s8[w] = v;
+  __syncthreads();
+  double m = 0.0;
+#pragma unroll
+  for (int k = 0; k < MT_CHUNK / 32; ++k)
+    if (k < w) m = fmax(m, s8[k]);
+  return fmax(v, m);
 }
 
 // Last block standing: exclusive prefix over `n` chunk sums with one 256-thread block.
@@ -1319,6 +1340,29 @@ extern "C" int mt_gather_f64(const double* d_in, const int32_t* d_anc, long long
 }
 
 // ------------------------------------------------------------------------- fused step
+// MT_TRACE builds (diagnostics, scripts/step_trace.py): every step kernel records the earliest start and the latest end
+// of its blocks (%globaltimer, ns) in words [8 + 2k, 8 + 2k + 1] of the context's debug buffer -- k = 0 k_step_a,
+// 1 k_step_meshq, 2 k_step_meshq2, 3 k_step_nnq, 4 k_step_bw -- and k_step_bw its phase boundaries in words 24..28.
+// mt_trace_read returns the buffer.  Off in the shipped library (no instructions emitted).
+#ifndef MT_TRACE
+#define MT_TRACE 0
+#endif
+__device__ __forceinline__ unsigned long long mt_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#if MT_TRACE
+#define MT_TRACE_BEGIN(buf, k) if (threadIdx.x == 0) atomicMin((buf) + 8 + 2 * (k), mt_now());
+#define MT_TRACE_END(buf, k) if ((threadIdx.x & 31) == 0) atomicMax((buf) + 9 + 2 * (k), mt_now());
+#define MT_TRACE_MAX(buf, w) if (threadIdx.x == 0) atomicMax((buf) + (w), mt_now());
+#define MT_TRACE_MIN(buf, w) if (threadIdx.x == 0) atomicMin((buf) + (w), mt_now());
+#else
+#define MT_TRACE_BEGIN(buf, k)
+#define MT_TRACE_END(buf, k)
+#define MT_TRACE_MAX(buf, w)
+#define MT_TRACE_MIN(buf, w)
+#endif
 struct StepDev {
   float4* soa_cur;
   float4* soa_next;
@@ -1413,11 +1457,15 @@ __device__ __forceinline__ long long step_count(const StepDev& p) {
 #ifndef MT_A_SCAN_CAP
 #define MT_A_SCAN_CAP 64
 #endif
+// (A persistent form of this kernel -- grid = resident blocks, grid-stride tiles, the next tile's hint / key / list head
+// prefetched one tile ahead -- was measured 10 % slower, 103 vs 93 us: the hardware block scheduler balances the
+// long-tailed scans better than a static tile assignment.)
 __global__ void __launch_bounds__(MT_A_BLOCK, MT_A_MINBLOCKS) k_step_a(StepDev p, NNTables T, MeshTables Mh) {
-  const long long i = (long long)blockIdx.x * MT_A_BLOCK + threadIdx.x;
   const long long n = step_count(p);
-  const bool valid = i < n;
   const int lane = threadIdx.x & 31;
+  MT_TRACE_BEGIN(p.xdbg, 0)
+  const long long i = (long long)blockIdx.x * MT_A_BLOCK + threadIdx.x;
+  const bool valid = i < n;
   double et2 = 0.0, ang2 = 0.0;
   bool on_surface = valid;
   int todo = 0;
@@ -1498,6 +1546,7 @@ __global__ void __launch_bounds__(MT_A_BLOCK, MT_A_MINBLOCKS) k_step_a(StepDev p
     p.wcnt[gw] = __popc(on);
     if (p.has_gt) p.wrm[2 * gw] = et2, p.wrm[2 * gw + 1] = ang2;
   }
+  MT_TRACE_END(p.xdbg, 0)
 }
 
 // Continuation of the hint-graph scans that k_step_a cut short: one thread per record, on compacted warps whose lanes
@@ -1591,6 +1640,7 @@ __global__ void __launch_bounds__(256) k_step_meshq(StepDev p, MeshTables Mh) {
   const unsigned mn = p.qctl[3];
   const int lane = threadIdx.x & 31;
   const unsigned span = gridDim.x * blockDim.x;
+  MT_TRACE_BEGIN(p.xdbg, 1)
   for (unsigned e0 = blockIdx.x * blockDim.x + threadIdx.x - lane; e0 < mn; e0 += span) {  // whole warps stay in the loop
     const unsigned e = e0 + lane;
     int res = 1;  // 1 within, 0 not within, 2 grid search
@@ -1611,21 +1661,25 @@ __global__ void __launch_bounds__(256) k_step_meshq(StepDev p, MeshTables Mh) {
       if (res == 2) p.queue2[base + __popc(m2 & ((1u << lane) - 1))] = (int)i;
     }
   }
+  MT_TRACE_END(p.xdbg, 1)
 }
 __global__ void __launch_bounds__(256) k_step_meshq2(StepDev p, MeshTables Mh) {
   const unsigned n2 = p.qctl[2];
   const unsigned gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  MT_TRACE_BEGIN(p.xdbg, 2)
   for (unsigned e = gw; e < n2; e += nw) {
     const long long i = p.queue2[e];
     const float x = p.soa_cur[i].w, y = p.soa_cur[p.stride + i].w, z = p.soa_cur[2 * p.stride + i].w;
     const bool on = mesh_search_warp(Mh, x, y, z, p.prune_dist);
     if (!on && (threadIdx.x & 31) == 0) mesh_mark_off(p, i);
   }
+  MT_TRACE_END(p.xdbg, 2)
 }
 
 __global__ void __launch_bounds__(32 * MT_NNQ_WARPS) k_step_nnq(StepDev p, NNTables T, MeshTables Mh) {
   const unsigned qn = p.qctl[0];
   const int lane = threadIdx.x & 31;
+  MT_TRACE_BEGIN(p.xdbg, 3)
   if (qn) {
     // the search index (boxes 0.1 MB + Morton-ordered keys 32 B each) was last touched a step ago: pull it into
     // L2 with one prefetch per 128-byte line, spread over the grid, so that the dependent rounds of the searches
@@ -1653,6 +1707,7 @@ __global__ void __launch_bounds__(32 * MT_NNQ_WARPS) k_step_nnq(StepDev p, NNTab
     if (lane == 0) e = W + atomicAdd(p.qctl + 1, 1u);
     e = __shfl_sync(0xffffffffu, e, 0);
   }
+  MT_TRACE_END(p.xdbg, 3)
 }
 
 // chunk sums of the weights + (last block) prefix for kernel B, RMSE, drift flag
@@ -1894,6 +1949,12 @@ __global__ void __launch_bounds__(256) k_step_b(StepDev p) {
 #ifndef MT_BW_PREFETCH
 #define MT_BW_PREFETCH 0
 #endif
+#ifndef MT_BW_FLAT
+#define MT_BW_FLAT 1  // barrier-free phase 2 when the block's weights fit in shared memory
+#endif
+#ifndef MT_BW_P1
+#define MT_BW_P1 4  // chunks whose look-ups phase 1 issues together
+#endif
 __global__ void __launch_bounds__(256, 4) k_step_bw(StepDev p, unsigned long long* bar, unsigned long long bar_target,
                                                  double* __restrict__ blocktot /* 3 x grid */, int* __restrict__ blockcnt) {
   __shared__ double s8[8];
@@ -1908,24 +1969,25 @@ __global__ void __launch_bounds__(256, 4) k_step_bw(StepDev p, unsigned long lon
   const int nwarps = (int)((n + 31) >> 5);
   const int per = (p.nchunks + G - 1) / G;
   const int c_lo = g * per, c_hi = min(c_lo + per, p.nchunks);
+  MT_TRACE_BEGIN(p.xdbg, 4)
   // ---- phase 1: weights of this block's chunks.  Up to MT_BW_FAST_PER chunks keep (match, weight) of
   // every particle in shared memory for phase 2; the look-ups are issued four chunks at a time so that
   // their DRAM / L2 latencies overlap.
   const bool cached = per <= MT_BW_FAST_PER;
   double tot = 0.0, ra = 0.0, rb = 0.0;
   int cnt = 0;
-  for (int c0 = c_lo; c0 < c_hi; c0 += 4) {
-    int st4[4];
-    double e4[4];
+  for (int c0 = c_lo; c0 < c_hi; c0 += MT_BW_P1) {
+    int st4[MT_BW_P1];
+    double e4[MT_BW_P1];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < MT_BW_P1; ++k) {
       const long long i = (long long)(c0 + k) * MT_CHUNK + threadIdx.x;
       st4[k] = (c0 + k < c_hi && i < n) ? mt_lds(p.nn_cur + i) : -1;
     }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) e4[k] = (st4[k] >= 0) ? mt_ldk(p.wtab + st4[k]) : 0.0;  // masked (< -1) and absent (-1): 0
+    for (int k = 0; k < MT_BW_P1; ++k) e4[k] = (st4[k] >= 0) ? mt_ldk(p.wtab + st4[k]) : 0.0;  // masked (< -1) and absent (-1): 0
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < MT_BW_P1; ++k) {
       const int c = c0 + k;
       if (c >= c_hi) break;
       if (cached) s_e[(c - c_lo) * MT_CHUNK + threadIdx.x] = e4[k], s_nn[(c - c_lo) * MT_CHUNK + threadIdx.x] = nn_index(st4[k]);
@@ -1947,46 +2009,43 @@ __global__ void __launch_bounds__(256, 4) k_step_bw(StepDev p, unsigned long lon
     blocktot[g] = tot, blocktot[G + g] = ra, blocktot[2 * G + g] = rb;
     blockcnt[g] = cnt;
     __threadfence();
+    MT_TRACE_MAX(p.xdbg, 24)
     atomicAdd(bar, 1ull);
     while (*(volatile unsigned long long*)bar < bar_target) {
     }
     __threadfence();
+    MT_TRACE_MIN(p.xdbg, 25)
+    MT_TRACE_MAX(p.xdbg, 26)
   }
   __syncthreads();
   // ---- phase 2
   for (int j = threadIdx.x; j < G; j += blockDim.x) s_tot[j] = __ldcg(blocktot + j);
   __syncthreads();
   {
-    // prefix of the G block totals, the same code (hence bit-identical values) in every block: thread t
-    // owns a contiguous run, E[t+1] = E[t] + (sum of run t) sequentially, values inside a run are
-    // E[t] + (local prefix from 0) -- so the end of run t IS E[t+1] and everything is monotone
+    // prefix of the G block totals, the same code (hence bit-identical values) in every block: thread t owns a
+    // contiguous run of totals, the run sums are block-scanned (monotone form) into E[0..256], and the values inside
+    // run t are E[t] + (local prefix), clamped to E[t+1]; a run's last end IS E[t+1], which is also where the next
+    // run starts -- so neighbouring blocks agree on their common boundary and everything is monotone
     __shared__ double s_loc[MT_CHUNK + 1];
-    const int per = (G + MT_CHUNK - 1) / MT_CHUNK;  // <= 5
-    const int b0 = threadIdx.x * per;
+    const int perb = (G + MT_CHUNK - 1) / MT_CHUNK;  // <= 5
+    const int b0 = threadIdx.x * perb;
     double loc = 0.0;
-    for (int k = 0; k < per; ++k)
+    for (int k = 0; k < perb; ++k)
       if (b0 + k < G) loc += s_tot[b0 + k];
-    s_loc[threadIdx.x + 1] = loc;
+    const double I = block_incl_scan_mono_256(loc, s8);
+    s_loc[threadIdx.x + 1] = I;
+    if (threadIdx.x == 0) s_loc[0] = 0.0;
+    if (threadIdx.x == MT_CHUNK - 1) s_bc[2] = I;
     __syncthreads();
-    if (threadIdx.x == 0) {
-      double e = 0.0;
-      s_loc[0] = 0.0;
-      for (int t = 0; t < MT_CHUNK; ++t) {
-        const double l = s_loc[t + 1];
-        s_loc[t + 1] = e + l;  // E[t+1]
-        e += l;
-      }
-      s_bc[2] = e;
-    }
-    __syncthreads();
-    const double E = s_loc[threadIdx.x];
+    const double E = s_loc[threadIdx.x], En = s_loc[threadIdx.x + 1];
     double lp = 0.0;
-    for (int k = 0; k < per; ++k) {
+    for (int k = 0; k < perb; ++k) {
       const int j = b0 + k;
       if (j < G) {
-        if (j == g) s_bc[0] = E + lp;
+        const double start = (k == 0) ? E : fmin(E + lp, En);
         lp += s_tot[j];
-        if (j == g) s_bc[1] = E + lp;
+        const double end = (k == perb - 1 || j == G - 1) ? En : fmin(E + lp, En);
+        if (j == g) s_bc[0] = start, s_bc[1] = end;
       }
     }
   }
@@ -2055,6 +2114,135 @@ __global__ void __launch_bounds__(256, 4) k_step_bw(StepDev p, unsigned long lon
     const long long N = p.n_global;
     slot_base = mt_count_below(A / S, N, (double)N, (double)(p.u / (float)N));
   }
+  MT_TRACE_MAX(p.xdbg, 27)
+#if MT_BW_FLAT
+  if (cached) {
+    // ---- phase 2, flat form: one scan over ALL of the block's weights (they sit in shared memory), then a scatter
+    // loop without a single block barrier.  The chunk-by-chunk form below synchronises the block five times per
+    // chunk, and a third of its stall cycles were barrier waits.
+    //  (a) transposed pass: thread t owns `per` consecutive particles of the block; sequential local prefix, monotone
+    //      block scan of the thread totals, CDF value = fmin((base_g + X_t) + local, base_g + X_{t+1}, next_g) -- a
+    //      non-decreasing sequence that starts at base_g and is pinned to next_g at the block's last particle, so
+    //      neighbouring blocks (and GPUs) still agree bit for bit on their boundary; slot counts replace the weights
+    //      in shared memory
+    //  (b) coalesced pass: particle (chunk, thread) reads its own and its predecessor's count and writes its children
+    const long long i0 = (long long)c_lo * MT_CHUNK;
+    const long long left = n - i0;
+    const int nloc = (int)(left < 0 ? 0 : (left < (long long)(c_hi - c_lo) * MT_CHUNK ? left : (long long)(c_hi - c_lo) * MT_CHUNK));
+    const long long N = p.n_global;
+    const double dN = (double)N;
+    const double off = (double)(p.u / (float)N);  // float32 division, then promoted (particle_filter.py:260)
+    const bool bad = !(S > 0.0) || !(S <= DBL_MAX);  // all-zero / NaN / Inf weights: identity (237-241)
+    long long* s_cntall = reinterpret_cast<long long*>(s_e);
+    __shared__ double s_x2[MT_CHUNK + 1];
+    __shared__ long long s_cbase;
+    if (!bad) {
+      const int j0 = threadIdx.x * per;
+      double v[MT_BW_FAST_PER];
+      double acc = 0.0;
+#pragma unroll
+      for (int k = 0; k < MT_BW_FAST_PER; ++k) {
+        if (k < per) {
+          if (j0 + k < nloc) acc += s_e[j0 + k];
+          v[k] = acc;
+        }
+      }
+      const double I = block_incl_scan_mono_256(acc, s8);
+      s_x2[threadIdx.x + 1] = I;
+      if (threadIdx.x == 0) {
+        s_x2[0] = 0.0;
+        s_cbase = mt_count_below(base_g / S, N, dN, off);
+      }
+      __syncthreads();
+      const double lo = base_g + s_x2[threadIdx.x], hi = fmin(base_g + s_x2[threadIdx.x + 1], next_g);
+#pragma unroll
+      for (int k = 0; k < MT_BW_FAST_PER; ++k) {
+        if (k < per && j0 + k < nloc) {
+          const bool is_end = (j0 + k == nloc - 1);
+          const double C = is_end ? next_g / S : fmin(lo + v[k], hi) / S;
+          s_cntall[j0 + k] = mt_count_below(C, N, dN, off);
+        }
+      }
+    } else if (threadIdx.x == 0) {
+      p.flags[1] = 1;
+    }
+    __syncthreads();
+    const long long cap = p.stride;
+    const int lane = threadIdx.x & 31;
+    for (int c = c_lo; c < c_hi; ++c) {
+      const int il = (c - c_lo) * MT_CHUNK + threadIdx.x;
+      const long long i = i0 + il;
+      const bool valid = il < nloc;
+      float P[3][4];
+      int nn = 0;
+      long long cnt = 0, prev = 0;
+      if (valid) {
+        load_pose_stream(p.soa_cur, p.stride, i, P);
+        nn = s_nn[il];
+        if (bad) {
+          // the reference returns the particles unchanged (237-241); when every particle has drifted off the mesh it
+          // first re-projects them onto the codebook (filter.py:176-179)
+          if (S == 0.0 && p.prune_dist > 0.0 && p.cb_poses) {
+            const float4 a = __ldg(p.cb_poses + 4 * (size_t)nn), b = __ldg(p.cb_poses + 4 * (size_t)nn + 1),
+                         c2 = __ldg(p.cb_poses + 4 * (size_t)nn + 2);
+            P[0][0] = a.x, P[0][1] = a.y, P[0][2] = a.z, P[0][3] = a.w;
+            P[1][0] = b.x, P[1][1] = b.y, P[1][2] = b.z, P[1][3] = b.w;
+            P[2][0] = c2.x, P[2][1] = c2.y, P[2][2] = c2.z, P[2][3] = c2.w;
+          }
+          cnt = i + 1, prev = i;
+        } else {
+          cnt = s_cntall[il];
+          prev = il > 0 ? s_cntall[il - 1] : s_cbase;
+        }
+        if (i == n - 1 && p.n_out) *p.n_out = cnt - (bad ? 0 : slot_base);
+      }
+      long long kids = valid ? (cnt - prev) : 0;
+      if (kids < 0) kids = 0;
+      const long long dst = prev - (bad ? 0 : slot_base);
+      const bool heavy = kids > 8;  // light parents write their own children; heavy parents are spread over the warp
+      if (!heavy) {
+        for (long long k = 0; k < kids; ++k) {
+          const long long sl = dst + k;
+          if (sl >= cap) {
+            p.flags[0] = 1;
+            break;
+          }
+          store_pose_stream(p.soa_next, p.stride, sl, P);
+          mt_sts(p.nn_next + sl, nn);
+          if (p.anc) mt_sts(p.anc + sl, (int)i);
+        }
+      }
+      unsigned hm = __ballot_sync(0xffffffffu, heavy);
+      while (hm) {
+        const int src = __ffs(hm) - 1;
+        hm &= hm - 1;
+        float Q[3][4];
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) Q[a][b] = __shfl_sync(0xffffffffu, P[a][b], src);
+        const long long d0 = __shfl_sync(0xffffffffu, dst, src);
+        const long long kn = __shfl_sync(0xffffffffu, kids, src);
+        const int pn = __shfl_sync(0xffffffffu, nn, src);
+        const long long pi = __shfl_sync(0xffffffffu, i, src);
+        for (long long k = lane; k < kn; k += 32) {
+          const long long sl = d0 + k;
+          if (sl >= cap) {
+            p.flags[0] = 1;
+            break;
+          }
+          store_pose_stream(p.soa_next, p.stride, sl, Q);
+          mt_sts(p.nn_next + sl, pn);
+          if (p.anc) mt_sts(p.anc + sl, (int)pi);
+        }
+      }
+#if MT_TRACE
+      if (c == c_lo) MT_TRACE_MAX(p.xdbg, 28)
+#endif
+    }
+  } else
+#endif
+  {
   double run = base_g;
 #if MT_BW_PREFETCH
   // the poses of chunk c + 1 are requested before chunk c is scanned and scattered: the block's chunks are a chain of
@@ -2091,7 +2279,12 @@ __global__ void __launch_bounds__(256, 4) k_step_bw(StepDev p, unsigned long lon
     }
     __syncthreads();  // s8 / s_cnt of the previous chunk are free
     step_b_chunk<true, true>(p, c, n, S, A, base, endv, s8, s_cnt, cur, slot_base);
+#if MT_TRACE
+    if (c == c_lo) MT_TRACE_MAX(p.xdbg, 28)
+#endif
   }
+  }
+  MT_TRACE_END(p.xdbg, 4)
   if (g == 0) {  // RMSE, drift flag, bookkeeping (what the last block of k_step_sums does)
     __syncthreads();
     double sa = 0.0, sb = 0.0;
@@ -2151,6 +2344,12 @@ __global__ void k_resample_seq(StepDev p) {
 
 // particles the grids must cover: with a device-resident count (d_n_in) the host only knows the capacity
 static long long step_cover(const mt_step_args* a) { return a->d_n_in ? a->stride : a->n; }
+// blocks of k_step_a: one per tile of MT_A_BLOCK particles
+static unsigned step_a_grid(const mt_ctx* c, long long cover) {
+  long long g = (cover + MT_A_BLOCK - 1) / MT_A_BLOCK;
+  (void)c;
+  return (unsigned)std::max(g, 1ll);
+}
 
 static int fill_step(mt_ctx* c, const mt_step_args* a, StepDev* d) {
   if (!c || !a) return set_err(MT_ERR_ARG, "step: null argument");
@@ -2278,6 +2477,23 @@ extern "C" int mt_dist_debug(mt_ctx* c, unsigned long long* h_out3) {
   return MT_OK;
 }
 
+extern "C" int mt_trace_read(mt_ctx* c, unsigned long long* h_out64, int reset) {
+  if (!c || !h_out64) return set_err(MT_ERR_ARG, "mt_trace_read: null");
+  CK(cudaSetDevice(c->device));
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(h_out64, c->d_xdbg, sizeof(unsigned long long) * 64, cudaMemcpyDeviceToHost));
+  if (reset) {  // "earliest" words (even trace slots, word 25) restart at the maximum, "latest" words at 0
+    unsigned long long init[64];
+    memcpy(init, h_out64, sizeof(init));
+    for (int k = 8; k < 64; ++k) init[k] = 0;
+    for (int k = 8; k < 24; k += 2) init[k] = ~0ull;
+    init[25] = ~0ull;
+    CK(cudaMemcpy(c->d_xdbg, init, sizeof(init), cudaMemcpyHostToDevice));
+  }
+  h_out64[63] = MT_TRACE;
+  return MT_OK;
+}
+
 extern "C" int mt_step_is_fused(mt_ctx* c, const mt_step_args* a, int* h_fused) {
   if (!c || !a || !h_fused) return set_err(MT_ERR_ARG, "mt_step_is_fused: null");
   *h_fused = step_fused(c, a) ? 1 : 0;
@@ -2295,7 +2511,7 @@ extern "C" int mt_step_a(mt_ctx* c, const mt_step_args* a, void* stream) {
   if (a->prune_dist > 0.0 && !c->mesh_ready) return set_err(MT_ERR_STATE, "mt_step_a: prune_dist given but no mesh uploaded");
   cudaStream_t st = (cudaStream_t)stream;
   if (c->timing[0]) CK(cudaEventRecord(c->timing[0], st));
-  k_step_a<<<(unsigned)((step_cover(a) + MT_A_BLOCK - 1) / MT_A_BLOCK), MT_A_BLOCK, 0, st>>>(d, tables_of(c), mesh_of(c));
+  k_step_a<<<step_a_grid(c, step_cover(a)), MT_A_BLOCK, 0, st>>>(d, tables_of(c), mesh_of(c));
   CK_LAUNCH();
 #if MT_A_SCAN_CAP < MT_NBR_K
   k_step_scanq<<<c->sm_count * 8, 256, 0, st>>>(d, tables_of(c));
@@ -2472,7 +2688,7 @@ extern "C" int mt_step(mt_ctx* c, const mt_step_args* a, const void* d_q, int q_
   void* args_bw[] = {&d, &bar, &target, &bw, &bwc};
   const bool has_mesh = d.prune_dist > 0.0;
   const void* f_a = (const void*)k_step_a;
-  const dim3 grid_a((unsigned)((cover + MT_A_BLOCK - 1) / MT_A_BLOCK)), block_a(MT_A_BLOCK);
+  const dim3 grid_a(step_a_grid(c, cover)), block_a(MT_A_BLOCK);
   const size_t smem_a = 0;
   void* args_s[] = {&d, &T};
   // configuration key: everything that is baked into the graph's topology or launch geometry

@@ -37,15 +37,36 @@ static inline float mt_nofma_add(float a, float b) { volatile float r = a + b; r
 #define MT_L2_HINTS 1
 #endif
 #if defined(__CUDACC__)
+// MT_POL_CONST: the two policies as immediate descriptors instead of a createpolicy instruction per use (what
+// createpolicy.fractional returns for fraction 1.0; the same 64-bit encodings CUTLASS passes as TMA cache hints:
+// cute/arch/copy_sm90_desc.hpp, CacheHintSm90::EVICT_FIRST / EVICT_LAST)
+#ifndef MT_POL_CONST
+#define MT_POL_CONST 1
+#endif
 __device__ __forceinline__ unsigned long long mt_pol_keep() {
+#if MT_POL_CONST
+  return 0x14F0000000000000ull;
+#else
   unsigned long long p;
   asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
   return p;
+#endif
 }
 __device__ __forceinline__ unsigned long long mt_pol_stream() {
+#if MT_POL_CONST
+  return 0x12F0000000000000ull;
+#else
   unsigned long long p;
   asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
   return p;
+#endif
+}
+// single-instruction square root (MUFU.SQRT, relative error <= 2^-22, subnormal inputs flush to zero): only for
+// quantities that enter inflated bounds or drawn noise, never for a compared distance or a key
+__device__ __forceinline__ float mt_sqrt_fast(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
 }
 #if MT_L2_HINTS
 // table loads (read-only data path, L2 evict_last)
@@ -395,7 +416,7 @@ MT_HD void mt_motion_normals(uint64_t seed, uint64_t step, uint64_t gid, float t
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
 #if defined(__CUDA_ARCH__)
-    const float r = sqrtf(-2.0f * __logf(mt_u01_21(ua[k])));
+    const float r = mt_sqrt_fast(-2.0f * __logf(mt_u01_21(ua[k])));  // argument in [2.4e-7, 30]
     float s, c;
     __sincosf(6.283185307179586f * mt_u01_21(ub[k]), &s, &c);
 #else

@@ -254,6 +254,22 @@ __device__ __forceinline__ void nn_prefetch(const NNTables& T, int hint) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(L + 16));
 }
 
+// Device form of mt_hint_limit: one MUFU.SQRT instead of the IEEE square root (8 instructions + a slow-path call).
+// Its error (2^-22 relative; a subnormal best_d flushes to 0, i.e. a term < 1.1e-19 is dropped) is covered by the
+// same 1e-5 inflation and by the absolute 1e-18 (far below the spacing of distinct float32 keys).
+__device__ __forceinline__ float mt_hint_limit_dev(float dh, float best_d) {
+  return fmaf(dh + mt_sqrt_fast(best_d), 1.00001f, 1e-18f);
+}
+// (distance, index) as one 64-bit word: distances are >= +0, so their bit patterns order like the floats, and the
+// unsigned comparison of two words is mt_better() -- smaller distance, ties to the lower index -- in two instructions.
+// A NaN distance (0x7fc00000) orders above everything finite and +Inf, like `d < best_d` being false.
+__device__ __forceinline__ unsigned long long mt_dist_word(float d, int i) {
+  return ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)i;
+}
+
+#ifndef MT_FAST_SCAN
+#define MT_FAST_SCAN 1
+#endif
 // (1) one thread per query, in two parts so that a kernel can cut the scan short and hand the rest to a compacted
 // second pass (the scan lengths are long-tailed; in lockstep a warp pays for its longest lane):
 //   nn_hint_begin  centre = hint or its near-pi partner, best = that key.  1: proven exact already, -1: no usable
@@ -283,13 +299,23 @@ __device__ __forceinline__ int nn_hint_begin(const NNTables& T, const float q[6]
     const float dp = mt_key_dist(q, kp);
     if (mt_better(dp, partner, best_d, best_i)) best_d = dp, best_i = partner, centre = partner, delta0 = dp0;
   }
+#if MT_FAST_SCAN
+  dh = mt_sqrt_fast(best_d);  // enters only the inflated stop bound
+  return delta0 > mt_hint_limit_dev(dh, best_d) ? 1 : 0;  // nearest other key of the centre already out of reach?
+#else
   dh = sqrtf(best_d);
-  return delta0 > mt_hint_limit(dh, best_d) ? 1 : 0;  // nearest other key of the centre already out of reach?
+  return delta0 > mt_hint_limit(dh, best_d) ? 1 : 0;
+#endif
 }
 
 __device__ __forceinline__ int nn_hint_scan(const NNTables& T, const float q[6], int centre, float dh, int j0, int j1, float& best_d,
                                             int& best_i) {
+#if MT_FAST_SCAN
+  float lim = mt_hint_limit_dev(dh, best_d);
+  unsigned long long bw = mt_dist_word(best_d, best_i);
+#else
   float lim = mt_hint_limit(dh, best_d);
+#endif
   const float4* __restrict__ L = T.nbr + (size_t)centre * (2 * MT_NBR_K);
   // Software pipeline: the two entries of the next half trip are requested before the current ones are evaluated, so
   // a trip waits for loads issued ~40 instructions (x the other resident warps) earlier.  The loads are volatile asm
@@ -297,6 +323,26 @@ __device__ __forceinline__ int nn_hint_scan(const NNTables& T, const float q[6],
   // exit tests.  Two register sets (x*, y*) alternate between "being evaluated" and "in flight".
   float4 xa0 = mt_ldnc(L + 2 * j0), xb0 = mt_ldnc(L + 2 * j0 + 1), xa1 = mt_ldnc(L + 2 * j0 + 2), xb1 = mt_ldnc(L + 2 * j0 + 3);
   float4 ya0, yb0, ya1, yb1;
+#if MT_FAST_SCAN
+#define MT_SCAN_DONE(r)                                                    \
+  {                                                                        \
+    best_d = __uint_as_float((unsigned)(bw >> 32)), best_i = (int)(unsigned)bw; \
+    return r;                                                              \
+  }
+#define MT_SCAN_ENTRY(A, B)                                                                             \
+  {                                                                                                     \
+    if (B.z > lim) MT_SCAN_DONE(1)                                                                      \
+    const float k[6] = {A.x, A.y, A.z, A.w, B.x, B.y};                                                  \
+    const float d = mt_key_dist(q, k);                                                                  \
+    const unsigned long long w = mt_dist_word(d, __float_as_int(B.w));                                  \
+    if (w < bw) bw = w;                                                                                 \
+  }
+// the stop bound only ever shrinks, so it may lag: it is refreshed once per pair of entries, unconditionally
+// (three instructions per pair instead of four predicated ones per entry)
+#define MT_SCAN_LIMIT() lim = mt_hint_limit_dev(dh, __uint_as_float((unsigned)(bw >> 32)));
+#else
+#define MT_SCAN_LIMIT()
+#define MT_SCAN_DONE(r) return r;
 #define MT_SCAN_ENTRY(A, B)                                                                             \
   {                                                                                                     \
     if (B.z > lim) return 1;                                                                            \
@@ -305,18 +351,23 @@ __device__ __forceinline__ int nn_hint_scan(const NNTables& T, const float q[6],
     const int idx = __float_as_int(B.w);                                                                \
     if (mt_better(d, idx, best_d, best_i)) best_d = d, best_i = idx, lim = mt_hint_limit(dh, d);        \
   }
+#endif
 #pragma unroll 1
   for (int j = j0; j < j1; j += 4) {
     ya0 = mt_ldnc(L + 2 * j + 4), yb0 = mt_ldnc(L + 2 * j + 5), ya1 = mt_ldnc(L + 2 * j + 6), yb1 = mt_ldnc(L + 2 * j + 7);
     MT_SCAN_ENTRY(xa0, xb0)
     MT_SCAN_ENTRY(xa1, xb1)
+    MT_SCAN_LIMIT()
     const int jn = min(j + 4, MT_NBR_K - 2);  // past the end of the list: a harmless re-read, never used
     xa0 = mt_ldnc(L + 2 * jn), xb0 = mt_ldnc(L + 2 * jn + 1), xa1 = mt_ldnc(L + 2 * jn + 2), xb1 = mt_ldnc(L + 2 * jn + 3);
     MT_SCAN_ENTRY(ya0, yb0)
     MT_SCAN_ENTRY(ya1, yb1)
+    MT_SCAN_LIMIT()
   }
+  MT_SCAN_DONE(0)
 #undef MT_SCAN_ENTRY
-  return 0;
+#undef MT_SCAN_DONE
+#undef MT_SCAN_LIMIT
 }
 
 __device__ __forceinline__ bool nn_hint_search(const NNTables& T, const float q[6], int hint, float& best_d, int& best_i) {
@@ -364,7 +415,9 @@ __device__ __forceinline__ int bvh_pick(float& lb, float& picked) {
 // one per lane.  The work depends on how many boxes the ball (q, sqrt(best)) touches in all six coordinates --
 // also for queries far off the key manifold, which a translation-only grid cannot prune.
 // stats (nullable): [0] += leaves visited, [3] = max leaves visited by one query.
+#ifndef MT_BVH_BATCH
 #define MT_BVH_BATCH 4
+#endif
 __device__ __noinline__ int nn_bvh_search(const NNTables& T, const float q[6], float best_d, int best_i, int* stats) {
   if (!(q[0] == q[0]) || !(q[1] == q[1]) || !(q[2] == q[2]) || !(q[3] == q[3]) || !(q[4] == q[4]) || !(q[5] == q[5]))
     return 0;  // NaN query: np.argmin semantics
