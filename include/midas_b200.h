@@ -79,7 +79,7 @@ int mt_ctx_set_timing_events(mt_ctx* ctx, void* const* events4);
 #define MT_STAT_DRIFTED 5       /* last mt_step_a: every particle failed the drift test */
 #define MT_STAT_ON_SURFACE 6    /* last mt_step_a: particles that passed the drift test */
 #define MT_STAT_MESH_DEFERRED 8 /* drift tests whose voxel was undecided and that ran the vertex search (cumulative) */
-#define MT_STAT_SCAN_DEFERRED 9 /* hint-graph scans cut short in the sweep and continued by the compacted pass (cumulative) */
+#define MT_STAT_SCAN_DEFERRED 9 /* unused (always 0): the two-pass hint scan was removed */
 int mt_ctx_stats(mt_ctx* ctx, long long* h_out, int reset);
 
 /* ---- mesh: particle_filter.__init__ (particle_filter.py:108-110) ------------------- */

@@ -103,7 +103,7 @@ struct mt_ctx {
   double* d_wpart;    // per-warp weight sums of kernel A (32 particles each)
   double* d_wrm;      // 2 x warp_cap rmse partials of kernel A
   int* d_wcnt;        // per-warp count of particles that passed the drift test
-  float4* d_rec;      // records of the scans k_step_a cut short (48 B each, k_step_scanq continues them)
+  float4* d_rec;      // search records of the queued particles (32 B each: key | best distance, best index), k_step_a -> k_step_nnq
   int* d_queue2;      // drift tests left for the grid search
   int* d_queue;       // particles whose hint-graph search was not conclusive (kernel A -> A2)
   unsigned int* d_qctl;  // [0] searches queued, [1] queue head, [3] deferred drift tests queued
@@ -141,6 +141,7 @@ static size_t nchunks_of(long long n) { return (size_t)((n + MT_CHUNK - 1) / MT_
 
 extern "C" int mt_ctx_create(int device, size_t capacity, int M, int D, mt_ctx** out) {
   if (!out || capacity == 0 || M <= 0 || D <= 0) return set_err(MT_ERR_ARG, "mt_ctx_create: bad argument");
+  if (capacity > 0x07ffffffull) return set_err(MT_ERR_CAPACITY, "mt_ctx_create: at most 2^27 - 1 particles per context (queue entries carry the index in 27 bits)");
   CK(cudaSetDevice(device));
   mt_ctx* c = new mt_ctx();
   memset(c, 0, sizeof(*c));
@@ -164,7 +165,7 @@ extern "C" int mt_ctx_create(int device, size_t capacity, int M, int D, mt_ctx**
   CK(cudaMalloc(&c->d_wcnt, sizeof(int) * c->warp_cap));
   CK(cudaMalloc(&c->d_queue, sizeof(int) * (capacity + 32)));
   CK(cudaMalloc(&c->d_queue2, sizeof(int) * (capacity + 32)));
-  CK(cudaMalloc(&c->d_rec, sizeof(float4) * 3 * (capacity + 32)));
+  CK(cudaMalloc(&c->d_rec, sizeof(float4) * 2 * (capacity + 32)));
   CK(cudaMalloc(&c->d_qctl, sizeof(unsigned int) * 8));
   CK(cudaMemset(c->d_qctl, 0, sizeof(unsigned int) * 8));
   CK(cudaMalloc(&c->d_bar, sizeof(unsigned long long)));
@@ -1399,7 +1400,7 @@ struct StepDev {
   double* wpart;
   double* wrm;
   int* wcnt;
-  float4* srec;         // scans cut short in k_step_a, 3 float4 each: key | k4,k5,best_d,dh | best_i,centre,particle,flags
+  float4* srec;         // search record of queue entry e, 2 float4: k0..k3 | k4, k5, best_d, best_i bits
   int* queue;
   int* queue2;          // drift tests that need the grid search (k_step_meshq -> k_step_meshq2)
   long long queue_cap;  // entries in `queue` (searches grow from the front, deferred drift tests from the back)
@@ -1440,7 +1441,7 @@ __device__ __forceinline__ long long step_count(const StepDev& p) {
 #define MT_A_BLOCK 64
 #endif
 #ifndef MT_A_MINBLOCKS
-#define MT_A_MINBLOCKS 16  // 64 registers (the pipelined scan keeps two trips of list entries in registers)
+#define MT_A_MINBLOCKS 18  // 56 registers: 36 warps per SM (measured: 16 -> 18 blocks = -1.5 us; 20 blocks need 51 registers)
 #endif
 #ifndef MT_MESH_DEFER
 #define MT_MESH_DEFER 1  // undecided voxels of the drift test go to the queue instead of stalling their warp
@@ -1448,15 +1449,10 @@ __device__ __forceinline__ long long step_count(const StepDev& p) {
 // queue entries: particle index | what is left to do for it
 #define MT_Q_NN 0x20000000    // the hint-graph search was not conclusive: box-hierarchy search
 #define MT_Q_MESH 0x40000000  // the voxel class was "undecided": vertex search of the drift test
-#define MT_Q_SCAN 0x10000000  // (k_step_a internal) the hint scan was cut at MT_A_SCAN_CAP: k_step_scanq continues it
-#define MT_Q_INDEX 0x0fffffff
-// MT_A_SCAN_CAP < 64 cuts the hint scan of k_step_a after that many list entries and lets k_step_scanq continue the rest on
-// compacted warps.  Measured on the bench workload (drill, 1e6 particles): 42 % of the scans need more than 16 entries,
-// 19 % more than 24 -- the tail is too fat for the second pass to pay (k_step_a + k_step_scanq: 105 us at 16, 102 us at
-// 24, 99 us uncut), so the default leaves the scan whole.
-#ifndef MT_A_SCAN_CAP
-#define MT_A_SCAN_CAP 64
-#endif
+#define MT_Q_MASKED 0x08000000  // the particle is already known to be masked (off the mesh / invalid pose)
+#define MT_Q_INDEX 0x07ffffff
+// (Cutting the hint scan after 16 / 24 list entries and continuing the rest in a second, compacted pass was measured
+// slower -- 105 / 102 us against 99 us for the whole scan: 42 % of the scans need more than 16 entries -- and is gone.)
 // (A persistent form of this kernel -- grid = resident blocks, grid-stride tiles, the next tile's hint / key / list head
 // prefetched one tile ahead -- was measured 10 % slower, 103 vs 93 us: the hardware block scheduler balances the
 // long-tailed scans better than a static tile assignment.)
@@ -1469,7 +1465,7 @@ __global__ void __launch_bounds__(MT_A_BLOCK, MT_A_MINBLOCKS) k_step_a(StepDev p
   double et2 = 0.0, ang2 = 0.0;
   bool on_surface = valid;
   int todo = 0;
-  float4 sq[3];
+  float4 sq[2];
   if (valid) {
     float P[3][4], t[3], r[3], O[3][4], key[6];
     load_pose_stream(p.soa_cur, p.stride, i, P);
@@ -1497,46 +1493,41 @@ __global__ void __launch_bounds__(MT_A_BLOCK, MT_A_MINBLOCKS) k_step_a(StepDev p
 #else
     on_surface = (mcls >= 2) ? mesh_within_search(Mh, O[0][3], O[1][3], O[2][3], p.prune_dist, mcls == 2 ? mk : -1) : (mcls == 1);
 #endif
-    // hint-graph search (optionally cut after MT_A_SCAN_CAP list entries, the rest continued by k_step_scanq)
+    // hint-graph search
     float bd, dh;
     int bi, centre;
     int st = nn_hint_begin(T, key, hint, bd, bi, centre, dh);
-    if (st == 0) st = nn_hint_scan(T, key, centre, dh, 0, MT_A_SCAN_CAP, bd, bi);
-    if (st < 0) todo |= MT_Q_NN;  // no usable hint: box-hierarchy search
-    else if (st == 0) todo |= (MT_A_SCAN_CAP < MT_NBR_K) ? MT_Q_SCAN : MT_Q_NN;  // continue the scan / list exhausted
+    if (st == 0) st = nn_hint_scan(T, key, centre, dh, 0, MT_NBR_K, bd, bi);
+    if (st <= 0) todo |= MT_Q_NN;  // no usable hint, or the list is exhausted: box-hierarchy search
     if (bi == INT_MAX) bi = -1;  // no usable hint
     const bool masked = !on_surface || invalid;
     // masked: weights *= m (particle_filter.py:398-401); a particle without any candidate yet
     // (-1) has its mask re-derived by k_step_nnq
     mt_sts(p.nn_cur + i, (bi >= 0 && masked) ? nn_masked(bi) : bi);
-    if (todo & MT_Q_SCAN) {
+    if (todo & MT_Q_NN) {  // the search record travels with the queue entry: the consumer starts from it, not from the pose
+      if (masked) todo |= MT_Q_MASKED;
       sq[0] = make_float4(key[0], key[1], key[2], key[3]);
-      sq[1] = make_float4(key[4], key[5], bd, dh);
-      sq[2] = make_float4(__int_as_float(bi), __int_as_float(centre), __int_as_float((int)i),
-                          __int_as_float((masked ? 1 : 0) | ((todo & MT_Q_MESH) ? 2 : 0)));
+      sq[1] = make_float4(key[4], key[5], bd, __int_as_float(bi));
     }
   }
   // queue what is left (one atomic per warp and queue).  Box-hierarchy searches go to the front of the queue array
-  // (one warp per entry later on), drift tests that need nothing else to its back (one thread per entry), scans to be
-  // continued to the record array.
+  // (one warp per entry later on) together with their search record, drift tests that need nothing else to its back
+  // (one thread per entry).
   const unsigned nm = __ballot_sync(0xffffffffu, (todo & MT_Q_NN) != 0);
-  const unsigned sm = __ballot_sync(0xffffffffu, (todo & MT_Q_SCAN) != 0);
   const unsigned mm = __ballot_sync(0xffffffffu, todo == MT_Q_MESH);
-  if (nm | sm | mm) {
-    unsigned base = 0, sbase = 0, mbase = 0;
+  if (nm | mm) {
+    unsigned base = 0, mbase = 0;
     if (lane == 0) {
       if (nm) base = atomicAdd(p.qctl, (unsigned)__popc(nm));
-      if (sm) sbase = atomicAdd(p.qctl + 4, (unsigned)__popc(sm));
       if (mm) mbase = atomicAdd(p.qctl + 3, (unsigned)__popc(mm));
     }
     base = __shfl_sync(0xffffffffu, base, 0);
-    sbase = __shfl_sync(0xffffffffu, sbase, 0);
     mbase = __shfl_sync(0xffffffffu, mbase, 0);
     const unsigned below = (1u << lane) - 1;
-    if (todo & MT_Q_NN) p.queue[base + __popc(nm & below)] = (int)i | (todo & (MT_Q_NN | MT_Q_MESH));
-    else if (todo & MT_Q_SCAN) {
-      float4* r = p.srec + 3 * (size_t)(sbase + __popc(sm & below));
-      r[0] = sq[0], r[1] = sq[1], r[2] = sq[2];
+    if (todo & MT_Q_NN) {
+      const unsigned e = base + __popc(nm & below);
+      p.queue[e] = (int)i | (todo & (MT_Q_NN | MT_Q_MESH | MT_Q_MASKED));
+      p.srec[2 * (size_t)e] = sq[0], p.srec[2 * (size_t)e + 1] = sq[1];
     } else if (todo) p.queue[p.queue_cap - 1 - (mbase + __popc(mm & below))] = (int)i;
   }
   const long long gw = i >> 5;  // global warp = 32 consecutive particles
@@ -1549,45 +1540,6 @@ __global__ void __launch_bounds__(MT_A_BLOCK, MT_A_MINBLOCKS) k_step_a(StepDev p
   MT_TRACE_END(p.xdbg, 0)
 }
 
-// Continuation of the hint-graph scans that k_step_a cut short: one thread per record, on compacted warps whose lanes
-// all still have list entries to read.  Proven -> the match is final (a pending drift test goes to its queue);
-// list exhausted -> box-hierarchy queue, seeded with the best candidate so far.
-__global__ void __launch_bounds__(256) k_step_scanq(StepDev p, NNTables T) {
-  const unsigned ns = p.qctl[4];
-  const int lane = threadIdx.x & 31;
-  const unsigned span = gridDim.x * blockDim.x;
-  for (unsigned e0 = blockIdx.x * blockDim.x + threadIdx.x - lane; e0 < ns; e0 += span) {  // whole warps stay in the loop
-    const unsigned e = e0 + lane;
-    int todo = 0, i = 0;
-    if (e < ns) {
-      const float4 r0 = p.srec[3 * (size_t)e], r1 = p.srec[3 * (size_t)e + 1], r2 = p.srec[3 * (size_t)e + 2];
-      const float key[6] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y};
-      float bd = r1.z;
-      int bi = __float_as_int(r2.x);
-      const int centre = __float_as_int(r2.y), fl = __float_as_int(r2.w);
-      i = __float_as_int(r2.z);
-      const int st = nn_hint_scan(T, key, centre, r1.w, MT_A_SCAN_CAP, MT_NBR_K, bd, bi);
-      p.nn_cur[i] = (fl & 1) ? nn_masked(bi) : bi;
-      if (!st) todo = MT_Q_NN | ((fl & 2) ? MT_Q_MESH : 0);
-      else if (fl & 2) todo = MT_Q_MESH;
-    }
-    const unsigned nm = __ballot_sync(0xffffffffu, (todo & MT_Q_NN) != 0);
-    const unsigned mm = __ballot_sync(0xffffffffu, todo == MT_Q_MESH);
-    if (nm | mm) {
-      unsigned base = 0, mbase = 0;
-      if (lane == 0) {
-        if (nm) base = atomicAdd(p.qctl, (unsigned)__popc(nm));
-        if (mm) mbase = atomicAdd(p.qctl + 3, (unsigned)__popc(mm));
-      }
-      base = __shfl_sync(0xffffffffu, base, 0);
-      mbase = __shfl_sync(0xffffffffu, mbase, 0);
-      const unsigned below = (1u << lane) - 1;
-      if (todo & MT_Q_NN) p.queue[base + __popc(nm & below)] = i | todo;
-      else if (todo) p.queue[p.queue_cap - 1 - (mbase + __popc(mm & below))] = i;
-    }
-  }
-}
-
 // queue consumer: one warp per entry.  MT_Q_NN: best-first search through the box hierarchy (nn_bvh_search)
 // seeded with the candidate the hint scan left behind.  MT_Q_MESH: the vertex search of the drift test.
 struct NnqEntry {
@@ -1597,33 +1549,24 @@ struct NnqEntry {
   int bi;
   bool masked;
 };
-__device__ __forceinline__ void nnq_load(const StepDev& p, const NNTables& T, const MeshTables& Mh, int raw, NnqEntry& q) {
+__device__ __forceinline__ void nnq_load(const StepDev& p, const MeshTables& Mh, unsigned e, NnqEntry& q) {
+  // queue word and search record are independent loads: one memory round trip, no pose / match / key re-reads
+  const int raw = p.queue[e];
+  const float4 r0 = p.srec[2 * (size_t)e], r1 = p.srec[2 * (size_t)e + 1];
   const long long i = raw & MT_Q_INDEX;
-  float P[3][4];
-  load_pose(p.soa_cur, p.stride, i, P);
-  mt_se3_key(P, q.key);
-  const int stored = p.nn_cur[i];
   q.i = i;
-  q.bi = nn_index(stored);
-  q.bd = FLT_MAX;
-  q.masked = nn_is_masked(stored);
-  if (q.bi >= 0) {
-    float kh[6];
-    load_key(T.keys_orig, q.bi, kh);
-    q.bd = mt_key_dist(q.key, kh);
-  } else {
-    q.bi = INT_MAX;
-  }
-  if (raw & MT_Q_MESH) {  // provisionally on the surface: look now
-    const bool on = mesh_within_warp(Mh, P[0][3], P[1][3], P[2][3], p.prune_dist);
-    if (!on) {
+  q.key[0] = r0.x, q.key[1] = r0.y, q.key[2] = r0.z, q.key[3] = r0.w, q.key[4] = r1.x, q.key[5] = r1.y;
+  q.bd = r1.z;
+  q.bi = __float_as_int(r1.w);
+  if (q.bi < 0) q.bi = INT_MAX, q.bd = FLT_MAX;  // no candidate yet
+  q.masked = (raw & MT_Q_MASKED) != 0;
+  if ((raw & MT_Q_MESH) && !q.masked) {  // provisionally on the surface: look now
+    const float x = p.soa_cur[i].w, y = p.soa_cur[p.stride + i].w, z = p.soa_cur[2 * p.stride + i].w;
+    if (!mesh_within_warp(Mh, x, y, z, p.prune_dist)) {
       q.masked = true;
       if ((threadIdx.x & 31) == 0) atomicSub(p.wcnt + (i >> 5), 1);
     }
-  } else if (stored == -1) {  // no candidate yet: the mask was not recorded, derive it again
-    q.masked = mt_pose_invalid(P) || (p.prune_dist > 0.0 && !mesh_within_warp(Mh, P[0][3], P[1][3], P[2][3], p.prune_dist));
   }
-  if (stored == -1 && (raw & MT_Q_MESH)) q.masked = q.masked || mt_pose_invalid(P);
 }
 #define MT_NNQ_WARPS 4
 // Deferred drift tests (voxel class "undecided" in k_step_a): the vertex search of remove_invalid_particles.  The
@@ -1699,10 +1642,22 @@ __global__ void __launch_bounds__(32 * MT_NNQ_WARPS) k_step_nnq(StepDev p, NNTab
   unsigned e = (threadIdx.x >> 5) * gridDim.x + blockIdx.x;
   while (e < qn) {
     NnqEntry q;
-    const int raw = p.queue[e];
-    nnq_load(p, T, Mh, raw, q);
+#if MT_TRACE
+    const unsigned long long tr0 = mt_now();
+#endif
+    nnq_load(p, Mh, e, q);
+#if MT_TRACE
+    const unsigned long long tr1 = mt_now();
+#endif
     const int res = nn_bvh_search(T, q.key, q.bd, q.bi, p.flags + 4);
     if (lane == 0) p.nn_cur[q.i] = q.masked ? nn_masked(res) : res;
+#if MT_TRACE
+    if (lane == 0) {  // words 30..35: slowest entry, sum over entries, entries, slowest load part, sum of load parts, latest entry start
+      const unsigned long long tr2 = mt_now();
+      atomicMax(p.xdbg + 30, tr2 - tr0), atomicAdd(p.xdbg + 31, tr2 - tr0), atomicAdd(p.xdbg + 32, 1ull);
+      atomicMax(p.xdbg + 33, tr1 - tr0), atomicAdd(p.xdbg + 34, tr1 - tr0), atomicMax(p.xdbg + 35, tr0);
+    }
+#endif
     if (qn <= W) break;
     if (lane == 0) e = W + atomicAdd(p.qctl + 1, 1u);
     e = __shfl_sync(0xffffffffu, e, 0);
@@ -1765,8 +1720,7 @@ __global__ void __launch_bounds__(256) k_step_sums(StepDev p) {
     p.flags[5] = (p.prune_dist > 0.0 && s_cnt == 0);  // drifted (particle_filter.py:402)
     p.flags[3] += (int)p.qctl[0];                     // searches that needed the box hierarchy (cumulative)
     p.flags[MT_STAT_MESH_DEFERRED] += (int)p.qctl[3];
-    p.flags[MT_STAT_SCAN_DEFERRED] += (int)p.qctl[4];
-    p.qctl[0] = 0, p.qctl[1] = 0, p.qctl[2] = 0, p.qctl[3] = 0, p.qctl[4] = 0;
+    p.qctl[0] = 0, p.qctl[1] = 0, p.qctl[2] = 0, p.qctl[3] = 0;
     *p.ticket = 0;
   }
 }
@@ -1952,6 +1906,9 @@ __global__ void __launch_bounds__(256) k_step_b(StepDev p) {
 #ifndef MT_BW_FLAT
 #define MT_BW_FLAT 1  // barrier-free phase 2 when the block's weights fit in shared memory
 #endif
+#ifndef MT_BW_L2PREFETCH
+#define MT_BW_L2PREFETCH 1
+#endif
 #ifndef MT_BW_P1
 #define MT_BW_P1 4  // chunks whose look-ups phase 1 issues together
 #endif
@@ -1964,6 +1921,7 @@ __global__ void __launch_bounds__(256, 4) k_step_bw(StepDev p, unsigned long lon
   __shared__ double s_bc[3];
   __shared__ double s_e[MT_BW_FAST_PER * MT_CHUNK];  // weight of every particle of the block's chunks
   __shared__ int s_nn[MT_BW_FAST_PER * MT_CHUNK];    // and its match (phase 2 does not go back to memory for them)
+  __shared__ double s_x2[MT_CHUNK + 1];              // flat form: exclusive prefix of the threads' runs of weights
   const int G = gridDim.x, g = blockIdx.x;
   const long long n = step_count(p);
   const int nwarps = (int)((n + 31) >> 5);
@@ -1976,6 +1934,77 @@ __global__ void __launch_bounds__(256, 4) k_step_bw(StepDev p, unsigned long lon
   const bool cached = per <= MT_BW_FAST_PER;
   double tot = 0.0, ra = 0.0, rb = 0.0;
   int cnt = 0;
+#if MT_BW_FLAT
+  if (cached) {
+    // flat form: only the block total is needed.  All look-ups of the thread are issued together, the thread adds its
+    // weights in chunk order and ONE fixed-topology block sum follows; kernel A's per-warp partials of the block's
+    // chunks are folded by the first 8 * per threads the same way.  While these latencies run, the poses the scatter
+    // of phase 2 will read are requested into L2 (one prefetch per 32-byte sector).
+    int stv[MT_BW_FAST_PER];
+#pragma unroll
+    for (int k = 0; k < MT_BW_FAST_PER; ++k) {
+      const long long i = (long long)(c_lo + k) * MT_CHUNK + threadIdx.x;
+      stv[k] = (k < per && c_lo + k < c_hi && i < n) ? mt_lds(p.nn_cur + i) : -1;
+    }
+    double mine = 0.0;
+#pragma unroll
+    for (int k = 0; k < MT_BW_FAST_PER; ++k) {
+      if (k < per && c_lo + k < c_hi) {
+        const double e = (stv[k] >= 0) ? mt_ldk(p.wtab + stv[k]) : 0.0;  // masked (< -1) and absent (-1): 0
+        s_e[k * MT_CHUNK + threadIdx.x] = e, s_nn[k * MT_CHUNK + threadIdx.x] = nn_index(stv[k]);
+        mine += e;
+      }
+    }
+#if MT_BW_L2PREFETCH
+    if (!(threadIdx.x & 1)) {
+#pragma unroll
+      for (int k = 0; k < MT_BW_FAST_PER; ++k) {
+        const long long i = (long long)(c_lo + k) * MT_CHUNK + threadIdx.x;
+        if (k < per && c_lo + k < c_hi && i < n) {
+#pragma unroll
+          for (int r = 0; r < 3; ++r) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.soa_cur + (size_t)r * p.stride + i));
+        }
+      }
+    }
+#endif
+    int mycnt = 0;
+    double mra = 0.0, mrb = 0.0;
+    {
+      const int gw = 8 * c_lo + (int)threadIdx.x;
+      if ((int)threadIdx.x < 8 * (c_hi - c_lo) && gw < nwarps) {
+        mycnt = p.wcnt[gw];
+        if (p.has_gt) mra = p.wrm[2 * gw], mrb = p.wrm[2 * gw + 1];
+      }
+    }
+    tot = block_sum_256(mine, s8);
+    if (p.has_gt) {
+      ra = block_sum_256(mra, s8);
+      rb = block_sum_256(mrb, s8);
+    }
+    cnt = (int)block_sum_256((double)mycnt, s8);  // exact: at most 2560 particles
+    // The in-block part of phase 2's scan needs neither the global sum nor the block's offset, so it runs here, while
+    // the slower blocks are still on their way to the grid barrier: thread t owns `per` consecutive particles of the
+    // block (transposed view of s_e), replaces their weights by the thread-local inclusive prefix, and the thread
+    // totals are block-scanned (monotone form) into s_x2.
+    {
+      const long long left = n - (long long)c_lo * MT_CHUNK;
+      const int nloc = (int)(left < 0 ? 0 : (left < (long long)(c_hi - c_lo) * MT_CHUNK ? left : (long long)(c_hi - c_lo) * MT_CHUNK));
+      const int j0 = threadIdx.x * per;
+      double acc = 0.0;
+      __syncthreads();  // s_e is complete
+#pragma unroll
+      for (int k = 0; k < MT_BW_FAST_PER; ++k) {
+        if (k < per && j0 + k < nloc) {
+          acc += s_e[j0 + k];
+          s_e[j0 + k] = acc;
+        }
+      }
+      const double I = block_incl_scan_mono_256(acc, s8);
+      s_x2[threadIdx.x + 1] = I;
+      if (threadIdx.x == 0) s_x2[0] = 0.0;
+    }
+  } else
+#endif
   for (int c0 = c_lo; c0 < c_hi; c0 += MT_BW_P1) {
     int st4[MT_BW_P1];
     double e4[MT_BW_P1];
@@ -2134,32 +2163,19 @@ __global__ void __launch_bounds__(256, 4) k_step_bw(StepDev p, unsigned long lon
     const double off = (double)(p.u / (float)N);  // float32 division, then promoted (particle_filter.py:260)
     const bool bad = !(S > 0.0) || !(S <= DBL_MAX);  // all-zero / NaN / Inf weights: identity (237-241)
     long long* s_cntall = reinterpret_cast<long long*>(s_e);
-    __shared__ double s_x2[MT_CHUNK + 1];
     __shared__ long long s_cbase;
     if (!bad) {
+      // C = x * (1 / S): one division per thread instead of one per particle; every block forms the same products of
+      // the same values, so the pinned interval ends still agree bit for bit
+      const double rS = 1.0 / S;
       const int j0 = threadIdx.x * per;
-      double v[MT_BW_FAST_PER];
-      double acc = 0.0;
-#pragma unroll
-      for (int k = 0; k < MT_BW_FAST_PER; ++k) {
-        if (k < per) {
-          if (j0 + k < nloc) acc += s_e[j0 + k];
-          v[k] = acc;
-        }
-      }
-      const double I = block_incl_scan_mono_256(acc, s8);
-      s_x2[threadIdx.x + 1] = I;
-      if (threadIdx.x == 0) {
-        s_x2[0] = 0.0;
-        s_cbase = mt_count_below(base_g / S, N, dN, off);
-      }
-      __syncthreads();
+      if (threadIdx.x == 0) s_cbase = mt_count_below(base_g * rS, N, dN, off);
       const double lo = base_g + s_x2[threadIdx.x], hi = fmin(base_g + s_x2[threadIdx.x + 1], next_g);
 #pragma unroll
       for (int k = 0; k < MT_BW_FAST_PER; ++k) {
         if (k < per && j0 + k < nloc) {
           const bool is_end = (j0 + k == nloc - 1);
-          const double C = is_end ? next_g / S : fmin(lo + v[k], hi) / S;
+          const double C = (is_end ? next_g : fmin(lo + s_e[j0 + k], hi)) * rS;
           s_cntall[j0 + k] = mt_count_below(C, N, dN, off);
         }
       }
@@ -2311,9 +2327,7 @@ __global__ void __launch_bounds__(256, 4) k_step_bw(StepDev p, unsigned long lon
       p.flags[5] = (p.prune_dist > 0.0 && s_on == 0);
       p.flags[3] += (int)p.qctl[0];
       p.flags[MT_STAT_MESH_DEFERRED] += (int)p.qctl[3];
-      p.flags[MT_STAT_SCAN_DEFERRED] += (int)p.qctl[4];
-    p.flags[MT_STAT_SCAN_DEFERRED] += (int)p.qctl[4];
-      p.qctl[0] = 0, p.qctl[1] = 0, p.qctl[2] = 0, p.qctl[3] = 0, p.qctl[4] = 0;
+      p.qctl[0] = 0, p.qctl[1] = 0, p.qctl[2] = 0, p.qctl[3] = 0;
     }
   }
 }
@@ -2513,10 +2527,6 @@ extern "C" int mt_step_a(mt_ctx* c, const mt_step_args* a, void* stream) {
   if (c->timing[0]) CK(cudaEventRecord(c->timing[0], st));
   k_step_a<<<step_a_grid(c, step_cover(a)), MT_A_BLOCK, 0, st>>>(d, tables_of(c), mesh_of(c));
   CK_LAUNCH();
-#if MT_A_SCAN_CAP < MT_NBR_K
-  k_step_scanq<<<c->sm_count * 8, 256, 0, st>>>(d, tables_of(c));
-  CK_LAUNCH();
-#endif
   if (c->timing[1]) CK(cudaEventRecord(c->timing[1], st));
   if (d.prune_dist > 0.0) {  // (a particle is in at most one of the two queues)
     k_step_meshq<<<c->sm_count * 4, 256, 0, st>>>(d, mesh_of(c));
@@ -2580,7 +2590,7 @@ struct StepGraph {
   unsigned long long key[20];
   cudaGraph_t graph;
   cudaGraphExec_t exec;
-  cudaGraphNode_t n_query, n_a, n_s, n_meshq, n_meshq2, n_nnq, n_bw;
+  cudaGraphNode_t n_query, n_a, n_meshq, n_meshq2, n_nnq, n_bw;
   bool has_mesh;
 };
 static void step_graphs_free(mt_ctx* c) {
@@ -2690,7 +2700,6 @@ extern "C" int mt_step(mt_ctx* c, const mt_step_args* a, const void* d_q, int q_
   const void* f_a = (const void*)k_step_a;
   const dim3 grid_a(step_a_grid(c, cover)), block_a(MT_A_BLOCK);
   const size_t smem_a = 0;
-  void* args_s[] = {&d, &T};
   // configuration key: everything that is baked into the graph's topology or launch geometry
   unsigned long long key[20] = {(unsigned long long)a->d_soa_cur, (unsigned long long)a->d_soa_next, (unsigned long long)a->d_nn_cur,
                                 (unsigned long long)a->d_nn_next, (unsigned long long)a->d_anc, (unsigned long long)a->stride,
@@ -2713,7 +2722,6 @@ extern "C" int mt_step(mt_ctx* c, const mt_step_args* a, const void* d_q, int q_
   };
   cudaKernelNodeParams P_q = kparams(Q.func, dim3(Q.grid), dim3(256), Q.smem, args_q);
   cudaKernelNodeParams P_a = kparams(f_a, grid_a, block_a, smem_a, args_a);
-  cudaKernelNodeParams P_s = kparams((const void*)k_step_scanq, dim3(c->sm_count * 8), dim3(256), 0, args_s);
   cudaKernelNodeParams P_m1 = kparams((const void*)k_step_meshq, dim3(c->sm_count * 4), dim3(256), 0, args_m);
   cudaKernelNodeParams P_m2 = kparams((const void*)k_step_meshq2, dim3(c->sm_count * 8), dim3(256), 0, args_m);
   cudaKernelNodeParams P_n = kparams((const void*)k_step_nnq, dim3(c->sm_count * 12), dim3(32 * MT_NNQ_WARPS), 0, args_a);
@@ -2729,13 +2737,7 @@ extern "C" int mt_step(mt_ctx* c, const mt_step_args* a, const void* d_q, int q_
     CK(cudaGraphCreate(&G->graph, 0));
     CK(cudaGraphAddKernelNode(&G->n_query, G->graph, nullptr, 0, &P_q));
     CK(cudaGraphAddKernelNode(&G->n_a, G->graph, nullptr, 0, &P_a));
-#if MT_A_SCAN_CAP < MT_NBR_K
-    CK(cudaGraphAddKernelNode(&G->n_s, G->graph, &G->n_a, 1, &P_s));
-    cudaGraphNode_t* after_a = &G->n_s;
-#else
     cudaGraphNode_t* after_a = &G->n_a;
-    (void)P_s;
-#endif
     std::vector<cudaGraphNode_t> deps_bw = {G->n_query};
     if (has_mesh) {
       CK(cudaGraphAddKernelNode(&G->n_meshq, G->graph, after_a, 1, &P_m1));
@@ -2755,9 +2757,6 @@ extern "C" int mt_step(mt_ctx* c, const mt_step_args* a, const void* d_q, int q_
     G->valid = true;
   } else {
     CK(cudaGraphExecKernelNodeSetParams(G->exec, G->n_a, &P_a));
-#if MT_A_SCAN_CAP < MT_NBR_K
-    CK(cudaGraphExecKernelNodeSetParams(G->exec, G->n_s, &P_s));
-#endif
     if (G->has_mesh) {
       CK(cudaGraphExecKernelNodeSetParams(G->exec, G->n_meshq, &P_m1));
       CK(cudaGraphExecKernelNodeSetParams(G->exec, G->n_meshq2, &P_m2));

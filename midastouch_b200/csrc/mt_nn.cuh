@@ -378,16 +378,6 @@ __device__ __forceinline__ bool nn_hint_search(const NNTables& T, const float q[
   return nn_hint_scan(T, q, centre, dh, 0, MT_NBR_K, best_d, best_i) != 0;
 }
 
-// warp-wide (best_d, best_i) = lexicographic min over lanes
-__device__ __forceinline__ void warp_best(float& d, int& i) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const float od = __shfl_xor_sync(0xffffffffu, d, o);
-    const int oi = __shfl_xor_sync(0xffffffffu, i, o);
-    if (mt_better(od, oi, d, i)) d = od, i = oi;
-  }
-}
-
 // bound of one node (3 float4 = lo[6] | hi[6])
 __device__ __forceinline__ float bvh_lower_bound(const float4* __restrict__ node, const float q[6]) {
   const float4 a = mt_ldk(node), b = mt_ldk(node + 1), c = mt_ldk(node + 2);
@@ -418,6 +408,16 @@ __device__ __forceinline__ int bvh_pick(float& lb, float& picked) {
 #ifndef MT_BVH_BATCH
 #define MT_BVH_BATCH 4
 #endif
+// warp-wide (best_d, best_i) = lexicographic min over lanes
+__device__ __forceinline__ void warp_best(float& d, int& i) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float od = __shfl_xor_sync(0xffffffffu, d, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, i, o);
+    if (mt_better(od, oi, d, i)) d = od, i = oi;
+  }
+}
+
 __device__ __noinline__ int nn_bvh_search(const NNTables& T, const float q[6], float best_d, int best_i, int* stats) {
   if (!(q[0] == q[0]) || !(q[1] == q[1]) || !(q[2] == q[2]) || !(q[3] == q[3]) || !(q[4] == q[4]) || !(q[5] == q[5]))
     return 0;  // NaN query: np.argmin semantics
@@ -482,6 +482,10 @@ __device__ __noinline__ int nn_bvh_search(const NNTables& T, const float q[6], f
   return best_i == INT_MAX ? 0 : best_i;  // Inf query: every distance is Inf/NaN
 }
 
+// (Measured and dropped: fetching the leaf boxes of four level-1 nodes per round trip, eight leaves per round trip, and
+// taking children in lane order from a ballot instead of best-first -- the first two were 10 % slower (a search is one
+// warp's dependent instruction stream, ~1 us per leaf; wider rounds add instructions, not overlap), the last one cut the
+// average by 5 % but tripled the leaves of the worst search (104 against 37), and the slowest search is what the step waits for.)
 __device__ __forceinline__ int nn_search_warp(const NNTables& T, const float q[6], float best_d, int best_i) {
   return nn_bvh_search(T, q, best_d, best_i, nullptr);
 }

@@ -53,8 +53,19 @@ for t in range(T):
     for w, nm in ((24, "bw_phase1_done_max"), (25, "bw_barrier_exit_min"), (26, "bw_barrier_exit_max"), (27, "bw_prefix_done_max"), (28, "bw_first_chunk_done_max")):
         if buf[w] not in (0, 2**64 - 1):
             row[nm] = (buf[w] - t0) / 1e3
+    if buf[32]:
+        row["nnq_entries"] = float(buf[32])
+        row["nnq_entry_us_max"] = buf[30] / 1e3
+        row["nnq_entry_us_avg"] = buf[31] / buf[32] / 1e3
+        row["nnq_entry_load_us_max"] = buf[33] / 1e3
+        row["nnq_entry_load_us_avg"] = buf[34] / buf[32] / 1e3
+        row["nnq_last_entry_start"] = (buf[35] - t0) / 1e3
     for k, v in row.items():
         acc[k] = acc.get(k, 0.0) + v
     cnt += 1
+st = eng.ctx.stats(reset=True)
+acc["leaves_per_search"] = cnt * st["grid_rows"] / max(1, st["nn_fallbacks"])
+acc["leaves_max_one_search"] = cnt * st["grid_rows_max"]
+acc["searches_per_step"] = cnt * st["nn_fallbacks"] / T
 print(json.dumps({"lib": os.path.basename(os.environ.get("MIDAS_B200_LIB", "default")), "graph": eng.use_graph, "steps": cnt,
                   "us_from_k_step_a_start": {k: round(v / cnt, 2) for k, v in acc.items()}}))
