@@ -1441,7 +1441,7 @@ __device__ __forceinline__ long long step_count(const StepDev& p) {
 #define MT_A_BLOCK 64
 #endif
 #ifndef MT_A_MINBLOCKS
-#define MT_A_MINBLOCKS 18  // 56 registers: 36 warps per SM (measured: 16 -> 18 blocks = -1.5 us; 20 blocks need 51 registers)
+#define MT_A_MINBLOCKS 21  // 48 registers: 42 warps per SM (measured: 16 -> 18 -> 21 blocks = 92.8 -> 91.0 -> 87.0 us)
 #endif
 #ifndef MT_MESH_DEFER
 #define MT_MESH_DEFER 1  // undecided voxels of the drift test go to the queue instead of stalling their warp
@@ -1453,9 +1453,17 @@ __device__ __forceinline__ long long step_count(const StepDev& p) {
 #define MT_Q_INDEX 0x07ffffff
 // (Cutting the hint scan after 16 / 24 list entries and continuing the rest in a second, compacted pass was measured
 // slower -- 105 / 102 us against 99 us for the whole scan: 42 % of the scans need more than 16 entries -- and is gone.)
+// (Splitting the sweep into a streaming kernel -- motion, voxel class, key, partials; 48 registers -- and a search kernel
+// that starts from a 32-byte key record -- 40 registers, 50 warps per SM -- was measured much slower: 116 us on the
+// spread cloud and 162 us on the converged one against 91 us fused.  The search is a chain of dependent list loads;
+// in the fused kernel the arithmetic of other warps fills those waits, in a search-only kernel nothing does.)
 // (A persistent form of this kernel -- grid = resident blocks, grid-stride tiles, the next tile's hint / key / list head
 // prefetched one tile ahead -- was measured 10 % slower, 103 vs 93 us: the hardware block scheduler balances the
 // long-tailed scans better than a static tile assignment.)
+// (Letting a block walk over 2 / 4 / 8 consecutive tiles with the next tile's pose + hint staged in shared memory by
+// cp.async -- to take the DRAM wait of the 52 input bytes off the warps' critical path -- was measured slower still:
+// 113 / 129 / 157 us against 91 us.  Every form in which a thread handles more than one particle lost; what the kernel
+// needs is more independent warps, which is what the register count below buys.)
 __global__ void __launch_bounds__(MT_A_BLOCK, MT_A_MINBLOCKS) k_step_a(StepDev p, NNTables T, MeshTables Mh) {
   const long long n = step_count(p);
   const int lane = threadIdx.x & 31;
@@ -2051,30 +2059,40 @@ __global__ void __launch_bounds__(256, 4) k_step_bw(StepDev p, unsigned long lon
   for (int j = threadIdx.x; j < G; j += blockDim.x) s_tot[j] = __ldcg(blocktot + j);
   __syncthreads();
   {
-    // prefix of the G block totals, the same code (hence bit-identical values) in every block: thread t owns a
-    // contiguous run of totals, the run sums are block-scanned (monotone form) into E[0..256], and the values inside
-    // run t are E[t] + (local prefix), clamped to E[t+1]; a run's last end IS E[t+1], which is also where the next
-    // run starts -- so neighbouring blocks agree on their common boundary and everything is monotone
-    __shared__ double s_loc[MT_CHUNK + 1];
-    const int perb = (G + MT_CHUNK - 1) / MT_CHUNK;  // <= 5
-    const int b0 = threadIdx.x * perb;
-    double loc = 0.0;
-    for (int k = 0; k < perb; ++k)
-      if (b0 + k < G) loc += s_tot[b0 + k];
-    const double I = block_incl_scan_mono_256(loc, s8);
-    s_loc[threadIdx.x + 1] = I;
-    if (threadIdx.x == 0) s_loc[0] = 0.0;
-    if (threadIdx.x == MT_CHUNK - 1) s_bc[2] = I;
-    __syncthreads();
-    const double E = s_loc[threadIdx.x], En = s_loc[threadIdx.x + 1];
-    double lp = 0.0;
-    for (int k = 0; k < perb; ++k) {
-      const int j = b0 + k;
-      if (j < G) {
-        const double start = (k == 0) ? E : fmin(E + lp, En);
-        lp += s_tot[j];
-        const double end = (k == perb - 1 || j == G - 1) ? En : fmin(E + lp, En);
-        if (j == g) s_bc[0] = start, s_bc[1] = end;
+    // prefix of the G block totals, the same code (hence bit-identical values) in every block, by ONE warp (no block
+    // barriers): lane l owns a contiguous run of totals; the run sums are scanned across the warp (Kogge-Stone plus a
+    // running maximum, which removes the ulp-sized inversions float64 rounding can leave) into E[0..32]; the values
+    // inside run l are E[l] + (local prefix), clamped to E[l+1]; a run's last end IS E[l+1], which is also where the
+    // next run starts -- so neighbouring blocks agree on their common boundary and everything is monotone
+    if (threadIdx.x < 32) {
+      const int lane = threadIdx.x;
+      const int perb = (G + 31) / 32;  // <= 37
+      const int b0 = lane * perb;
+      double loc = 0.0;
+      for (int k = 0; k < perb; ++k)
+        if (b0 + k < G) loc += s_tot[b0 + k];
+      double I = loc;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const double t = __shfl_up_sync(0xffffffffu, I, o);
+        if (lane >= o) I += t;
+      }
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const double t = __shfl_up_sync(0xffffffffu, I, o);
+        if (lane >= o) I = fmax(I, t);
+      }
+      double E = __shfl_up_sync(0xffffffffu, I, 1);
+      if (lane == 0) E = 0.0;
+      const double En = I;
+      if (lane == 31) s_bc[2] = I;
+      if (g >= b0 && g < b0 + perb) {
+        double lp = 0.0;
+        for (int j = b0; j < g; ++j) lp += s_tot[j];
+        const double start = (g == b0) ? E : fmin(E + lp, En);
+        lp += s_tot[g];
+        const double end = (g == b0 + perb - 1 || g == G - 1) ? En : fmin(E + lp, En);
+        s_bc[0] = start, s_bc[1] = end;
       }
     }
   }
