@@ -121,6 +121,12 @@ int mt_soa_to_aos(const float* d_soa, long long stride, long long n, float* d_ao
 /* ---- SE3_NN (tactile_tree.py:43-58) --------------------------------------------- */
 /* R3_SE3 keys of n poses -> d_keys (n,6) float32 */
 int mt_se3_keys(const float* d_soa, long long stride, long long n, float* d_keys, void* stream);
+/* the same with R3_SE3's weight w as an argument (tactile_tree.py:73: key = [(1 - w) t, w Log(R)]; mt_se3_keys is w = 0.01,
+ * the value the codebook's own keys are built with) */
+int mt_se3_keys_w(const float* d_soa, long long stride, long long n, double w, float* d_keys, void* stream);
+/* SE3_NN(nn = k > 1) (tactile_tree.py:43-52): d_idx (n,k) int32 = the k <= 64 nearest codebook keys of every query key,
+ * ascending (distance, index) like kneighbors(); exhaustive search, meant for small n */
+int mt_nn_topk(mt_ctx* ctx, const float* d_keys, long long n, int k, int32_t* d_idx, void* stream);
 /* exact L2 1-NN of n keys in the codebook; ties -> lowest index.  d_hint (nullable):
  * a codebook index per query that seeds the search bound (any valid index is correct).
  * mode 0 = hint graph + grid search (mt_nn.cuh), 1 = exhaustive (tiled).  d_idx: (n,) int32. */

@@ -73,6 +73,8 @@ _SIGS = {
     "mt_aos_to_soa": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_void_p]),
     "mt_soa_to_aos": (C.c_int, [C.c_void_p, C.c_longlong, C.c_longlong, C.c_void_p, C.c_void_p]),
     "mt_se3_keys": (C.c_int, [C.c_void_p, C.c_longlong, C.c_longlong, C.c_void_p, C.c_void_p]),
+    "mt_se3_keys_w": (C.c_int, [C.c_void_p, C.c_longlong, C.c_longlong, C.c_double, C.c_void_p, C.c_void_p]),
+    "mt_nn_topk": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p]),
     "mt_nn_assign": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "mt_gather_rows_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p]),
     "mt_motion": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -263,9 +263,9 @@ extern "C" int mt_codebook_upload(mt_ctx* c, const float* h_keys, const void* d_
   CK(cudaMemcpy(c->d_bvh + 3 * ((size_t)bp.n_leaf + bp.n_l1), l2.data(), sizeof(float) * l2.size(), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(c->d_keys_orig, ko.data(), sizeof(float) * 8 * M, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(c->d_keys_sorted, ks.data(), sizeof(float) * 8 * M, cudaMemcpyHostToDevice));
-  k_build_nbr<false><<<(M + 7) / 8, 256>>>(c->d_keys_orig, M, c->d_nbr, nullptr);
+  k_build_nbr<0><<<(M + 7) / 8, 256>>>(c->d_keys_orig, M, c->d_nbr, nullptr);
   CK_LAUNCH();
-  k_build_nbr<true><<<(M + 7) / 8, 256>>>(c->d_keys_orig, M, nullptr, c->d_sorted_orig);
+  k_build_nbr<1><<<(M + 7) / 8, 256>>>(c->d_keys_orig, M, nullptr, c->d_sorted_orig);
   CK_LAUNCH();
   k_set_partner<<<(M + 255) / 256, 256>>>(c->d_keys_orig, M, c->d_sorted_orig, c->d_nbr);
   CK_LAUNCH();
@@ -1140,20 +1140,36 @@ static NNTables tables_of(mt_ctx* c) {
   return T;
 }
 
-__global__ void k_se3_keys(const float4* __restrict__ soa, long long stride, long long n, float* __restrict__ keys) {
+// wt / wr: the float32 factors (1 - w) and w of R3_SE3 (tactile_tree.py:73-77); the codebook's own keys use w = 0.01
+__global__ void k_se3_keys(const float4* __restrict__ soa, long long stride, long long n, float* __restrict__ keys, float wt, float wr) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  float P[3][4], key[6];
+  float P[3][4], lg[3];
   load_pose(soa, stride, i, P);
-  mt_se3_key(P, key);
-#pragma unroll
-  for (int k = 0; k < 6; ++k) keys[6 * i + k] = key[k];
+  mt_so3_log(P, lg);
+  keys[6 * i] = wt * P[0][3], keys[6 * i + 1] = wt * P[1][3], keys[6 * i + 2] = wt * P[2][3];
+  keys[6 * i + 3] = wr * lg[0], keys[6 * i + 4] = wr * lg[1], keys[6 * i + 5] = wr * lg[2];
 }
 
-extern "C" int mt_se3_keys(const float* d_soa, long long stride, long long n, float* d_keys, void* stream) {
-  if (n < 0 || stride < n || (n && (!d_soa || !d_keys))) return set_err(MT_ERR_ARG, "mt_se3_keys: bad argument");
+extern "C" int mt_se3_keys_w(const float* d_soa, long long stride, long long n, double w, float* d_keys, void* stream) {
+  if (n < 0 || stride < n || (n && (!d_soa || !d_keys)) || !(w == w)) return set_err(MT_ERR_ARG, "mt_se3_keys: bad argument");
   if (!n) return MT_OK;
-  k_se3_keys<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const float4*)d_soa, stride, n, d_keys);
+  // torch multiplies a float32 tensor by the Python scalars (1.0 - w) and w: both rounded to float32 first
+  k_se3_keys<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const float4*)d_soa, stride, n, d_keys, (float)(1.0 - w), (float)w);
+  CK_LAUNCH();
+  return MT_OK;
+}
+extern "C" int mt_se3_keys(const float* d_soa, long long stride, long long n, float* d_keys, void* stream) {
+  return mt_se3_keys_w(d_soa, stride, n, 0.01, d_keys, stream);
+}
+
+// SE3_NN with nn > 1 (tactile_tree.py:43-52): the k <= 64 nearest codebook keys of every query key, ascending
+// (distance, index) like kneighbors(); exhaustive (every query streams the codebook).
+extern "C" int mt_nn_topk(mt_ctx* c, const float* d_keys, long long n, int k, int32_t* d_idx, void* stream) {
+  if (!c || !c->cb_ready) return set_err(MT_ERR_STATE, "mt_nn_topk: no codebook");
+  if (n < 0 || k < 1 || k > MT_NBR_K || k > c->M || (n && (!d_keys || !d_idx)) || n > 0x7fffffffll / 8) return set_err(MT_ERR_ARG, "mt_nn_topk: bad argument (1 <= k <= min(64, M))");
+  if (!n) return MT_OK;
+  k_build_nbr<2><<<(unsigned)((n + 7) / 8), 256, 0, (cudaStream_t)stream>>>(c->d_keys_orig, c->M, nullptr, nullptr, d_keys, (int)n, k, d_idx);
   CK_LAUNCH();
   return MT_OK;
 }

@@ -516,19 +516,31 @@ __device__ __forceinline__ int nn_assign(const NNTables& T, bool active, const f
 // Build kernel (codebook upload).  One warp per key; the running sorted list of 64 entries lives
 // in registers, two per lane (slot l in `lo`, slot 32 + l in `hi`); the codebook streams
 // through shared memory.
-//   PARTNER = false: the MT_NBR_K nearest other keys of every key, ascending (distance, index)
-//   PARTNER = true : the key nearest to the antipodal image of every near-pi key -> partner[h]
-template <bool PARTNER>
+//   MODE 0: the MT_NBR_K nearest other keys of every key, ascending (distance, index)
+//   MODE 1: the key nearest to the antipodal image of every near-pi key -> partner[h]
+//   MODE 2: the k <= 64 nearest keys of nq external query keys (SE3_NN with nn > 1, tactile_tree.py:43-52):
+//           out_idx[h * k + j] = index of the j-th nearest key of query h, ascending (distance, index) -- exhaustive,
+//           every query streams the whole codebook (meant for the handful of queries such calls make)
+template <int MODE>
 __global__ void __launch_bounds__(256) k_build_nbr(const float4* __restrict__ keys, int M, float4* __restrict__ nbr,
-                                                   int* __restrict__ partner) {
+                                                   int* __restrict__ partner, const float* __restrict__ qkeys = nullptr,
+                                                   int nq = 0, int k_out = 0, int* __restrict__ out_idx = nullptr) {
   static_assert(MT_NBR_K == 64, "two list slots per lane");
+  constexpr bool PARTNER = MODE == 1;
+  constexpr bool QUERY = MODE == 2;
   __shared__ float4 sk[2 * 256];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int h = blockIdx.x * 8 + warp;
+  const int H = QUERY ? nq : M;
   float kh[6] = {0, 0, 0, 0, 0, 0};
-  bool act = h < M;
+  bool act = h < H;
   if (act) {
-    load_key(keys, h, kh);
+    if (QUERY) {
+#pragma unroll
+      for (int k = 0; k < 6; ++k) kh[k] = qkeys[6 * (size_t)h + k];
+    } else {
+      load_key(keys, h, kh);
+    }
     if (PARTNER) {
       float ka[6];
       act = mt_key_antipode(kh, ka);
@@ -547,7 +559,7 @@ __global__ void __launch_bounds__(256) k_build_nbr(const float4* __restrict__ ke
     for (int s0 = 0; s0 < cnt; s0 += 32) {
       const int m = m0 + s0 + lane;
       float d = FLT_MAX;
-      if (s0 + lane < cnt && (PARTNER || m != h)) {
+      if (s0 + lane < cnt && (PARTNER || QUERY || m != h)) {
         const float4 a = sk[2 * (s0 + lane)], b = sk[2 * (s0 + lane) + 1];
         const float k[6] = {a.x, a.y, a.z, a.w, b.x, b.y};
         d = mt_key_dist(kh, k);
@@ -576,9 +588,12 @@ __global__ void __launch_bounds__(256) k_build_nbr(const float4* __restrict__ ke
       }
     }
   }
-  if (h >= M) return;
+  if (h >= H) return;
   if constexpr (PARTNER) {
     if (lane == 0) partner[h] = act ? lo_i : -1;
+  } else if constexpr (QUERY) {
+    if (lane < k_out) out_idx[(size_t)h * k_out + lane] = lo_i;
+    if (32 + lane < k_out) out_idx[(size_t)h * k_out + 32 + lane] = hi_i;
   } else {
 #pragma unroll
   for (int half = 0; half < 2; ++half) {

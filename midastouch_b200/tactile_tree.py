@@ -16,15 +16,13 @@ from .context import Context, aos_to_soa, dtype_code, require_cuda
 
 def R3_SE3(poses: torch.Tensor, w: float = 0.01) -> torch.Tensor:
     """tactile_tree.py:73-77 on the GPU: (N,4,4) -> (N,6) float32 keys."""
-    if w != 0.01:
-        raise MidasError("R3_SE3: the CUDA path implements the reference's w=0.01 only")
     require_cuda(poses, "poses")
     poses = poses.reshape(-1, 4, 4)
     n = poses.shape[0]
     soa = aos_to_soa(poses)
     keys = torch.empty((n, 6), dtype=torch.float32, device=poses.device)
     with torch.cuda.device(poses.device):
-        call("mt_se3_keys", ptr(soa), n, n, ptr(keys), stream_ptr())
+        call("mt_se3_keys_w", ptr(soa), n, n, float(w), ptr(keys), stream_ptr())
     return keys
 
 
@@ -105,9 +103,17 @@ class tactile_tree(torch.nn.Module):
     def SE3_NN(self, _query, nn=1):
         """tactile_tree.py:43-58: best SE(3) match of every query pose; returns the gathered
         (poses, cam_poses, embeddings) like the reference (squeezed for a single query)."""
-        if nn != 1:
-            raise MidasError("SE3_NN: only nn=1 (the value every reference call site uses)")
         query = _query.reshape(-1, 4, 4)
+        if nn != 1:  # kneighbors(n_neighbors=nn): (N, nn) indices, nearest first (exhaustive search in the library)
+            if not 1 <= int(nn) <= min(64, self.tree_size):
+                raise MidasError("SE3_NN: nn must be between 1 and min(64, codebook size)")
+            keys = R3_SE3(query)
+            n = keys.shape[0]
+            idx = torch.empty((n, int(nn)), dtype=torch.int32, device=keys.device)
+            with torch.cuda.device(keys.device):
+                call("mt_nn_topk", self.ctx.h, ptr(keys), n, int(nn), ptr(idx), stream_ptr())
+            ii = idx.long().squeeze()  # the reference's indices_p.squeeze()
+            return self.poses[ii], self.cam_poses[ii], self.embeddings[ii]
         idx = self.SE3_NN_idx(query)
         p, c, e = self._gather(self.poses, idx), self._gather(self.cam_poses, idx), self._gather(self.embeddings, idx)
         if idx.shape[0] == 1:  # the reference's indices_p.squeeze()

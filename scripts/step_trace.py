@@ -40,7 +40,7 @@ for t in range(T):
     call("mt_trace_read", eng.ctx.h, buf, 0)
     if buf[63] != 1:
         print(json.dumps({"error": "library was not built with -DMT_TRACE=1"})); sys.exit(0)
-    if t < 10:
+    if t < int(os.environ.get("AB_SKIP", 10)):
         continue
     t0 = buf[8]
     row = {"event_step": e0.elapsed_time(e1) * 1e3}

@@ -214,6 +214,37 @@ def test_se3_nn_dropin(mt, dev, cb_big):
     assert torch.equal(p.cpu(), cbs.poses[idx]) and torch.equal(c.cpu(), cbs.cam_poses[idx]) and torch.equal(e.cpu(), cbs.embeddings[idx])
 
 
+def test_r3_se3_other_weights(mt, dev, cb_small):
+    """R3_SE3(poses, w) for w != 0.01 (tactile_tree.py:73-77) against the oracle."""
+    cbs, _ = cb_small
+    for w in (0.01, 0.05, 0.5):
+        got = mt.tt.R3_SE3(cbs.poses.to(dev), w=w).cpu()
+        assert torch.allclose(got, O.r3_se3(cbs.poses, w=w), rtol=1e-5, atol=2e-7)
+
+
+@pytest.mark.parametrize("nn", [2, 5, 64])
+def test_se3_nn_k_neighbours(mt, dev, cb_small, nn):
+    """SE3_NN(query, nn > 1) (tactile_tree.py:43-58): the nn nearest codebook poses of every query, nearest first,
+    against a float32 brute force in the library's accumulation order on the library's keys."""
+    cbs, cb = cb_small
+    g = torch.Generator().manual_seed(1)
+    sel = torch.randint(0, 4096, (37,), generator=g)
+    poses = cbs.poses[sel].clone()
+    poses[:, :3, 3] += 5e-4 * torch.randn(37, 3, generator=g)
+    p, c, e = cb.SE3_NN(poses.to(dev), nn=nn)
+    assert p.shape == (37, nn, 4, 4) and c.shape == (37, nn, 4, 4) and e.shape == (37, nn, cbs.embeddings.shape[1])
+    keys_cb = cb.logmap_pose.cpu().numpy()
+    qk = mt.tt.R3_SE3(poses.to(dev)).cpu().numpy()
+    for j in range(37):
+        d = O.l2_sq_f32(keys_cb, qk[j]).astype(np.float32)
+        order = np.lexsort((np.arange(4096), d))[:nn]  # ascending (distance, index)
+        assert torch.equal(p[j].cpu(), cbs.poses[torch.from_numpy(order)])
+        assert torch.equal(e[j].cpu(), cbs.embeddings[torch.from_numpy(order)])
+    # a single query is squeezed like the reference's indices_p.squeeze()
+    p1, _, _ = cb.SE3_NN(poses[:1].to(dev), nn=nn)
+    assert p1.shape == (nn, 4, 4) and torch.equal(p1.cpu(), p[0].cpu())
+
+
 # ----------------------------------------------------------------------------- motion
 def test_motion_vs_reference_golden(mt, dev, golden, box):
     g = golden("motion")
