@@ -1949,8 +1949,11 @@ __global__ void __launch_bounds__(256, 4) k_step_bw(StepDev p, unsigned long lon
   const int G = gridDim.x, g = blockIdx.x;
   const long long n = step_count(p);
   const int nwarps = (int)((n + 31) >> 5);
-  const int per = (p.nchunks + G - 1) / G;
-  const int c_lo = g * per, c_hi = min(c_lo + per, p.nchunks);
+  // chunks per block from the ACTUAL particle count (sharded runs size buffers and grids from the capacity, 1.5 x the
+  // nominal shard: dividing the capacity's chunks would leave a third of the blocks idle and the others with 10 chunks)
+  const int nch = (int)min((long long)p.nchunks, (n + MT_CHUNK - 1) / MT_CHUNK);
+  const int per = max(1, (nch + G - 1) / G);
+  const int c_lo = min(g * per, nch), c_hi = min(c_lo + per, nch);
   MT_TRACE_BEGIN(p.xdbg, 4)
   // ---- phase 1: weights of this block's chunks.  Up to MT_BW_FAST_PER chunks keep (match, weight) of
   // every particle in shared memory for phase 2; the look-ups are issued four chunks at a time so that
