@@ -72,10 +72,18 @@ class FilterEngine:
         self.soa = [torch.zeros((3, self.capacity, 4), dtype=torch.float32, device=d) for _ in range(2)]
         self.nn = [torch.full((self.capacity,), -1, dtype=torch.int32, device=d) for _ in range(2)]
         self.anc = torch.zeros(self.capacity, dtype=torch.int32, device=d)
-        self.rmse = torch.zeros(2, dtype=torch.float32, device=d)
+        # step outputs (rmse) and the tactile code are double-buffered by the parity of the particle buffers, so that the
+        # copies of step t +- 1 (host -> device code, device -> host rmse) can run on a copy stream beside step t's kernels
+        self._rm = [torch.zeros(2, dtype=torch.float32, device=d) for _ in range(2)]
+        self._rm_last = 0
         self.n_dev = [torch.zeros(1, dtype=torch.int64, device=d) for _ in range(2)]
         self.shard_sums = torch.zeros(max(self.world, 1), dtype=torch.float64, device=d)
-        self.q_dev = torch.zeros(codebook.embeddings.shape[1], dtype=torch.float64, device=d)
+        self._q = [torch.zeros(codebook.embeddings.shape[1], dtype=torch.float64, device=d) for _ in range(2)]
+        self._io = torch.cuda.Stream(device=d)  # copy stream
+        self._ev_q = [torch.cuda.Event() for _ in range(2)]     # code of parity p has landed
+        self._ev_step = [torch.cuda.Event() for _ in range(2)]  # the last step that used the buffers of parity p is done
+        self._ev_read = torch.cuda.Event()
+        self._ev_rd = [None, None]  # pending read_rmse_async of the result buffer of parity p
         self.cur = 0
         self._n_children = 0  # single GPU: children to draw in the next resampling (0 = as many as there are particles)
         self.n = 0  # host-side upper bound of the local particle count
@@ -212,6 +220,24 @@ class FilterEngine:
     def ancestors(self) -> torch.Tensor:
         return self.anc[: self.count()]
 
+    @property
+    def rmse(self) -> torch.Tensor:
+        """(2,) float32 CUDA tensor: translation / rotation RMSE of the last step that was given a ground truth."""
+        return self._rm[self._rm_last]
+
+    def read_rmse_async(self, out_pinned: torch.Tensor) -> torch.cuda.Event:
+        """Copy the last step's rmse (8 bytes) into a pinned host tensor on the engine's copy stream, i.e. beside the next
+        step's kernels instead of between two launches on the compute stream; returns the event to synchronise on.
+        The result buffers alternate with the particle buffers, so the value stays valid for one more step."""
+        self._ev_read.record(torch.cuda.current_stream(self.dev))
+        self._io.wait_event(self._ev_read)
+        ev = torch.cuda.Event()
+        with torch.cuda.stream(self._io):
+            out_pinned.copy_(self._rm[self._rm_last], non_blocking=True)
+            ev.record(self._io)
+        self._ev_rd[self._rm_last] = ev
+        return ev
+
     # ------------------------------------------------------------------ one filter step
     def _fill(self, odom, u, tn, rot, gt, softmax, prune=True, resample=True):
         a = self._a
@@ -225,7 +251,7 @@ class FilterEngine:
         a.seed, a.step, a.first_gid = self.seed, self.t, self.rank * (1 << 40)
         a.softmax, a.u, a.resample = int(bool(softmax)), float(u), int(bool(resample))
         a.gt = ptr(gt) if gt is not None else None
-        a.d_rmse2 = ptr(self.rmse)
+        a.d_rmse2 = ptr(self._rm[self.cur])
         a.rank, a.world = self.rank, self.world
         a.n_global = int(self.n_global if (self.world > 1 and self.n_global is not None) else self._n_children)
         a.d_shard_sums = ptr(self.shard_sums) if self.world > 1 else None
@@ -250,10 +276,24 @@ class FilterEngine:
         self._refresh_ctx()
         if u is None:
             u = float(torch.rand(1, generator=self._rng).item())
-        # the code goes into the engine's own buffer (H2D for a host tensor: the step's only per-frame tensor input,
-        # D*8 bytes): the step graph is keyed on that address
-        self.q_dev.copy_(code.reshape(-1), non_blocking=True)
-        q = self.q_dev
+        # the code goes into the engine's own buffer of this parity (the step graph is keyed on that address).  A host
+        # tensor -- the step's only per-frame tensor input, D*8 bytes -- is copied on the copy stream: the transfer
+        # runs beside the previous step's kernels instead of between two graph launches on the compute stream.
+        par = self.cur
+        q = self._q[par]
+        src = code.reshape(-1)
+        main = torch.cuda.current_stream(self.dev)
+        if self._ev_rd[par] is not None:  # this parity's result buffer is about to be rewritten
+            main.wait_event(self._ev_rd[par])
+            self._ev_rd[par] = None
+        if src.device.type == "cpu":
+            self._io.wait_event(self._ev_step[par])  # the last step that read this buffer has finished
+            with torch.cuda.stream(self._io):
+                q.copy_(src, non_blocking=True)
+                self._ev_q[par].record(self._io)
+            main.wait_event(self._ev_q[par])
+        else:
+            q.copy_(src, non_blocking=True)
         odom16 = odom if isinstance(odom, Odom16) else prepare_odom(odom)
         gt_h = None
         if gt is not None:
@@ -274,6 +314,8 @@ class FilterEngine:
                 call("mt_step_a", self.ctx.h, C.byref(a), s)
                 self._allgather_sums()
                 call("mt_step_b", self.ctx.h, C.byref(a), s)
+        self._ev_step[par].record(main)
+        self._rm_last = par
         if resample:
             self.cur = 1 - self.cur
             if self.world > 1:
