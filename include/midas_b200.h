@@ -58,7 +58,9 @@ int mt_codebook_upload(mt_ctx* ctx, const float* h_keys, const void* d_emb, int 
 int mt_codebook_grid_info(mt_ctx* ctx, float* h, int dims[3], int* occupied);
 
 /* neighbour-graph introspection (tests): device pointer to the (M, k, 8) float32 table
- * [key(6), delta, index bits] of every key's k nearest other keys, ascending. */
+ * [key(6), delta, index bits] of every key's k nearest other keys, ascending.  k = 64, or 128 / 256 on dense codebooks
+ * (median 64th-neighbour distance below 1e-2 / 8e-3 key units; chosen by mt_codebook_upload, environment variable
+ * MIDAS_B200_NBR_K = 64 | 128 | 256 overrides). */
 int mt_codebook_nbr_info(mt_ctx* ctx, const float** d_nbr, int* k);
 /* d_rank[m] = position of codebook row m in the library's spatial (grid-cell) order; sorting
  * particles by the rank of their match keeps neighbouring threads on neighbouring keys. */

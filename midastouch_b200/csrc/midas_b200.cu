@@ -71,7 +71,8 @@ struct mt_ctx {
   float4* d_keys_sorted;  // same, sorted by grid cell
   int* d_sorted_orig;     // scratch: partner index per key during upload
   float4* d_bvh;          // boxes of the search index: leaves | level 1 | level 2 (3 float4 each)
-  float4* d_nbr;          // M x MT_NBR_K x 2 float4 neighbour lists (mt_nn.cuh)
+  float4* d_nbr;          // M x nbr_k x 2 float4 neighbour lists (mt_nn.cuh)
+  int nbr_k;              // list length: 64, 128 or 256 (chosen at upload)
   BvhParams bvh;
   const void* d_emb;
   int emb_dtype;
@@ -155,6 +156,7 @@ extern "C" int mt_ctx_create(int device, size_t capacity, int M, int D, mt_ctx**
   CK(cudaMalloc(&c->d_keys_sorted, sizeof(float4) * 2 * M));
   CK(cudaMalloc(&c->d_sorted_orig, sizeof(int) * M));
   CK(cudaMalloc(&c->d_nbr, sizeof(float4) * 2 * MT_NBR_K * (size_t)M));
+  c->nbr_k = MT_NBR_K;
   CK(cudaMalloc(&c->d_sim, sizeof(double) * M));
   CK(cudaMalloc(&c->d_esim, sizeof(double) * M));
   CK(cudaMalloc(&c->d_rnorm, sizeof(double) * M));
@@ -263,11 +265,64 @@ extern "C" int mt_codebook_upload(mt_ctx* c, const float* h_keys, const void* d_
   CK(cudaMemcpy(c->d_bvh + 3 * ((size_t)bp.n_leaf + bp.n_l1), l2.data(), sizeof(float) * l2.size(), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(c->d_keys_orig, ko.data(), sizeof(float) * 8 * M, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(c->d_keys_sorted, ks.data(), sizeof(float) * 8 * M, cudaMemcpyHostToDevice));
-  k_build_nbr<0><<<(M + 7) / 8, 256>>>(c->d_keys_orig, M, c->d_nbr, nullptr);
+  // ---- neighbour lists.  Pass 0 builds the 64 nearest other keys of every key.  On a dense codebook (thin parts:
+  // thousands of keys per cm of a rod) the particles sit further off the key manifold -- in rotation -- than the 64th
+  // neighbour is away, the triangle-inequality ball of the hint scan then holds more than 64 keys and most scans end
+  // inconclusive (measured on the cotter-pin stand-in: 60 % of the particles, each then a 20-leaf box search).  Such
+  // codebooks get longer lists: 128 or 256 entries, built in further passes of 64 (each admits only keys beyond the
+  // previous pass's last entry).  Criterion (a heuristic): median 64th-neighbour distance below 1e-2 / 8e-3 key units
+  // (the stand-ins: cotter pin 4.4e-3, sugar box 1.1e-2, mug 1.2e-2, drill 1.3e-2); MIDAS_B200_NBR_K = 64 | 128 | 256
+  // overrides it.  Measured on the cotter-pin stand-in at 2^20 particles: 64 -> 128 -> 256 entries = 597k -> 417k ->
+  // 301k box searches per step, 2.47 -> 2.14 -> 1.96 ms per step -- a help, not a cure: a particle that slides 0.7 mm
+  // round a 3 mm rod is 27 degrees (4.7e-3 key units) away from every key at its new position.
+  if (c->nbr_k != MT_NBR_K) {
+    cudaFree(c->d_nbr);
+    c->d_nbr = nullptr;
+    CK(cudaMalloc(&c->d_nbr, sizeof(float4) * 2 * MT_NBR_K * (size_t)M));
+    c->nbr_k = MT_NBR_K;
+  }
+  float2* d_bound = nullptr;
+  CK(cudaMalloc(&d_bound, sizeof(float2) * (size_t)M));
+  k_build_nbr<0><<<(M + 7) / 8, 256>>>(c->d_keys_orig, M, c->d_nbr, nullptr, nullptr, 0, 0, nullptr, MT_NBR_K, 0, d_bound);
   CK_LAUNCH();
+  int want = MT_NBR_K;
+  if (const char* e = getenv("MIDAS_B200_NBR_K")) {
+    want = atoi(e);
+    if (want != 64 && want != 128 && want != 256) {
+      cudaFree(d_bound);
+      return set_err(MT_ERR_ARG, "MIDAS_B200_NBR_K must be 64, 128 or 256");
+    }
+  } else if (M > MT_NBR_K_MAX) {
+    float* d_last = nullptr;
+    CK(cudaMalloc(&d_last, sizeof(float) * (size_t)M));
+    k_nbr_last_delta<<<(M + 255) / 256, 256>>>(c->d_nbr, M, MT_NBR_K, d_last);
+    CK_LAUNCH();
+    std::vector<float> last(M);
+    CK(cudaMemcpy(last.data(), d_last, sizeof(float) * (size_t)M, cudaMemcpyDeviceToHost));
+    cudaFree(d_last);
+    std::nth_element(last.begin(), last.begin() + M / 2, last.end());
+    const float med = last[M / 2];
+    want = med < 8e-3f ? 256 : (med < 1e-2f ? 128 : 64);
+  }
+  if (want > MT_NBR_K && M > want) {
+    float4* big = nullptr;
+    CK(cudaMalloc(&big, sizeof(float4) * 2 * (size_t)want * (size_t)M));
+    const size_t tot = (size_t)M * MT_NBR_K * 2;
+    k_nbr_restride<<<(unsigned)((tot + 255) / 256), 256>>>(c->d_nbr, M, want, big);
+    CK_LAUNCH();
+    for (int pass = 1; pass < want / MT_NBR_K; ++pass) {
+      k_build_nbr<0><<<(M + 7) / 8, 256>>>(c->d_keys_orig, M, big, nullptr, nullptr, 0, 0, nullptr, want, pass, d_bound);
+      CK_LAUNCH();
+    }
+    CK(cudaDeviceSynchronize());
+    cudaFree(c->d_nbr);
+    c->d_nbr = big;
+    c->nbr_k = want;
+  }
+  cudaFree(d_bound);
   k_build_nbr<1><<<(M + 7) / 8, 256>>>(c->d_keys_orig, M, nullptr, c->d_sorted_orig);
   CK_LAUNCH();
-  k_set_partner<<<(M + 255) / 256, 256>>>(c->d_keys_orig, M, c->d_sorted_orig, c->d_nbr);
+  k_set_partner<<<(M + 255) / 256, 256>>>(c->d_keys_orig, M, c->d_sorted_orig, c->d_nbr, c->nbr_k);
   CK_LAUNCH();
   CK(cudaDeviceSynchronize());
   c->bvh = bp;
@@ -291,7 +346,7 @@ extern "C" int mt_codebook_grid_info(mt_ctx* c, float* h, int dims[3], int* occu
 extern "C" int mt_codebook_nbr_info(mt_ctx* c, const float** d_nbr, int* k) {
   if (!c || !c->cb_ready) return set_err(MT_ERR_STATE, "mt_codebook_nbr_info: no codebook");
   if (d_nbr) *d_nbr = (const float*)c->d_nbr;
-  if (k) *k = MT_NBR_K;
+  if (k) *k = c->nbr_k;
   return MT_OK;
 }
 
@@ -1137,6 +1192,7 @@ static NNTables tables_of(mt_ctx* c) {
   T.nbr = c->d_nbr;
   T.b = c->bvh;
   T.M = c->M;
+  T.K = c->nbr_k;
   return T;
 }
 
@@ -1521,7 +1577,7 @@ __global__ void __launch_bounds__(MT_A_BLOCK, MT_A_MINBLOCKS) k_step_a(StepDev p
     float bd, dh;
     int bi, centre;
     int st = nn_hint_begin(T, key, hint, bd, bi, centre, dh);
-    if (st == 0) st = nn_hint_scan(T, key, centre, dh, 0, MT_NBR_K, bd, bi);
+    if (st == 0) st = nn_hint_scan(T, key, centre, dh, 0, T.K, bd, bi);
     if (st <= 0) todo |= MT_Q_NN;  // no usable hint, or the list is exhausted: box-hierarchy search
     if (bi == INT_MAX) bi = -1;  // no usable hint
     const bool masked = !on_surface || invalid;

@@ -32,7 +32,8 @@
 #ifndef MT_NN_BLOCK
 #define MT_NN_BLOCK 256
 #endif
-#define MT_NBR_K 64  // neighbours per key (the build kernel keeps two per lane)
+#define MT_NBR_K 64  // neighbours per key and build pass (the build kernel keeps two per lane); lists are 1, 2 or 4 passes long
+#define MT_NBR_K_MAX 256
 
 // Search index of the fallback path: the keys in 6-D Morton order, 32 consecutive keys per leaf, and two
 // levels of 32-ary inner nodes above the leaves; every node stores its axis-aligned bounding box in all six
@@ -49,9 +50,10 @@ struct NNTables {
   const float4* bvh_leaf;     // n_leaf x 3 float4
   const float4* bvh_l1;       // n_l1 x 3 float4 (node j covers leaves 32j .. 32j+31)
   const float4* bvh_l2;       // n_l2 x 3 float4 (node j covers level-1 nodes 32j .. 32j+31)
-  const float4* nbr;          // M x MT_NBR_K x 2 float4: (k0..k3 | k4,k5,delta,idx bits)
+  const float4* nbr;          // M x K x 2 float4: (k0..k3 | k4,k5,delta,idx bits)
   BvhParams b;
   int M;
+  int K;                      // neighbours per key: MT_NBR_K, or a multiple of it for dense codebooks (mt_codebook_upload)
 };
 #endif
 
@@ -247,7 +249,7 @@ __device__ __forceinline__ float4 mt_ldnc(const float4* p) {
 // these prefetches turn it into cache hits.
 __device__ __forceinline__ void nn_prefetch(const NNTables& T, int hint) {
   if (hint < 0 || hint >= T.M) return;
-  const float4* L = T.nbr + (size_t)hint * (2 * MT_NBR_K);
+  const float4* L = T.nbr + (size_t)hint * (2 * T.K);
   asm volatile("prefetch.global.L1 [%0];" ::"l"(T.keys_orig + 2 * (size_t)hint));
   asm volatile("prefetch.global.L1 [%0];" ::"l"(L));
   asm volatile("prefetch.global.L2 [%0];" ::"l"(L + 8));
@@ -316,7 +318,7 @@ __device__ __forceinline__ int nn_hint_scan(const NNTables& T, const float q[6],
 #else
   float lim = mt_hint_limit(dh, best_d);
 #endif
-  const float4* __restrict__ L = T.nbr + (size_t)centre * (2 * MT_NBR_K);
+  const float4* __restrict__ L = T.nbr + (size_t)centre * (2 * T.K);
   // Software pipeline: the two entries of the next half trip are requested before the current ones are evaluated, so
   // a trip waits for loads issued ~40 instructions (x the other resident warps) earlier.  The loads are volatile asm
   // (plain ld.global.nc underneath, i.e. cached in L1 like __ldg) so that neither NVVM nor ptxas sinks them below the
@@ -358,7 +360,7 @@ __device__ __forceinline__ int nn_hint_scan(const NNTables& T, const float q[6],
     MT_SCAN_ENTRY(xa0, xb0)
     MT_SCAN_ENTRY(xa1, xb1)
     MT_SCAN_LIMIT()
-    const int jn = min(j + 4, MT_NBR_K - 2);  // past the end of the list: a harmless re-read, never used
+    const int jn = min(j + 4, T.K - 2);  // past the end of the list: a harmless re-read, never used
     xa0 = mt_ldnc(L + 2 * jn), xb0 = mt_ldnc(L + 2 * jn + 1), xa1 = mt_ldnc(L + 2 * jn + 2), xb1 = mt_ldnc(L + 2 * jn + 3);
     MT_SCAN_ENTRY(ya0, yb0)
     MT_SCAN_ENTRY(ya1, yb1)
@@ -375,7 +377,7 @@ __device__ __forceinline__ bool nn_hint_search(const NNTables& T, const float q[
   float dh;
   const int st = nn_hint_begin(T, q, hint, best_d, best_i, centre, dh);
   if (st) return st > 0;
-  return nn_hint_scan(T, q, centre, dh, 0, MT_NBR_K, best_d, best_i) != 0;
+  return nn_hint_scan(T, q, centre, dh, 0, T.K, best_d, best_i) != 0;
 }
 
 // bound of one node (3 float4 = lo[6] | hi[6])
@@ -521,10 +523,14 @@ __device__ __forceinline__ int nn_assign(const NNTables& T, bool active, const f
 //   MODE 2: the k <= 64 nearest keys of nq external query keys (SE3_NN with nn > 1, tactile_tree.py:43-52):
 //           out_idx[h * k + j] = index of the j-th nearest key of query h, ascending (distance, index) -- exhaustive,
 //           every query streams the whole codebook (meant for the handful of queries such calls make)
+//   MODE 0 builds lists longer than 64 in passes of 64: pass p writes entries [64 p, 64 p + 64) of the K-entry list and
+//   only admits keys that come strictly after the previous pass's last entry in (squared distance, index) order
+//   (`bound`: 2 floats per key = that entry's squared distance and index bits, read and then overwritten).
 template <int MODE>
 __global__ void __launch_bounds__(256) k_build_nbr(const float4* __restrict__ keys, int M, float4* __restrict__ nbr,
                                                    int* __restrict__ partner, const float* __restrict__ qkeys = nullptr,
-                                                   int nq = 0, int k_out = 0, int* __restrict__ out_idx = nullptr) {
+                                                   int nq = 0, int k_out = 0, int* __restrict__ out_idx = nullptr,
+                                                   int K = MT_NBR_K, int pass = 0, float2* __restrict__ bound = nullptr) {
   static_assert(MT_NBR_K == 64, "two list slots per lane");
   constexpr bool PARTNER = MODE == 1;
   constexpr bool QUERY = MODE == 2;
@@ -550,6 +556,12 @@ __global__ void __launch_bounds__(256) k_build_nbr(const float4* __restrict__ ke
   }
   float lo_v = FLT_MAX, hi_v = FLT_MAX;  // squared distances, ascending over (lo[0..31], hi[0..31])
   int lo_i = -1, hi_i = -1;
+  float lb_d = -1.f;  // admit only (d, m) > (lb_d, lb_i) lexicographically
+  int lb_i = -1;
+  if (MODE == 0 && pass > 0 && act) {
+    const float2 b = bound[h];
+    lb_d = b.x, lb_i = __float_as_int(b.y);
+  }
   for (int m0 = 0; m0 < M; m0 += 256) {
     const int cnt = min(256, M - m0);
     __syncthreads();
@@ -564,6 +576,7 @@ __global__ void __launch_bounds__(256) k_build_nbr(const float4* __restrict__ ke
         const float k[6] = {a.x, a.y, a.z, a.w, b.x, b.y};
         d = mt_key_dist(kh, k);
         if (!(d == d)) d = FLT_MAX;
+        if (MODE == 0 && (d < lb_d || (d == lb_d && m <= lb_i))) d = FLT_MAX;  // taken by an earlier pass
       }
       unsigned cand = __ballot_sync(0xffffffffu, d < __shfl_sync(0xffffffffu, hi_v, 31));
       while (cand) {
@@ -605,20 +618,33 @@ __global__ void __launch_bounds__(256) k_build_nbr(const float4* __restrict__ ke
       const float4 kb = keys[2 * (size_t)idx + 1];
       b = make_float4(kb.x, kb.y, sqrtf(val), __int_as_float(idx));
     }
-    const size_t slot = (size_t)h * MT_NBR_K + 32 * half + lane;
+    const size_t slot = (size_t)h * K + (size_t)MT_NBR_K * pass + 32 * half + lane;
     nbr[slot * 2] = a;
     nbr[slot * 2 + 1] = b;
+    if (bound && half == 1 && lane == 31) bound[h] = make_float2(idx >= 0 ? val : FLT_MAX, __int_as_float(idx >= 0 ? idx : INT_MAX));
   }
   }
 }
 
 // keys_orig padding: (partner index bits, delta_0 = distance to the nearest other key)
 __global__ void k_set_partner(float4* __restrict__ keys, int M, const int* __restrict__ partner,
-                              const float4* __restrict__ nbr) {
+                              const float4* __restrict__ nbr, int K) {
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= M) return;
   keys[2 * (size_t)m + 1].z = __int_as_float(partner[m]);
-  keys[2 * (size_t)m + 1].w = nbr[(size_t)m * MT_NBR_K * 2 + 1].z;
+  keys[2 * (size_t)m + 1].w = nbr[(size_t)m * K * 2 + 1].z;
+}
+// the 64th-neighbour distance of every key (decides the list length at upload)
+__global__ void k_nbr_last_delta(const float4* __restrict__ nbr, int M, int K, float* __restrict__ out) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m < M) out[m] = nbr[((size_t)m * K + MT_NBR_K - 1) * 2 + 1].z;
+}
+// re-strides 64-entry lists into the first 64 entries of K-entry lists
+__global__ void k_nbr_restride(const float4* __restrict__ in, int M, int K, float4* __restrict__ out) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t)M * MT_NBR_K * 2) return;
+  const size_t m = t / (MT_NBR_K * 2), r = t % (MT_NBR_K * 2);
+  out[m * K * 2 + r] = in[t];
 }
 
 // rank[m] = position of key m in the cell-sorted order (engine: spatial sort of particles)

@@ -884,16 +884,28 @@ def test_engine_on_other_objects(mt, dev, name, M):
     assert cb.ctx.stats()["overflow"] == 0
 
 
-def test_engine_heavy_fallback_is_exact(mt, dev):
+_FALLBACKS_64 = {}
+
+
+@pytest.mark.parametrize("nbr_k", [64, 0])
+def test_engine_heavy_fallback_is_exact(mt, dev, monkeypatch, nbr_k):
     """thin rod (cotter-pin stand-in): after a few steps the particles' rotations have drifted off the key
-    manifold, a large share of the hint scans is inconclusive and the box-hierarchy search carries the load.
-    The matches must still be the exact nearest keys, and the hierarchy must prune (a search that visited
-    every leaf would also be exact)."""
+    manifold.  With 64-entry neighbour lists (forced) a large share of the hint scans is inconclusive and the
+    box-hierarchy search carries the load; the matches must still be the exact nearest keys, and the hierarchy must
+    prune (a search that visited every leaf would also be exact).  With the list length left to the upload (0: a
+    codebook this dense gets longer lists) the same matches must come out with far fewer box searches."""
+    if nbr_k:
+        monkeypatch.setenv("MIDAS_B200_NBR_K", str(nbr_k))
+    else:
+        monkeypatch.delenv("MIDAS_B200_NBR_K", raising=False)
     obj = synth.make_object("cotter-pin")
     M, N, D = 20000, 40000, 32
     cbs = synth.make_codebook(obj, M=M, D=D, seed=9, embedding="smooth")
     cb = mt.tt.tactile_tree(cbs.poses, cbs.cam_poses, cbs.embeddings)
     cb.to_device(dev)
+    kk = C.c_int(0)
+    mt.lib.call("mt_codebook_nbr_info", cb.ctx.h, None, C.byref(kk))
+    assert kk.value == 64 if nbr_k else kk.value in (128, 256), kk.value
     g = torch.Generator().manual_seed(9)
     sel = torch.randint(0, M, (N,), generator=g)
     gt, meas = synth.make_trajectory(obj, T=16, seed=9, step=1e-4)
@@ -911,7 +923,11 @@ def test_engine_heavy_fallback_is_exact(mt, dev):
     gk = mt.tt.R3_SE3(moved[sub.to(dev)]).cpu().numpy()
     assert np.array_equal(nn[sub.numpy()], O.nn_exact(cb.logmap_pose.cpu().numpy(), gk, k=32))
     n_leaf = cb.ctx.grid_info()[1][0]
-    assert st["nn_fallbacks"] > N // 4, st       # the fallback path really was exercised (13 steps x N particles)
+    if nbr_k:
+        assert st["nn_fallbacks"] > N // 4, st   # the fallback path really was exercised (13 steps x N particles)
+        _FALLBACKS_64["n"] = st["nn_fallbacks"]
+    elif "n" in _FALLBACKS_64:
+        assert st["nn_fallbacks"] < 0.8 * _FALLBACKS_64["n"], (st, _FALLBACKS_64)  # the longer lists settle a good part of them
     assert 0 < st["grid_rows_max"] < (3 * n_leaf) // 4, (st, n_leaf)
     assert st["overflow"] == 0
 
