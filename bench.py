@@ -293,7 +293,9 @@ def run_ours(args):
         if world > 1:
             dist.all_reduce(conv_ms, op=dist.ReduceOp.MAX)
         conv = {"frames": "150..180 (graph replays) / 120..150 (per-kernel events)", "value": n * world * 30 / (float(conv_ms.item()) * 1e-3),
-                "ms_per_step": float(conv_ms.item()) / 30, "k_step_a_ms": sum(e[1].elapsed_time(e[2]) for e in evc) / 30,
+                "ms_per_step": float(conv_ms.item()) / 30, "step_ms_every_3rd": [round(e[0].elapsed_time(e[1]), 4) for e in evg[::3]],
+                "stream_form_step_ms": sum(e[0].elapsed_time(e[5]) for e in evc) / 30,
+                "k_step_a_ms": sum(e[1].elapsed_time(e[2]) for e in evc) / 30,
                 "k_step_a_frac": A_BYTES_PER_UPDATE * n / (sum(e[1].elapsed_time(e[2]) for e in evc) / 30 * 1e-3) / 1e9 / peaks()[0]}
     per_rank = None
     if world > 1:

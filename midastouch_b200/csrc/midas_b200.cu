@@ -380,6 +380,12 @@ extern "C" int mt_ctx_stats(mt_ctx* c, long long* h_out, int reset) {
 
 // ------------------------------------------------------------------------- mesh (drift test)
 static MeshTables mesh_of(mt_ctx* c);
+#ifndef MT_VOX_DIV
+#define MT_VOX_DIV 4.0   // voxel edge of the drift-test classes = invalid_dist / MT_VOX_DIV ...
+#endif
+#ifndef MT_VOX_MAX
+#define MT_VOX_MAX 48.0e6  // ... unless that needs more voxels than this (4 B each + 2 bits each)
+#endif
 extern "C" int mt_mesh_upload(mt_ctx* c, const double* h_vertices, long long V, double cell) {
   if (!c || !h_vertices || V <= 0 || !(cell > 0.0)) return set_err(MT_ERR_ARG, "mt_mesh_upload: bad argument");
   CK(cudaSetDevice(c->device));
@@ -447,13 +453,13 @@ extern "C" int mt_mesh_upload(mt_ctx* c, const double* h_vertices, long long V, 
   // at most 64 M voxels
   {
     const double dist = cell0;
-    double v = dist / 4.0;
+    double v = dist / MT_VOX_DIV;
     MeshVoxels vx;
     memset(&vx, 0, sizeof(vx));
     for (;;) {
       double total = 1;
       for (int k = 0; k < 3; ++k) vx.dims[k] = (int)ceil((hi[k] - lo[k] + 2.0 * (dist + 2.0 * v)) / v) + 1, total *= vx.dims[k];
-      if (total <= 48.0e6) break;
+      if (total <= MT_VOX_MAX) break;
       v *= 1.26;
     }
     for (int k = 0; k < 3; ++k) vx.org[k] = (float)(lo[k] - (dist + 2.0 * v));
@@ -1715,10 +1721,61 @@ __global__ void __launch_bounds__(32 * MT_NNQ_WARPS) k_step_nnq(StepDev p, NNTab
       asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
     }
   }
+  // Few entries (the usual few hundred): one BLOCK per entry, its four warps search as a team (nn_bvh_search_team); a
+  // drift test that is still pending for the particle is done by the fourth warp meanwhile.  Many entries (rod-like
+  // objects: hundreds of thousands): one warp per entry, pulled from a shared counter -- throughput, not the tail, matters.
+  __shared__ unsigned long long s_best;
+  __shared__ int s_leaves, s_masked;
+  const unsigned W = gridDim.x * MT_NNQ_WARPS;
+  if (qn <= gridDim.x) {
+    const int warp = threadIdx.x >> 5;
+    for (unsigned e = blockIdx.x; e < qn; e += gridDim.x) {  // (at most one trip; block-uniform)
+#if MT_TRACE
+      const unsigned long long tr0 = mt_now();
+#endif
+      const int raw = p.queue[e];
+      const float4 r0 = p.srec[2 * (size_t)e], r1 = p.srec[2 * (size_t)e + 1];
+      const long long i = raw & MT_Q_INDEX;
+      const float key[6] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y};
+      const bool masked0 = (raw & MT_Q_MASKED) != 0;
+      const bool mesh = (raw & MT_Q_MESH) && !masked0;
+      const bool nan = !(key[0] == key[0]) || !(key[1] == key[1]) || !(key[2] == key[2]) || !(key[3] == key[3]) || !(key[4] == key[4]) || !(key[5] == key[5]);
+      if (threadIdx.x == 0) {
+        const int bi = __float_as_int(r1.w);
+        s_best = bi < 0 ? mt_dist_word(FLT_MAX, INT_MAX) : mt_dist_word(r1.z, bi);
+        s_leaves = 0;
+        s_masked = masked0 ? 1 : 0;
+      }
+      __syncthreads();
+      if (mesh && warp == MT_NNQ_WARPS - 1) {
+        const float x = p.soa_cur[i].w, y = p.soa_cur[p.stride + i].w, z = p.soa_cur[2 * p.stride + i].w;
+        if (!mesh_within_warp(Mh, x, y, z, p.prune_dist) && lane == 0) {
+          s_masked = 1;
+          atomicSub(p.wcnt + (i >> 5), 1);
+        }
+      } else if (!nan) {
+        nn_bvh_search_team(T, key, warp, mesh ? MT_NNQ_WARPS - 1 : MT_NNQ_WARPS, &s_best, &s_leaves);
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        const int bi = (int)(unsigned)s_best;
+        const int res = (nan || bi == INT_MAX) ? 0 : bi;  // NaN / Inf query: np.argmin semantics
+        p.nn_cur[i] = s_masked ? nn_masked(res) : res;
+        atomicAdd(p.flags + 4, s_leaves);
+        atomicMax(p.flags + 4 + 3, s_leaves);
+#if MT_TRACE
+        const unsigned long long tr2 = mt_now();
+        atomicMax(p.xdbg + 30, tr2 - tr0), atomicAdd(p.xdbg + 31, tr2 - tr0), atomicAdd(p.xdbg + 32, 1ull), atomicMax(p.xdbg + 35, tr0);
+#endif
+      }
+      __syncthreads();
+    }
+    MT_TRACE_END(p.xdbg, 3)
+    return;
+  }
   // the first entry of every warp is assigned statically (one per block first, so that they spread over the SMs):
   // with the usual few hundred entries nobody touches the shared counter -- thousands of warps opening with an
   // atomic on one address serialised in L2 and were most of this kernel's duration.  Further entries are pulled.
-  const unsigned W = gridDim.x * MT_NNQ_WARPS;
   unsigned e = (threadIdx.x >> 5) * gridDim.x + blockIdx.x;
   while (e < qn) {
     NnqEntry q;

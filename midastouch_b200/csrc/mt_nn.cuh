@@ -484,6 +484,84 @@ __device__ __noinline__ int nn_bvh_search(const NNTables& T, const float q[6], f
   return best_i == INT_MAX ? 0 : best_i;  // Inf query: every distance is Inf/NaN
 }
 
+// The same search by a TEAM of warps (one query, `nparts` warps of one block, this warp = `part`): every warp walks the
+// same best-first sequence of level-1 nodes but only opens those whose rank in that sequence is congruent to `part`;
+// the team's best (distance bits << 32 | index, mt_dist_word) lives in shared memory, is improved with atomicMin and
+// re-read before every pruning test.  A pruning test against a stale (larger) best only opens a box too many, never
+// one too few, so the result is the same exact argmin.  The step waits for its slowest search (a single warp needs
+// ~0.65 us per leaf, 25 us for the 38-leaf worst case); a team cuts that tail.
+__device__ __noinline__ void nn_bvh_search_team(const NNTables& T, const float q[6], int part, int nparts,
+                                                unsigned long long* s_best, int* s_leaves) {
+  const int lane = threadIdx.x & 31;
+  const float INF = __int_as_float(0x7f800000);
+  float best_d;
+  int best_i;
+#define MT_TEAM_REFRESH()                                                   \
+  {                                                                         \
+    const unsigned long long w_ = *(volatile unsigned long long*)s_best;    \
+    best_d = __uint_as_float((unsigned)(w_ >> 32)), best_i = (int)(unsigned)w_; \
+  }
+  MT_TEAM_REFRESH()
+  int leaves = 0;
+  for (int c2 = 0; c2 < T.b.n_l2; c2 += 32) {
+    float lb2 = (c2 + lane < T.b.n_l2) ? bvh_lower_bound(T.bvh_l2 + 3 * (size_t)(c2 + lane), q) : INF;
+    for (;;) {
+      float v2;
+      const int w2 = bvh_pick(lb2, v2);
+      MT_TEAM_REFRESH()
+      if (!mt_box_may_hold(v2, best_d)) break;
+      const int i1 = 32 * (c2 + w2) + lane;
+      float lb1 = (i1 < T.b.n_l1) ? bvh_lower_bound(T.bvh_l1 + 3 * (size_t)i1, q) : INF;
+      for (int rank = 0;; ++rank) {
+        float v1;
+        const int w1 = bvh_pick(lb1, v1);
+        MT_TEAM_REFRESH()
+        if (!mt_box_may_hold(v1, best_d)) break;
+        if (rank % nparts != part) continue;  // a team mate's node
+        const int il = 32 * (32 * (c2 + w2) + w1) + lane;
+        float lbl = (il < T.b.n_leaf) ? bvh_lower_bound(T.bvh_leaf + 3 * (size_t)il, q) : INF;
+        for (;;) {
+          int base[MT_BVH_BATCH];
+          int nb = 0;
+#pragma unroll
+          for (int bq = 0; bq < MT_BVH_BATCH; ++bq) {
+            base[bq] = -1;
+            if (nb == bq) {
+              float vl;
+              const int wl = bvh_pick(lbl, vl);
+              if (mt_box_may_hold(vl, best_d)) base[bq] = 32 * (32 * (32 * (c2 + w2) + w1) + wl), ++nb;
+            }
+          }
+          if (nb == 0) break;
+          float d = INF;
+          int o = INT_MAX;
+#pragma unroll
+          for (int bq = 0; bq < MT_BVH_BATCH; ++bq) {
+            const int pidx = base[bq] + lane;
+            if (base[bq] >= 0 && pidx < T.M) {
+              float k[6];
+              const int ob = load_key(T.keys_sorted, pidx, k);
+              float db = mt_key_dist(q, k);
+              if (!(db == db)) db = INF;
+              if (mt_better(db, ob, d, o)) d = db, o = ob;
+            }
+          }
+          const unsigned dm = __reduce_min_sync(0xffffffffu, __float_as_uint(d));  // distances are >= +0
+          const unsigned om = __reduce_min_sync(0xffffffffu, __float_as_uint(d) == dm ? (unsigned)o : 0x7fffffffu);
+          if (om != 0x7fffffffu && mt_better(__uint_as_float(dm), (int)om, best_d, best_i) && lane == 0)
+            atomicMin(s_best, ((unsigned long long)dm << 32) | om);
+          __syncwarp();
+          MT_TEAM_REFRESH()
+          leaves += nb;
+          if (nb < MT_BVH_BATCH) break;
+        }
+      }
+    }
+  }
+#undef MT_TEAM_REFRESH
+  if (lane == 0) atomicAdd(s_leaves, leaves);
+}
+
 // (Measured and dropped: fetching the leaf boxes of four level-1 nodes per round trip, eight leaves per round trip, and
 // taking children in lane order from a ballot instead of best-first -- the first two were 10 % slower (a search is one
 // warp's dependent instruction stream, ~1 us per leaf; wider rounds add instructions, not overlap), the last one cut the
