@@ -1660,27 +1660,34 @@ __device__ __forceinline__ void nnq_load(const StepDev& p, const MeshTables& Mh,
 //   k_step_meshq   one thread per entry: the two quick certificates (mesh_quick) settle ~3/4 of the entries with one
 //                  vertex load; the rest is compacted into a second list
 //   k_step_meshq2  one warp per entry of that list: grid search, the lanes over the candidate vertices
-__device__ __forceinline__ void mesh_mark_off(const StepDev& p, long long i) {
-  const int stored = p.nn_cur[i];
-  if (stored >= 0) p.nn_cur[i] = nn_masked(stored);
+// Both kernels are chains of dependent memory round trips (count -> entry -> point -> tables -> match), ~1.2 us each,
+// with next to no arithmetic: the first trip's entry is therefore requested before the count is known (a stale or
+// uninitialised entry is clamped to a valid particle and dropped once the count has arrived), and the particle's point
+// and stored match are requested together.
+__device__ __forceinline__ void mesh_mark_off(const StepDev& p, long long i, int stored) {
+  if (stored >= 0) p.nn_cur[i] = nn_masked(stored);  // (nobody else touches a queued particle's match meanwhile)
   atomicSub(p.wcnt + (i >> 5), 1);
 }
 __global__ void __launch_bounds__(256) k_step_meshq(StepDev p, MeshTables Mh) {
-  const unsigned mn = p.qctl[3];
   const int lane = threadIdx.x & 31;
   const unsigned span = gridDim.x * blockDim.x;
+  const unsigned first = blockIdx.x * blockDim.x + threadIdx.x;
+  int raw = ((long long)first < p.queue_cap) ? p.queue[p.queue_cap - 1 - first] : 0;  // speculative
+  const unsigned mn = p.qctl[3];
   MT_TRACE_BEGIN(p.xdbg, 1)
-  for (unsigned e0 = blockIdx.x * blockDim.x + threadIdx.x - lane; e0 < mn; e0 += span) {  // whole warps stay in the loop
+  for (unsigned e0 = first - lane; e0 < mn; e0 += span) {  // whole warps stay in the loop
     const unsigned e = e0 + lane;
+    if (e0 != first - lane && e < mn) raw = p.queue[p.queue_cap - 1 - e];
+    const long long n_cov = p.stride;
+    const long long i = raw < 0 ? 0 : ((long long)raw >= n_cov ? n_cov - 1 : raw);
+    const float x = p.soa_cur[i].w, y = p.soa_cur[p.stride + i].w, z = p.soa_cur[2 * p.stride + i].w;
+    const int stored = p.nn_cur[i];
     int res = 1;  // 1 within, 0 not within, 2 grid search
-    long long i = 0;
     if (e < mn) {
-      i = p.queue[p.queue_cap - 1 - e];
-      const float x = p.soa_cur[i].w, y = p.soa_cur[p.stride + i].w, z = p.soa_cur[2 * p.stride + i].w;
       int k = -1;
       const int c = mesh_voxel_class(Mh, x, y, z, p.prune_dist, &k);
       res = c < 2 ? c : (c == 2 ? mesh_quick(Mh, x, y, z, p.prune_dist, k) : 2);
-      if (res == 0) mesh_mark_off(p, i);
+      if (res == 0) mesh_mark_off(p, i, stored);
     }
     const unsigned m2 = __ballot_sync(0xffffffffu, res == 2);
     if (m2) {
@@ -1693,14 +1700,17 @@ __global__ void __launch_bounds__(256) k_step_meshq(StepDev p, MeshTables Mh) {
   MT_TRACE_END(p.xdbg, 1)
 }
 __global__ void __launch_bounds__(256) k_step_meshq2(StepDev p, MeshTables Mh) {
-  const unsigned n2 = p.qctl[2];
   const unsigned gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  int raw = ((long long)gw < p.queue_cap) ? p.queue2[gw] : 0;  // speculative
+  const unsigned n2 = p.qctl[2];
   MT_TRACE_BEGIN(p.xdbg, 2)
   for (unsigned e = gw; e < n2; e += nw) {
-    const long long i = p.queue2[e];
+    if (e != gw) raw = p.queue2[e];
+    const long long i = raw < 0 ? 0 : ((long long)raw >= p.stride ? p.stride - 1 : raw);
     const float x = p.soa_cur[i].w, y = p.soa_cur[p.stride + i].w, z = p.soa_cur[2 * p.stride + i].w;
+    const int stored = p.nn_cur[i];
     const bool on = mesh_search_warp(Mh, x, y, z, p.prune_dist);
-    if (!on && (threadIdx.x & 31) == 0) mesh_mark_off(p, i);
+    if (!on && (threadIdx.x & 31) == 0) mesh_mark_off(p, i, stored);
   }
   MT_TRACE_END(p.xdbg, 2)
 }
