@@ -511,6 +511,7 @@ def tcn_time(dev, reps=20):
     xy = rng.uniform(-1, 1, size=(4096, 2))
     z = 0.3 * (xy[:, 0] ** 2 + xy[:, 1] ** 2) - 0.2
     cloud = torch.from_numpy(np.concatenate([xy, z[:, None]], 1).astype("float32")).to(dev)[None]
+    tcn_time.last = (tcn, cloud)  # (scripts/tcn_prof.py)
     for _ in range(3):
         tcn.embed_clouds(cloud)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

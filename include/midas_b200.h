@@ -304,12 +304,20 @@ int mt_tcn_set_conv(mt_tcn* t, int conv_id, const float* h_kernel, int kvol, int
 int mt_tcn_set_bn(mt_tcn* t, int bn_id, const float* h_weight, const float* h_bias, const float* h_mean, const float* h_var,
                   int c, float eps);
 int mt_tcn_set_gem(mt_tcn* t, float p, float eps);
-/* d_keys: n sorted unique 64-bit coordinates of the quantised clouds of `batch` frames
+/* d_keys: n 64-bit coordinates of the quantised clouds of `batch` frames, batch-major
  * (batch << 54 | (x + 2^17) << 36 | (y + 2^17) << 18 | (z + 2^17); ME.utils.sparse_quantize +
- * batched_coordinates, tcn.py:124-131).  d_out: (batch, feature) float64 descriptors, L2-normalised
- * when normalize != 0 (tcn.py:138-148).  d_counts (nullable): active points per level (4 ints). */
+ * batched_coordinates, tcn.py:124-131; duplicates are merged).  d_out: (batch, feature) float64
+ * descriptors, L2-normalised when normalize != 0 (tcn.py:138-148).  d_counts (nullable): active
+ * points per level (4 ints). */
 int mt_tcn_forward(mt_tcn* t, const unsigned long long* d_keys, int n, int batch, int normalize, double* d_out,
                    int* d_counts, void* stream);
+/* The same from the sampled, scaled clouds of tcn.py:96-123: d_clouds (batch, points, 3) float32;
+ * voxel = floor(x * inv_q) with inv_q = the float32 reciprocal torch multiplies by when it evaluates
+ * `cloud / q` on CUDA (tcn.py:124-130; float32(1 / q) in torch 2.x) -- duplicate voxels merged in the library (no
+ * sort, no host synchronisation; rows = voxels in order of their first point).  A voxel coordinate
+ * beyond +-131071 (or NaN) turns the descriptors of the call into NaN. */
+int mt_tcn_embed(mt_tcn* t, const float* d_clouds, int batch, int points, float inv_q, int normalize, double* d_out,
+                 int* d_counts, void* stream);
 
 #ifdef __cplusplus
 }

@@ -93,6 +93,7 @@ _SIGS = {
     "mt_tcn_set_bn": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float]),
     "mt_tcn_set_gem": (C.c_int, [C.c_void_p, C.c_float, C.c_float]),
     "mt_tcn_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mt_tcn_embed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mt_dist_export": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mt_dist_import": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "mt_dist_debug": (C.c_int, [C.c_void_p, C.POINTER(C.c_ulonglong)]),

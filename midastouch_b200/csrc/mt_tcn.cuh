@@ -4,9 +4,25 @@
 // shipped configuration (config/tcn/default.yaml: planes 32,64,64, layers 1,1,1, one top-down
 // block, conv0 kernel 5, 256-d output).  Sparse tensors are (sorted unique 64-bit coordinate
 // keys, row-major float32 features); a coordinate map is an open-addressing hash table
-// key -> row.  One generic kernel evaluates every convolution: one warp per output point,
-// lanes over output channels, kernel offsets resolved by hash look-ups (gather form: no
-// atomics, fixed summation order), BatchNorm(eval) / residual / ReLU fused in the epilogue.
+// key -> row.  Per forward pass:
+//   1. k_tcn_insert_all / k_tcn_count_all / k_tcn_scatter_all: the raw points (float clouds, quantised
+//      in the kernel, or packed keys) register with the coordinate maps of all four levels at once;
+//      the rows of a level are its distinct keys in order of their first raw point (deterministic,
+//      batch-major), found by an ordered multi-block compaction -- this replaces torch.unique (a
+//      64-bit radix sort) and three single-block passes.
+//   2. k_tcn_kmaps: the kernel maps (row of every kernel offset, -1 = absent, + a bit mask of the
+//      offsets present) of the 3x3x3, the strided 2x2x2 and the transposed 2x2x2 convolutions: the
+//      hash tables are probed once per (point, offset), not once per layer.
+//   3. k_tcn_conv_mma: every convolution with >= 8 input channels as a gather-GEMM on the tensor
+//      cores: one warp = 16 output points x (8 NT) output channels, offsets in ascending order (fixed
+//      summation order, no atomics), only the offsets some point of the tile has; operands straight
+//      from L1/L2 into mma.sync.m16n8k8 TF32 fragments, every product as three MMAs on the
+//      (big, small) TF32 split of both operands (3xTF32: float32-grade accuracy); BatchNorm(eval) /
+//      residual / accumulate / ReLU fused in the epilogue.  The weights of an offset are read once per
+//      16 points instead of once per point (the CUDA-core kernel below was bound by exactly that L1
+//      traffic: 1 GB for the 256 -> 256 transposed convolution).
+//   k_tcn_conv (one warp per output point, hash look-ups) remains for conv0 (one dummy input
+//   feature: a sum of kernel rows) and for channel widths the MMA tiling does not divide.
 // Semantics restated in oracle/tcn_oracle.py (parity unpinned against MinkowskiEngine itself).
 //
 // Included at the end of midas_b200.cu (same translation unit: shares set_err / CK).
@@ -14,6 +30,10 @@
 
 #define TCN_EMPTY 0xFFFFFFFFFFFFFFFFull
 #define TCN_NCONV 16
+#define TCN_CTL_PAIRS 8
+#define TCN_CTL_BLO 256
+#define TCN_CTL_BHI 768
+#define TCN_CTL_INTS 1280
 #define TCN_NBN 13
 // conv ids
 #define TCN_CONV0 0
@@ -42,8 +62,12 @@ struct TcnBn {
 };
 struct TcnTable {
   unsigned long long* keys;
-  int* vals;
+  int* vals;      // smallest raw point index that maps to the key (its deterministic representative)
+  int* rows;      // row of the key in the level's feature matrix
   unsigned mask;  // capacity - 1 (power of two)
+};
+struct TcnTabs {
+  TcnTable t[4];
 };
 
 struct mt_tcn {
@@ -54,7 +78,23 @@ struct mt_tcn {
   unsigned cap;            // hash capacity per level
   TcnTable tab[4];         // level 0..3 (tensor stride 1,2,4,8)
   unsigned long long* keys[4];
-  int* d_n;                // [4] active points per level (device)
+  int* d_n;                // control block (device): [0..3] active points per level | [4] status flag (coordinate out of
+                           // range) | [8 + 32 m + i] pairs of kernel offset i in map m, [8 + 32 m + 31] pairs of map m
+                           // | [TCN_CTL_BLO + b], [TCN_CTL_BHI + b] level-2 row range of batch element b
+  int2* plist[7];          // map m (0..2: 3x3x3 at level 1..3, 3..5: children of level 1..3, 6: parent of level 2): kvol x
+                           // max_points (input row, partial-sum slot) pairs, grouped by kernel offset
+  int* pbase[7];           // first partial-sum slot of every output point (its pairs follow in ascending offset order)
+  float* partial;          // partial sums of the pair GEMM: one row of cout floats per pair
+  size_t partial_floats;
+  int* slot_of;            // 4 x max_points: hash slot of raw point i at level l
+  int* blk_cnt;            // 4 x ceil(max_points / 1024): first-point counts per block (ordered compaction)
+  int* kmap3[4];           // level 1..3: n x 27 rows of the 3x3x3 neighbourhood (dilation = level stride)
+  int* kmap2[4];           // level 1..3: n x 8 rows of the children at level l - 1
+  int* kmapt;              // level 2: n x 8, the parent's row at level 3 in column "position inside the parent"
+  unsigned* kmask3[4];     // bit i set: offset i present
+  unsigned* kmask2[4];
+  unsigned* kmaskt;
+  int gem_slices;
   float* pool;             // feature scratch
   double* gem_part;        // max_batch x TCN_GEM_SLICES x 256 GeM partial sums
   size_t pool_floats;
@@ -88,7 +128,7 @@ __device__ __forceinline__ int tcn_lookup(const TcnTable& t, unsigned long long 
   unsigned s = tcn_hash(key) & t.mask;
   for (;;) {
     const unsigned long long k = t.keys[s];
-    if (k == key) return t.vals[s];
+    if (k == key) return t.rows[s];
     if (k == TCN_EMPTY) return -1;
     s = (s + 1) & t.mask;
   }
@@ -103,75 +143,403 @@ __device__ __forceinline__ unsigned tcn_insert(const TcnTable& t, unsigned long 
   }
 }
 
-__global__ void k_tcn_clear(TcnTable t) {
+__global__ void k_tcn_clear_all(TcnTabs T, int* d_n) {
   const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i <= t.mask) t.keys[i] = TCN_EMPTY, t.vals[i] = INT_MAX;
-}
-
-// level 0: table[key_i] = i
-__global__ void k_tcn_index(const unsigned long long* __restrict__ keys, const int* __restrict__ d_n, TcnTable t) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= *d_n) return;
-  t.vals[tcn_insert(t, keys[i])] = i;
-}
-
-// coarser level, step 1: every child registers with its parent (floor to 2*stride); the parent
-// remembers its first child (smallest row) -- a deterministic representative
-__global__ void k_tcn_parent_first(const unsigned long long* __restrict__ keys, const int* __restrict__ d_n, int stride2, TcnTable t) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= *d_n) return;
-  int b, x, y, z;
-  tcn_unpack(keys[i], b, x, y, z);
-  const unsigned long long pk = tcn_pack(b, tcn_floor_to(x, stride2), tcn_floor_to(y, stride2), tcn_floor_to(z, stride2));
-  atomicMin(t.vals + tcn_insert(t, pk), i);
-}
-
-// step 2 (one block): parents ordered by their first child -> rows; writes the parent keys, the row
-// into the table and the level's point count
-__global__ void __launch_bounds__(1024) k_tcn_parent_rows(const unsigned long long* __restrict__ keys, const int* __restrict__ d_n,
-                                                          int stride2, TcnTable t, unsigned long long* __restrict__ pkeys,
-                                                          int* __restrict__ d_n_next) {
-  __shared__ int s_w[32];
-  __shared__ int s_base;
-  const int n = *d_n, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  if (threadIdx.x == 0) s_base = 0;
-  __syncthreads();
-  for (int i0 = 0; i0 < n; i0 += 1024) {
-    const int i = i0 + threadIdx.x;
-    unsigned long long pk = 0;
-    unsigned slot = 0;
-    int first = 0;
-    if (i < n) {
-      int b, x, y, z;
-      tcn_unpack(keys[i], b, x, y, z);
-      pk = tcn_pack(b, tcn_floor_to(x, stride2), tcn_floor_to(y, stride2), tcn_floor_to(z, stride2));
-      slot = tcn_insert(t, pk);  // exists: returns its slot
-      first = (t.vals[slot] == i);
-    }
-    int v = first;
+  if (i < TCN_CTL_BLO) d_n[i] = 0;
+  if (i < 512) d_n[TCN_CTL_BLO + i] = INT_MAX, d_n[TCN_CTL_BHI + i] = 0;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int u = __shfl_up_sync(0xffffffffu, v, o);
-      if (lane >= o) v += u;
-    }
-    if (lane == 31) s_w[w] = v;
-    __syncthreads();
-    int carry = s_base;
-    for (int k = 0; k < w; ++k) carry += s_w[k];
-    int total = 0;
-    for (int k = 0; k < 32; ++k) total += s_w[k];
-    if (first) pkeys[carry + v - 1] = pk;
-    __syncthreads();
-    // the row replaces the first-child marker only after every thread of this pass has read it
-    if (first) t.vals[slot] = -(carry + v - 1) - 2;  // tagged (negative) until the final pass below
-    if (threadIdx.x == 0) s_base += total;
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) *d_n_next = s_base;
+  for (int l = 0; l < 4; ++l)
+    if (i <= T.t[l].mask) T.t[l].keys[i] = TCN_EMPTY, T.t[l].vals[i] = INT_MAX;
 }
-__global__ void k_tcn_untag(TcnTable t) {
-  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i <= t.mask && t.keys[i] != TCN_EMPTY && t.vals[i] < 0) t.vals[i] = -(t.vals[i] + 2);
+
+// Every raw point registers with the coordinate maps of all four levels (tensor stride 1, 2, 4, 8: the key of level l
+// is the level-0 key floored to 2^l, which equals flooring level by level); a key remembers its first raw point.
+// pts != NULL: (n_raw, 3) float32 clouds of P points each, voxel = floor(x * inv_q) -- torch's `cloud / q` on CUDA is a
+// multiplication by a float32 reciprocal (tcn.py:124-130), reproduced bit for bit; keys_in otherwise (packed).
+__global__ void __launch_bounds__(256) k_tcn_insert_all(const float* __restrict__ pts, const unsigned long long* __restrict__ keys_in,
+                                                        int n_raw, int P, float inv_q, TcnTabs T, int* __restrict__ slot_of,
+                                                        int stride, int* __restrict__ d_flag) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = tid >> 2, l = tid & 3;  // four threads per raw point, one per level: four independent atomic chains
+  if (i >= n_raw) return;
+  int b, x, y, z;
+  if (keys_in) {
+    tcn_unpack(keys_in[i], b, x, y, z);
+  } else {
+    const float fx = floorf(__fmul_rn(pts[3 * (size_t)i], inv_q)), fy = floorf(__fmul_rn(pts[3 * (size_t)i + 1], inv_q)),
+                fz = floorf(__fmul_rn(pts[3 * (size_t)i + 2], inv_q));
+    const float lim = 131071.f;  // 18-bit coordinates
+    const bool ok = fabsf(fx) <= lim && fabsf(fy) <= lim && fabsf(fz) <= lim;  // (false for NaN too)
+    if (!ok) *d_flag = 1;  // the descriptors of this call are poisoned with NaN (k_tcn_gem)
+    b = i / P;
+    x = ok ? (int)fx : 0, y = ok ? (int)fy : 0, z = ok ? (int)fz : 0;
+  }
+  const int m = 1 << l;
+  const TcnTable tl = l == 0 ? T.t[0] : (l == 1 ? T.t[1] : (l == 2 ? T.t[2] : T.t[3]));
+  const unsigned s = tcn_insert(tl, tcn_pack(b, tcn_floor_to(x, m), tcn_floor_to(y, m), tcn_floor_to(z, m)));
+  atomicMin(tl.vals + s, i);
+  slot_of[(size_t)l * stride + i] = (int)s;
+}
+
+// ordered compaction, pass 1: first points (the representative of their key) per block of 1024 raw points and level
+__global__ void __launch_bounds__(1024) k_tcn_count_all(int n_raw, TcnTabs T, const int* __restrict__ slot_of, int stride,
+                                                        int* __restrict__ blk_cnt, int nblk) {
+  __shared__ int s_w[4][32];
+  const int i = blockIdx.x * 1024 + threadIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int l = 0; l < 4; ++l) {
+    const bool f = i < n_raw && T.t[l].vals[slot_of[(size_t)l * stride + i]] == i;
+    const unsigned bal = __ballot_sync(0xffffffffu, f);
+    if (lane == 0) s_w[l][w] = __popc(bal);
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    int c = 0;
+    for (int k = 0; k < 32; ++k) c += s_w[threadIdx.x][k];
+    blk_cnt[threadIdx.x * nblk + blockIdx.x] = c;
+  }
+}
+// pass 2: row = number of first points before this one; writes the level's keys, the key's row and the level counts
+__global__ void __launch_bounds__(1024) k_tcn_scatter_all(int n_raw, TcnTabs T, const int* __restrict__ slot_of, int stride,
+                                                          const int* __restrict__ blk_cnt, int nblk,
+                                                          unsigned long long* __restrict__ k0, unsigned long long* __restrict__ k1,
+                                                          unsigned long long* __restrict__ k2, unsigned long long* __restrict__ k3,
+                                                          int* __restrict__ d_n) {
+  __shared__ int s_w[4][32];
+  __shared__ int s_carry[4];
+  const int i = blockIdx.x * 1024 + threadIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (w < 4) {  // warp l: first points of level l in the blocks before this one
+    int c = 0;
+    for (int bq = lane; bq < (int)blockIdx.x; bq += 32) c += blk_cnt[w * nblk + bq];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (lane == 0) s_carry[w] = c;
+  }
+  bool f[4];
+  unsigned below[4];
+  int slot[4];
+#pragma unroll
+  for (int l = 0; l < 4; ++l) {
+    slot[l] = i < n_raw ? slot_of[(size_t)l * stride + i] : 0;
+    f[l] = i < n_raw && T.t[l].vals[slot[l]] == i;
+    const unsigned bal = __ballot_sync(0xffffffffu, f[l]);
+    below[l] = __popc(bal & ((1u << lane) - 1));
+    if (lane == 0) s_w[l][w] = __popc(bal);
+  }
+  __syncthreads();
+  unsigned long long* const kk[4] = {k0, k1, k2, k3};
+#pragma unroll
+  for (int l = 0; l < 4; ++l) {
+    int base = s_carry[l];
+    for (int k = 0; k < w; ++k) base += s_w[l][k];
+    if (f[l]) {
+      const int row = base + (int)below[l];
+      const unsigned long long key = T.t[l].keys[slot[l]];
+      T.t[l].rows[slot[l]] = row;
+      kk[l][row] = key;
+      if (l == 2) {  // rows are batch-major: the GeM pooling reads its row range from here
+        const int bq = (int)(key >> 54);
+        atomicMin(d_n + TCN_CTL_BLO + bq, row), atomicMax(d_n + TCN_CTL_BHI + bq, row + 1);
+      }
+    }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 1023) d_n[l] = base + s_w[l][31];
+  }
+}
+
+// Kernel maps, one warp per (level 1..3, point): rows of the 27 neighbours at the level's own dilation (BasicBlock
+// convolutions), of the 8 children one level below (strided 2x2x2 convolution, offset index x fastest like
+// MinkowskiEngine's kernel layout) and -- level 2 only -- of the parent at level 3 in the column of the point's
+// position inside it (transposed 2x2x2 convolution).  -1 = absent; the masks carry one bit per offset present.
+struct TcnMaps {  // index: level 1..3 (0 unused)
+  int* m3[4];
+  int* m2[4];
+  int* mt;
+  unsigned* q3[4];
+  unsigned* q2[4];
+  unsigned* qt;
+  int2* pl[7];
+  int* pb[7];
+  int ncap;
+};
+// one warp, one output point: append its (input row, partial-sum slot) pairs to the lists of their kernel offsets
+__device__ __forceinline__ void tcn_pairs(int* __restrict__ ctr, int2* __restrict__ pl, int* __restrict__ pb, int ncap, int p, int row,
+                                          int lane) {
+  const unsigned bal = __ballot_sync(0xffffffffu, row >= 0);
+  int base = 0;
+  if (lane == 0) {
+    base = atomicAdd(ctr + 31, __popc(bal));
+    pb[p] = base;
+  }
+  base = __shfl_sync(0xffffffffu, base, 0);
+  if (row >= 0) pl[(size_t)lane * ncap + atomicAdd(ctr + lane, 1)] = make_int2(row, base + __popc(bal & ((1u << lane) - 1)));
+}
+__global__ void __launch_bounds__(256) k_tcn_kmaps(TcnTabs T, const unsigned long long* __restrict__ k1, const unsigned long long* __restrict__ k2,
+                                                   const unsigned long long* __restrict__ k3, int* __restrict__ d_n, TcnMaps M) {
+  const int l = blockIdx.y + 1, lane = threadIdx.x & 31;
+  const int p = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (p >= d_n[l]) return;
+  const unsigned long long* keys = l == 1 ? k1 : (l == 2 ? k2 : k3);
+  int* m3 = l == 1 ? M.m3[1] : (l == 2 ? M.m3[2] : M.m3[3]);
+  int* m2 = l == 1 ? M.m2[1] : (l == 2 ? M.m2[2] : M.m2[3]);
+  unsigned* q3 = l == 1 ? M.q3[1] : (l == 2 ? M.q3[2] : M.q3[3]);
+  unsigned* q2 = l == 1 ? M.q2[1] : (l == 2 ? M.q2[2] : M.q2[3]);
+  int2* pl3 = l == 1 ? M.pl[0] : (l == 2 ? M.pl[1] : M.pl[2]);
+  int2* pl2 = l == 1 ? M.pl[3] : (l == 2 ? M.pl[4] : M.pl[5]);
+  int* pb3 = l == 1 ? M.pb[0] : (l == 2 ? M.pb[1] : M.pb[2]);
+  int* pb2 = l == 1 ? M.pb[3] : (l == 2 ? M.pb[4] : M.pb[5]);
+  const TcnTable tl = l == 1 ? T.t[1] : (l == 2 ? T.t[2] : T.t[3]), tc = l == 1 ? T.t[0] : (l == 2 ? T.t[1] : T.t[2]);
+  int b, x, y, z;
+  tcn_unpack(keys[p], b, x, y, z);
+  const int s = 1 << l, h = s >> 1;
+  int row = -1;
+  if (lane < 27) {
+    row = tcn_lookup(tl, tcn_pack(b, x + (lane % 3 - 1) * s, y + ((lane / 3) % 3 - 1) * s, z + (lane / 9 - 1) * s));
+    m3[(size_t)p * 27 + lane] = row;
+  }
+  unsigned bal = __ballot_sync(0xffffffffu, row >= 0);
+  if (lane == 0) q3[p] = bal;
+  tcn_pairs(d_n + TCN_CTL_PAIRS + 32 * (l - 1), pl3, pb3, M.ncap, p, row, lane);
+  row = -1;
+  if (lane < 8) {
+    row = tcn_lookup(tc, tcn_pack(b, x + (lane & 1) * h, y + ((lane >> 1) & 1) * h, z + (lane >> 2) * h));
+    m2[(size_t)p * 8 + lane] = row;
+  }
+  bal = __ballot_sync(0xffffffffu, row >= 0);
+  if (lane == 0) q2[p] = bal;
+  tcn_pairs(d_n + TCN_CTL_PAIRS + 32 * (l + 2), pl2, pb2, M.ncap, p, row, lane);
+  if (l == 2) {
+    const int px = tcn_floor_to(x, 8), py = tcn_floor_to(y, 8), pz = tcn_floor_to(z, 8);
+    const int wi = ((z - pz) / 4 * 2 + (y - py) / 4) * 2 + (x - px) / 4;
+    int prow = -1;
+    if (lane == 0) prow = tcn_lookup(T.t[3], tcn_pack(b, px, py, pz));
+    prow = __shfl_sync(0xffffffffu, prow, 0);
+    row = (lane == wi) ? prow : -1;
+    if (lane < 8) M.mt[(size_t)p * 8 + lane] = row;
+    if (lane == 0) M.qt[p] = prow >= 0 ? (1u << wi) : 0u;
+    tcn_pairs(d_n + TCN_CTL_PAIRS + 32 * 6, M.pl[6], M.pb[6], M.ncap, p, row, lane);
+  }
+}
+
+// Gather-GEMM convolution on the tensor cores (see the head of this file).  map: (n_out, kvol) input rows or NULL (1x1: the
+// point itself); hitmask: (n_out) offsets present or NULL.  One warp: output points [16 mt, 16 mt + 16) x channels
+// [8 NT slab, 8 NT (slab + 1)); fragments of mma.sync.m16n8k8 (row.col, TF32 in, float32 accumulate):
+//   A (16 x 8)  a0 (g, t)  a1 (g + 8, t)  a2 (g, t + 4)  a3 (g + 8, t + 4)       g = lane / 4, t = lane % 4
+//   B (8 x 8)   b0 (t, g)  b1 (t + 4, g)
+//   C (16 x 8)  c0 (g, 2t) c1 (g, 2t + 1) c2 (g + 8, 2t) c3 (g + 8, 2t + 1)
+__device__ __forceinline__ void tcn_split_tf32(float x, unsigned& big, unsigned& small) {
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(big) : "f"(x));
+  const float r = x - __uint_as_float(big);  // exact
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(small) : "f"(r));
+}
+__device__ __forceinline__ void tcn_mma_tf32(float c[4], const unsigned a[4], unsigned b0, unsigned b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+template <int NT>
+__global__ void __launch_bounds__(128) k_tcn_conv_mma(const int* __restrict__ map, const unsigned* __restrict__ hitmask, int kvol,
+                                                      const int* __restrict__ d_nout, const float* __restrict__ in_feat, int cin,
+                                                      const float* __restrict__ W, int cout, const float* __restrict__ scale,
+                                                      const float* __restrict__ shift, const float* __restrict__ residual, int relu,
+                                                      int accumulate, float* __restrict__ out_feat) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int nslab = cout / (8 * NT);
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int p0 = (wid / nslab) * 16, n0 = (wid % nslab) * 8 * NT;
+  const int n = *d_nout;
+  if (p0 >= n) return;
+  const int plo = p0 + g, phi = p0 + g + 8;
+  const bool vlo = plo < n, vhi = phi < n;
+  unsigned m = 1u;
+  if (hitmask) m = __reduce_or_sync(0xffffffffu, (lane < 16 && p0 + lane < n) ? hitmask[p0 + lane] : 0u);
+  float acc[NT][4];
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+  while (m) {  // ascending offsets: the summation order of every output is fixed
+    const int i = __ffs(m) - 1;
+    m &= m - 1;
+    const int rlo = vlo ? (map ? map[(size_t)plo * kvol + i] : plo) : -1;
+    const int rhi = vhi ? (map ? map[(size_t)phi * kvol + i] : phi) : -1;
+    const float* __restrict__ xlo = in_feat + (size_t)(rlo < 0 ? 0 : rlo) * cin + t;
+    const float* __restrict__ xhi = in_feat + (size_t)(rhi < 0 ? 0 : rhi) * cin + t;
+    const float* __restrict__ Wi = W + ((size_t)i * cin + t) * cout + n0 + g;
+#pragma unroll 2
+    for (int k0 = 0; k0 < cin; k0 += 8) {
+      float af[4];
+      af[0] = rlo >= 0 ? __ldg(xlo + k0) : 0.f;
+      af[1] = rhi >= 0 ? __ldg(xhi + k0) : 0.f;
+      af[2] = rlo >= 0 ? __ldg(xlo + k0 + 4) : 0.f;
+      af[3] = rhi >= 0 ? __ldg(xhi + k0 + 4) : 0.f;
+      float bf[NT][2];
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        bf[nt][0] = __ldg(Wi + (size_t)k0 * cout + 8 * nt);
+        bf[nt][1] = __ldg(Wi + (size_t)(k0 + 4) * cout + 8 * nt);
+      }
+      unsigned ab[4], as[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) tcn_split_tf32(af[q], ab[q], as[q]);
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        unsigned bb0, bs0, bb1, bs1;
+        tcn_split_tf32(bf[nt][0], bb0, bs0);
+        tcn_split_tf32(bf[nt][1], bb1, bs1);
+        tcn_mma_tf32(acc[nt], as, bb0, bb1);  // small terms first
+        tcn_mma_tf32(acc[nt], ab, bs0, bs1);
+        tcn_mma_tf32(acc[nt], ab, bb0, bb1);
+      }
+    }
+  }
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+    const int c = n0 + 8 * nt + 2 * t;
+    float sc0 = 1.f, sc1 = 1.f, sh0 = 0.f, sh1 = 0.f;
+    if (scale) sc0 = scale[c], sc1 = scale[c + 1], sh0 = shift[c], sh1 = shift[c + 1];
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      const int p = hh ? phi : plo;
+      if (!(hh ? vhi : vlo)) continue;
+      float v0 = acc[nt][2 * hh], v1 = acc[nt][2 * hh + 1];
+      if (scale) v0 = v0 * sc0 + sh0, v1 = v1 * sc1 + sh1;
+      float2* o = (float2*)(out_feat + (size_t)p * cout + c);
+      if (residual) {
+        const float2 r = *(const float2*)(residual + (size_t)p * cout + c);
+        v0 += r.x, v1 += r.y;
+      }
+      if (accumulate) {
+        const float2 r = *o;
+        v0 += r.x, v1 += r.y;
+      }
+      if (relu) v0 = fmaxf(v0, 0.f), v1 = fmaxf(v1, 0.f);
+      *o = make_float2(v0, v1);
+    }
+  }
+}
+
+// Pair form of the gather-GEMM: work proportional to the (output point, kernel offset) pairs that exist.  k_tcn_kmaps
+// grouped the pairs by kernel offset; a work item is up to 32 pairs of ONE offset (two m16 tiles sharing their B
+// fragments) x 8 NT output channels, so no MMA row is spent on an absent neighbour and the weights of an offset are
+// read once per 32 pairs.  The product rows go to `partial` (one row per pair; a point's rows are consecutive, in
+// ascending offset order) and k_tcn_pair_reduce adds them up per point in that order -- the result does not depend
+// on how the atomics of k_tcn_kmaps ordered the lists -- and applies BatchNorm / residual / accumulate / ReLU.
+// Persistent grid: every warp derives the tile table from the kvol pair counters and strides over the items.
+template <int NT>
+__global__ void __launch_bounds__(128) k_tcn_pair_mma(const int2* __restrict__ pl, const int* __restrict__ ctr, int kvol, int ncap,
+                                                      const float* __restrict__ in_feat, int cin, const float* __restrict__ W, int cout,
+                                                      float* __restrict__ partial) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int nslab = cout / (8 * NT);
+  const int cnt_i = lane < kvol ? ctr[lane] : 0;
+  const int tiles_i = (cnt_i + 31) >> 5;
+  int incl = tiles_i;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int u = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += u;
+  }
+  const int total = __shfl_sync(0xffffffffu, incl, 31) * nslab;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; item < total; item += nwarps) {
+    const int tile = item / nslab, n0 = (item % nslab) * 8 * NT;
+    const int i = __ffs(__ballot_sync(0xffffffffu, incl > tile)) - 1;  // the offset this tile belongs to
+    const int first = __shfl_sync(0xffffffffu, incl - tiles_i, i), c_i = __shfl_sync(0xffffffffu, cnt_i, i);
+    const int pair0 = (tile - first) * 32;
+    const bool two = c_i - pair0 > 16;  // second m16 tile in use
+    int2 e[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int idx = pair0 + g + 8 * q;
+      e[q] = idx < c_i ? pl[(size_t)i * ncap + idx] : make_int2(-1, -1);
+    }
+    const float* __restrict__ xr[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) xr[q] = in_feat + (size_t)(e[q].x < 0 ? 0 : e[q].x) * cin + t;
+    const float* __restrict__ Wi = W + ((size_t)i * cin + t) * cout + n0 + g;
+    float acc[2][NT][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = acc[mt][nt][2] = acc[mt][nt][3] = 0.f;
+#pragma unroll 2
+    for (int k0 = 0; k0 < cin; k0 += 8) {
+      float af[2][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const bool on = mt == 0 || two;
+        af[mt][0] = (on && e[2 * mt].x >= 0) ? __ldg(xr[2 * mt] + k0) : 0.f;
+        af[mt][1] = (on && e[2 * mt + 1].x >= 0) ? __ldg(xr[2 * mt + 1] + k0) : 0.f;
+        af[mt][2] = (on && e[2 * mt].x >= 0) ? __ldg(xr[2 * mt] + k0 + 4) : 0.f;
+        af[mt][3] = (on && e[2 * mt + 1].x >= 0) ? __ldg(xr[2 * mt + 1] + k0 + 4) : 0.f;
+      }
+      float bf[NT][2];
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        bf[nt][0] = __ldg(Wi + (size_t)k0 * cout + 8 * nt);
+        bf[nt][1] = __ldg(Wi + (size_t)(k0 + 4) * cout + 8 * nt);
+      }
+      unsigned ab[2][4], as[2][4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) tcn_split_tf32(af[0][q], ab[0][q], as[0][q]);
+      if (two) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) tcn_split_tf32(af[1][q], ab[1][q], as[1][q]);
+      }
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        unsigned bb0, bs0, bb1, bs1;
+        tcn_split_tf32(bf[nt][0], bb0, bs0);
+        tcn_split_tf32(bf[nt][1], bb1, bs1);
+        tcn_mma_tf32(acc[0][nt], as[0], bb0, bb1);  // small terms first
+        tcn_mma_tf32(acc[0][nt], ab[0], bs0, bs1);
+        tcn_mma_tf32(acc[0][nt], ab[0], bb0, bb1);
+        if (two) {
+          tcn_mma_tf32(acc[1][nt], as[1], bb0, bb1);
+          tcn_mma_tf32(acc[1][nt], ab[1], bs0, bs1);
+          tcn_mma_tf32(acc[1][nt], ab[1], bb0, bb1);
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {  // q = 2 mt + half: rows g (+8) of m16 tile mt
+      if (e[q].y < 0) continue;
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+        *(float2*)(partial + (size_t)e[q].y * cout + n0 + 8 * nt + 2 * t) =
+            make_float2(acc[q >> 1][nt][2 * (q & 1)], acc[q >> 1][nt][2 * (q & 1) + 1]);
+    }
+  }
+}
+// out[p] = epilogue(sum of the point's partial rows, ascending kernel offset); one thread = four channels
+__global__ void __launch_bounds__(256) k_tcn_pair_reduce(const int* __restrict__ pbase, const unsigned* __restrict__ hitmask,
+                                                         const int* __restrict__ d_nout, const float* __restrict__ partial, int cout,
+                                                         const float* __restrict__ scale, const float* __restrict__ shift,
+                                                         const float* __restrict__ residual, int relu, int accumulate,
+                                                         float* __restrict__ out_feat) {
+  const int q4 = cout >> 2;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int p = (int)(idx / q4), c = (int)(idx % q4) * 4;
+  if (p >= *d_nout) return;
+  const int base = pbase[p], cnt = __popc(hitmask[p]);
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int j = 0; j < cnt; ++j) {
+    const float4 a = *(const float4*)(partial + (size_t)(base + j) * cout + c);
+    v.x += a.x, v.y += a.y, v.z += a.z, v.w += a.w;
+  }
+  if (scale) {
+    const float4 sc = *(const float4*)(scale + c), sh = *(const float4*)(shift + c);
+    v.x = v.x * sc.x + sh.x, v.y = v.y * sc.y + sh.y, v.z = v.z * sc.z + sh.z, v.w = v.w * sc.w + sh.w;
+  }
+  float4* o = (float4*)(out_feat + (size_t)p * cout + c);
+  if (residual) {
+    const float4 r = *(const float4*)(residual + (size_t)p * cout + c);
+    v.x += r.x, v.y += r.y, v.z += r.z, v.w += r.w;
+  }
+  if (accumulate) {
+    const float4 r = *o;
+    v.x += r.x, v.y += r.y, v.z += r.z, v.w += r.w;
+  }
+  if (relu) v.x = fmaxf(v.x, 0.f), v.y = fmaxf(v.y, 0.f), v.z = fmaxf(v.z, 0.f), v.w = fmaxf(v.w, 0.f);
+  *o = v;
 }
 
 // Generic sparse convolution, one warp per output point.
@@ -286,48 +654,39 @@ __global__ void __launch_bounds__(256) k_tcn_conv(const unsigned long long* __re
 
 // GeM pooling (minkloc.py:84-95) over the points of every batch element + optional L2
 // normalisation (tcn.py:140-143) -> float64 (tcn.py:148).  Points of a batch element are contiguous
-// (keys are batch-major).  Pass 1: grid (batch, TCN_GEM_SLICES), thread = channel, every block sums
+// (rows are batch-major).  Pass 1: grid (batch, slices), thread = channel, every block sums
 // clamp(x)^p over its slice of the points; pass 2: one block per batch element combines the slices in
-// a fixed order.
+// a fixed order.  slices = 256 for small batches (16 points per thread at 4096 points), 64 otherwise.
 #define TCN_GEM_SLICES 64
-__device__ __forceinline__ void tcn_batch_range(const unsigned long long* __restrict__ keys, int n, int b, int& lo_out, int& hi_out) {
-  int r[2];
-  for (int s = 0; s < 2; ++s) {  // first row with batch >= b + s
-    const unsigned long long target = (unsigned long long)(b + s);
-    int lo = 0, hi = n;
-    while (lo < hi) {
-      const int mid = (lo + hi) >> 1;
-      if ((keys[mid] >> 54) < target) lo = mid + 1; else hi = mid;
-    }
-    r[s] = lo;
-  }
-  lo_out = r[0], hi_out = r[1];
-}
-__global__ void __launch_bounds__(256) k_tcn_gem_partial(const unsigned long long* __restrict__ keys, const int* __restrict__ d_n,
-                                                         const float* __restrict__ feat, int c, float p, float eps,
-                                                         double* __restrict__ part /* batch x slices x c */) {
-  int lo, hi;
-  tcn_batch_range(keys, *d_n, blockIdx.x, lo, hi);
-  const int per = (hi - lo + TCN_GEM_SLICES - 1) / TCN_GEM_SLICES;
+__global__ void __launch_bounds__(256) k_tcn_gem_partial(const int* __restrict__ ctl, const float* __restrict__ feat, int c, float p,
+                                                         float eps, double* __restrict__ part /* batch x slices x c */) {
+  int lo = ctl[TCN_CTL_BLO + blockIdx.x];
+  const int hi = ctl[TCN_CTL_BHI + blockIdx.x];
+  if (hi == 0) lo = 0;  // no point in this batch element
+  const int slices = gridDim.y;
+  const int per = (hi - lo + slices - 1) / slices;
   const int s0 = lo + blockIdx.y * per, s1 = min(s0 + per, hi);
   for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
     double acc = 0.0;
-    for (int r = s0; r < s1; ++r) acc += (double)powf(fmaxf(feat[(size_t)r * c + ch], eps), p);
-    part[((size_t)blockIdx.x * TCN_GEM_SLICES + blockIdx.y) * c + ch] = acc;
+#pragma unroll 4
+    for (int r = s0; r < s1; ++r) acc += (double)powf(fmaxf(__ldg(feat + (size_t)r * c + ch), eps), p);
+    part[((size_t)blockIdx.x * slices + blockIdx.y) * c + ch] = acc;
   }
 }
-__global__ void __launch_bounds__(256) k_tcn_gem(const unsigned long long* __restrict__ keys, const int* __restrict__ d_n,
-                                                 const double* __restrict__ part, int c, float p, int normalize,
-                                                 double* __restrict__ out) {
+__global__ void __launch_bounds__(256) k_tcn_gem(const int* __restrict__ ctl, const double* __restrict__ part, int slices, int c, float p,
+                                                 int normalize, double* __restrict__ out) {
   __shared__ double s_sq[8];
-  int lo, hi;
-  tcn_batch_range(keys, *d_n, blockIdx.x, lo, hi);
+  int lo = ctl[TCN_CTL_BLO + blockIdx.x];
+  const int hi = ctl[TCN_CTL_BHI + blockIdx.x];
+  if (hi == 0) lo = 0;
   const int b = blockIdx.x;
+  const bool poisoned = ctl[4] != 0;  // a voxel coordinate did not fit the 18-bit key fields (or was NaN)
   double acc_total = 0.0;
   for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
     double acc = 0.0;
-    for (int sl = 0; sl < TCN_GEM_SLICES; ++sl) acc += part[((size_t)b * TCN_GEM_SLICES + sl) * c + ch];
-    const double g = (hi > lo) ? pow(acc / (double)(hi - lo), 1.0 / (double)p) : 0.0;
+    for (int sl = 0; sl < slices; ++sl) acc += part[((size_t)b * slices + sl) * c + ch];
+    double g = (hi > lo) ? pow(acc / (double)(hi - lo), 1.0 / (double)p) : 0.0;
+    if (poisoned) g = __longlong_as_double(0x7ff8000000000000ll);
     out[(size_t)b * c + ch] = g;
     acc_total += g * g;
   }
@@ -355,13 +714,31 @@ extern "C" int mt_tcn_create(int device, int max_points, int max_batch, mt_tcn**
   for (int l = 0; l < 4; ++l) {
     CK(cudaMalloc(&t->tab[l].keys, sizeof(unsigned long long) * cap));
     CK(cudaMalloc(&t->tab[l].vals, sizeof(int) * cap));
+    CK(cudaMalloc(&t->tab[l].rows, sizeof(int) * cap));
     t->tab[l].mask = cap - 1;
     CK(cudaMalloc(&t->keys[l], sizeof(unsigned long long) * max_points));
+    if (l >= 1) {
+      CK(cudaMalloc(&t->kmap3[l], sizeof(int) * 27 * (size_t)max_points));
+      CK(cudaMalloc(&t->kmap2[l], sizeof(int) * 8 * (size_t)max_points));
+      CK(cudaMalloc(&t->kmask3[l], sizeof(unsigned) * (size_t)max_points));
+      CK(cudaMalloc(&t->kmask2[l], sizeof(unsigned) * (size_t)max_points));
+    }
   }
-  CK(cudaMalloc(&t->d_n, sizeof(int) * 4));
+  CK(cudaMalloc(&t->kmapt, sizeof(int) * 8 * (size_t)max_points));
+  CK(cudaMalloc(&t->kmaskt, sizeof(unsigned) * (size_t)max_points));
+  CK(cudaMalloc(&t->d_n, sizeof(int) * TCN_CTL_INTS));
+  for (int m = 0; m < 7; ++m) {
+    CK(cudaMalloc(&t->plist[m], sizeof(int2) * (m < 3 ? 27 : 8) * (size_t)max_points));
+    CK(cudaMalloc(&t->pbase[m], sizeof(int) * (size_t)max_points));
+  }
+  t->partial_floats = (size_t)max_points * 2048;  // 27 offsets x 64 channels / 8 offsets x 256 channels per point
+  CK(cudaMalloc(&t->partial, sizeof(float) * t->partial_floats));
+  CK(cudaMalloc(&t->slot_of, sizeof(int) * 4 * (size_t)max_points));
+  CK(cudaMalloc(&t->blk_cnt, sizeof(int) * 4 * (size_t)((max_points + 1023) / 1024)));
   t->pool_floats = (size_t)max_points * 1184;
   CK(cudaMalloc(&t->pool, sizeof(float) * t->pool_floats));
-  CK(cudaMalloc(&t->gem_part, sizeof(double) * (size_t)max_batch * 64 * 256));
+  t->gem_slices = max_batch * TCN_GEM_SLICES > 256 ? max_batch * TCN_GEM_SLICES : 256;  // rows of the partial-sum buffer
+  CK(cudaMalloc(&t->gem_part, sizeof(double) * (size_t)t->gem_slices * 256));
   *out = t;
   return MT_OK;
 }
@@ -369,7 +746,12 @@ extern "C" int mt_tcn_create(int device, int max_points, int max_batch, mt_tcn**
 extern "C" int mt_tcn_destroy(mt_tcn* t) {
   if (!t) return MT_OK;
   cudaSetDevice(t->device);
-  for (int l = 0; l < 4; ++l) cudaFree(t->tab[l].keys), cudaFree(t->tab[l].vals), cudaFree(t->keys[l]);
+  for (int l = 0; l < 4; ++l) {
+    cudaFree(t->tab[l].keys), cudaFree(t->tab[l].vals), cudaFree(t->tab[l].rows), cudaFree(t->keys[l]);
+    cudaFree(t->kmap3[l]), cudaFree(t->kmap2[l]), cudaFree(t->kmask3[l]), cudaFree(t->kmask2[l]);
+  }
+  cudaFree(t->kmapt), cudaFree(t->kmaskt), cudaFree(t->slot_of), cudaFree(t->blk_cnt), cudaFree(t->partial);
+  for (int m = 0; m < 7; ++m) cudaFree(t->plist[m]), cudaFree(t->pbase[m]);
   for (int i = 0; i < TCN_NCONV; ++i) cudaFree(t->conv[i].w);
   for (int i = 0; i < TCN_NBN; ++i) cudaFree(t->bn[i].scale), cudaFree(t->bn[i].shift);
   cudaFree(t->d_n), cudaFree(t->pool), cudaFree(t->gem_part);
@@ -416,17 +798,54 @@ extern "C" int mt_tcn_set_gem(mt_tcn* t, float p, float eps) {
   return MT_OK;
 }
 
+// One convolution.  map / hitmask / kvol describe the gather (NULL: 1x1, the point itself); layers whose widths the MMA
+// tiling divides (cin % 8 == 0, cout % 16 == 0: every layer of the shipped network but conv0) run on the tensor cores,
+// the others through the hash-probing CUDA-core kernel (mode / k / dil / in_tab as before).
 static int tcn_conv_launch(mt_tcn* t, int mode, int conv_id, int bn_id, const unsigned long long* out_keys, const int* d_nout,
-                           int nmax, const TcnTable& in_tab, const float* in_feat, int k, int dil, const float* residual, int relu,
-                           int accumulate, float* out_feat, cudaStream_t st) {
+                           int nmax, const TcnTable& in_tab, const float* in_feat, int k, int dil, const int* map,
+                           const unsigned* hitmask, int map_id, const float* residual, int relu, int accumulate, float* out_feat,
+                           cudaStream_t st) {
   const TcnConv& c = t->conv[conv_id];
   if (!c.w) return set_err(MT_ERR_STATE, "mt_tcn_forward: a convolution has no weights (mt_tcn_set_conv)");
   if (mode == 0 && c.kvol != k * k * k) return set_err(MT_ERR_STATE, "mt_tcn_forward: kernel volume does not match the layer");
+  if (mode == 1 && c.kvol != 8) return set_err(MT_ERR_STATE, "mt_tcn_forward: the transposed convolution has 8 kernel offsets");
   const float* sc = nullptr;
   const float* sh = nullptr;
   if (bn_id >= 0) {
     if (!t->bn[bn_id].scale || t->bn[bn_id].c != c.cout) return set_err(MT_ERR_STATE, "mt_tcn_forward: BatchNorm missing / wrong width");
     sc = t->bn[bn_id].scale, sh = t->bn[bn_id].shift;
+  }
+  const bool have_map = map != nullptr || k == 1;
+  static const bool no_mma = getenv("MIDAS_B200_TCN_NO_MMA") != nullptr;  // diagnostics: every layer through the CUDA-core kernel
+  static const bool no_pairs = getenv("MIDAS_B200_TCN_NO_PAIRS") != nullptr;  // diagnostics: dense tiles instead of pair lists
+  if (!no_mma && !no_pairs && in_feat && map && map_id >= 0 && c.cin % 8 == 0 && c.cout % 16 == 0 &&
+      (size_t)c.kvol * c.cout * t->max_points <= t->partial_floats) {
+    // work proportional to the pairs present: pair GEMM into `partial`, then the per-point sum + epilogue
+    const int* ctr = t->d_n + TCN_CTL_PAIRS + 32 * map_id;
+    const long long items = ((long long)(nmax + 31) / 32 + c.kvol) * (c.cout / 16);  // at least the centre offset's tiles
+    const unsigned grid = (unsigned)std::min<long long>((items + 3) / 4, 148 * 12);
+    k_tcn_pair_mma<2><<<grid, 128, 0, st>>>(t->plist[map_id], ctr, c.kvol, t->max_points, in_feat, c.cin, c.w, c.cout, t->partial);
+    CK_LAUNCH();
+    const long long thr = (long long)nmax * (c.cout / 4);
+    k_tcn_pair_reduce<<<(unsigned)((thr + 255) / 256), 256, 0, st>>>(t->pbase[map_id], hitmask, d_nout, t->partial, c.cout, sc, sh, residual, relu,
+                                                                   accumulate, out_feat);
+    CK_LAUNCH();
+    return MT_OK;
+  }
+  if (!no_mma && in_feat && have_map && c.cin % 8 == 0 && c.cout % 16 == 0) {
+    const int mtiles = (nmax + 15) / 16;
+    const int kvol = map ? c.kvol : 1;
+    if (c.cout % 32 == 0 && (long long)mtiles * (c.cout / 16) > 4096) {  // many tiles: wider slabs, fewer re-reads of the gathered rows
+      const long long warps = (long long)mtiles * (c.cout / 32);
+      k_tcn_conv_mma<4><<<(unsigned)((warps + 3) / 4), 128, 0, st>>>(map, hitmask, kvol, d_nout, in_feat, c.cin, c.w, c.cout, sc, sh, residual,
+                                                                   relu, accumulate, out_feat);
+    } else {
+      const long long warps = (long long)mtiles * (c.cout / 16);
+      k_tcn_conv_mma<2><<<(unsigned)((warps + 3) / 4), 128, 0, st>>>(map, hitmask, kvol, d_nout, in_feat, c.cin, c.w, c.cout, sc, sh, residual,
+                                                                   relu, accumulate, out_feat);
+    }
+    CK_LAUNCH();
+    return MT_OK;
   }
   // few points and many channels: four warps per point split the input channels (shorter FMA chains);
   // conv0 (one input feature) keeps a warp per point
@@ -444,78 +863,105 @@ static int tcn_conv_launch(mt_tcn* t, int mode, int conv_id, int bn_id, const un
   return MT_OK;
 }
 
-// d_keys: n sorted unique packed coordinates (tcn_pack: batch | x | y | z) of the quantised clouds
-// d_out: (batch, feature) float64.  d_counts (nullable): active points per level (4 ints, device).
-extern "C" int mt_tcn_forward(mt_tcn* t, const unsigned long long* d_keys, int n, int batch, int normalize, double* d_out,
-                              int* d_counts, void* stream) {
-  if (!t || !d_keys || !d_out || n <= 0 || batch <= 0) return set_err(MT_ERR_ARG, "mt_tcn_forward: bad argument");
-  if (n > t->max_points || batch > t->max_batch) return set_err(MT_ERR_CAPACITY, "mt_tcn_forward: n / batch exceed the context capacity");
-  cudaStream_t st = (cudaStream_t)stream;
-  const unsigned tg = (t->cap + 255) / 256, ng = (unsigned)((n + 255) / 256);
-  for (int l = 0; l < 4; ++l) {
-    k_tcn_clear<<<tg, 256, 0, st>>>(t->tab[l]);
-    CK_LAUNCH();
-  }
-  CK(cudaMemcpyAsync(t->keys[0], d_keys, sizeof(unsigned long long) * n, cudaMemcpyDeviceToDevice, st));
-  CK(cudaMemcpyAsync(t->d_n, &n, sizeof(int), cudaMemcpyHostToDevice, st));  // n is copied at enqueue time (pageable source)
-  k_tcn_index<<<ng, 256, 0, st>>>(t->keys[0], t->d_n, t->tab[0]);
-  CK_LAUNCH();
-  for (int l = 1; l < 4; ++l) {  // coordinate maps at tensor stride 2, 4, 8
-    const int stride2 = 1 << l;
-    k_tcn_parent_first<<<ng, 256, 0, st>>>(t->keys[l - 1], t->d_n + l - 1, stride2, t->tab[l]);
-    CK_LAUNCH();
-    k_tcn_parent_rows<<<1, 1024, 0, st>>>(t->keys[l - 1], t->d_n + l - 1, stride2, t->tab[l], t->keys[l], t->d_n + l);
-    CK_LAUNCH();
-    k_tcn_untag<<<tg, 256, 0, st>>>(t->tab[l]);
-    CK_LAUNCH();
-  }
-  // feature buffers carved from the pool (upper bound n rows each)
+// the whole forward pass from n raw points (float clouds or packed keys)
+static int tcn_run(mt_tcn* t, const float* d_pts, const unsigned long long* d_keys, int n, int P, float inv_q, int batch,
+                   int normalize, double* d_out, int* d_counts, cudaStream_t st) {
   const int c0 = t->conv[TCN_CONV0].cout, p0 = t->conv[TCN_BLK_C2(0)].cout, p1 = t->conv[TCN_BLK_C2(1)].cout,
             p2 = t->conv[TCN_BLK_C2(2)].cout, f = t->conv[TCN_LAT0].cout;
   if (!c0 || !p0 || !p1 || !p2 || !f) return set_err(MT_ERR_STATE, "mt_tcn_forward: weights not loaded");
+  if (f > 256) return set_err(MT_ERR_STATE, "mt_tcn_forward: feature size above 256");
   const int widths[] = {c0, c0, p0, p0, p0, p0, p1, p1, p1, p1, p2, p2, p2, f, f};
   size_t need = 0;
   for (int w : widths) need += (size_t)n * w;
   if (need > t->pool_floats) return set_err(MT_ERR_CAPACITY, "mt_tcn_forward: feature pool too small for these channel widths");
+  TcnTabs T;
+  for (int l = 0; l < 4; ++l) T.t[l] = t->tab[l];
+  int* d_flag = t->d_n + 4;
+  const int nblk = (n + 1023) / 1024, stride = t->max_points;
+  k_tcn_clear_all<<<(t->cap + 255) / 256, 256, 0, st>>>(T, t->d_n);
+  CK_LAUNCH();
+  k_tcn_insert_all<<<(4 * n + 255) / 256, 256, 0, st>>>(d_pts, d_keys, n, P, inv_q, T, t->slot_of, stride, d_flag);
+  CK_LAUNCH();
+  k_tcn_count_all<<<nblk, 1024, 0, st>>>(n, T, t->slot_of, stride, t->blk_cnt, nblk);
+  CK_LAUNCH();
+  k_tcn_scatter_all<<<nblk, 1024, 0, st>>>(n, T, t->slot_of, stride, t->blk_cnt, nblk, t->keys[0], t->keys[1], t->keys[2], t->keys[3], t->d_n);
+  CK_LAUNCH();
+  TcnMaps M;
+  memset(&M, 0, sizeof(M));
+  for (int l = 1; l < 4; ++l) M.m3[l] = t->kmap3[l], M.m2[l] = t->kmap2[l], M.q3[l] = t->kmask3[l], M.q2[l] = t->kmask2[l];
+  M.mt = t->kmapt, M.qt = t->kmaskt, M.ncap = t->max_points;
+  for (int m = 0; m < 7; ++m) M.pl[m] = t->plist[m], M.pb[m] = t->pbase[m];
+  k_tcn_kmaps<<<dim3((n + 7) / 8, 3), 256, 0, st>>>(T, t->keys[1], t->keys[2], t->keys[3], t->d_n, M);
+  CK_LAUNCH();
+  // feature buffers carved from the pool (upper bound n rows each)
   float* ptr = t->pool;
   auto take = [&](int w) { float* r = ptr; ptr += (size_t)n * w; return r; };
   float* x0 = take(c0);
   int r;
 #define TCN_RUN(call) if ((r = (call)) != MT_OK) return r
   // conv0 + bn0 + relu (minkfpn.py:113-115)
-  TCN_RUN(tcn_conv_launch(t, 0, TCN_CONV0, TCN_BN0, t->keys[0], t->d_n, n, t->tab[0], nullptr, 5, 1, nullptr, 1, 0, x0, st));
+  TCN_RUN(tcn_conv_launch(t, 0, TCN_CONV0, TCN_BN0, t->keys[0], t->d_n, n, t->tab[0], nullptr, 5, 1, nullptr, nullptr, -1, nullptr, 1, 0, x0, st));
   float* x = x0;
   float* fmap = nullptr;
   for (int s = 0; s < 3; ++s) {  // bottom-up: strided conv + bn + relu + BasicBlock (minkfpn.py:120-126)
-    const int stride = 1 << s, l = s + 1, pl = t->conv[TCN_BLK_C2(s)].cout;
+    const int stride_in = 1 << s, l = s + 1, pl = t->conv[TCN_BLK_C2(s)].cout;
     float* xa = take(t->conv[TCN_DOWN(s)].cout);
-    TCN_RUN(tcn_conv_launch(t, 0, TCN_DOWN(s), TCN_BN_DOWN(s), t->keys[l], t->d_n + l, n, t->tab[l - 1], x, 2, stride, nullptr, 1, 0, xa, st));
+    TCN_RUN(tcn_conv_launch(t, 0, TCN_DOWN(s), TCN_BN_DOWN(s), t->keys[l], t->d_n + l, n, t->tab[l - 1], x, 2, stride_in, t->kmap2[l],
+                            t->kmask2[l], 3 + s, nullptr, 1, 0, xa, st));
     float* y = take(pl);
-    TCN_RUN(tcn_conv_launch(t, 0, TCN_BLK_C1(s), TCN_BN_N1(s), t->keys[l], t->d_n + l, n, t->tab[l], xa, 3, 2 * stride, nullptr, 1, 0, y, st));
+    TCN_RUN(tcn_conv_launch(t, 0, TCN_BLK_C1(s), TCN_BN_N1(s), t->keys[l], t->d_n + l, n, t->tab[l], xa, 3, 2 * stride_in, t->kmap3[l],
+                            t->kmask3[l], s, nullptr, 1, 0, y, st));
     const float* res = xa;
     if (t->conv[TCN_BLK_DS(s)].w) {  // channel change: residual = bn(conv1x1(x)) (resnet.py:89-101)
       float* rs = take(pl);
-      TCN_RUN(tcn_conv_launch(t, 0, TCN_BLK_DS(s), TCN_BN_DS(s), t->keys[l], t->d_n + l, n, t->tab[l], xa, 1, 2 * stride, nullptr, 0, 0, rs, st));
+      TCN_RUN(tcn_conv_launch(t, 0, TCN_BLK_DS(s), TCN_BN_DS(s), t->keys[l], t->d_n + l, n, t->tab[l], xa, 1, 2 * stride_in, nullptr, nullptr,
+                              -1, nullptr, 0, 0, rs, st));
       res = rs;
     } else if (t->conv[TCN_DOWN(s)].cout != pl) {
       return set_err(MT_ERR_STATE, "mt_tcn_forward: block changes width but has no downsample branch");
     }
     float* xo = take(pl);
-    TCN_RUN(tcn_conv_launch(t, 0, TCN_BLK_C2(s), TCN_BN_N2(s), t->keys[l], t->d_n + l, n, t->tab[l], y, 3, 2 * stride, res, 1, 0, xo, st));
+    TCN_RUN(tcn_conv_launch(t, 0, TCN_BLK_C2(s), TCN_BN_N2(s), t->keys[l], t->d_n + l, n, t->tab[l], y, 3, 2 * stride_in, t->kmap3[l],
+                            t->kmask3[l], s, res, 1, 0, xo, st));
     x = xo;
     if (s == 1) fmap = xo;
   }
   // lateral 1x1 at the top, transposed conv down to stride 4, + lateral 1x1 of the stage-1 map (minkfpn.py:130-136)
   float* z = take(f);
-  TCN_RUN(tcn_conv_launch(t, 0, TCN_LAT0, -1, t->keys[3], t->d_n + 3, n, t->tab[3], x, 1, 8, nullptr, 0, 0, z, st));
+  TCN_RUN(tcn_conv_launch(t, 0, TCN_LAT0, -1, t->keys[3], t->d_n + 3, n, t->tab[3], x, 1, 8, nullptr, nullptr, -1, nullptr, 0, 0, z, st));
   float* fp = take(f);
-  TCN_RUN(tcn_conv_launch(t, 0, TCN_LAT1, -1, t->keys[2], t->d_n + 2, n, t->tab[2], fmap, 1, 4, nullptr, 0, 0, fp, st));
-  TCN_RUN(tcn_conv_launch(t, 1, TCN_TCONV, -1, t->keys[2], t->d_n + 2, n, t->tab[3], z, 2, 4, nullptr, 0, 1, fp, st));
+  TCN_RUN(tcn_conv_launch(t, 0, TCN_LAT1, -1, t->keys[2], t->d_n + 2, n, t->tab[2], fmap, 1, 4, nullptr, nullptr, -1, nullptr, 0, 0, fp, st));
+  TCN_RUN(tcn_conv_launch(t, 1, TCN_TCONV, -1, t->keys[2], t->d_n + 2, n, t->tab[3], z, 2, 4, t->kmapt, t->kmaskt, 6, nullptr, 0, 1, fp, st));
 #undef TCN_RUN
-  k_tcn_gem_partial<<<dim3(batch, TCN_GEM_SLICES), 256, 0, st>>>(t->keys[2], t->d_n + 2, fp, f, t->gem_p, t->gem_eps, t->gem_part);
+  const int slices = ((long long)batch * 256 <= t->gem_slices) ? 256 : TCN_GEM_SLICES;
+  k_tcn_gem_partial<<<dim3(batch, slices), 256, 0, st>>>(t->d_n, fp, f, t->gem_p, t->gem_eps, t->gem_part);
   CK_LAUNCH();
-  k_tcn_gem<<<batch, 256, 0, st>>>(t->keys[2], t->d_n + 2, t->gem_part, f, t->gem_p, normalize, d_out);
+  k_tcn_gem<<<batch, 256, 0, st>>>(t->d_n, t->gem_part, slices, f, t->gem_p, normalize, d_out);
   CK_LAUNCH();
   if (d_counts) CK(cudaMemcpyAsync(d_counts, t->d_n, sizeof(int) * 4, cudaMemcpyDeviceToDevice, st));
   return MT_OK;
+}
+
+// d_keys: n packed coordinates (tcn_pack: batch | x | y | z) of the quantised clouds, batch-major (sorted unique keys as
+// ME.utils.sparse_quantize + batched_coordinates produce them; duplicates are merged)
+// d_out: (batch, feature) float64.  d_counts (nullable): active points per level (4 ints, device).
+extern "C" int mt_tcn_forward(mt_tcn* t, const unsigned long long* d_keys, int n, int batch, int normalize, double* d_out,
+                              int* d_counts, void* stream) {
+  if (!t || !d_keys || !d_out || n <= 0 || batch <= 0) return set_err(MT_ERR_ARG, "mt_tcn_forward: bad argument");
+  if (n > t->max_points || batch > t->max_batch) return set_err(MT_ERR_CAPACITY, "mt_tcn_forward: n / batch exceed the context capacity");
+  CK(cudaSetDevice(t->device));
+  return tcn_run(t, nullptr, d_keys, n, 1, 0.f, batch, normalize, d_out, d_counts, (cudaStream_t)stream);
+}
+
+// d_clouds: (batch, points, 3) float32, the sampled and scaled clouds of tcn.py:96-123; quantisation (floor(x * inv_q),
+// inv_q = the float32 reciprocal torch's `cloud / q` multiplies by on CUDA: float32(1 / q) in torch 2.x), duplicate removal
+// and the network run in one enqueue -- no sort, no host synchronisation.  A coordinate beyond +-131071 voxels (or NaN)
+// poisons the descriptors of the call with NaN.
+extern "C" int mt_tcn_embed(mt_tcn* t, const float* d_clouds, int batch, int points, float inv_q, int normalize, double* d_out,
+                            int* d_counts, void* stream) {
+  if (!t || !d_clouds || !d_out || batch <= 0 || points <= 0 || !(inv_q > 0.f)) return set_err(MT_ERR_ARG, "mt_tcn_embed: bad argument");
+  const long long n = (long long)batch * points;
+  if (n > t->max_points || batch > t->max_batch) return set_err(MT_ERR_CAPACITY, "mt_tcn_embed: batch x points / batch exceed the context capacity");
+  CK(cudaSetDevice(t->device));
+  return tcn_run(t, d_clouds, nullptr, (int)n, points, inv_q, batch, normalize, d_out, d_counts, (cudaStream_t)stream);
 }

@@ -83,6 +83,7 @@ class TCN:
         self.index = self.device.index if self.device.index is not None else torch.cuda.current_device()
         self._h = C.c_void_p()
         self._cap = (0, 0)
+        self._inv_q = None
         self.state = None
         if weights is not None:
             self.load_weights(weights)
@@ -136,21 +137,25 @@ class TCN:
     def embed_clouds(self, clouds: torch.Tensor) -> torch.Tensor:
         """clouds: (B, P, 3) float32 CUDA, already scaled to [-1, 1] -> (B, D) float64.
         Quantisation = ME.utils.sparse_quantize + batched_coordinates (tcn.py:124-131): floor(c / q),
-        unique per cloud."""
+        unique per cloud -- done inside the library (mt_tcn_embed): one enqueue, no sort, no host sync."""
         if self.state is None:
             raise MidasError("TCN: load_weights first")
         if not clouds.is_cuda:
             raise MidasError("TCN: clouds must be CUDA tensors; there is no CPU path")
         B, Pn, _ = clouds.shape
-        ijk = torch.floor(clouds.reshape(-1, 3).float() / self.quantization_size).to(torch.int64)
-        bidx = torch.arange(B, device=clouds.device).repeat_interleave(Pn)
-        keys = torch.unique(pack_coordinates(bidx, ijk))  # sorted: batch-major, deterministic row order
-        n = keys.numel()
-        self._ensure(n, B)
+        if B > 511:
+            raise MidasError("TCN: at most 511 clouds per call (batch_size)")
+        pts = clouds.float().contiguous()
+        self._ensure(B * Pn, B)
         out = torch.empty((B, self.output_dim), dtype=torch.float64, device=clouds.device)
+        if self._inv_q is None:
+            # `cloud / q` on a CUDA tensor is a multiplication by a float32 reciprocal of the Python scalar (torch 2.x
+            # forms it in float64: float32(1 / q)); taken from torch itself, once, so the voxels are the reference's
+            self._inv_q = float((torch.ones(1, dtype=torch.float32, device=clouds.device) / self.quantization_size).item())
         with torch.cuda.device(self.index):
-            call("mt_tcn_forward", self._h, ptr(keys), n, B, int(self.normalize_embeddings), ptr(out), 0, stream_ptr())
-        return out
+            call("mt_tcn_embed", self._h, ptr(pts), B, Pn, C.c_float(self._inv_q), int(self.normalize_embeddings), ptr(out), 0,
+                 stream_ptr())
+        return out  # (a voxel coordinate outside +-131071 poisons the codes of the call with NaN)
 
     def cloud_to_tactile_code(self, tac_render, heightmaps, masks) -> torch.Tensor:
         """tcn.py:52-148: height maps + contact masks -> point clouds (``tac_render.heightmap2Pointcloud``)

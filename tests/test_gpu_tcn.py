@@ -135,3 +135,43 @@ def test_cpu_input_rejected(net):
 
     with pytest.raises(MidasError):
         net[0].embed_clouds(torch.zeros(1, 16, 3))
+
+
+def test_embed_entry_equals_keys_entry(net):
+    """mt_tcn_embed (float clouds: quantisation + duplicate removal in the library, rows in order of first
+    occurrence) against mt_tcn_forward on torch's sorted unique keys: the same voxel sets, the same per-point
+    sums; only the GeM summation order differs (float64 partial sums)."""
+    tcn, P = net
+    from midastouch_b200 import _lib
+    from midastouch_b200.tcn import pack_coordinates
+
+    rng = np.random.default_rng(21)
+    # dense enough for real neighbourhoods and duplicate voxels: coordinates span +-60 voxels
+    clouds = (rng.uniform(-0.06, 0.06, size=(3, 3000, 3))).astype(np.float32)
+    clouds[:, :, 2] = 0.3 * (clouds[:, :, 0] ** 2 + clouds[:, :, 1] ** 2) * 10
+    cl = torch.from_numpy(clouds).cuda()
+    got = tcn.embed_clouds(cl)
+    B, Pn, _ = cl.shape
+    ijk = torch.floor(cl.reshape(-1, 3) / tcn.quantization_size).to(torch.int64)
+    keys = torch.unique(pack_coordinates(torch.arange(B, device="cuda").repeat_interleave(Pn), ijk))
+    assert keys.numel() < B * Pn  # duplicates present
+    out = torch.empty((B, 256), dtype=torch.float64, device="cuda")
+    counts = torch.zeros(4, dtype=torch.int32, device="cuda")
+    _lib.call("mt_tcn_forward", tcn._h, keys.data_ptr(), keys.numel(), B, 1, out.data_ptr(), counts.data_ptr(), _lib.stream_ptr())
+    assert int(counts[0]) == keys.numel()
+    assert torch.isfinite(got).all()
+    assert torch.allclose(got, out, rtol=1e-9, atol=1e-12), (got - out).abs().max()
+    # and against the oracle on the same voxels (dense neighbourhoods exercise every kernel offset)
+    coords = T.batched(torch_quantize(clouds))
+    P32 = {k: np.asarray(v, np.float32).astype(np.float64) for k, v in P.items()}
+    ref, _ = T.minkloc_forward(coords, P32)
+    assert np.allclose(got.cpu().numpy(), T.l2_normalize(ref), rtol=2e-4, atol=1e-6)
+
+
+def test_voxel_out_of_range_poisons(net):
+    tcn, _ = net
+    cl = torch.zeros((1, 64, 3), device="cuda")
+    cl[0, 5, 1] = 200.0  # 200 / 0.001 voxels: beyond the 18-bit key fields
+    assert torch.isnan(tcn.embed_clouds(cl)).all()
+    cl[0, 5, 1] = 0.5
+    assert torch.isfinite(tcn.embed_clouds(cl)).all()
