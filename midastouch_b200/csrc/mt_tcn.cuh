@@ -261,23 +261,46 @@ struct TcnMaps {  // index: level 1..3 (0 unused)
   int* pb[7];
   int ncap;
 };
-// one warp, one output point: append its (input row, partial-sum slot) pairs to the lists of their kernel offsets
+// one warp, one output point (8 per block): append its (input row, partial-sum slot) pairs to the lists of their kernel
+// offsets.  The block aggregates: one atomic per (block, offset) and one for the block's partial-sum slots -- the centre
+// offset is present at every point, and one atomic per point on its counter was most of this kernel's time.
 __device__ __forceinline__ void tcn_pairs(int* __restrict__ ctr, int2* __restrict__ pl, int* __restrict__ pb, int ncap, int p, int row,
-                                          int lane) {
+                                          int lane, int w, bool valid, int (*s_hit)[32], int* s_np, int* s_gbase, int* s_sbase) {
   const unsigned bal = __ballot_sync(0xffffffffu, row >= 0);
-  int base = 0;
-  if (lane == 0) {
-    base = atomicAdd(ctr + 31, __popc(bal));
-    pb[p] = base;
+  s_hit[w][lane] = row >= 0;
+  if (lane == 0) s_np[w] = __popc(bal);
+  __syncthreads();
+  int rank = 0, tot = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int hk = s_hit[k][lane];
+    rank += (k < w) ? hk : 0;
+    tot += hk;
   }
-  base = __shfl_sync(0xffffffffu, base, 0);
-  if (row >= 0) pl[(size_t)lane * ncap + atomicAdd(ctr + lane, 1)] = make_int2(row, base + __popc(bal & ((1u << lane) - 1)));
+  if (w == 0) {
+    if (tot) s_gbase[lane] = atomicAdd(ctr + lane, tot);
+    if (lane == 0) {
+      int np = 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) np += s_np[k];
+      *s_sbase = np ? atomicAdd(ctr + 31, np) : 0;
+    }
+  }
+  __syncthreads();
+  int base = *s_sbase;
+  for (int k = 0; k < w; ++k) base += s_np[k];
+  if (valid && lane == 0) pb[p] = base;
+  if (row >= 0) pl[(size_t)lane * ncap + s_gbase[lane] + rank] = make_int2(row, base + __popc(bal & ((1u << lane) - 1)));
+  __syncthreads();  // the shared arrays are reused by the next map
 }
 __global__ void __launch_bounds__(256) k_tcn_kmaps(TcnTabs T, const unsigned long long* __restrict__ k1, const unsigned long long* __restrict__ k2,
                                                    const unsigned long long* __restrict__ k3, int* __restrict__ d_n, TcnMaps M) {
-  const int l = blockIdx.y + 1, lane = threadIdx.x & 31;
-  const int p = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (p >= d_n[l]) return;
+  __shared__ int s_hit[8][32];
+  __shared__ int s_np[8], s_gbase[32], s_sbase;
+  const int l = blockIdx.y + 1, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int p = blockIdx.x * 8 + w;
+  if (blockIdx.x * 8 >= d_n[l]) return;  // (block-uniform)
+  const bool valid = p < d_n[l];
   const unsigned long long* keys = l == 1 ? k1 : (l == 2 ? k2 : k3);
   int* m3 = l == 1 ? M.m3[1] : (l == 2 ? M.m3[2] : M.m3[3]);
   int* m2 = l == 1 ? M.m2[1] : (l == 2 ? M.m2[2] : M.m2[3]);
@@ -288,35 +311,35 @@ __global__ void __launch_bounds__(256) k_tcn_kmaps(TcnTabs T, const unsigned lon
   int* pb3 = l == 1 ? M.pb[0] : (l == 2 ? M.pb[1] : M.pb[2]);
   int* pb2 = l == 1 ? M.pb[3] : (l == 2 ? M.pb[4] : M.pb[5]);
   const TcnTable tl = l == 1 ? T.t[1] : (l == 2 ? T.t[2] : T.t[3]), tc = l == 1 ? T.t[0] : (l == 2 ? T.t[1] : T.t[2]);
-  int b, x, y, z;
-  tcn_unpack(keys[p], b, x, y, z);
+  int b = 0, x = 0, y = 0, z = 0;
+  if (valid) tcn_unpack(keys[p], b, x, y, z);
   const int s = 1 << l, h = s >> 1;
-  int row = -1;
-  if (lane < 27) {
-    row = tcn_lookup(tl, tcn_pack(b, x + (lane % 3 - 1) * s, y + ((lane / 3) % 3 - 1) * s, z + (lane / 9 - 1) * s));
-    m3[(size_t)p * 27 + lane] = row;
-  }
-  unsigned bal = __ballot_sync(0xffffffffu, row >= 0);
-  if (lane == 0) q3[p] = bal;
-  tcn_pairs(d_n + TCN_CTL_PAIRS + 32 * (l - 1), pl3, pb3, M.ncap, p, row, lane);
-  row = -1;
-  if (lane < 8) {
-    row = tcn_lookup(tc, tcn_pack(b, x + (lane & 1) * h, y + ((lane >> 1) & 1) * h, z + (lane >> 2) * h));
-    m2[(size_t)p * 8 + lane] = row;
-  }
-  bal = __ballot_sync(0xffffffffu, row >= 0);
-  if (lane == 0) q2[p] = bal;
-  tcn_pairs(d_n + TCN_CTL_PAIRS + 32 * (l + 2), pl2, pb2, M.ncap, p, row, lane);
-  if (l == 2) {
+  // the three groups of look-ups are independent: all of them are requested before any list is written
+  int row3 = -1, row2 = -1, rowt = -1, wi = 0;
+  if (valid && lane < 27) row3 = tcn_lookup(tl, tcn_pack(b, x + (lane % 3 - 1) * s, y + ((lane / 3) % 3 - 1) * s, z + (lane / 9 - 1) * s));
+  if (valid && lane < 8) row2 = tcn_lookup(tc, tcn_pack(b, x + (lane & 1) * h, y + ((lane >> 1) & 1) * h, z + (lane >> 2) * h));
+  if (l == 2 && valid) {
     const int px = tcn_floor_to(x, 8), py = tcn_floor_to(y, 8), pz = tcn_floor_to(z, 8);
-    const int wi = ((z - pz) / 4 * 2 + (y - py) / 4) * 2 + (x - px) / 4;
-    int prow = -1;
-    if (lane == 0) prow = tcn_lookup(T.t[3], tcn_pack(b, px, py, pz));
-    prow = __shfl_sync(0xffffffffu, prow, 0);
-    row = (lane == wi) ? prow : -1;
-    if (lane < 8) M.mt[(size_t)p * 8 + lane] = row;
-    if (lane == 0) M.qt[p] = prow >= 0 ? (1u << wi) : 0u;
-    tcn_pairs(d_n + TCN_CTL_PAIRS + 32 * 6, M.pl[6], M.pb[6], M.ncap, p, row, lane);
+    wi = ((z - pz) / 4 * 2 + (y - py) / 4) * 2 + (x - px) / 4;
+    if (lane == wi) rowt = tcn_lookup(T.t[3], tcn_pack(b, px, py, pz));
+  }
+  if (valid) {
+    if (lane < 27) m3[(size_t)p * 27 + lane] = row3;
+    if (lane < 8) m2[(size_t)p * 8 + lane] = row2;
+  }
+  unsigned bal = __ballot_sync(0xffffffffu, row3 >= 0);
+  if (valid && lane == 0) q3[p] = bal;
+  tcn_pairs(d_n + TCN_CTL_PAIRS + 32 * (l - 1), pl3, pb3, M.ncap, p, row3, lane, w, valid, s_hit, s_np, s_gbase, &s_sbase);
+  bal = __ballot_sync(0xffffffffu, row2 >= 0);
+  if (valid && lane == 0) q2[p] = bal;
+  tcn_pairs(d_n + TCN_CTL_PAIRS + 32 * (l + 2), pl2, pb2, M.ncap, p, row2, lane, w, valid, s_hit, s_np, s_gbase, &s_sbase);
+  if (l == 2) {
+    bal = __ballot_sync(0xffffffffu, rowt >= 0);
+    if (valid) {
+      if (lane < 8) M.mt[(size_t)p * 8 + lane] = rowt;
+      if (lane == 0) M.qt[p] = bal;
+    }
+    tcn_pairs(d_n + TCN_CTL_PAIRS + 32 * 6, M.pl[6], M.pb[6], M.ncap, p, rowt, lane, w, valid, s_hit, s_np, s_gbase, &s_sbase);
   }
 }
 
@@ -363,7 +386,7 @@ __global__ void __launch_bounds__(128) k_tcn_conv_mma(const int* __restrict__ ma
     const float* __restrict__ xlo = in_feat + (size_t)(rlo < 0 ? 0 : rlo) * cin + t;
     const float* __restrict__ xhi = in_feat + (size_t)(rhi < 0 ? 0 : rhi) * cin + t;
     const float* __restrict__ Wi = W + ((size_t)i * cin + t) * cout + n0 + g;
-#pragma unroll 2
+#pragma unroll 4
     for (int k0 = 0; k0 < cin; k0 += 8) {
       float af[4];
       af[0] = rlo >= 0 ? __ldg(xlo + k0) : 0.f;
@@ -416,6 +439,44 @@ __global__ void __launch_bounds__(128) k_tcn_conv_mma(const int* __restrict__ ma
   }
 }
 
+// conv0 (minkfpn.py:113-115): the reference gives every point the dummy feature 1 (tcn.py:131-134), so the layer is the
+// sum of the kernel rows of the offsets present + BatchNorm + ReLU.  One warp per point; the lanes probe the hash map
+// for all k^3 <= 128 offsets first (independent chains, one round trip), then add the rows in ascending offset order.
+__global__ void __launch_bounds__(256) k_tcn_conv0(const unsigned long long* __restrict__ keys, const int* __restrict__ d_n, TcnTable tab,
+                                                   const float* __restrict__ W, int cout, int k, const float* __restrict__ scale,
+                                                   const float* __restrict__ shift, float* __restrict__ out_feat) {
+  const int lane = threadIdx.x & 31, p = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (p >= *d_n) return;
+  int b, x, y, z;
+  tcn_unpack(keys[p], b, x, y, z);
+  const int kvol = k * k * k, centre = k >> 1;
+  bool hit[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int i = 32 * r + lane;
+    hit[r] = i < kvol && tcn_lookup(tab, tcn_pack(b, x + i % k - centre, y + (i / k) % k - centre, z + i / (k * k) - centre)) >= 0;
+  }
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    unsigned m = __ballot_sync(0xffffffffu, hit[r]);
+    while (m) {
+      const int i = 32 * r + __ffs(m) - 1;
+      m &= m - 1;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (lane + 32 * j < cout) acc[j] += __ldg(W + (size_t)i * cout + lane + 32 * j);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = lane + 32 * j;
+    if (c < cout) out_feat[(size_t)p * cout + c] = fmaxf(scale ? acc[j] * scale[c] + shift[c] : acc[j], 0.f);
+  }
+}
+
 // Pair form of the gather-GEMM: work proportional to the (output point, kernel offset) pairs that exist.  k_tcn_kmaps
 // grouped the pairs by kernel offset; a work item is up to 32 pairs of ONE offset (two m16 tiles sharing their B
 // fragments) x 8 NT output channels, so no MMA row is spent on an absent neighbour and the weights of an offset are
@@ -460,7 +521,7 @@ __global__ void __launch_bounds__(128) k_tcn_pair_mma(const int2* __restrict__ p
     for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = acc[mt][nt][2] = acc[mt][nt][3] = 0.f;
-#pragma unroll 2
+#pragma unroll 4
     for (int k0 = 0; k0 < cin; k0 += 8) {
       float af[2][4];
 #pragma unroll
@@ -673,31 +734,41 @@ __global__ void __launch_bounds__(256) k_tcn_gem_partial(const int* __restrict__
     part[((size_t)blockIdx.x * slices + blockIdx.y) * c + ch] = acc;
   }
 }
-__global__ void __launch_bounds__(256) k_tcn_gem(const int* __restrict__ ctl, const double* __restrict__ part, int slices, int c, float p,
-                                                 int normalize, double* __restrict__ out) {
+__global__ void __launch_bounds__(1024) k_tcn_gem(const int* __restrict__ ctl, const double* __restrict__ part, int slices, int c, float p,
+                                                  int normalize, double* __restrict__ out) {
+  __shared__ double s_grp[4][256];
   __shared__ double s_sq[8];
   int lo = ctl[TCN_CTL_BLO + blockIdx.x];
   const int hi = ctl[TCN_CTL_BHI + blockIdx.x];
   if (hi == 0) lo = 0;
   const int b = blockIdx.x;
   const bool poisoned = ctl[4] != 0;  // a voxel coordinate did not fit the 18-bit key fields (or was NaN)
-  double acc_total = 0.0;
-  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
-    double acc = 0.0;
-    for (int sl = 0; sl < slices; ++sl) acc += part[((size_t)b * slices + sl) * c + ch];
-    double g = (hi > lo) ? pow(acc / (double)(hi - lo), 1.0 / (double)p) : 0.0;
+  // thread = (channel, quarter of the slices): the loads of a quarter are independent, the quarters are added in order
+  const int ch = threadIdx.x & 255, grp = threadIdx.x >> 8;
+  const int per = (slices + 3) >> 2, s0 = grp * per, s1 = min(s0 + per, slices);
+  double acc = 0.0;
+  if (ch < c) {
+#pragma unroll 8
+    for (int sl = s0; sl < s1; ++sl) acc += part[((size_t)b * slices + sl) * c + ch];
+  }
+  s_grp[grp][ch] = acc;
+  __syncthreads();
+  double g = 0.0;
+  if (threadIdx.x < 256 && ch < c) {
+    const double tot = ((s_grp[0][ch] + s_grp[1][ch]) + s_grp[2][ch]) + s_grp[3][ch];
+    g = (hi > lo) ? pow(tot / (double)(hi - lo), 1.0 / (double)p) : 0.0;
     if (poisoned) g = __longlong_as_double(0x7ff8000000000000ll);
-    out[(size_t)b * c + ch] = g;
-    acc_total += g * g;
+    if (!normalize) out[(size_t)b * c + ch] = g;
   }
   if (!normalize) return;
-  acc_total = warp_sum(acc_total);
-  if ((threadIdx.x & 31) == 0) s_sq[threadIdx.x >> 5] = acc_total;
+  double sq = (threadIdx.x < 256) ? warp_sum(g * g) : 0.0;
+  if (threadIdx.x < 256 && (threadIdx.x & 31) == 0) s_sq[threadIdx.x >> 5] = sq;
   __syncthreads();
-  double tot = 0.0;
-  for (int k = 0; k < (int)(blockDim.x >> 5); ++k) tot += s_sq[k];
-  const double inv = 1.0 / fmax(sqrt(tot), 1e-12);  // F.normalize eps
-  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) out[(size_t)b * c + ch] *= inv;
+  if (threadIdx.x < 256 && ch < c) {
+    double tot = 0.0;
+    for (int k = 0; k < 8; ++k) tot += s_sq[k];
+    out[(size_t)b * c + ch] = g * (1.0 / fmax(sqrt(tot), 1e-12));  // F.normalize eps
+  }
 }
 
 // ------------------------------------------------------------------------- C ABI
@@ -900,7 +971,17 @@ static int tcn_run(mt_tcn* t, const float* d_pts, const unsigned long long* d_ke
   int r;
 #define TCN_RUN(call) if ((r = (call)) != MT_OK) return r
   // conv0 + bn0 + relu (minkfpn.py:113-115)
-  TCN_RUN(tcn_conv_launch(t, 0, TCN_CONV0, TCN_BN0, t->keys[0], t->d_n, n, t->tab[0], nullptr, 5, 1, nullptr, nullptr, -1, nullptr, 1, 0, x0, st));
+  {
+    const TcnConv& cv = t->conv[TCN_CONV0];
+    int k0 = 1;
+    while (k0 * k0 * k0 < cv.kvol) ++k0;
+    if (cv.cin == 1 && (k0 & 1) && k0 * k0 * k0 == cv.kvol && cv.kvol <= 128 && t->bn[TCN_BN0].scale && t->bn[TCN_BN0].c == cv.cout) {
+      k_tcn_conv0<<<(n + 7) / 8, 256, 0, st>>>(t->keys[0], t->d_n, t->tab[0], cv.w, cv.cout, k0, t->bn[TCN_BN0].scale, t->bn[TCN_BN0].shift, x0);
+      CK_LAUNCH();
+    } else {
+      TCN_RUN(tcn_conv_launch(t, 0, TCN_CONV0, TCN_BN0, t->keys[0], t->d_n, n, t->tab[0], nullptr, k0, 1, nullptr, nullptr, -1, nullptr, 1, 0, x0, st));
+    }
+  }
   float* x = x0;
   float* fmap = nullptr;
   for (int s = 0; s < 3; ++s) {  // bottom-up: strided conv + bn + relu + BasicBlock (minkfpn.py:120-126)
@@ -936,7 +1017,7 @@ static int tcn_run(mt_tcn* t, const float* d_pts, const unsigned long long* d_ke
   const int slices = ((long long)batch * 256 <= t->gem_slices) ? 256 : TCN_GEM_SLICES;
   k_tcn_gem_partial<<<dim3(batch, slices), 256, 0, st>>>(t->d_n, fp, f, t->gem_p, t->gem_eps, t->gem_part);
   CK_LAUNCH();
-  k_tcn_gem<<<batch, 256, 0, st>>>(t->d_n, t->gem_part, slices, f, t->gem_p, normalize, d_out);
+  k_tcn_gem<<<batch, 1024, 0, st>>>(t->d_n, t->gem_part, slices, f, t->gem_p, normalize, d_out);
   CK_LAUNCH();
   if (d_counts) CK(cudaMemcpyAsync(d_counts, t->d_n, sizeof(int) * 4, cudaMemcpyDeviceToDevice, st));
   return MT_OK;

@@ -175,3 +175,20 @@ def test_voxel_out_of_range_poisons(net):
     assert torch.isnan(tcn.embed_clouds(cl)).all()
     cl[0, 5, 1] = 0.5
     assert torch.isfinite(tcn.embed_clouds(cl)).all()
+
+
+def test_many_clouds_ordered_compaction(net):
+    """40 clouds x 1100 points: more than 32 compaction blocks (strided carry), batch ranges of every element,
+    each cloud's code equal to the code it gets alone."""
+    tcn, _ = net
+    rng = np.random.default_rng(33)
+    clouds = rng.uniform(-0.2, 0.2, size=(40, 1100, 3)).astype(np.float32)
+    clouds[:, :, 2] = 0.5 * clouds[:, :, 0] * clouds[:, :, 1]
+    clouds[7] = clouds[3]  # two identical clouds: identical codes
+    cl = torch.from_numpy(clouds).cuda()
+    out = tcn.embed_clouds(cl)
+    assert out.shape == (40, 256) and torch.isfinite(out).all()
+    assert torch.equal(out[7], out[3])
+    for b in (0, 3, 19, 39):
+        one = tcn.embed_clouds(cl[b:b + 1])
+        assert torch.allclose(one[0], out[b], rtol=1e-9, atol=1e-12), (b, (one[0] - out[b]).abs().max())
