@@ -52,7 +52,8 @@
 #define TCN_BN_DS(s) (10 + (s))
 
 struct TcnConv {
-  float* w;  // (kvol, cin, cout)
+  float* w;   // (kvol, cin, cout)
+  float* wt;  // (kvol, cout, cin): the B fragments of the MMA kernels are 16-byte loads along cin
   int kvol, cin, cout;
 };
 struct TcnBn {
@@ -143,7 +144,30 @@ __device__ __forceinline__ unsigned tcn_insert(const TcnTable& t, unsigned long 
   }
 }
 
+
+// Programmatic dependent launch: the 31 kernels of a forward pass are short and strictly dependent, so the gap between
+// them (~1.5 us each) is a fifth of the pass.  Every kernel opens with tcn_pdl(): it lets the NEXT kernel's blocks be
+// scheduled right away (they park in their own griddepcontrol.wait) and then waits until the PREVIOUS kernel has
+// completed and its writes are visible -- the data dependence is unchanged, only the launch latency is overlapped.
+__device__ __forceinline__ void tcn_pdl() {
+  asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+template <typename... KArgs, typename... Args>
+static void tcn_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, Args&&... args) {
+  static const bool no_pdl = getenv("MIDAS_B200_TCN_NO_PDL") != nullptr;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid, cfg.blockDim = block, cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at, cfg.numAttrs = no_pdl ? 0 : 1;
+  cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);  // (errors surface in the CK_LAUNCH() that follows every launch)
+}
+
 __global__ void k_tcn_clear_all(TcnTabs T, int* d_n) {
+  tcn_pdl();
   const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < TCN_CTL_BLO) d_n[i] = 0;
   if (i < 512) d_n[TCN_CTL_BLO + i] = INT_MAX, d_n[TCN_CTL_BHI + i] = 0;
@@ -159,6 +183,7 @@ __global__ void k_tcn_clear_all(TcnTabs T, int* d_n) {
 __global__ void __launch_bounds__(256) k_tcn_insert_all(const float* __restrict__ pts, const unsigned long long* __restrict__ keys_in,
                                                         int n_raw, int P, float inv_q, TcnTabs T, int* __restrict__ slot_of,
                                                         int stride, int* __restrict__ d_flag) {
+  tcn_pdl();
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const int i = tid >> 2, l = tid & 3;  // four threads per raw point, one per level: four independent atomic chains
   if (i >= n_raw) return;
@@ -184,6 +209,7 @@ __global__ void __launch_bounds__(256) k_tcn_insert_all(const float* __restrict_
 // ordered compaction, pass 1: first points (the representative of their key) per block of 1024 raw points and level
 __global__ void __launch_bounds__(1024) k_tcn_count_all(int n_raw, TcnTabs T, const int* __restrict__ slot_of, int stride,
                                                         int* __restrict__ blk_cnt, int nblk) {
+  tcn_pdl();
   __shared__ int s_w[4][32];
   const int i = blockIdx.x * 1024 + threadIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 #pragma unroll
@@ -205,6 +231,7 @@ __global__ void __launch_bounds__(1024) k_tcn_scatter_all(int n_raw, TcnTabs T, 
                                                           unsigned long long* __restrict__ k0, unsigned long long* __restrict__ k1,
                                                           unsigned long long* __restrict__ k2, unsigned long long* __restrict__ k3,
                                                           int* __restrict__ d_n) {
+  tcn_pdl();
   __shared__ int s_w[4][32];
   __shared__ int s_carry[4];
   const int i = blockIdx.x * 1024 + threadIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -295,6 +322,7 @@ __device__ __forceinline__ void tcn_pairs(int* __restrict__ ctr, int2* __restric
 }
 __global__ void __launch_bounds__(256) k_tcn_kmaps(TcnTabs T, const unsigned long long* __restrict__ k1, const unsigned long long* __restrict__ k2,
                                                    const unsigned long long* __restrict__ k3, int* __restrict__ d_n, TcnMaps M) {
+  tcn_pdl();
   __shared__ int s_hit[8][32];
   __shared__ int s_np[8], s_gbase[32], s_sbase;
   const int l = blockIdx.y + 1, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -359,12 +387,17 @@ __device__ __forceinline__ void tcn_mma_tf32(float c[4], const unsigned a[4], un
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+// K is consumed 16 channels at a time with one 16-byte load per operand row: lane (g, t) holds channels 4t .. 4t+3 of
+// its rows, and the two MMAs of the chunk take channels (4t, 4t+1) and (4t+2, 4t+3) as their k slots (t, t+4) -- the
+// assignment of channels to k slots is free as long as A and B agree.  Wt is the (kvol, cout, cin) copy of the weights.
+__device__ __forceinline__ float tcn_f4(const float4& v, int j) { return j == 0 ? v.x : (j == 1 ? v.y : (j == 2 ? v.z : v.w)); }
 template <int NT>
 __global__ void __launch_bounds__(128) k_tcn_conv_mma(const int* __restrict__ map, const unsigned* __restrict__ hitmask, int kvol,
                                                       const int* __restrict__ d_nout, const float* __restrict__ in_feat, int cin,
-                                                      const float* __restrict__ W, int cout, const float* __restrict__ scale,
+                                                      const float* __restrict__ Wt, int cout, const float* __restrict__ scale,
                                                       const float* __restrict__ shift, const float* __restrict__ residual, int relu,
                                                       int accumulate, float* __restrict__ out_feat) {
+  tcn_pdl();
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int nslab = cout / (8 * NT);
   const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -378,38 +411,38 @@ __global__ void __launch_bounds__(128) k_tcn_conv_mma(const int* __restrict__ ma
   float acc[NT][4];
 #pragma unroll
   for (int nt = 0; nt < NT; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
   while (m) {  // ascending offsets: the summation order of every output is fixed
     const int i = __ffs(m) - 1;
     m &= m - 1;
     const int rlo = vlo ? (map ? map[(size_t)plo * kvol + i] : plo) : -1;
     const int rhi = vhi ? (map ? map[(size_t)phi * kvol + i] : phi) : -1;
-    const float* __restrict__ xlo = in_feat + (size_t)(rlo < 0 ? 0 : rlo) * cin + t;
-    const float* __restrict__ xhi = in_feat + (size_t)(rhi < 0 ? 0 : rhi) * cin + t;
-    const float* __restrict__ Wi = W + ((size_t)i * cin + t) * cout + n0 + g;
-#pragma unroll 4
-    for (int k0 = 0; k0 < cin; k0 += 8) {
-      float af[4];
-      af[0] = rlo >= 0 ? __ldg(xlo + k0) : 0.f;
-      af[1] = rhi >= 0 ? __ldg(xhi + k0) : 0.f;
-      af[2] = rlo >= 0 ? __ldg(xlo + k0 + 4) : 0.f;
-      af[3] = rhi >= 0 ? __ldg(xhi + k0 + 4) : 0.f;
-      float bf[NT][2];
+    const float* __restrict__ xlo = in_feat + (size_t)(rlo < 0 ? 0 : rlo) * cin + 4 * t;
+    const float* __restrict__ xhi = in_feat + (size_t)(rhi < 0 ? 0 : rhi) * cin + 4 * t;
+    const float* __restrict__ Wi = Wt + ((size_t)i * cout + n0 + g) * cin + 4 * t;
+#pragma unroll 2
+    for (int k0 = 0; k0 < cin; k0 += 16) {
+      const float4 alo = rlo >= 0 ? __ldg((const float4*)(xlo + k0)) : zero4;
+      const float4 ahi = rhi >= 0 ? __ldg((const float4*)(xhi + k0)) : zero4;
+      float4 bv[NT];
 #pragma unroll
-      for (int nt = 0; nt < NT; ++nt) {
-        bf[nt][0] = __ldg(Wi + (size_t)k0 * cout + 8 * nt);
-        bf[nt][1] = __ldg(Wi + (size_t)(k0 + 4) * cout + 8 * nt);
-      }
-      unsigned ab[4], as[4];
+      for (int nt = 0; nt < NT; ++nt) bv[nt] = __ldg((const float4*)(Wi + (size_t)8 * nt * cin + k0));
 #pragma unroll
-      for (int q = 0; q < 4; ++q) tcn_split_tf32(af[q], ab[q], as[q]);
+      for (int h = 0; h < 2; ++h) {
+        unsigned ab[4], as[4];
+        tcn_split_tf32(tcn_f4(alo, 2 * h), ab[0], as[0]);
+        tcn_split_tf32(tcn_f4(ahi, 2 * h), ab[1], as[1]);
+        tcn_split_tf32(tcn_f4(alo, 2 * h + 1), ab[2], as[2]);
+        tcn_split_tf32(tcn_f4(ahi, 2 * h + 1), ab[3], as[3]);
 #pragma unroll
-      for (int nt = 0; nt < NT; ++nt) {
-        unsigned bb0, bs0, bb1, bs1;
-        tcn_split_tf32(bf[nt][0], bb0, bs0);
-        tcn_split_tf32(bf[nt][1], bb1, bs1);
-        tcn_mma_tf32(acc[nt], as, bb0, bb1);  // small terms first
-        tcn_mma_tf32(acc[nt], ab, bs0, bs1);
-        tcn_mma_tf32(acc[nt], ab, bb0, bb1);
+        for (int nt = 0; nt < NT; ++nt) {
+          unsigned bb0, bs0, bb1, bs1;
+          tcn_split_tf32(tcn_f4(bv[nt], 2 * h), bb0, bs0);
+          tcn_split_tf32(tcn_f4(bv[nt], 2 * h + 1), bb1, bs1);
+          tcn_mma_tf32(acc[nt], as, bb0, bb1);  // small terms first
+          tcn_mma_tf32(acc[nt], ab, bs0, bs1);
+          tcn_mma_tf32(acc[nt], ab, bb0, bb1);
+        }
       }
     }
   }
@@ -445,6 +478,7 @@ __global__ void __launch_bounds__(128) k_tcn_conv_mma(const int* __restrict__ ma
 __global__ void __launch_bounds__(256) k_tcn_conv0(const unsigned long long* __restrict__ keys, const int* __restrict__ d_n, TcnTable tab,
                                                    const float* __restrict__ W, int cout, int k, const float* __restrict__ scale,
                                                    const float* __restrict__ shift, float* __restrict__ out_feat) {
+  tcn_pdl();
   const int lane = threadIdx.x & 31, p = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (p >= *d_n) return;
   int b, x, y, z;
@@ -486,8 +520,9 @@ __global__ void __launch_bounds__(256) k_tcn_conv0(const unsigned long long* __r
 // Persistent grid: every warp derives the tile table from the kvol pair counters and strides over the items.
 template <int NT>
 __global__ void __launch_bounds__(128) k_tcn_pair_mma(const int2* __restrict__ pl, const int* __restrict__ ctr, int kvol, int ncap,
-                                                      const float* __restrict__ in_feat, int cin, const float* __restrict__ W, int cout,
+                                                      const float* __restrict__ in_feat, int cin, const float* __restrict__ Wt, int cout,
                                                       float* __restrict__ partial) {
+  tcn_pdl();
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int nslab = cout / (8 * NT);
   const int cnt_i = lane < kvol ? ctr[lane] : 0;
@@ -514,49 +549,48 @@ __global__ void __launch_bounds__(128) k_tcn_pair_mma(const int2* __restrict__ p
     }
     const float* __restrict__ xr[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) xr[q] = in_feat + (size_t)(e[q].x < 0 ? 0 : e[q].x) * cin + t;
-    const float* __restrict__ Wi = W + ((size_t)i * cin + t) * cout + n0 + g;
+    for (int q = 0; q < 4; ++q) xr[q] = in_feat + (size_t)(e[q].x < 0 ? 0 : e[q].x) * cin + 4 * t;
+    const float* __restrict__ Wi = Wt + ((size_t)i * cout + n0 + g) * cin + 4 * t;
     float acc[2][NT][4];
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = acc[mt][nt][2] = acc[mt][nt][3] = 0.f;
-#pragma unroll 4
-    for (int k0 = 0; k0 < cin; k0 += 8) {
-      float af[2][4];
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 2
+    for (int k0 = 0; k0 < cin; k0 += 16) {  // (channel -> k slot assignment: see k_tcn_conv_mma)
+      float4 av[4];
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt) {
-        const bool on = mt == 0 || two;
-        af[mt][0] = (on && e[2 * mt].x >= 0) ? __ldg(xr[2 * mt] + k0) : 0.f;
-        af[mt][1] = (on && e[2 * mt + 1].x >= 0) ? __ldg(xr[2 * mt + 1] + k0) : 0.f;
-        af[mt][2] = (on && e[2 * mt].x >= 0) ? __ldg(xr[2 * mt] + k0 + 4) : 0.f;
-        af[mt][3] = (on && e[2 * mt + 1].x >= 0) ? __ldg(xr[2 * mt + 1] + k0 + 4) : 0.f;
-      }
-      float bf[NT][2];
+      for (int q = 0; q < 4; ++q) av[q] = (e[q].x >= 0) ? __ldg((const float4*)(xr[q] + k0)) : zero4;  // (rows 2, 3 absent unless `two`)
+      float4 bv[NT];
 #pragma unroll
-      for (int nt = 0; nt < NT; ++nt) {
-        bf[nt][0] = __ldg(Wi + (size_t)k0 * cout + 8 * nt);
-        bf[nt][1] = __ldg(Wi + (size_t)(k0 + 4) * cout + 8 * nt);
-      }
-      unsigned ab[2][4], as[2][4];
+      for (int nt = 0; nt < NT; ++nt) bv[nt] = __ldg((const float4*)(Wi + (size_t)8 * nt * cin + k0));
 #pragma unroll
-      for (int q = 0; q < 4; ++q) tcn_split_tf32(af[0][q], ab[0][q], as[0][q]);
-      if (two) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) tcn_split_tf32(af[1][q], ab[1][q], as[1][q]);
-      }
-#pragma unroll
-      for (int nt = 0; nt < NT; ++nt) {
-        unsigned bb0, bs0, bb1, bs1;
-        tcn_split_tf32(bf[nt][0], bb0, bs0);
-        tcn_split_tf32(bf[nt][1], bb1, bs1);
-        tcn_mma_tf32(acc[0][nt], as[0], bb0, bb1);  // small terms first
-        tcn_mma_tf32(acc[0][nt], ab[0], bs0, bs1);
-        tcn_mma_tf32(acc[0][nt], ab[0], bb0, bb1);
+      for (int h = 0; h < 2; ++h) {
+        unsigned ab[2][4], as[2][4];
+        tcn_split_tf32(tcn_f4(av[0], 2 * h), ab[0][0], as[0][0]);
+        tcn_split_tf32(tcn_f4(av[1], 2 * h), ab[0][1], as[0][1]);
+        tcn_split_tf32(tcn_f4(av[0], 2 * h + 1), ab[0][2], as[0][2]);
+        tcn_split_tf32(tcn_f4(av[1], 2 * h + 1), ab[0][3], as[0][3]);
         if (two) {
-          tcn_mma_tf32(acc[1][nt], as[1], bb0, bb1);
-          tcn_mma_tf32(acc[1][nt], ab[1], bs0, bs1);
-          tcn_mma_tf32(acc[1][nt], ab[1], bb0, bb1);
+          tcn_split_tf32(tcn_f4(av[2], 2 * h), ab[1][0], as[1][0]);
+          tcn_split_tf32(tcn_f4(av[3], 2 * h), ab[1][1], as[1][1]);
+          tcn_split_tf32(tcn_f4(av[2], 2 * h + 1), ab[1][2], as[1][2]);
+          tcn_split_tf32(tcn_f4(av[3], 2 * h + 1), ab[1][3], as[1][3]);
+        }
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          unsigned bb0, bs0, bb1, bs1;
+          tcn_split_tf32(tcn_f4(bv[nt], 2 * h), bb0, bs0);
+          tcn_split_tf32(tcn_f4(bv[nt], 2 * h + 1), bb1, bs1);
+          tcn_mma_tf32(acc[0][nt], as[0], bb0, bb1);  // small terms first
+          tcn_mma_tf32(acc[0][nt], ab[0], bs0, bs1);
+          tcn_mma_tf32(acc[0][nt], ab[0], bb0, bb1);
+          if (two) {
+            tcn_mma_tf32(acc[1][nt], as[1], bb0, bb1);
+            tcn_mma_tf32(acc[1][nt], ab[1], bs0, bs1);
+            tcn_mma_tf32(acc[1][nt], ab[1], bb0, bb1);
+          }
         }
       }
     }
@@ -576,6 +610,7 @@ __global__ void __launch_bounds__(256) k_tcn_pair_reduce(const int* __restrict__
                                                          const float* __restrict__ scale, const float* __restrict__ shift,
                                                          const float* __restrict__ residual, int relu, int accumulate,
                                                          float* __restrict__ out_feat) {
+  tcn_pdl();
   const int q4 = cout >> 2;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int p = (int)(idx / q4), c = (int)(idx % q4) * 4;
@@ -615,6 +650,7 @@ __global__ void __launch_bounds__(256) k_tcn_conv(const unsigned long long* __re
                                                   const float* __restrict__ scale, const float* __restrict__ shift,
                                                   const float* __restrict__ residual, int relu, int accumulate,
                                                   float* __restrict__ out_feat) {
+  tcn_pdl();
   constexpr int PPB = 8 / WPP;  // points per 256-thread block
   __shared__ float s_acc[WPP > 1 ? 8 : 1][256];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -721,6 +757,7 @@ __global__ void __launch_bounds__(256) k_tcn_conv(const unsigned long long* __re
 #define TCN_GEM_SLICES 64
 __global__ void __launch_bounds__(256) k_tcn_gem_partial(const int* __restrict__ ctl, const float* __restrict__ feat, int c, float p,
                                                          float eps, double* __restrict__ part /* batch x slices x c */) {
+  tcn_pdl();
   int lo = ctl[TCN_CTL_BLO + blockIdx.x];
   const int hi = ctl[TCN_CTL_BHI + blockIdx.x];
   if (hi == 0) lo = 0;  // no point in this batch element
@@ -736,6 +773,7 @@ __global__ void __launch_bounds__(256) k_tcn_gem_partial(const int* __restrict__
 }
 __global__ void __launch_bounds__(1024) k_tcn_gem(const int* __restrict__ ctl, const double* __restrict__ part, int slices, int c, float p,
                                                   int normalize, double* __restrict__ out) {
+  tcn_pdl();
   __shared__ double s_grp[4][256];
   __shared__ double s_sq[8];
   int lo = ctl[TCN_CTL_BLO + blockIdx.x];
@@ -823,7 +861,7 @@ extern "C" int mt_tcn_destroy(mt_tcn* t) {
   }
   cudaFree(t->kmapt), cudaFree(t->kmaskt), cudaFree(t->slot_of), cudaFree(t->blk_cnt), cudaFree(t->partial);
   for (int m = 0; m < 7; ++m) cudaFree(t->plist[m]), cudaFree(t->pbase[m]);
-  for (int i = 0; i < TCN_NCONV; ++i) cudaFree(t->conv[i].w);
+  for (int i = 0; i < TCN_NCONV; ++i) cudaFree(t->conv[i].w), cudaFree(t->conv[i].wt);
   for (int i = 0; i < TCN_NBN; ++i) cudaFree(t->bn[i].scale), cudaFree(t->bn[i].shift);
   cudaFree(t->d_n), cudaFree(t->pool), cudaFree(t->gem_part);
   delete t;
@@ -834,11 +872,17 @@ extern "C" int mt_tcn_set_conv(mt_tcn* t, int id, const float* h_kernel, int kvo
   if (!t || id < 0 || id >= TCN_NCONV || !h_kernel || kvol <= 0 || cin <= 0 || cout <= 0 || cout > 256)
     return set_err(MT_ERR_ARG, "mt_tcn_set_conv: bad argument (cout <= 256)");
   CK(cudaSetDevice(t->device));
-  cudaFree(t->conv[id].w);
-  t->conv[id].w = nullptr;
+  cudaFree(t->conv[id].w), cudaFree(t->conv[id].wt);
+  t->conv[id].w = t->conv[id].wt = nullptr;
   const size_t n = (size_t)kvol * cin * cout;
   CK(cudaMalloc(&t->conv[id].w, sizeof(float) * n));
   CK(cudaMemcpy(t->conv[id].w, h_kernel, sizeof(float) * n, cudaMemcpyHostToDevice));
+  std::vector<float> tr(n);
+  for (int i = 0; i < kvol; ++i)
+    for (int k = 0; k < cin; ++k)
+      for (int c = 0; c < cout; ++c) tr[((size_t)i * cout + c) * cin + k] = h_kernel[((size_t)i * cin + k) * cout + c];
+  CK(cudaMalloc(&t->conv[id].wt, sizeof(float) * n));
+  CK(cudaMemcpy(t->conv[id].wt, tr.data(), sizeof(float) * n, cudaMemcpyHostToDevice));
   t->conv[id].kvol = kvol, t->conv[id].cin = cin, t->conv[id].cout = cout;
   return MT_OK;
 }
@@ -870,7 +914,7 @@ extern "C" int mt_tcn_set_gem(mt_tcn* t, float p, float eps) {
 }
 
 // One convolution.  map / hitmask / kvol describe the gather (NULL: 1x1, the point itself); layers whose widths the MMA
-// tiling divides (cin % 8 == 0, cout % 16 == 0: every layer of the shipped network but conv0) run on the tensor cores,
+// tiling divides (cin % 16 == 0, cout % 16 == 0: every layer of the shipped network but conv0) run on the tensor cores,
 // the others through the hash-probing CUDA-core kernel (mode / k / dil / in_tab as before).
 static int tcn_conv_launch(mt_tcn* t, int mode, int conv_id, int bn_id, const unsigned long long* out_keys, const int* d_nout,
                            int nmax, const TcnTable& in_tab, const float* in_feat, int k, int dil, const int* map,
@@ -889,30 +933,30 @@ static int tcn_conv_launch(mt_tcn* t, int mode, int conv_id, int bn_id, const un
   const bool have_map = map != nullptr || k == 1;
   static const bool no_mma = getenv("MIDAS_B200_TCN_NO_MMA") != nullptr;  // diagnostics: every layer through the CUDA-core kernel
   static const bool no_pairs = getenv("MIDAS_B200_TCN_NO_PAIRS") != nullptr;  // diagnostics: dense tiles instead of pair lists
-  if (!no_mma && !no_pairs && in_feat && map && map_id >= 0 && c.cin % 8 == 0 && c.cout % 16 == 0 &&
+  if (!no_mma && !no_pairs && in_feat && map && map_id >= 0 && c.cin % 16 == 0 && c.cout % 16 == 0 &&
       (size_t)c.kvol * c.cout * t->max_points <= t->partial_floats) {
     // work proportional to the pairs present: pair GEMM into `partial`, then the per-point sum + epilogue
     const int* ctr = t->d_n + TCN_CTL_PAIRS + 32 * map_id;
     const long long items = ((long long)(nmax + 31) / 32 + c.kvol) * (c.cout / 16);  // at least the centre offset's tiles
     const unsigned grid = (unsigned)std::min<long long>((items + 3) / 4, 148 * 12);
-    k_tcn_pair_mma<2><<<grid, 128, 0, st>>>(t->plist[map_id], ctr, c.kvol, t->max_points, in_feat, c.cin, c.w, c.cout, t->partial);
+    tcn_launch(k_tcn_pair_mma<2>, grid, 128, st, t->plist[map_id], ctr, c.kvol, t->max_points, in_feat, c.cin, c.wt, c.cout, t->partial);
     CK_LAUNCH();
     const long long thr = (long long)nmax * (c.cout / 4);
-    k_tcn_pair_reduce<<<(unsigned)((thr + 255) / 256), 256, 0, st>>>(t->pbase[map_id], hitmask, d_nout, t->partial, c.cout, sc, sh, residual, relu,
+    tcn_launch(k_tcn_pair_reduce, (unsigned)((thr + 255) / 256), 256, st, t->pbase[map_id], hitmask, d_nout, t->partial, c.cout, sc, sh, residual, relu,
                                                                    accumulate, out_feat);
     CK_LAUNCH();
     return MT_OK;
   }
-  if (!no_mma && in_feat && have_map && c.cin % 8 == 0 && c.cout % 16 == 0) {
+  if (!no_mma && in_feat && have_map && c.cin % 16 == 0 && c.cout % 16 == 0) {
     const int mtiles = (nmax + 15) / 16;
     const int kvol = map ? c.kvol : 1;
     if (c.cout % 32 == 0 && (long long)mtiles * (c.cout / 16) > 4096) {  // many tiles: wider slabs, fewer re-reads of the gathered rows
       const long long warps = (long long)mtiles * (c.cout / 32);
-      k_tcn_conv_mma<4><<<(unsigned)((warps + 3) / 4), 128, 0, st>>>(map, hitmask, kvol, d_nout, in_feat, c.cin, c.w, c.cout, sc, sh, residual,
+      tcn_launch(k_tcn_conv_mma<4>, (unsigned)((warps + 3) / 4), 128, st, map, hitmask, kvol, d_nout, in_feat, c.cin, c.wt, c.cout, sc, sh, residual,
                                                                    relu, accumulate, out_feat);
     } else {
       const long long warps = (long long)mtiles * (c.cout / 16);
-      k_tcn_conv_mma<2><<<(unsigned)((warps + 3) / 4), 128, 0, st>>>(map, hitmask, kvol, d_nout, in_feat, c.cin, c.w, c.cout, sc, sh, residual,
+      tcn_launch(k_tcn_conv_mma<2>, (unsigned)((warps + 3) / 4), 128, st, map, hitmask, kvol, d_nout, in_feat, c.cin, c.wt, c.cout, sc, sh, residual,
                                                                    relu, accumulate, out_feat);
     }
     CK_LAUNCH();
@@ -923,13 +967,13 @@ static int tcn_conv_launch(mt_tcn* t, int mode, int conv_id, int bn_id, const un
   const bool split = in_feat != nullptr && c.cin >= 32;
   const unsigned grid = (unsigned)(split ? (nmax + 1) / 2 : (nmax + 7) / 8);
   if (mode == 0 && split)
-    k_tcn_conv<0, 4><<<grid, 256, 0, st>>>(out_keys, d_nout, in_tab, in_feat, c.cin, c.w, c.cout, k, dil, sc, sh, residual, relu, accumulate, out_feat);
+    tcn_launch(k_tcn_conv<0, 4>, grid, 256, st, out_keys, d_nout, in_tab, in_feat, c.cin, c.w, c.cout, k, dil, sc, sh, residual, relu, accumulate, out_feat);
   else if (mode == 0)
-    k_tcn_conv<0, 1><<<grid, 256, 0, st>>>(out_keys, d_nout, in_tab, in_feat, c.cin, c.w, c.cout, k, dil, sc, sh, residual, relu, accumulate, out_feat);
+    tcn_launch(k_tcn_conv<0, 1>, grid, 256, st, out_keys, d_nout, in_tab, in_feat, c.cin, c.w, c.cout, k, dil, sc, sh, residual, relu, accumulate, out_feat);
   else if (split)
-    k_tcn_conv<1, 4><<<grid, 256, 0, st>>>(out_keys, d_nout, in_tab, in_feat, c.cin, c.w, c.cout, k, dil, sc, sh, residual, relu, accumulate, out_feat);
+    tcn_launch(k_tcn_conv<1, 4>, grid, 256, st, out_keys, d_nout, in_tab, in_feat, c.cin, c.w, c.cout, k, dil, sc, sh, residual, relu, accumulate, out_feat);
   else
-    k_tcn_conv<1, 1><<<grid, 256, 0, st>>>(out_keys, d_nout, in_tab, in_feat, c.cin, c.w, c.cout, k, dil, sc, sh, residual, relu, accumulate, out_feat);
+    tcn_launch(k_tcn_conv<1, 1>, grid, 256, st, out_keys, d_nout, in_tab, in_feat, c.cin, c.w, c.cout, k, dil, sc, sh, residual, relu, accumulate, out_feat);
   CK_LAUNCH();
   return MT_OK;
 }
@@ -949,20 +993,20 @@ static int tcn_run(mt_tcn* t, const float* d_pts, const unsigned long long* d_ke
   for (int l = 0; l < 4; ++l) T.t[l] = t->tab[l];
   int* d_flag = t->d_n + 4;
   const int nblk = (n + 1023) / 1024, stride = t->max_points;
-  k_tcn_clear_all<<<(t->cap + 255) / 256, 256, 0, st>>>(T, t->d_n);
+  tcn_launch(k_tcn_clear_all, (t->cap + 255) / 256, 256, st, T, t->d_n);
   CK_LAUNCH();
-  k_tcn_insert_all<<<(4 * n + 255) / 256, 256, 0, st>>>(d_pts, d_keys, n, P, inv_q, T, t->slot_of, stride, d_flag);
+  tcn_launch(k_tcn_insert_all, (4 * n + 255) / 256, 256, st, d_pts, d_keys, n, P, inv_q, T, t->slot_of, stride, d_flag);
   CK_LAUNCH();
-  k_tcn_count_all<<<nblk, 1024, 0, st>>>(n, T, t->slot_of, stride, t->blk_cnt, nblk);
+  tcn_launch(k_tcn_count_all, nblk, 1024, st, n, T, t->slot_of, stride, t->blk_cnt, nblk);
   CK_LAUNCH();
-  k_tcn_scatter_all<<<nblk, 1024, 0, st>>>(n, T, t->slot_of, stride, t->blk_cnt, nblk, t->keys[0], t->keys[1], t->keys[2], t->keys[3], t->d_n);
+  tcn_launch(k_tcn_scatter_all, nblk, 1024, st, n, T, t->slot_of, stride, t->blk_cnt, nblk, t->keys[0], t->keys[1], t->keys[2], t->keys[3], t->d_n);
   CK_LAUNCH();
   TcnMaps M;
   memset(&M, 0, sizeof(M));
   for (int l = 1; l < 4; ++l) M.m3[l] = t->kmap3[l], M.m2[l] = t->kmap2[l], M.q3[l] = t->kmask3[l], M.q2[l] = t->kmask2[l];
   M.mt = t->kmapt, M.qt = t->kmaskt, M.ncap = t->max_points;
   for (int m = 0; m < 7; ++m) M.pl[m] = t->plist[m], M.pb[m] = t->pbase[m];
-  k_tcn_kmaps<<<dim3((n + 7) / 8, 3), 256, 0, st>>>(T, t->keys[1], t->keys[2], t->keys[3], t->d_n, M);
+  tcn_launch(k_tcn_kmaps, dim3((n + 7) / 8, 3), 256, st, T, t->keys[1], t->keys[2], t->keys[3], t->d_n, M);
   CK_LAUNCH();
   // feature buffers carved from the pool (upper bound n rows each)
   float* ptr = t->pool;
@@ -976,7 +1020,7 @@ static int tcn_run(mt_tcn* t, const float* d_pts, const unsigned long long* d_ke
     int k0 = 1;
     while (k0 * k0 * k0 < cv.kvol) ++k0;
     if (cv.cin == 1 && (k0 & 1) && k0 * k0 * k0 == cv.kvol && cv.kvol <= 128 && t->bn[TCN_BN0].scale && t->bn[TCN_BN0].c == cv.cout) {
-      k_tcn_conv0<<<(n + 7) / 8, 256, 0, st>>>(t->keys[0], t->d_n, t->tab[0], cv.w, cv.cout, k0, t->bn[TCN_BN0].scale, t->bn[TCN_BN0].shift, x0);
+      tcn_launch(k_tcn_conv0, (n + 7) / 8, 256, st, t->keys[0], t->d_n, t->tab[0], cv.w, cv.cout, k0, t->bn[TCN_BN0].scale, t->bn[TCN_BN0].shift, x0);
       CK_LAUNCH();
     } else {
       TCN_RUN(tcn_conv_launch(t, 0, TCN_CONV0, TCN_BN0, t->keys[0], t->d_n, n, t->tab[0], nullptr, k0, 1, nullptr, nullptr, -1, nullptr, 1, 0, x0, st));
@@ -1015,9 +1059,9 @@ static int tcn_run(mt_tcn* t, const float* d_pts, const unsigned long long* d_ke
   TCN_RUN(tcn_conv_launch(t, 1, TCN_TCONV, -1, t->keys[2], t->d_n + 2, n, t->tab[3], z, 2, 4, t->kmapt, t->kmaskt, 6, nullptr, 0, 1, fp, st));
 #undef TCN_RUN
   const int slices = ((long long)batch * 256 <= t->gem_slices) ? 256 : TCN_GEM_SLICES;
-  k_tcn_gem_partial<<<dim3(batch, slices), 256, 0, st>>>(t->d_n, fp, f, t->gem_p, t->gem_eps, t->gem_part);
+  tcn_launch(k_tcn_gem_partial, dim3(batch, slices), 256, st, t->d_n, fp, f, t->gem_p, t->gem_eps, t->gem_part);
   CK_LAUNCH();
-  k_tcn_gem<<<batch, 1024, 0, st>>>(t->d_n, t->gem_part, slices, f, t->gem_p, normalize, d_out);
+  tcn_launch(k_tcn_gem, batch, 1024, st, t->d_n, t->gem_part, slices, f, t->gem_p, normalize, d_out);
   CK_LAUNCH();
   if (d_counts) CK(cudaMemcpyAsync(d_counts, t->d_n, sizeof(int) * 4, cudaMemcpyDeviceToDevice, st));
   return MT_OK;

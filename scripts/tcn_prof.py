@@ -8,7 +8,8 @@ from midastouch_b200._lib import call, ptr, stream_ptr
 from midastouch_b200.tcn import pack_coordinates
 
 dev = torch.device("cuda:0")
-out = {"embed_clouds_ms": bench.tcn_time(dev, reps=50)}
+quick = bool(os.environ.get("TCN_NO_KINETO"))  # under ncu: a few forwards only
+out = {"embed_clouds_ms": bench.tcn_time(dev, reps=2 if quick else 50)}
 tcn, cloud = bench.tcn_time.last  # (set by tcn_time)
 
 
@@ -27,6 +28,9 @@ def ev_time(fn, reps=50):
     return {"device_ms": e0.elapsed_time(e1) / reps, "host_issue_ms": (t1 - t0) * 1e3 / reps}
 
 
+if quick:
+    print(json.dumps(out))
+    sys.exit(0)
 out["embed_clouds"] = ev_time(lambda: tcn.embed_clouds(cloud))
 if True:
     B, Pn, _ = cloud.shape
