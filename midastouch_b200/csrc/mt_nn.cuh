@@ -14,7 +14,7 @@
 //     Rotation vectors flip sign at angle pi, so a pose that was matched to key h can jump
 //     2*pi*w away from it in key space; keys within 0.35 rad of pi therefore carry a
 //     "partner" (the key nearest to their antipodal image) which is tried as the centre too.
-//  2. box-hierarchy search (one warp per query): the keys in 6-D Morton order, leaves of 32
+//  2. box-hierarchy search (one warp per query): the keys in k-d tree leaf order, leaves of 32
 //     keys and two 32-ary levels of bounding boxes (all six coordinates) above them; the
 //     lanes evaluate the bounds of 32 siblings at once and the warp descends best-first until
 //     no remaining box can hold a key as close as the best one found.
@@ -35,18 +35,18 @@
 #define MT_NBR_K 64  // neighbours per key and build pass (the build kernel keeps two per lane); lists are 1, 2 or 4 passes long
 #define MT_NBR_K_MAX 256
 
-// Search index of the fallback path: the keys in 6-D Morton order, 32 consecutive keys per leaf, and two
+// Search index of the fallback path: the keys in the leaf order of a balanced k-d tree, 32 consecutive keys per leaf, and two
 // levels of 32-ary inner nodes above the leaves; every node stores its axis-aligned bounding box in all six
 // key coordinates (12 floats = 3 float4: lo0..lo3 | lo4,lo5,hi0,hi1 | hi2..hi5).
 struct BvhParams {
   int n_leaf, n_l1, n_l2;
-  float cell;  // Morton cell edge (diagnostic)
+  float cell;  // largest key extent / 1023 (diagnostic)
 };
 
 #if defined(__CUDACC__)
 struct NNTables {
   const float4* keys_orig;    // M x 2 float4 (k0..k3 | k4,k5,partner bits,delta_0), original order
-  const float4* keys_sorted;  // M x 2 float4 (k0..k3 | k4,k5,original index bits,0), 6-D Morton order
+  const float4* keys_sorted;  // M x 2 float4 (k0..k3 | k4,k5,original index bits,0), k-d tree leaf order
   const float4* bvh_leaf;     // n_leaf x 3 float4
   const float4* bvh_l1;       // n_l1 x 3 float4 (node j covers leaves 32j .. 32j+31)
   const float4* bvh_l2;       // n_l2 x 3 float4 (node j covers level-1 nodes 32j .. 32j+31)
@@ -130,10 +130,10 @@ MT_HD bool mt_box_may_hold(float bound, float best_d) { return bound * 0.9999f <
 #include <algorithm>
 #include <numeric>
 #include <vector>
-// Host side of the search index (mt_codebook_upload): 6-D Morton order, leaves of 32 keys, two 32-ary levels.
+// Host side of the search index (mt_codebook_upload): k-d tree leaf order, leaves of 32 keys, two 32-ary levels.
 struct MtBvhHost {
   BvhParams bp;
-  std::vector<int> order;             // order[j] = original index of the j-th key in Morton order
+  std::vector<int> order;             // order[j] = original index of the j-th key in leaf (k-d tree) order
   std::vector<float> keys_sorted;     // M x 8 floats: key, original index bits, 0
   std::vector<float> leaf, l1, l2;    // 12 floats per node
 };
@@ -150,22 +150,46 @@ inline bool mt_bvh_build(const float* h_keys, int M, MtBvhHost& out) {
   float maxext = 0.f;
   for (int k = 0; k < 6; ++k) maxext = std::max(maxext, hi[k] - lo[k]);
   if (!(maxext > 0.f) || !(maxext <= FLT_MAX)) maxext = 1e-3f;
-  const float cell = maxext / 1023.f;  // the same cell edge in every coordinate: Morton cells are cubes
-  std::vector<unsigned long long> code(M);
-  for (int m = 0; m < M; ++m) {
-    unsigned long long cd = 0;
-    unsigned qk[6];
-    for (int k = 0; k < 6; ++k) {
-      const float f = floorf((h_keys[6 * m + k] - lo[k]) / cell);
-      qk[k] = (f < 0.f) ? 0u : (f > 1023.f ? 1023u : (unsigned)f);
-    }
-    for (int bit = 9; bit >= 0; --bit)
-      for (int k = 0; k < 6; ++k) cd = (cd << 1) | ((qk[k] >> bit) & 1u);
-    code[m] = cd;
-  }
+  const float cell = maxext / 1023.f;  // (diagnostic only)
+  // Order = leaves of a balanced k-d tree: a range of keys is split at the median of its widest coordinate until 32
+  // keys are left; the left part always holds a multiple of the node size of its level (32 keys below 1024, 1024 below
+  // 32768, ...), so leaves, level-1 and level-2 nodes are whole subtrees with disjoint, tight boxes.  (Round 1 sorted
+  // by a 6-D Morton code: a run of 32 consecutive codes straddles cell boundaries of every level, and on the curved
+  // key manifold of a real codebook its bounding box is several times larger -- measured on the stand-ins, leaves a
+  // search has to open with a perfect seed: cotter pin 13.7 -> 4.7, drill 5.9 -> 2.7, worst case 102 -> 47 / 33 -> 15.)
+  // Ties in a coordinate are broken by the index, so the partition is unique; leaves are stored in index order.
   out.order.resize(M);
   std::iota(out.order.begin(), out.order.end(), 0);
-  std::stable_sort(out.order.begin(), out.order.end(), [&](int a, int b) { return code[a] < code[b]; });
+  {
+    std::vector<std::pair<int, int>> todo;  // [begin, end)
+    todo.emplace_back(0, M);
+    while (!todo.empty()) {
+      const int a = todo.back().first, b = todo.back().second, n = b - a;
+      todo.pop_back();
+      if (n <= 32) {
+        std::sort(out.order.begin() + a, out.order.begin() + b);
+        continue;
+      }
+      float klo[6], khi[6];
+      for (int k = 0; k < 6; ++k) klo[k] = FLT_MAX, khi[k] = -FLT_MAX;
+      for (int j = a; j < b; ++j)
+        for (int k = 0; k < 6; ++k) {
+          const float v = h_keys[6 * (size_t)out.order[j] + k];
+          klo[k] = std::min(klo[k], v), khi[k] = std::max(khi[k], v);
+        }
+      int dim = 0;
+      for (int k = 1; k < 6; ++k)
+        if (khi[k] - klo[k] > khi[dim] - klo[dim]) dim = k;
+      const int unit = n <= 1024 ? 32 : (n <= 32768 ? 1024 : (n <= 1048576 ? 32768 : 1048576));
+      const int nl = ((n + unit - 1) / unit / 2) * unit;  // >= unit: n > unit here
+      std::nth_element(out.order.begin() + a, out.order.begin() + a + nl, out.order.begin() + b, [&](int x, int y) {
+        const float vx = h_keys[6 * (size_t)x + dim], vy = h_keys[6 * (size_t)y + dim];
+        return vx < vy || (vx == vy && x < y);
+      });
+      todo.emplace_back(a + nl, b);
+      todo.emplace_back(a, a + nl);
+    }
+  }
   out.keys_sorted.assign(8 * (size_t)M, 0.f);
   for (int m = 0; m < M; ++m) {
     for (int k = 0; k < 6; ++k) out.keys_sorted[8 * (size_t)m + k] = h_keys[6 * (size_t)out.order[m] + k];
@@ -325,6 +349,11 @@ __device__ __forceinline__ int nn_hint_scan(const NNTables& T, const float q[6],
   // exit tests.  Two register sets (x*, y*) alternate between "being evaluated" and "in flight".
   float4 xa0 = mt_ldnc(L + 2 * j0), xb0 = mt_ldnc(L + 2 * j0 + 1), xa1 = mt_ldnc(L + 2 * j0 + 2), xb1 = mt_ldnc(L + 2 * j0 + 3);
   float4 ya0, yb0, ya1, yb1;
+  // (64-entry lists -- sparse codebooks, where an inconclusive scan is a 1-in-2000 event -- keep the plain loop: there
+  // the test would only add instructions to every trip)
+  [[maybe_unused]] const int jbail = T.K > MT_NBR_K ? 8 : INT_MAX;
+  [[maybe_unused]] float dlast = FLT_MAX;
+  if (T.K > MT_NBR_K) dlast = mt_ldnc(L + 2 * (T.K - 1) + 1).z;  // delta of the list's last entry (requested with the first trip)
 #if MT_FAST_SCAN
 #define MT_SCAN_DONE(r)                                                    \
   {                                                                        \
@@ -342,8 +371,16 @@ __device__ __forceinline__ int nn_hint_scan(const NNTables& T, const float q[6],
 // the stop bound only ever shrinks, so it may lag: it is refreshed once per pair of entries, unconditionally
 // (three instructions per pair instead of four predicated ones per entry)
 #define MT_SCAN_LIMIT() lim = mt_hint_limit_dev(dh, __uint_as_float((unsigned)(bw >> 32)));
+// Hopeless scans leave early: the list certifies the answer only if its last delta exceeds d_h + sqrt(best); once 12
+// entries have been seen (a decent seed for the box search) a scan whose bound would still be beyond the end of the
+// list even if `best` halved is handed to the queue right away instead of walking the whole list first.  (A wrong
+// guess costs a box search, never the result.)  On dense codebooks (256-entry lists, 30 % of the scans inconclusive)
+// every warp used to walk all 64 trips for its hopeless lanes.
+#define MT_SCAN_BAIL()                                                                                          \
+  if (j >= jbail && fmaf(0.7071f, mt_sqrt_fast(__uint_as_float((unsigned)(bw >> 32))), dh) > dlast) MT_SCAN_DONE(0)
 #else
 #define MT_SCAN_LIMIT()
+#define MT_SCAN_BAIL()
 #define MT_SCAN_DONE(r) return r;
 #define MT_SCAN_ENTRY(A, B)                                                                             \
   {                                                                                                     \
@@ -365,8 +402,10 @@ __device__ __forceinline__ int nn_hint_scan(const NNTables& T, const float q[6],
     MT_SCAN_ENTRY(ya0, yb0)
     MT_SCAN_ENTRY(ya1, yb1)
     MT_SCAN_LIMIT()
+    MT_SCAN_BAIL()
   }
   MT_SCAN_DONE(0)
+#undef MT_SCAN_BAIL
 #undef MT_SCAN_ENTRY
 #undef MT_SCAN_DONE
 #undef MT_SCAN_LIMIT
