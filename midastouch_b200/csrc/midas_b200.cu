@@ -1668,7 +1668,8 @@ __device__ __forceinline__ void nnq_load(const StepDev& p, const MeshTables& Mh,
 // Both kernels are chains of dependent memory round trips (count -> entry -> point -> tables -> match), ~1.2 us each,
 // with next to no arithmetic: the first trip's entry is therefore requested before the count is known (a stale or
 // uninitialised entry is clamped to a valid particle and dropped once the count has arrived), and the particle's point
-// and stored match are requested together.
+// and stored match are requested together.  (Doing the grid search of the left-over quarter right inside k_step_meshq, one
+// thread per entry, instead of compacting it for the warp-per-entry kernel: 55 us against 12.5 + 2.3 + 12 us.)
 __device__ __forceinline__ void mesh_mark_off(const StepDev& p, long long i, int stored) {
   if (stored >= 0) p.nn_cur[i] = nn_masked(stored);  // (nobody else touches a queued particle's match meanwhile)
   atomicSub(p.wcnt + (i >> 5), 1);

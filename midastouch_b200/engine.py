@@ -157,7 +157,7 @@ class FilterEngine:
     def load_particles(self, poses: torch.Tensor, nn_hint: torch.Tensor | None = None, spatial_sort: bool = False):
         """poses: (n,4,4) CUDA.  nn_hint: optional codebook index per particle (any valid index is
         correct; a good one makes the first search cheap).  spatial_sort=True reorders the
-        particles by the 6-D Morton rank of their codebook match so that neighbouring threads walk
+        particles by the rank of their codebook match in the search index (k-d tree leaf order) so that neighbouring threads walk
         neighbouring keys (systematic resampling preserves the order afterwards); the applied
         permutation is returned (poses[perm] is what the engine holds), else None."""
         require_cuda(poses, "poses")
