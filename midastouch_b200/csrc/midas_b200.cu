@@ -1588,7 +1588,7 @@ __global__ void __launch_bounds__(MT_A_BLOCK, MT_A_MINBLOCKS) k_step_a(StepDev p
     float bd, dh;
     int bi, centre;
     int st = nn_hint_begin(T, key, hint, bd, bi, centre, dh);
-    if (st == 0) st = nn_hint_scan(T, key, centre, dh, 0, T.K, bd, bi);
+    if (st == 0) st = nn_hint_scan_all(T, key, centre, dh, bd, bi);
     if (st <= 0) todo |= MT_Q_NN;  // no usable hint, or the list is exhausted: box-hierarchy search
     if (bi == INT_MAX) bi = -1;  // no usable hint
     const bool masked = !on_surface || invalid;

@@ -334,26 +334,27 @@ __device__ __forceinline__ int nn_hint_begin(const NNTables& T, const float q[6]
 #endif
 }
 
-__device__ __forceinline__ int nn_hint_scan(const NNTables& T, const float q[6], int centre, float dh, int j0, int j1, float& best_d,
-                                            int& best_i) {
+template <bool BAIL>  // BAIL: long-list codebooks (T.K > MT_NBR_K), see MT_SCAN_BAIL
+__device__ __forceinline__ int nn_hint_scan_t(const NNTables& T, const float q[6], int centre, float dh, int j0, int j1, float& best_d,
+                                              int& best_i) {
 #if MT_FAST_SCAN
   float lim = mt_hint_limit_dev(dh, best_d);
   unsigned long long bw = mt_dist_word(best_d, best_i);
 #else
   float lim = mt_hint_limit(dh, best_d);
 #endif
-  const float4* __restrict__ L = T.nbr + (size_t)centre * (2 * T.K);
+  const int K = BAIL ? T.K : MT_NBR_K;  // (!BAIL <=> T.K == MT_NBR_K: the list stride and the loop bounds are constants then)
+  const float4* __restrict__ L = T.nbr + (size_t)centre * (2 * K);
   // Software pipeline: the two entries of the next half trip are requested before the current ones are evaluated, so
   // a trip waits for loads issued ~40 instructions (x the other resident warps) earlier.  The loads are volatile asm
   // (plain ld.global.nc underneath, i.e. cached in L1 like __ldg) so that neither NVVM nor ptxas sinks them below the
   // exit tests.  Two register sets (x*, y*) alternate between "being evaluated" and "in flight".
   float4 xa0 = mt_ldnc(L + 2 * j0), xb0 = mt_ldnc(L + 2 * j0 + 1), xa1 = mt_ldnc(L + 2 * j0 + 2), xb1 = mt_ldnc(L + 2 * j0 + 3);
   float4 ya0, yb0, ya1, yb1;
-  // (64-entry lists -- sparse codebooks, where an inconclusive scan is a 1-in-2000 event -- keep the plain loop: there
-  // the test would only add instructions to every trip)
-  [[maybe_unused]] const int jbail = T.K > MT_NBR_K ? 8 : INT_MAX;
+  // (64-entry lists -- sparse codebooks, where an inconclusive scan is a 1-in-2000 event -- run the plain loop, BAIL =
+  // false: there the test only added instructions to every trip, +1.6 us on the drill)
   [[maybe_unused]] float dlast = FLT_MAX;
-  if (T.K > MT_NBR_K) dlast = mt_ldnc(L + 2 * (T.K - 1) + 1).z;  // delta of the list's last entry (requested with the first trip)
+  if (BAIL) dlast = mt_ldnc(L + 2 * (K - 1) + 1).z;  // delta of the list's last entry (requested with the first trip)
 #if MT_FAST_SCAN
 #define MT_SCAN_DONE(r)                                                    \
   {                                                                        \
@@ -377,7 +378,7 @@ __device__ __forceinline__ int nn_hint_scan(const NNTables& T, const float q[6],
 // guess costs a box search, never the result.)  On dense codebooks (256-entry lists, 30 % of the scans inconclusive)
 // every warp used to walk all 64 trips for its hopeless lanes.
 #define MT_SCAN_BAIL()                                                                                          \
-  if (j >= jbail && fmaf(0.7071f, mt_sqrt_fast(__uint_as_float((unsigned)(bw >> 32))), dh) > dlast) MT_SCAN_DONE(0)
+  if (BAIL && j >= 8 && fmaf(0.7071f, mt_sqrt_fast(__uint_as_float((unsigned)(bw >> 32))), dh) > dlast) MT_SCAN_DONE(0)
 #else
 #define MT_SCAN_LIMIT()
 #define MT_SCAN_BAIL()
@@ -397,7 +398,7 @@ __device__ __forceinline__ int nn_hint_scan(const NNTables& T, const float q[6],
     MT_SCAN_ENTRY(xa0, xb0)
     MT_SCAN_ENTRY(xa1, xb1)
     MT_SCAN_LIMIT()
-    const int jn = min(j + 4, T.K - 2);  // past the end of the list: a harmless re-read, never used
+    const int jn = min(j + 4, K - 2);  // past the end of the list: a harmless re-read, never used
     xa0 = mt_ldnc(L + 2 * jn), xb0 = mt_ldnc(L + 2 * jn + 1), xa1 = mt_ldnc(L + 2 * jn + 2), xb1 = mt_ldnc(L + 2 * jn + 3);
     MT_SCAN_ENTRY(ya0, yb0)
     MT_SCAN_ENTRY(ya1, yb1)
@@ -411,12 +412,23 @@ __device__ __forceinline__ int nn_hint_scan(const NNTables& T, const float q[6],
 #undef MT_SCAN_LIMIT
 }
 
+__device__ __forceinline__ int nn_hint_scan(const NNTables& T, const float q[6], int centre, float dh, int j0, int j1, float& best_d,
+                                            int& best_i) {
+  return T.K > MT_NBR_K ? nn_hint_scan_t<true>(T, q, centre, dh, j0, j1, best_d, best_i)
+                        : nn_hint_scan_t<false>(T, q, centre, dh, j0, j1, best_d, best_i);
+}
+// the whole list
+__device__ __forceinline__ int nn_hint_scan_all(const NNTables& T, const float q[6], int centre, float dh, float& best_d, int& best_i) {
+  return T.K > MT_NBR_K ? nn_hint_scan_t<true>(T, q, centre, dh, 0, T.K, best_d, best_i)
+                        : nn_hint_scan_t<false>(T, q, centre, dh, 0, MT_NBR_K, best_d, best_i);
+}
+
 __device__ __forceinline__ bool nn_hint_search(const NNTables& T, const float q[6], int hint, float& best_d, int& best_i) {
   int centre;
   float dh;
   const int st = nn_hint_begin(T, q, hint, best_d, best_i, centre, dh);
   if (st) return st > 0;
-  return nn_hint_scan(T, q, centre, dh, 0, T.K, best_d, best_i) != 0;
+  return nn_hint_scan_all(T, q, centre, dh, best_d, best_i) != 0;
 }
 
 // bound of one node (3 float4 = lo[6] | hi[6])

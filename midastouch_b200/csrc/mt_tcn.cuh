@@ -88,7 +88,7 @@ struct mt_tcn {
   float* partial;          // partial sums of the pair GEMM: one row of cout floats per pair
   size_t partial_floats;
   int* slot_of;            // 4 x max_points: hash slot of raw point i at level l
-  int* blk_cnt;            // 4 x ceil(max_points / 1024): first-point counts per block (ordered compaction)
+  int* blk_cnt;            // 4 x ceil(max_points / TCN_CBLOCK): first-point counts per block (ordered compaction)
   int* kmap3[4];           // level 1..3: n x 27 rows of the 3x3x3 neighbourhood (dilation = level stride)
   int* kmap2[4];           // level 1..3: n x 8 rows of the children at level l - 1
   int* kmapt;              // level 2: n x 8, the parent's row at level 3 in column "position inside the parent"
@@ -206,12 +206,15 @@ __global__ void __launch_bounds__(256) k_tcn_insert_all(const float* __restrict_
   slot_of[(size_t)l * stride + i] = (int)s;
 }
 
-// ordered compaction, pass 1: first points (the representative of their key) per block of 1024 raw points and level
-__global__ void __launch_bounds__(1024) k_tcn_count_all(int n_raw, TcnTabs T, const int* __restrict__ slot_of, int stride,
+// ordered compaction, pass 1: first points (the representative of their key) per block of TCN_CBLOCK raw points and level.
+// (Blocks of 256, not 1024: one frame is 4096 raw points, and four blocks of 1024 threads put 4096 dependent look-ups
+// per level on each of only four SMs -- more than their load queues hold: 10.5 us for the second pass.)
+#define TCN_CBLOCK 256
+__global__ void __launch_bounds__(TCN_CBLOCK) k_tcn_count_all(int n_raw, TcnTabs T, const int* __restrict__ slot_of, int stride,
                                                         int* __restrict__ blk_cnt, int nblk) {
   tcn_pdl();
-  __shared__ int s_w[4][32];
-  const int i = blockIdx.x * 1024 + threadIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  __shared__ int s_w[4][TCN_CBLOCK / 32];
+  const int i = blockIdx.x * TCN_CBLOCK + threadIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 #pragma unroll
   for (int l = 0; l < 4; ++l) {
     const bool f = i < n_raw && T.t[l].vals[slot_of[(size_t)l * stride + i]] == i;
@@ -221,20 +224,21 @@ __global__ void __launch_bounds__(1024) k_tcn_count_all(int n_raw, TcnTabs T, co
   __syncthreads();
   if (threadIdx.x < 4) {
     int c = 0;
-    for (int k = 0; k < 32; ++k) c += s_w[threadIdx.x][k];
+    for (int k = 0; k < TCN_CBLOCK / 32; ++k) c += s_w[threadIdx.x][k];
     blk_cnt[threadIdx.x * nblk + blockIdx.x] = c;
   }
 }
 // pass 2: row = number of first points before this one; writes the level's keys, the key's row and the level counts
-__global__ void __launch_bounds__(1024) k_tcn_scatter_all(int n_raw, TcnTabs T, const int* __restrict__ slot_of, int stride,
+__global__ void __launch_bounds__(TCN_CBLOCK) k_tcn_scatter_all(int n_raw, TcnTabs T, const int* __restrict__ slot_of, int stride,
                                                           const int* __restrict__ blk_cnt, int nblk,
                                                           unsigned long long* __restrict__ k0, unsigned long long* __restrict__ k1,
                                                           unsigned long long* __restrict__ k2, unsigned long long* __restrict__ k3,
                                                           int* __restrict__ d_n) {
   tcn_pdl();
-  __shared__ int s_w[4][32];
+  __shared__ int s_w[4][TCN_CBLOCK / 32];
   __shared__ int s_carry[4];
-  const int i = blockIdx.x * 1024 + threadIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int i = blockIdx.x * TCN_CBLOCK + threadIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  static_assert(TCN_CBLOCK >= 128, "four warps compute the carries");
   if (w < 4) {  // warp l: first points of level l in the blocks before this one
     int c = 0;
     for (int bq = lane; bq < (int)blockIdx.x; bq += 32) c += blk_cnt[w * nblk + bq];
@@ -269,7 +273,7 @@ __global__ void __launch_bounds__(1024) k_tcn_scatter_all(int n_raw, TcnTabs T, 
         atomicMin(d_n + TCN_CTL_BLO + bq, row), atomicMax(d_n + TCN_CTL_BHI + bq, row + 1);
       }
     }
-    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 1023) d_n[l] = base + s_w[l][31];
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == TCN_CBLOCK - 1) d_n[l] = base + s_w[l][TCN_CBLOCK / 32 - 1];
   }
 }
 
@@ -767,7 +771,8 @@ __global__ void __launch_bounds__(256) k_tcn_gem_partial(const int* __restrict__
   for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
     double acc = 0.0;
 #pragma unroll 4
-    for (int r = s0; r < s1; ++r) acc += (double)powf(fmaxf(__ldg(feat + (size_t)r * c + ch), eps), p);
+    for (int r = s0; r < s1; ++r)  // x^p = 2^(p log2 x), x >= eps > 0: two MUFU operations (~1e-6 relative on the terms that matter)
+      acc += (double)exp2f(p * __log2f(fmaxf(__ldg(feat + (size_t)r * c + ch), eps)));
     part[((size_t)blockIdx.x * slices + blockIdx.y) * c + ch] = acc;
   }
 }
@@ -843,7 +848,7 @@ extern "C" int mt_tcn_create(int device, int max_points, int max_batch, mt_tcn**
   t->partial_floats = (size_t)max_points * 2048;  // 27 offsets x 64 channels / 8 offsets x 256 channels per point
   CK(cudaMalloc(&t->partial, sizeof(float) * t->partial_floats));
   CK(cudaMalloc(&t->slot_of, sizeof(int) * 4 * (size_t)max_points));
-  CK(cudaMalloc(&t->blk_cnt, sizeof(int) * 4 * (size_t)((max_points + 1023) / 1024)));
+  CK(cudaMalloc(&t->blk_cnt, sizeof(int) * 4 * (size_t)((max_points + 255) / 256)));
   t->pool_floats = (size_t)max_points * 1184;
   CK(cudaMalloc(&t->pool, sizeof(float) * t->pool_floats));
   t->gem_slices = max_batch * TCN_GEM_SLICES > 256 ? max_batch * TCN_GEM_SLICES : 256;  // rows of the partial-sum buffer
@@ -992,14 +997,14 @@ static int tcn_run(mt_tcn* t, const float* d_pts, const unsigned long long* d_ke
   TcnTabs T;
   for (int l = 0; l < 4; ++l) T.t[l] = t->tab[l];
   int* d_flag = t->d_n + 4;
-  const int nblk = (n + 1023) / 1024, stride = t->max_points;
+  const int nblk = (n + TCN_CBLOCK - 1) / TCN_CBLOCK, stride = t->max_points;
   tcn_launch(k_tcn_clear_all, (t->cap + 255) / 256, 256, st, T, t->d_n);
   CK_LAUNCH();
   tcn_launch(k_tcn_insert_all, (4 * n + 255) / 256, 256, st, d_pts, d_keys, n, P, inv_q, T, t->slot_of, stride, d_flag);
   CK_LAUNCH();
-  tcn_launch(k_tcn_count_all, nblk, 1024, st, n, T, t->slot_of, stride, t->blk_cnt, nblk);
+  tcn_launch(k_tcn_count_all, nblk, TCN_CBLOCK, st, n, T, t->slot_of, stride, t->blk_cnt, nblk);
   CK_LAUNCH();
-  tcn_launch(k_tcn_scatter_all, nblk, 1024, st, n, T, t->slot_of, stride, t->blk_cnt, nblk, t->keys[0], t->keys[1], t->keys[2], t->keys[3], t->d_n);
+  tcn_launch(k_tcn_scatter_all, nblk, TCN_CBLOCK, st, n, T, t->slot_of, stride, t->blk_cnt, nblk, t->keys[0], t->keys[1], t->keys[2], t->keys[3], t->d_n);
   CK_LAUNCH();
   TcnMaps M;
   memset(&M, 0, sizeof(M));
