@@ -150,6 +150,15 @@ class FilterEngine:
             ok.zero_()
         dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)  # all ranks take the same path
         self.peer_exchange = bool(ok.item())
+        # rebalance() moves particles with an all-to-all: NCCL sets its point-to-point channels up on first use
+        # (hundreds of milliseconds); do that here, at set-up time, not in the middle of a run (step 64)
+        try:
+            for elems in (1, 1 << 18):  # a tiny and a 1 MB-per-peer message: both protocols' buffers get set up
+                one = torch.zeros(self.world * elems, dtype=torch.float32, device=self.dev)
+                dist.all_to_all_single(torch.empty_like(one), one, group=self.group)
+            torch.cuda.synchronize(self.dev)
+        except RuntimeError:  # a backend without all-to-all: rebalance() will say so when it is needed
+            pass
         self._ctx_gen = self.ctx.generation
         return self.peer_exchange
 
