@@ -123,6 +123,15 @@ int h_bvh_search(const float* keys, long long M, const float* q, long long n, co
   }
   return 0;
 }
+// leaf order and boxes of the search index: order (M), leaf boxes (n_leaf x 12), level-1 boxes (n_l1 x 12)
+int h_bvh_layout(const float* keys, long long M, int* order, float* leaf, float* l1) {
+  MtBvhHost B;
+  if (!mt_bvh_build(keys, (int)M, B)) return -1;
+  for (long long m = 0; m < M; ++m) order[m] = B.order[m];
+  for (size_t k = 0; k < B.leaf.size(); ++k) leaf[k] = B.leaf[k];
+  for (size_t k = 0; k < B.l1.size(); ++k) l1[k] = B.l1[k];
+  return 0;
+}
 // categorical draws from an inclusive CDF (mt_cdf_draw) with the uniforms the kernel would use
 void h_cdf_draws(const double* C, long long n, double S, unsigned long long seed, unsigned long long stream_id, long long n_draws,
                  int* idx, double* u_out) {

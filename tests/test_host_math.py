@@ -252,6 +252,51 @@ def test_box_hierarchy_search_is_exact(H):
     assert H.h_bvh_search(P(bad), ctypes.c_longlong(M), P(q), ctypes.c_longlong(1), P(np.full(1, -1, dtype=np.int32)), P(idx2), P(vis2), P(dims)) == -1
 
 
+def test_search_index_is_a_kd_tree_layout(H):
+    """mt_bvh_build orders the keys as the leaves of a balanced k-d tree (median split of the widest coordinate, left part
+    a multiple of the level's node size): the order is a permutation, leaves are stored in index order, level-1 nodes
+    (1024 keys) and leaves (32 keys) are whole subtrees -- sibling boxes are disjoint along some coordinate -- and on a curved
+    codebook-like manifold the leaf boxes are clearly smaller than those of runs of a 6-D Morton order."""
+    rng = np.random.default_rng(5)
+    M = 50000
+    u, th, yaw = rng.uniform(0, 0.05, M), rng.uniform(0, 2 * np.pi, M), rng.uniform(-0.3, 0.3, M)
+    keys = np.stack([u, 0.0015 * np.cos(th), 0.0015 * np.sin(th), 0.01 * np.cos(th) * 3, 0.01 * np.sin(th) * 3, 0.01 * yaw], 1).astype(np.float32)
+    n_leaf, n_l1 = (M + 31) // 32, ((M + 31) // 32 + 31) // 32
+    order, leaf, l1 = np.zeros(M, np.int32), np.zeros((n_leaf, 12), np.float32), np.zeros((n_l1, 12), np.float32)
+    assert H.h_bvh_layout(P(keys), ctypes.c_longlong(M), P(order), P(leaf), P(l1)) == 0
+    assert np.array_equal(np.sort(order), np.arange(M))
+    full = order[: (M // 32) * 32].reshape(-1, 32)
+    assert (np.diff(full, axis=1) > 0).all()  # leaves in index order
+    ks = keys[order]
+    for j in range(n_leaf):  # the stored boxes are the boxes of the leaves' keys
+        blk = ks[32 * j:32 * j + 32]
+        assert np.array_equal(leaf[j, :6], blk.min(0)) and np.array_equal(leaf[j, 6:], blk.max(0))
+    # two leaves of the same level-1 node never overlap in all six coordinates at once (interiors): they were separated by a split
+    for g in (0, 7, n_l1 - 2):
+        L = leaf[32 * g:32 * g + 32]
+        lo, hi = L[:, None, :6], L[None, :, 6:]
+        overlap = (np.maximum(L[:, None, :6], L[None, :, :6]) < np.minimum(L[:, None, 6:], L[None, :, 6:])).all(2)
+        np.fill_diagonal(overlap, False)
+        assert not overlap.any()
+    # against runs of 32 of the round-1 order (6-D Morton code): the mean box diagonal is a third smaller
+    lo6, hi6 = keys.min(0), keys.max(0)
+    cell = (hi6 - lo6).max() / 1023.0
+    qk = np.clip(np.floor((keys - lo6) / cell), 0, 1023).astype(np.uint64)
+    code = np.zeros(M, dtype=np.uint64)
+    for bit in range(9, -1, -1):
+        for k in range(6):
+            code = (code << np.uint64(1)) | ((qk[:, k] >> np.uint64(bit)) & np.uint64(1))
+    mo = np.argsort(code, kind="stable")
+    km = keys[mo][: (M // 32) * 32].reshape(-1, 32, 6)
+    diag_morton = np.linalg.norm(km.max(1) - km.min(1), axis=1).mean()
+    diag_kd = np.linalg.norm(leaf[: M // 32, 6:] - leaf[: M // 32, :6], axis=1).mean()
+    assert diag_kd < 0.75 * diag_morton, (diag_kd, diag_morton)
+    # deterministic
+    order2 = np.zeros(M, np.int32)
+    H.h_bvh_layout(P(keys), ctypes.c_longlong(M), P(order2), P(leaf.copy()), P(l1.copy()))
+    assert np.array_equal(order, order2)
+
+
 def test_categorical_draw_from_cdf(H):
     """mt_cdf_draw / mt_u01_53 (the multinomial resampler's per-draw arithmetic): equals
     searchsorted(C, u*S, side='right'), never returns an item of zero weight, handles u*S landing on or
