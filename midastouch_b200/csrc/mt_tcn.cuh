@@ -2,8 +2,8 @@
 //
 // Replaces the MinkowskiEngine calls of contrib/tcn_minkloc/{tcn,minkloc,minkfpn}.py for the
 // shipped configuration (config/tcn/default.yaml: planes 32,64,64, layers 1,1,1, one top-down
-// block, conv0 kernel 5, 256-d output).  Sparse tensors are (sorted unique 64-bit coordinate
-// keys, row-major float32 features); a coordinate map is an open-addressing hash table
+// block, conv0 kernel 5, 256-d output).  Sparse tensors are (unique 64-bit coordinate keys in order of
+// first occurrence, row-major float32 features); a coordinate map is an open-addressing hash table
 // key -> row.  Per forward pass:
 //   1. k_tcn_insert_all / k_tcn_count_all / k_tcn_scatter_all: the raw points (float clouds, quantised
 //      in the kernel, or packed keys) register with the coordinate maps of all four levels at once;
@@ -12,17 +12,22 @@
 //      64-bit radix sort) and three single-block passes.
 //   2. k_tcn_kmaps: the kernel maps (row of every kernel offset, -1 = absent, + a bit mask of the
 //      offsets present) of the 3x3x3, the strided 2x2x2 and the transposed 2x2x2 convolutions: the
-//      hash tables are probed once per (point, offset), not once per layer.
-//   3. k_tcn_conv_mma: every convolution with >= 8 input channels as a gather-GEMM on the tensor
-//      cores: one warp = 16 output points x (8 NT) output channels, offsets in ascending order (fixed
-//      summation order, no atomics), only the offsets some point of the tile has; operands straight
-//      from L1/L2 into mma.sync.m16n8k8 TF32 fragments, every product as three MMAs on the
-//      (big, small) TF32 split of both operands (3xTF32: float32-grade accuracy); BatchNorm(eval) /
-//      residual / accumulate / ReLU fused in the epilogue.  The weights of an offset are read once per
-//      16 points instead of once per point (the CUDA-core kernel below was bound by exactly that L1
-//      traffic: 1 GB for the 256 -> 256 transposed convolution).
-//   k_tcn_conv (one warp per output point, hash look-ups) remains for conv0 (one dummy input
-//   feature: a sum of kernel rows) and for channel widths the MMA tiling does not divide.
+//      hash tables are probed once per (point, offset), not once per layer.  The same kernel groups the
+//      (output point, kernel offset) pairs that exist by offset (pair lists).
+//   3. k_tcn_pair_mma + k_tcn_pair_reduce: every gathering convolution as a gather-GEMM on the tensor
+//      cores with work proportional to the pairs present: a work item is up to 32 pairs of one offset x 16
+//      output channels, operands straight from L1/L2 into mma.sync.m16n8k8 TF32 fragments (16-byte loads,
+//      channels permuted onto the k slots), every product as three MMAs on the (big, small) TF32 split
+//      of both operands (3xTF32: float32-grade accuracy); the product rows of a point are added in
+//      ascending offset order (fixed summation order, no float atomics) with BatchNorm(eval) / residual /
+//      accumulate / ReLU in that pass.  1x1 layers use the direct form k_tcn_conv_mma (one warp = 16
+//      output points x 8 NT channels).  The weights of an offset are read once per 32 pairs instead of
+//      once per point (the CUDA-core kernel was bound by exactly that L1 traffic: 1 GB for the 256 -> 256
+//      transposed convolution).
+//   4. every kernel is launched with programmatic dependent launch (tcn_pdl / tcn_launch): the ~30 short,
+//      strictly dependent kernels overlap their launch latencies.
+//   k_tcn_conv0 serves conv0 (one dummy input feature: a sum of kernel rows); k_tcn_conv (one warp per
+//   output point, hash look-ups, CUDA cores) remains for channel widths the MMA tiling does not divide.
 // Semantics restated in oracle/tcn_oracle.py (parity unpinned against MinkowskiEngine itself).
 //
 // Included at the end of midas_b200.cu (same translation unit: shares set_err / CK).
