@@ -392,7 +392,8 @@ def run_ours(args):
             "data": "synthetic (seeded stand-ins for YCB-Slide assets; no datasets offline)",
             "config": cfg, "run": run_info,
             "roofline": {"bound": "hbm", "achieved": a_gbs, "peak": peak, "unit": "GB/s", "frac": a_gbs / peak,
-                         "traffic": traffic, "peak_source": how, "kernel": "k_step_a (motion + drift voxel test + hint-graph SE3_NN)",
+                         "traffic": traffic, "traffic_source": "profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel (round 2), not measured in this run",
+                         "peak_source": how, "kernel": "k_step_a (motion + drift voxel test + hint-graph SE3_NN)",
                          "algorithmic_bytes_per_launch": A_BYTES_PER_UPDATE * n, "avg_launch_ms": k_a,
                          "timed": f"CUDA events between the kernels, stream-launch form, frames {args.warmup}..{args.warmup + kb}",
                          "sweep": {"kernels_ms": {"k_step_a": k_a, "queue consumers (k_step_meshq + k_step_meshq2 + k_step_nnq)": k_q,
