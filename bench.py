@@ -350,6 +350,8 @@ def run_ours(args):
 
     # ---- tactile code network (one forward per frame; random weights, 4096-point contact patch)
     tcn_ms = tcn_time(dev) if rank == 0 else None
+    # ---- tactile depth network (image -> height map -> contact mask; cuDNN, random weights)
+    tdn_ms = tdn_time(dev) if rank == 0 else None
     # ---- batched codebook query on the tensor cores (tcgen05, 3xTF32): 1024 codes against the codebook
     gemm = gemm_time(cb, dev) if rank == 0 else None
     # ---- a whole frame: tactile code network on the frame's 4096-point cloud, then the filter step, in stream order
@@ -408,7 +410,7 @@ def run_ours(args):
             "e2e": {"value": e2e, "unit": "particle-updates/s", "h2d_bytes_per_step": D * 8 + 64 + 64 + 4, "d2h_bytes_per_step": 8,
                     "readback": "rmse of every step, asynchronous into pinned memory on the engine's copy stream (FilterEngine.read_rmse_async), consumed one step later; the code is uploaded on the same copy stream, double-buffered", "l2": "not flushed"},
             "converged_cloud": conv,
-            "tcn_forward_ms": tcn_ms, "frame_with_tcn": frame, "codebook_gemm": gemm,
+            "tcn_forward_ms": tcn_ms, "tdn_forward_ms": tdn_ms, "frame_with_tcn": frame, "codebook_gemm": gemm,
             "gpu_launches": int(replays.value) * (6 if eng.prune else 4) if not args.no_graph else None,
             "graph": {"replays_so_far": int(replays.value), "instantiated": int(ncached.value), "kernel_nodes_per_replay": 6 if eng.prune else 4},
             "clocks": clk.summary(),
@@ -540,6 +542,39 @@ def tcn_time(dev, reps=20):
     e0.record()
     for _ in range(reps):
         tcn.embed_clouds(cloud)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def tdn_time(dev, reps=20):
+    """device time of TDN.image2heightmap + heightmap2mask on one 320 x 240 tactile frame (FCRN-ResNet50-UpProj through
+    cuDNN, BatchNorms folded, fused up-projections; random weights), host image in: normalisation and upload included"""
+    import numpy as np
+    import types
+
+    from midastouch_b200.tdn import TDN, fcrn_parameter_shapes
+
+    g = torch.Generator().manual_seed(0)
+    S = {}
+    for name, shape in fcrn_parameter_shapes().items():
+        if len(shape) == 4:
+            S[name] = torch.randn(shape, generator=g) * (2.0 / (shape[2] * shape[3] * shape[0])) ** 0.5
+        elif name.endswith("running_var") or name.endswith(".weight"):
+            S[name] = torch.ones(shape)
+        else:
+            S[name] = torch.zeros(shape, dtype=torch.long if name.endswith("tracked") else torch.float32)
+    fc = types.SimpleNamespace(blend_sz=0, border=1, ratio=0.2, clip=5, batch_size=1)
+    rng = np.random.default_rng(0)
+    img = rng.integers(0, 255, (320, 240, 3)).astype(np.uint8)
+    t = TDN(types.SimpleNamespace(tdn_weights="", fcrn=types.SimpleNamespace(sim=fc, real=fc)), bg=np.zeros((320, 240), np.float32), device=dev, weights=S)
+    for _ in range(3):
+        t.heightmap2mask(t.image2heightmap(img))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        t.heightmap2mask(t.image2heightmap(img))
     e1.record()
     torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps

@@ -123,6 +123,49 @@ def load_reference():
     return pf, pose
 
 
+def load_reference_tdn():
+    """Returns (fcrn_module, tdn_module) of the unmodified reference (contrib/tdn_fcrn/fcrn.py, tdn.py).  fcrn.py needs
+    torch only; tdn.py imports the renderer, the visualiser, hydra, PIL and cv2 at module level (tdn.py:10-25) without
+    using them in the methods exercised here (blend_heightmaps, image2heightmap, heightmap2mask): those imports are
+    satisfied by empty stand-ins when the real packages are absent."""
+    if not os.path.isfile(os.path.join(REF_ROOT, "midastouch/contrib/tdn_fcrn/fcrn.py")):
+        raise RuntimeError("reference TDN not present under %s" % REF_ROOT)
+    _install_stubs()
+    for pkg in ("midastouch", "midastouch.modules", "midastouch.contrib", "midastouch.contrib.tdn_fcrn", "midastouch.render",
+                "midastouch.viz"):
+        if pkg not in sys.modules:
+            m = types.ModuleType(pkg)
+            m.__path__ = []
+            sys.modules[pkg] = m
+
+    def stub(name, **attrs):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            for k, v in attrs.items():
+                setattr(m, k, v)
+            sys.modules[name] = m
+
+    stub("midastouch.render.digit_renderer", digit_renderer=object)
+    stub("midastouch.viz.visualizer", Viz=object)
+    stub("midastouch.modules.misc", view_subplots=lambda *a, **k: None, DIRS={"weights": ""}, get_device=lambda cpu=False: "cpu")
+    try:
+        import hydra  # noqa: F401
+    except ImportError:
+        stub("hydra", main=lambda **kw: (lambda f: f))
+    try:
+        import PIL  # noqa: F401
+    except ImportError:
+        stub("PIL", Image=object)
+    try:
+        import cv2  # noqa: F401
+    except ImportError:
+        stub("cv2")
+    _load("midastouch.modules.pose", "midastouch/modules/pose.py")
+    fcrn = _load("midastouch.contrib.tdn_fcrn.fcrn", "midastouch/contrib/tdn_fcrn/fcrn.py")
+    tdn = _load("midastouch.contrib.tdn_fcrn.tdn", "midastouch/contrib/tdn_fcrn/tdn.py")
+    return fcrn, tdn
+
+
 class Cfg(dict):
     """attribute-access dict standing in for omegaconf.DictConfig"""
 
