@@ -32,6 +32,18 @@ def _new_stats(cfg, pf, codebook, traj_size, init_particles):
             "num_particles": [], "log_id": str(cfg.expt.log_id).zfill(2), "trial_id": 0}
 
 
+def tactile_code_fn(tdn, tcn, tac_render, tactile_images, small_parts: bool = False):
+    """the front of a frame as filter.py:140-147 runs it -- image -> height map (``TDN.image2heightmap``) -> contact mask
+    (``TDN.heightmap2mask``) -> tactile code (``TCN.cloud_to_tactile_code``) -- as the ``code_fn`` of the loops below"""
+
+    def code_fn(idx):
+        heightmap = tdn.image2heightmap(tactile_images[idx])
+        mask = tdn.heightmap2mask(heightmap, small_parts=small_parts)
+        return tcn.cloud_to_tactile_code(tac_render, heightmap, mask)
+
+    return code_fn
+
+
 def run_filter(cfg, pf: particle_filter, codebook, code_fn, gt_p: torch.Tensor, meas_p: torch.Tensor, schedule=None,
                softmax: bool = True, floor: int = 1000, resample: str | None = None) -> dict:
     """drop-in classes, reference order.  code_fn(idx) -> (1,D) tactile code.  gt_p / meas_p: (T,4,4) CUDA."""

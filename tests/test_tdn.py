@@ -154,3 +154,28 @@ def test_image2heightmap_on_the_gpu(gold):
     t2 = TDN(cfg(), bg=gold["mask_bg"], device="cuda:0")
     m = t2.heightmap2mask(torch.from_numpy(gold["mask_heightmap"]).cuda())
     assert m.is_cuda and np.array_equal(m.cpu().numpy(), gold["mask_sim"]) and bg.is_cuda
+
+
+@pytest.mark.gpu
+def test_frame_front_end_image_to_code(gold):
+    """filter.py:140-147 on the drop-ins: image -> TDN height map -> mask -> TCN code (random weights: shapes, dtypes,
+    determinism, and an all-background frame giving the empty-contact code)"""
+    from midastouch_b200.filter_loop import tactile_code_fn
+    from midastouch_b200.tcn import TCN, PointcloudRenderer
+    from midastouch_b200.tdn import TDN
+    from oracle import tcn_oracle as TC
+
+    tdn = TDN(cfg(), bg=np.zeros((320, 240), np.float32), device="cuda:0", weights=TO.synthetic_fcrn_state(seed=7))
+    m = types.SimpleNamespace(tcn_weights="", model="MinkFPN", num_points=2048, batch_size=100, mink_quantization_size=0.001,
+                              planes="32,64,64", layers="1,1,1", num_top_down=1, conv0_kernel_size=5, feature_size=256, output_dim=256)
+    tcn = TCN(types.SimpleNamespace(model=m, train=types.SimpleNamespace(normalize_embeddings=True)), device="cuda:0",
+              weights={k: torch.from_numpy(np.asarray(v)) for k, v in TC.random_state_dict(seed=5).items()})
+    images = [TO.synthetic_tactile_image(seed=s) for s in (1, 2)]
+    fn = tactile_code_fn(tdn, tcn, PointcloudRenderer(200.0, 240, 320), images)
+    torch.manual_seed(3)
+    c0 = fn(0)
+    assert c0.shape == (1, 256) and c0.dtype == torch.float64 and c0.is_cuda and torch.isfinite(c0).all()
+    assert abs(float(c0.norm()) - 1.0) < 1e-9
+    torch.manual_seed(3)
+    assert torch.equal(fn(0), c0)  # same image, same sampling seed, same bits
+    assert not torch.equal(fn(1), c0)
