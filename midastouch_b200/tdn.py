@@ -244,8 +244,21 @@ class TDN:
         return torch.sum((stack * w[:, None, None]) / w.sum(), dim=0)
 
     def _image_tensor(self, image) -> torch.Tensor:
-        image = normalize_minmax_255(image.detach().cpu().numpy() if torch.is_tensor(image) else image)
-        return torch.from_numpy(np.ascontiguousarray(image)).permute(2, 0, 1).to(self.device).float()[None]
+        """(H,W,3) image -> (1,3,H,W) float32 on the device, min-max normalised to [0, 255] like ``normalize_minmax_255``
+        (tdn.py:108-110) -- but evaluated on the device: the raw frame is uploaded as it is (230 KB for a uint8 DIGIT frame)
+        and the normalisation is a handful of tiny kernels without a host synchronisation, instead of ~1 ms of numpy"""
+        t = image if torch.is_tensor(image) else torch.from_numpy(np.ascontiguousarray(image))
+        integer = not t.dtype.is_floating_point
+        info = torch.iinfo(t.dtype) if integer else None
+        x = t.to(self.device).to(torch.float64)
+        lo, hi = x.min(), x.max()
+        scale = torch.where(hi > lo, 255.0 / (hi - lo).clamp_min(1e-300), torch.zeros_like(hi))
+        x = (x - lo) * scale
+        if integer:  # OpenCV's saturate_cast: round half to even, clamp to the type's range
+            x = torch.round(x).clamp_(info.min, info.max)
+        elif t.dtype != torch.float64:
+            x = x.to(t.dtype)
+        return x.permute(2, 0, 1).float()[None].contiguous()
 
     # ------------------------------------------------------------------ tdn.py:94-115
     def image2heightmap(self, image: np.ndarray) -> torch.Tensor:

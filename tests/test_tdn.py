@@ -179,3 +179,17 @@ def test_frame_front_end_image_to_code(gold):
     torch.manual_seed(3)
     assert torch.equal(fn(0), c0)  # same image, same sampling seed, same bits
     assert not torch.equal(fn(1), c0)
+
+
+def test_device_side_normalisation_equals_the_numpy_restatement():
+    from midastouch_b200.tdn import TDN, normalize_minmax_255
+
+    t = TDN(cfg(), device="cpu")
+    rng = np.random.default_rng(1)
+    for img in (TO.synthetic_tactile_image(seed=5), rng.integers(3, 90, (40, 30, 3)).astype(np.uint8), np.full((8, 6, 3), 7, np.uint8),
+                rng.normal(size=(16, 12, 3)).astype(np.float32)):
+        want = torch.from_numpy(normalize_minmax_255(img)).permute(2, 0, 1).float()[None]
+        got = t._image_tensor(img)
+        assert got.shape == want.shape and got.dtype == torch.float32
+        assert torch.equal(got, want) if img.dtype == np.uint8 else torch.allclose(got, want, rtol=1e-6, atol=1e-5)
+        assert torch.equal(t._image_tensor(torch.from_numpy(img)), got)  # tensors are accepted as well
